@@ -1,0 +1,177 @@
+/*
+ * qrad_cuda.h -- C ABI of libqrad_cuda, the B200 (sm_100a) implementation of the
+ * qrad3 radiosity hot path of klaussilveira/qengine.
+ *
+ * The reference has no plugin / FFI interface: qrad3 is one executable whose
+ * phases talk through process-global arrays.  The entry
+ * points below sit exactly at the five seams of RadWorld() and take the same
+ * data those globals hold, as plain pointers and sizes:
+ *
+ *   qrad_cuda_upload_bsp        replaces  MakeTnodes(&dmodels[0])             src/tools/qrad3/qrad3.c:500, trace.c:47-88
+ *                               (+ the PVS / leaf data behind PvsForOrigin,   qrad3.c:131-175, common/bspfile.c:129-154)
+ *   qrad_cuda_upload_patches    receives  patches[] / face_patches[]          qrad3.c:503-506, qrad.h:65-100
+ *   qrad_cuda_upload_lights     receives  directlights[cluster] lists         qrad3.c:509, lightmap.c:721-838
+ *   qrad_cuda_build_facelights  replaces  RunThreadsOnIndividual(numfaces, BuildFacelights)      qrad3.c:512, lightmap.c:967-1056
+ *   qrad_cuda_make_transfers    replaces  RunThreadsOnIndividual(num_patches, MakeTransfers)     qrad3.c:516, qrad3.c:185-293
+ *   qrad_cuda_bounce            replaces  BounceLight() = numbounce x {ShootLight, CollectLight}  qrad3.c:520, 383-473
+ *   qrad_cuda_final_light       replaces  RunThreadsOnIndividual(numfaces, FinalLightFace)        qrad3.c:535, lightmap.c:1066-1201
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure with
+ * the message available from qrad_cuda_last_error() so a C host can route it
+ * into its Error() (common/cmdlib.c:142).  The library owns all device memory;
+ * the caller owns every pointer it passes and it only needs to stay valid for
+ * the duration of the call.  One context drives one GPU from one host thread.
+ * There is no CPU fallback: without a CUDA device qrad_cuda_create fails.
+ *
+ * All structs below are plain-old-data with the on-disk IBSP v38 layouts of
+ * common/qfiles.h:252-469 where a lump is passed through untouched.
+ */
+#ifndef QRAD_CUDA_H
+#define QRAD_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QRAD_CUDA_ABI_VERSION 1
+
+typedef struct qrad_cuda_ctx qrad_cuda_ctx;
+
+/* ---- IBSP v38 on-disk records (little endian), qfiles.h:283-447 ---- */
+typedef struct { float normal[3]; float dist; int32_t type; } qrad_dplane_t;                     /* 20 B */
+typedef struct { int32_t planenum; int32_t children[2]; int16_t mins[3], maxs[3];
+                 uint16_t firstface, numfaces; } qrad_dnode_t;                                   /* 28 B */
+typedef struct { int32_t contents; int16_t cluster, area; int16_t mins[3], maxs[3];
+                 uint16_t firstleafface, numleaffaces, firstleafbrush, numleafbrushes; } qrad_dleaf_t; /* 28 B */
+typedef struct { uint16_t planenum; int16_t side; int32_t firstedge; int16_t numedges; int16_t texinfo;
+                 uint8_t styles[4]; int32_t lightofs; } qrad_dface_t;                            /* 20 B */
+typedef struct { float vecs[2][4]; int32_t flags; int32_t value; char texture[32]; int32_t nexttexinfo; } qrad_texinfo_t; /* 76 B */
+
+/* The lumps the device needs for ray tests, point location and PVS. */
+typedef struct {
+  const qrad_dplane_t *planes; int32_t numplanes;
+  const qrad_dnode_t  *nodes;  int32_t numnodes;
+  const qrad_dleaf_t  *leafs;  int32_t numleafs;
+  const uint8_t       *visdata; int32_t visdatasize;   /* dvis_t header + RLE rows; 0 = un-vised map */
+} qrad_bsp_view;
+
+/* patches[] as structure-of-arrays; N = num_patches (qrad.h:65-91). */
+typedef struct {
+  int32_t      num_patches;
+  const float *origin;        /* [N][3] patch->origin (centroid + 1 * normal)            */
+  const float *normal;        /* [N][3] patch->plane->normal                              */
+  const float *area;          /* [N]                                                      */
+  const int32_t *cluster;     /* [N]    -1 = in solid                                     */
+  const uint8_t *sky;         /* [N]                                                      */
+  const float *reflectivity;  /* [N][3]                                                   */
+  const float *baselight;     /* [N][3]                                                   */
+  const float *totallight;    /* [N][3] state after CreateDirectLights (emissive cleared) */
+  const float *bounds;        /* [N][6] WindingBounds mins, maxs (AddSampleToPatch)       */
+  const int32_t *face;        /* [N]    owning face                                       */
+  const int32_t *next;        /* [N]    next patch on the face list, -1 = end (patch->next)  */
+  int32_t      numfaces;
+  const int32_t *face_head;   /* [numfaces] face_patches[f], -1 = none                    */
+} qrad_patches_view;
+
+/* directlights[] flattened: lights of cluster c are light_first[c] .. light_first[c+1]-1,
+   stored in the reference's list order (LIFO of creation, lightmap.c:751,785). */
+typedef struct {
+  int32_t      numclusters;
+  const int32_t *light_first; /* [numclusters+1] */
+  int32_t      numlights;
+  const int32_t *type;        /* 0 emit_surface, 1 emit_point, 2 emit_spotlight (qrad.h:34-39) */
+  const float *intensity;
+  const int32_t *style;
+  const float *origin;        /* [L][3] */
+  const float *color;         /* [L][3] */
+  const float *normal;        /* [L][3] */
+  const float *stopdot;
+} qrad_lights_view;
+
+/* Per-face lightmap frame = the lightinfo_t fields CalcFaceVectors / CalcFaceExtents
+   produce (lightmap.c:480-603); computed by the host in the reference's float/double mix. */
+typedef struct {
+  int32_t      numfaces;
+  const uint8_t *lit;         /* [F] 0 for SURF_WARP|SURF_SKY faces (lightmap.c:981)  */
+  const float *facenormal;    /* [F][3] */
+  const float *texorg;        /* [F][3] */
+  const float *textoworld;    /* [F][2][3] */
+  const float *exactmins;     /* [F][2] */
+  const float *exactmaxs;     /* [F][2] */
+  const int32_t *texmins;     /* [F][2] */
+  const int32_t *texsize;     /* [F][2] */
+  const float *face_bounds;   /* [F][6] vertex bounds (FinalLightFace facemins/facemaxs, lightmap.c:1109-1117) */
+  const int32_t *planelink_head; /* [F] first face on the same (side, plane) list as walked by lightmap.c:1123 (0 = empty) */
+  const int32_t *facelinks;   /* [F] facelinks[] (lightmap.c:42-52) */
+  const float *minlight;      /* [F] FloatForKey(face_entity, "_minlight") * 128 */
+  const float *plane_normal;  /* [F][3] dplanes[f->planenum].normal (triangulation plane, NOT flipped by side) */
+} qrad_faces_view;
+
+typedef struct {
+  float ambient, maxlight, lightscale, subdiv;
+  int32_t numbounce;
+} qrad_final_params;
+
+typedef struct {
+  int64_t rays_transfers;     /* root TestLine_r calls issued by MakeTransfers (qrad3.c:244)      */
+  int64_t rays_direct;        /* root TestLine_r calls of CalcPoints + GatherSampleLight          */
+  int64_t node_visits;        /* BSP node visits of all rays (0 unless counting was enabled)      */
+  int64_t candidate_pairs;    /* PVS-visible (i, j) pairs examined by MakeTransfers               */
+  int64_t total_transfers;    /* nnz of the transfer matrix (total_transfer, qrad3.c:183)         */
+  int64_t transfer_bytes;     /* bytes of the gather-form matrix streamed per bounce              */
+  int64_t padded_entries;     /* stored entries including slice padding                           */
+  int32_t num_patches, num_luxels, num_clusters, tree_depth;
+  float   ms_upload, ms_facelights, ms_transfers, ms_transfers_trace, ms_bounce, ms_bounce_kernel, ms_final;
+  int32_t kernel_launches;    /* kernels launched by this context so far                          */
+} qrad_cuda_stats;
+
+int  qrad_cuda_abi_version(void);
+const char *qrad_cuda_last_error(void);
+
+int  qrad_cuda_create(int device, qrad_cuda_ctx **out);
+void qrad_cuda_destroy(qrad_cuda_ctx *ctx);
+/* Restrict this context to a shard of the work (multi-GPU, one process per GPU):
+   source rows of the transfer matrix and faces are split into `world` contiguous shards. */
+int  qrad_cuda_set_shard(qrad_cuda_ctx *ctx, int rank, int world);
+int  qrad_cuda_set_count_nodes(qrad_cuda_ctx *ctx, int enable);
+
+int  qrad_cuda_upload_bsp(qrad_cuda_ctx *ctx, const qrad_bsp_view *bsp);
+int  qrad_cuda_upload_patches(qrad_cuda_ctx *ctx, const qrad_patches_view *patches);
+int  qrad_cuda_upload_lights(qrad_cuda_ctx *ctx, const qrad_lights_view *lights);
+int  qrad_cuda_upload_faces(qrad_cuda_ctx *ctx, const qrad_faces_view *faces);
+
+/* Batched TestLine_r(0, start, stop) (trace.c:92-142): results[i] = 1 if blocked. */
+int  qrad_cuda_test_lines(qrad_cuda_ctx *ctx, int64_t n, const float *starts, const float *stops, uint8_t *results);
+/* PointInLeafnum (qrad3.c:131-150) for a batch of points. */
+int  qrad_cuda_point_in_leaf(qrad_cuda_ctx *ctx, int64_t n, const float *points, int32_t *leafnums);
+
+int  qrad_cuda_build_facelights(qrad_cuda_ctx *ctx, int extrasamples, int numbounce);
+int  qrad_cuda_make_transfers(qrad_cuda_ctx *ctx, int nopvs, int64_t *total_transfer);
+/* numbounce x {ShootLight, CollectLight}; added_out (may be NULL) receives CollectLight()'s return per bounce. */
+int  qrad_cuda_bounce(qrad_cuda_ctx *ctx, int numbounce, float *added_out);
+/* Writes the lighting lump.  dlightdata_out must hold lightdata_capacity bytes (MAX_MAP_LIGHTING = 0x200000). */
+int  qrad_cuda_final_light(qrad_cuda_ctx *ctx, const qrad_final_params *params,
+                           uint8_t *dlightdata_out, int32_t lightdata_capacity, int32_t *lightdatasize,
+                           int32_t *lightofs_out /*[F]*/, uint8_t *styles_out /*[F][4]*/);
+
+/* ---- inspection (parity tests, multi-GPU exchange); not needed by a production host ---- */
+int  qrad_cuda_get_stats(qrad_cuda_ctx *ctx, qrad_cuda_stats *out);
+/* numtransfers per patch (patch->numtransfers). */
+int  qrad_cuda_download_numtransfers(qrad_cuda_ctx *ctx, int32_t *out /*[N]*/);
+/* All transfer rows in the reference's order (by source patch, receivers ascending): row_ptr[N+1],
+   then `patch` / `transfer` arrays of total_transfer entries (transfer_t, qrad.h:57-61; patch widened to u32). */
+int  qrad_cuda_download_transfers(qrad_cuda_ctx *ctx, int64_t *row_ptr, uint32_t *patch, uint16_t *transfer);
+int  qrad_cuda_download_patch_light(qrad_cuda_ctx *ctx, float *totallight /*[N][3]*/, float *samplelight /*[N][3]*/,
+                                    int32_t *samples /*[N]*/, float *radiosity /*[N][3]*/);
+int  qrad_cuda_upload_patch_light(qrad_cuda_ctx *ctx, const float *totallight, const float *samplelight, const int32_t *samples);
+/* facelight[]: luxel_first[F+1]; origins [num_luxels][3]; numstyles[F]; stylenums[F][32];
+   samples for style slot s of face f at samples[(slot_first[f]+s) ...] -- see qengine_b200/qrad.py */
+int  qrad_cuda_facelight_layout(qrad_cuda_ctx *ctx, int32_t *luxel_first /*[F+1]*/, int32_t *numstyles /*[F]*/, int32_t *stylenums /*[F][32]*/);
+int  qrad_cuda_download_facelight(qrad_cuda_ctx *ctx, float *origins /*[L][3]*/, int32_t style_slot, float *samples /*[L][3]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QRAD_CUDA_H */

@@ -1,0 +1,354 @@
+// extern "C" surface of the host half (include/qrad_host.h): scene life-cycle, the
+// views handed to libqrad_cuda's upload calls, RadWorld and the qrad3 command line.
+#include <chrono>
+#include <memory>
+#include <cstdio>
+#include <cstdlib>
+
+#include "host_scene.hpp"
+
+using namespace qrad;
+
+static thread_local std::string g_host_error;
+
+template <class F> static int guarded(F &&f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception &e) {
+    g_host_error = e.what();
+    return 1;
+  }
+}
+
+extern "C" {
+
+const char *qrad_host_last_error(void) { return g_host_error.c_str(); }
+
+void qrad_host_default_params(qrad_host_params *p) {  // qrad3.c:49-74
+  memset(p, 0, sizeof *p);
+  p->numbounce = 8;
+  p->subdiv = 64;
+  p->ambient = 0;
+  p->maxlight = 196;
+  p->lightscale = 1.0f;
+  p->direct_scale = 0.4f;
+  p->entity_scale = 1.0f;
+}
+
+int qrad_host_load(const char *bsp_path, qrad_host_scene **out) {
+  *out = nullptr;
+  return guarded([&] {
+    std::unique_ptr<qrad_host_scene> s(new qrad_host_scene);
+    set_gamedir_from_path(bsp_path, s->scene.bsp);
+    load_bsp(bsp_path, s->scene.bsp);
+    calc_texture_reflectivity(s->scene);
+    *out = s.release();
+  });
+}
+
+void qrad_host_free(qrad_host_scene *s) { delete s; }
+
+int qrad_host_prepare(qrad_host_scene *hs, qrad_host_params *params) {
+  return guarded([&] {
+    Scene &s = hs->scene;
+    if (!s.bsp.visdatasize()) {  // qrad3.c:627-631
+      printf("No vis information, direct lighting only.\n");
+      params->numbounce = 0;
+      params->ambient = 0.1f;
+    }
+    s.params = *params;
+    if (s.bsp.numnodes() == 0 || s.bsp.numfaces() == 0) fail("Empty map");
+    s.winding.clear(); s.origin.clear(); s.normal.clear(); s.reflectivity.clear(); s.baselight.clear();
+    s.totallight.clear(); s.planedist.clear(); s.area.clear(); s.cluster.clear(); s.face.clear();
+    s.next.clear(); s.sky.clear();
+    make_patches(s);
+    subdivide_patches(s);
+    if (s.bounds.size() != (size_t) s.num_patches() * 6) {  // subdiv < 1: no dicing, bounds still needed
+      s.bounds.resize((size_t) s.num_patches() * 6);
+      for (int i = 0; i < s.num_patches(); i++) {
+        float *mn = &s.bounds[i * 6], *mx = mn + 3;
+        mn[0] = mn[1] = mn[2] = 99999;
+        mx[0] = mx[1] = mx[2] = -99999;
+        for (auto &p : s.winding[i].p)
+          for (int k = 0; k < 3; k++) {
+            if (p[k] < mn[k]) mn[k] = p[k];
+            if (p[k] > mx[k]) mx[k] = p[k];
+          }
+      }
+    }
+    create_direct_lights(s);
+    build_face_frames(s);
+    s.prepared = true;
+  });
+}
+
+int qrad_host_bsp_view(qrad_host_scene *hs, qrad_bsp_view *o) {
+  const Bsp &b = hs->scene.bsp;
+  o->planes = b.as<qrad_dplane_t>(kLumpPlanes);
+  o->numplanes = b.numplanes();
+  o->nodes = b.as<qrad_dnode_t>(kLumpNodes);
+  o->numnodes = b.numnodes();
+  o->leafs = b.as<qrad_dleaf_t>(kLumpLeafs);
+  o->numleafs = b.numleafs();
+  o->visdata = b.lump[kLumpVisibility].data();
+  o->visdatasize = b.visdatasize();
+  return 0;
+}
+
+int qrad_host_patches_view(qrad_host_scene *hs, qrad_patches_view *o) {
+  Scene &s = hs->scene;
+  if (!s.prepared) { g_host_error = "scene not prepared"; return 1; }
+  o->num_patches = s.num_patches();
+  o->origin = s.origin.data()->v;
+  o->normal = s.normal.data()->v;
+  o->area = s.area.data();
+  o->cluster = s.cluster.data();
+  o->sky = s.sky.data();
+  o->reflectivity = s.reflectivity.data()->v;
+  o->baselight = s.baselight.data()->v;
+  o->totallight = s.totallight.data()->v;
+  o->bounds = s.bounds.data();
+  o->face = s.face.data();
+  o->next = s.next.data();
+  o->numfaces = s.bsp.numfaces();
+  o->face_head = s.face_head.data();
+  return 0;
+}
+
+int qrad_host_lights_view(qrad_host_scene *hs, qrad_lights_view *o) {
+  Scene &s = hs->scene;
+  if (!s.prepared) { g_host_error = "scene not prepared"; return 1; }
+  o->numclusters = s.bsp.numclusters();
+  o->light_first = s.light_first.data();
+  o->numlights = (int32_t) s.light_type.size();
+  o->type = s.light_type.data();
+  o->intensity = s.light_intensity.data();
+  o->style = s.light_style.data();
+  o->origin = s.light_origin.data()->v;
+  o->color = s.light_color.data()->v;
+  o->normal = s.light_normal.data()->v;
+  o->stopdot = s.light_stopdot.data();
+  return 0;
+}
+
+int qrad_host_faces_view(qrad_host_scene *hs, qrad_faces_view *o) {
+  Scene &s = hs->scene;
+  if (!s.prepared) { g_host_error = "scene not prepared"; return 1; }
+  o->numfaces = s.bsp.numfaces();
+  o->lit = s.face_lit.data();
+  o->facenormal = s.facenormal.data()->v;
+  o->texorg = s.texorg.data()->v;
+  o->textoworld = s.textoworld.data();
+  o->exactmins = s.exactmins.data();
+  o->exactmaxs = s.exactmaxs.data();
+  o->texmins = s.texmins.data();
+  o->texsize = s.texsize.data();
+  o->face_bounds = s.face_bounds.data();
+  o->planelink_head = s.planelink_head.data();
+  o->facelinks = s.facelinks.data();
+  o->minlight = s.minlight.data();
+  o->plane_normal = s.plane_normal.data()->v;
+  return 0;
+}
+
+int qrad_host_counts(qrad_host_scene *hs, int32_t *o) {
+  Scene &s = hs->scene;
+  o[0] = s.bsp.numfaces();
+  o[1] = s.num_patches();
+  o[2] = s.numdlights;
+  o[3] = s.bsp.numclusters();
+  o[4] = s.bsp.numnodes();
+  o[5] = s.bsp.numleafs();
+  o[6] = s.bsp.numtexinfo();
+  o[7] = (int32_t) s.bsp.entities.size();
+  return 0;
+}
+
+int qrad_host_reflectivity(qrad_host_scene *hs, float *out) {
+  Scene &s = hs->scene;
+  for (int i = 0; i < s.bsp.numtexinfo(); i++)
+    for (int k = 0; k < 3; k++) out[i * 3 + k] = s.texture_reflectivity[i][k];
+  return 0;
+}
+
+int qrad_host_windings(qrad_host_scene *hs, int32_t *numpoints, float *pts) {
+  Scene &s = hs->scene;
+  size_t o = 0;
+  for (int i = 0; i < s.num_patches(); i++) {
+    numpoints[i] = (int32_t) s.winding[i].p.size();
+    if (pts)
+      for (auto &p : s.winding[i].p) {
+        pts[o++] = p[0];
+        pts[o++] = p[1];
+        pts[o++] = p[2];
+      }
+  }
+  return 0;
+}
+
+int qrad_host_store_lighting(qrad_host_scene *hs, const uint8_t *data, int32_t size, const int32_t *lightofs,
+                             const uint8_t *styles) {
+  return guarded([&] {
+    Scene &s = hs->scene;
+    if (size < 0 || size > kMaxMapLighting) fail("MAX_MAP_LIGHTING");
+    memcpy(s.bsp.lighting.data(), data, (size_t) size);
+    s.bsp.lightdatasize = size;
+    qrad_dface_t *faces = s.bsp.as_mut<qrad_dface_t>(kLumpFaces);
+    for (int f = 0; f < s.bsp.numfaces(); f++) {
+      if (!s.face_lit[f]) continue;  // skipped faces keep their input lightofs/styles (lightmap.c:1083)
+      faces[f].lightofs = lightofs[f];
+      memcpy(faces[f].styles, styles + f * 4, 4);
+    }
+  });
+}
+
+int qrad_host_lighting(qrad_host_scene *hs, const uint8_t **data, int32_t *size) {
+  *data = hs->scene.bsp.lighting.data();
+  *size = hs->scene.bsp.lightdatasize;
+  return 0;
+}
+
+int qrad_host_write(qrad_host_scene *hs, const char *path) {
+  return guarded([&] { write_bsp(hs->scene.bsp, path); });
+}
+
+// RadWorld, qrad3.c:494-536, with the five dispatch sites replaced by libqrad_cuda calls.
+int qrad_rad_world(qrad_host_scene *hs, qrad_cuda_ctx *ctx, const qrad_host_params *p, float *added_out) {
+  return guarded([&] {
+    Scene &s = hs->scene;
+    auto ck = [&](int rc) {
+      if (rc) fail("%s", qrad_cuda_last_error());
+    };
+    qrad_bsp_view bv;
+    qrad_patches_view pv;
+    qrad_lights_view lv;
+    qrad_faces_view fv;
+    qrad_host_bsp_view(hs, &bv);
+    if (qrad_host_patches_view(hs, &pv) || qrad_host_lights_view(hs, &lv) || qrad_host_faces_view(hs, &fv))
+      fail("%s", g_host_error.c_str());
+    ck(qrad_cuda_upload_bsp(ctx, &bv));
+    ck(qrad_cuda_upload_patches(ctx, &pv));
+    ck(qrad_cuda_upload_lights(ctx, &lv));
+    ck(qrad_cuda_upload_faces(ctx, &fv));
+    ck(qrad_cuda_build_facelights(ctx, p->extrasamples, p->numbounce));
+    if (p->numbounce > 0) {
+      int64_t total = 0;
+      ck(qrad_cuda_make_transfers(ctx, p->nopvs, &total));
+      if (p->verbose) printf("transfer lists: %5.1f megs\n", (float) total * 4 / (1024 * 1024));
+      std::vector<float> added(p->numbounce);
+      ck(qrad_cuda_bounce(ctx, p->numbounce, (p->verbose || added_out) ? added.data() : nullptr));
+      for (int i = 0; i < p->numbounce; i++) {
+        if (p->verbose) printf("bounce:%i added:%f\n", i, added[i]);
+        if (added_out) added_out[i] = added[i];
+      }
+    }
+    qrad_final_params fp;
+    fp.ambient = p->ambient;
+    fp.maxlight = p->maxlight;
+    fp.lightscale = p->lightscale;
+    fp.subdiv = p->subdiv;
+    fp.numbounce = p->numbounce;
+    std::vector<uint8_t> light(kMaxMapLighting);
+    std::vector<int32_t> lightofs(s.bsp.numfaces());
+    std::vector<uint8_t> styles((size_t) s.bsp.numfaces() * 4);
+    int32_t size = 0;
+    ck(qrad_cuda_final_light(ctx, &fp, light.data(), kMaxMapLighting, &size, lightofs.data(), styles.data()));
+    if (qrad_host_store_lighting(hs, light.data(), size, lightofs.data(), styles.data())) fail("%s", g_host_error.c_str());
+  });
+}
+
+// main(), qrad3.c:545-643.  Same flags, same messages where they are part of the contract.
+int qrad3_main(int argc, char **argv) {
+  printf("----- Radiosity ----\n");
+  qrad_host_params p;
+  qrad_host_default_params(&p);
+  int device = 0;
+  int i;
+  for (i = 1; i < argc; i++) {
+    const char *a = argv[i];
+    auto arg = [&]() -> const char * { return (i + 1 < argc) ? argv[++i] : "0"; };
+    if (!strcmp(a, "-dump")) {
+      // patch dumps (bounceN.txt) are a debugging aid of the reference; accepted and ignored
+    } else if (!strcmp(a, "-bounce"))
+      p.numbounce = atoi(arg());
+    else if (!strcmp(a, "-v"))
+      p.verbose = 1;
+    else if (!strcmp(a, "-extra")) {
+      p.extrasamples = 1;
+      printf("extrasamples = true\n");
+    } else if (!strcmp(a, "-threads"))
+      (void) arg();  // parsed and discarded, as on the reference's Linux build (threads.c:379-420)
+    else if (!strcmp(a, "-chop"))
+      p.subdiv = (float) atoi(arg());
+    else if (!strcmp(a, "-scale"))
+      p.lightscale = (float) atof(arg());
+    else if (!strcmp(a, "-direct")) {
+      p.direct_scale *= atof(arg());
+      printf("direct light scaling at %f\n", p.direct_scale);
+    } else if (!strcmp(a, "-entity")) {
+      p.entity_scale *= atof(arg());
+      printf("entity light scaling at %f\n", p.entity_scale);
+    } else if (!strcmp(a, "-glview")) {
+      printf("glview = true\n");
+    } else if (!strcmp(a, "-nopvs")) {
+      p.nopvs = 1;
+      printf("nopvs = true\n");
+    } else if (!strcmp(a, "-ambient"))
+      p.ambient = (float) (atof(arg()) * 128);
+    else if (!strcmp(a, "-maxlight"))
+      p.maxlight = (float) (atof(arg()) * 128);
+    else if (!strcmp(a, "-gpu"))  // extension: CUDA device ordinal
+      device = atoi(arg());
+    else if (!strcmp(a, "-tmpin") || !strcmp(a, "-tmpout")) {
+      fprintf(stderr, "-tmpin/-tmpout are not supported\n");
+    } else
+      break;
+  }
+  if (p.maxlight > 255) p.maxlight = 255;
+  auto die = [](const std::string &msg) {  // Error(), cmdlib.c:142-155
+    printf("\n************ ERROR ************\n%s\n", msg.c_str());
+    return 1;
+  };
+  if (i != argc - 1)
+    return die("usage: qrad [-v] [-chop num] [-scale num] [-ambient num] [-maxlight num] [-threads num] bspfile");
+  auto t0 = std::chrono::steady_clock::now();
+  std::string name = argv[i];
+  {  // StripExtension + DefaultExtension(".bsp")
+    size_t slash = name.find_last_of('/');
+    size_t dot = name.find_last_of('.');
+    if (dot != std::string::npos && (slash == std::string::npos || dot > slash)) name.resize(dot);
+    name += ".bsp";
+  }
+  printf("reading %s\n", name.c_str());
+  qrad_host_scene *hs = nullptr;
+  if (qrad_host_load(name.c_str(), &hs)) return die(g_host_error);
+  if (qrad_host_prepare(hs, &p)) {
+    qrad_host_free(hs);
+    return die(g_host_error);
+  }
+  qrad_cuda_ctx *ctx = nullptr;
+  if (qrad_cuda_create(device, &ctx)) {
+    qrad_host_free(hs);
+    return die(qrad_cuda_last_error());
+  }
+  int rc = qrad_rad_world(hs, ctx, &p, nullptr);
+  if (rc == 0) {
+    printf("writing %s\n", name.c_str());
+    rc = qrad_host_write(hs, name.c_str());
+  }
+  if (p.verbose && rc == 0) {
+    qrad_cuda_stats st;
+    if (!qrad_cuda_get_stats(ctx, &st))
+      printf("gpu: facelights %.2f ms, transfers %.2f ms, bounce %.2f ms, final %.2f ms; %lld rays\n", st.ms_facelights,
+             st.ms_transfers, st.ms_bounce, st.ms_final, (long long) (st.rays_transfers + st.rays_direct));
+  }
+  qrad_cuda_destroy(ctx);
+  qrad_host_free(hs);
+  if (rc) return die(g_host_error);
+  double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  printf("%5.0f seconds elapsed\n", secs);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,666 @@
+// Host-side set-up of the qrad3 drop-in: texture reflectivity, patches and their
+// dicing, the direct-light lists and the per-face lightmap frames.  These run once
+// per map in milliseconds; they stay on the host but must be result-identical to
+// the reference because patch origins / areas / clusters feed every kernel
+// (SURVEY.md section 8a, row a12).  The float/double mix of each expression follows
+// the reference's C promotion rules (vec_t = float, FLT_EVAL_METHOD 0, no FMA):
+// see the comments citing common/mathlib.c and common/polylib.c below.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "host_scene.hpp"
+
+namespace qrad {
+namespace {
+
+// ---- math with the reference's rounding points --------------------------------
+inline float dot3(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// VectorNormalize, mathlib.c:106-122: sqrt and reciprocal are evaluated in double and rounded to float
+inline float normalize(const float *in, float *out) {
+  float length = (float) sqrt((double) (in[0] * in[0] + in[1] * in[1] + in[2] * in[2]));
+  if (length == 0) {
+    out[0] = out[1] = out[2] = 0;
+    return 0;
+  }
+  float ilength = (float) (1.0 / (double) length);
+  out[0] = in[0] * ilength;
+  out[1] = in[1] * ilength;
+  out[2] = in[2] * ilength;
+  return length;
+}
+// VectorLength, mathlib.c:30-41: float products accumulated in double
+inline double length_d(const float *v) {
+  double l = 0;
+  for (int i = 0; i < 3; i++) l += (double) (v[i] * v[i]);
+  return sqrt(l);
+}
+// VectorMA, mathlib.c:59-64: double multiply-add, rounded to float on store
+inline void vector_ma(const float *va, double scale, const float *vb, float *vc) {
+  vc[0] = (float) ((double) va[0] + scale * (double) vb[0]);
+  vc[1] = (float) ((double) va[1] + scale * (double) vb[1]);
+  vc[2] = (float) ((double) va[2] + scale * (double) vb[2]);
+}
+// ColorNormalize, mathlib.c:124-141; returns max, leaves out untouched when max == 0
+inline float color_normalize(const float *in, float *out) {
+  float max = in[0];
+  if (in[1] > max) max = in[1];
+  if (in[2] > max) max = in[2];
+  if (max == 0) return 0;
+  float scale = (float) (1.0 / (double) max);
+  out[0] = scale * in[0];
+  out[1] = scale * in[1];
+  out[2] = scale * in[2];
+  return max;
+}
+inline void cross(const float *a, const float *b, float *c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// ---- windings (common/polylib.c) --------------------------------------------
+float winding_area(const Winding &w) {  // :137-151
+  float total = 0;
+  for (size_t i = 2; i < w.p.size(); i++) {
+    float d1[3], d2[3], c[3];
+    for (int k = 0; k < 3; k++) {
+      d1[k] = w.p[i - 1][k] - w.p[0][k];
+      d2[k] = w.p[i][k] - w.p[0][k];
+    }
+    cross(d1, d2, c);
+    total = (float) ((double) total + 0.5 * length_d(c));
+  }
+  return total;
+}
+void winding_bounds(const Winding &w, float *mins, float *maxs) {  // :153-170
+  mins[0] = mins[1] = mins[2] = 99999;
+  maxs[0] = maxs[1] = maxs[2] = -99999;
+  for (auto &p : w.p)
+    for (int j = 0; j < 3; j++) {
+      if (p[j] < mins[j]) mins[j] = p[j];
+      if (p[j] > maxs[j]) maxs[j] = p[j];
+    }
+}
+void winding_center(const Winding &w, float *c) {  // :177-188
+  c[0] = c[1] = c[2] = 0;
+  for (auto &p : w.p)
+    for (int j = 0; j < 3; j++) c[j] = p[j] + c[j];
+  float scale = (float) (1.0 / (double) (int) w.p.size());
+  for (int j = 0; j < 3; j++) c[j] = scale * c[j];
+}
+void remove_colinear(Winding &w) {  // :86-117
+  int n = (int) w.p.size();
+  std::vector<Vec3> keep;
+  for (int i = 0; i < n; i++) {
+    int j = (i + 1) % n, k = (i + n - 1) % n;
+    float v1[3], v2[3];
+    for (int a = 0; a < 3; a++) {
+      v1[a] = w.p[j][a] - w.p[i][a];
+      v2[a] = w.p[i][a] - w.p[k][a];
+    }
+    normalize(v1, v1);
+    normalize(v2, v2);
+    if ((double) dot3(v1, v2) < 0.999) keep.push_back(w.p[i]);
+  }
+  if ((int) keep.size() != n) w.p.swap(keep);
+}
+// ClipWindingEpsilon, :297-392, for an axial split normal; epsilon is a float parameter (0.1f)
+void clip_winding(const Winding &in, const float *normal, float dist, float epsilon, Winding &front, Winding &back,
+                  bool &has_front, bool &has_back) {
+  int n = (int) in.p.size();
+  std::vector<float> dists(n + 1);
+  std::vector<int> sides(n + 1);
+  int counts[3] = {0, 0, 0};
+  for (int i = 0; i < n; i++) {
+    float d = dot3(in.p[i].v, normal);
+    d -= dist;
+    dists[i] = d;
+    sides[i] = d > epsilon ? 0 : (d < -epsilon ? 1 : 2);
+    counts[sides[i]]++;
+  }
+  sides[n] = sides[0];
+  dists[n] = dists[0];
+  front.p.clear();
+  back.p.clear();
+  has_front = has_back = false;
+  if (!counts[0]) {
+    back = in;
+    has_back = true;
+    return;
+  }
+  if (!counts[1]) {
+    front = in;
+    has_front = true;
+    return;
+  }
+  has_front = has_back = true;
+  for (int i = 0; i < n; i++) {
+    const Vec3 &p1 = in.p[i];
+    if (sides[i] == 2) {
+      front.p.push_back(p1);
+      back.p.push_back(p1);
+      continue;
+    }
+    if (sides[i] == 0) front.p.push_back(p1);
+    if (sides[i] == 1) back.p.push_back(p1);
+    if (sides[i + 1] == 2 || sides[i + 1] == sides[i]) continue;
+    const Vec3 &p2 = in.p[(i + 1) % n];
+    float d = dists[i] / (dists[i] - dists[i + 1]);
+    Vec3 mid;
+    for (int j = 0; j < 3; j++) {
+      if (normal[j] == 1)
+        mid[j] = dist;
+      else if (normal[j] == -1)
+        mid[j] = -dist;
+      else
+        mid[j] = p1[j] + d * (p2[j] - p1[j]);
+    }
+    front.p.push_back(mid);
+    back.p.push_back(mid);
+  }
+  if (front.p.size() > 64 || back.p.size() > 64) fail("ClipWinding: MAX_POINTS_ON_WINDING");
+}
+
+std::vector<uint8_t> read_file(const std::string &path, bool required) {
+  std::vector<uint8_t> out;
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) {
+    if (required) fail("Error opening %s: %s", path.c_str(), strerror(errno));
+    return out;
+  }
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out.resize((size_t) n + 1);  // + NUL like LoadFile (cmdlib.c:560-575); size()-1 is the length
+  if (n && fread(out.data(), 1, (size_t) n, f) != (size_t) n) {
+    fclose(f);
+    fail("File read failure");
+  }
+  fclose(f);
+  out[(size_t) n] = 0;
+  return out;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// CalcTextureReflectivity, patches.c:40-112
+void calc_texture_reflectivity(Scene &s) {
+  const Bsp &b = s.bsp;
+  std::string pal_path = b.gamedir + "../pics/colormap.pcx";
+  std::vector<uint8_t> pcx = read_file(pal_path, true);
+  size_t len = pcx.size() - 1;
+  // LoadPCX header checks, lbmlib.c:373-376
+  if (len < 128 + 768 || pcx[0] != 0x0a || pcx[1] != 5 || pcx[2] != 1 || pcx[3] != 8 ||
+      (pcx[8] | (pcx[9] << 8)) >= 640 || (pcx[10] | (pcx[11] << 8)) >= 480)
+    fail("Bad pcx file %s", pal_path.c_str());
+  const uint8_t *palette = pcx.data() + len - 768;
+
+  int nt = b.numtexinfo();
+  const qrad_texinfo_t *ti = b.as<qrad_texinfo_t>(kLumpTexinfo);
+  s.texture_reflectivity.assign(nt > 0 ? nt : 1, Vec3{{0, 0, 0}});
+  s.texture_reflectivity[0] = Vec3{{0.5f, 0.5f, 0.5f}};
+  for (int i = 0; i < nt; i++) {
+    int j;
+    for (j = 0; j < i; j++)
+      if (!strncmp(ti[i].texture, ti[j].texture, 32)) {
+        s.texture_reflectivity[i] = s.texture_reflectivity[j];
+        break;
+      }
+    if (j != i) continue;
+    char name[33];
+    memcpy(name, ti[i].texture, 32);
+    name[32] = 0;
+    std::string path = b.gamedir + "../textures/" + name + ".wal";
+    std::vector<uint8_t> wal = read_file(path, false);
+    if (wal.empty()) {
+      printf("Couldn't load %s\n", path.c_str());
+      s.texture_reflectivity[i] = Vec3{{0.5f, 0.5f, 0.5f}};
+      continue;
+    }
+    size_t wlen = wal.size() - 1;
+    if (wlen < 100) fail("%s: truncated miptex", path.c_str());
+    uint32_t width, height, ofs0;
+    memcpy(&width, wal.data() + 32, 4);
+    memcpy(&height, wal.data() + 36, 4);
+    memcpy(&ofs0, wal.data() + 40, 4);
+    int texels = (int) (width * height);
+    if (texels <= 0 || (size_t) ofs0 + (size_t) texels > wlen) fail("%s: bad miptex", path.c_str());
+    int color[3] = {0, 0, 0};
+    for (int t = 0; t < texels; t++) {
+      int texel = wal[ofs0 + t];
+      for (int k = 0; k < 3; k++) color[k] += palette[texel * 3 + k];
+    }
+    float *r = s.texture_reflectivity[i].v;
+    for (int k = 0; k < 3; k++) r[k] = (float) ((double) (color[k] / texels) / 255.0);
+    float scale = color_normalize(r, r);
+    if ((double) scale < 0.5) {
+      scale *= 2;
+      for (int k = 0; k < 3; k++) r[k] = scale * r[k];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+namespace {
+
+int entity_for_model(const Scene &s, int modnum) {  // patches.c:253-268
+  char name[16];
+  snprintf(name, sizeof name, "*%i", modnum);
+  for (size_t i = 0; i < s.bsp.entities.size(); i++)
+    if (!strcmp(s.bsp.entities[i].value("model"), name)) return (int) i;
+  return 0;
+}
+
+// the tail shared by MakePatchForFace (:222-236) and FinishSplit (:326-352)
+void place_patch(Scene &s, int p) {
+  float c[3];
+  winding_center(s.winding[p], c);
+  for (int k = 0; k < 3; k++) s.origin[p][k] = c[k] + s.normal[p][k];
+  int leaf = s.bsp.point_in_leaf(s.origin[p].v);
+  s.cluster[p] = s.bsp.as<qrad_dleaf_t>(kLumpLeafs)[leaf].cluster;
+  if (s.cluster[p] == -1 && s.params.verbose) printf("patch->cluster == -1\n");
+}
+
+int new_patch(Scene &s) {
+  if (s.params.max_patches && s.num_patches() == s.params.max_patches) fail("MAX_PATCHES");
+  s.winding.emplace_back();
+  s.origin.push_back(Vec3{{0, 0, 0}});
+  s.normal.push_back(Vec3{{0, 0, 0}});
+  s.reflectivity.push_back(Vec3{{0, 0, 0}});
+  s.baselight.push_back(Vec3{{0, 0, 0}});
+  s.totallight.push_back(Vec3{{0, 0, 0}});
+  s.planedist.push_back(0);
+  s.area.push_back(0);
+  s.cluster.push_back(-1);
+  s.face.push_back(-1);
+  s.next.push_back(-1);
+  s.sky.push_back(0);
+  return s.num_patches() - 1;
+}
+
+// DicePatch, patches.c:425-470 (recursion order: first the front half, then the back half)
+void dice_patch(Scene &s, int p) {
+  float mins[3], maxs[3];
+  winding_bounds(s.winding[p], mins, maxs);
+  const float subdiv = s.params.subdiv;
+  int i;
+  for (i = 0; i < 3; i++)
+    if (floor((double) ((mins[i] + 1) / subdiv)) < floor((double) ((maxs[i] - 1) / subdiv))) break;
+  if (i == 3) return;
+  float split[3] = {0, 0, 0};
+  split[i] = 1;
+  float dist = (float) ((double) subdiv * (1 + floor((double) ((mins[i] + 1) / subdiv))));
+  Winding o1, o2;
+  bool hf, hb;
+  clip_winding(s.winding[p], split, dist, 0.1f, o1, o2, hf, hb);
+  if (!hf || !hb) fail("DicePatch: split produced an empty side");
+  int np = new_patch(s);
+  s.next[np] = s.next[p];
+  s.next[p] = np;
+  s.winding[p] = std::move(o1);
+  s.winding[np] = std::move(o2);
+  // FinishSplit
+  s.baselight[np] = s.baselight[p];
+  s.totallight[np] = s.totallight[p];
+  s.reflectivity[np] = s.reflectivity[p];
+  s.normal[np] = s.normal[p];
+  s.planedist[np] = s.planedist[p];
+  s.sky[np] = s.sky[p];
+  s.face[np] = s.face[p];
+  s.area[p] = winding_area(s.winding[p]);
+  s.area[np] = winding_area(s.winding[np]);
+  if (s.area[p] <= 1) s.area[p] = 1;
+  if (s.area[np] <= 1) s.area[np] = 1;
+  place_patch(s, p);
+  place_patch(s, np);
+  dice_patch(s, p);
+  dice_patch(s, np);
+}
+
+}  // namespace
+
+// MakePatches + MakePatchForFace, patches.c:187-309
+void make_patches(Scene &s) {
+  const Bsp &b = s.bsp;
+  const qrad_dface_t *faces = b.as<qrad_dface_t>(kLumpFaces);
+  const qrad_dplane_t *planes = b.as<qrad_dplane_t>(kLumpPlanes);
+  const qrad_texinfo_t *ti = b.as<qrad_texinfo_t>(kLumpTexinfo);
+  const DModel *models = b.as<DModel>(kLumpModels);
+  const int32_t *surfedges = b.as<int32_t>(kLumpSurfEdges);
+  const DEdge *edges = b.as<DEdge>(kLumpEdges);
+  const DVertex *verts = b.as<DVertex>(kLumpVertexes);
+  int nf = b.numfaces();
+  s.face_head.assign(nf, -1);
+  s.face_offset.assign(nf, Vec3{{0, 0, 0}});
+  s.face_entity.assign(nf, 0);
+  s.totalarea = 0;
+  float totalarea = 0;
+  if (s.params.verbose) printf("%i faces\n", nf);
+  for (int m = 0; m < b.nummodels(); m++) {
+    const DModel &mod = models[m];
+    int ent = entity_for_model(s, m);
+    float origin[3];
+    s.bsp.entities.empty() ? (void) (origin[0] = origin[1] = origin[2] = 0) : s.bsp.entities[ent].vector("origin", origin);
+    for (int j = 0; j < mod.numfaces; j++) {
+      int fn = mod.firstface + j;
+      if (fn < 0 || fn >= nf) fail("model %d references face %d out of range", m, fn);
+      s.face_entity[fn] = ent;
+      for (int k = 0; k < 3; k++) s.face_offset[fn][k] = origin[k];
+      const qrad_dface_t &f = faces[fn];
+      // WindingFromFace, :122-145
+      Winding w;
+      w.p.resize(f.numedges);
+      for (int e = 0; e < f.numedges; e++) {
+        int se = surfedges[f.firstedge + e];
+        int v = se < 0 ? edges[-se].v[1] : edges[se].v[0];
+        for (int k = 0; k < 3; k++) w.p[e][k] = verts[v].point[k];
+      }
+      remove_colinear(w);
+      for (auto &p : w.p)
+        for (int k = 0; k < 3; k++) p[k] = p[k] + origin[k];
+      // MakePatchForFace
+      float area = winding_area(w);
+      totalarea += area;
+      int p = new_patch(s);
+      s.next[p] = s.face_head[fn];
+      s.face_head[fn] = p;
+      s.face[p] = fn;
+      s.winding[p] = std::move(w);
+      const qrad_dplane_t &pl = planes[f.planenum];
+      if (f.side) {  // backplanes[], qrad3.c:88-96
+        for (int k = 0; k < 3; k++) s.normal[p][k] = 0 - pl.normal[k];
+        s.planedist[p] = -pl.dist;
+      } else {
+        for (int k = 0; k < 3; k++) s.normal[p][k] = pl.normal[k];
+        s.planedist[p] = pl.dist;
+      }
+      if (origin[0] || origin[1] || origin[2])  // origin-offset bmodel faces get a shifted plane (:214-223)
+        s.planedist[p] += dot3(origin, s.normal[p].v);
+      place_patch(s, p);
+      s.area[p] = area;
+      if (s.area[p] <= 1) s.area[p] = 1;
+      s.sky[p] = (ti[f.texinfo].flags & kSurfSky) ? 1 : 0;
+      s.reflectivity[p] = s.texture_reflectivity[f.texinfo];
+      if (fn < models[0].numfaces) {  // non-bmodel patches can emit light
+        const qrad_texinfo_t &tx = ti[f.texinfo];
+        float *bl = s.baselight[p].v;
+        if (!(tx.flags & kSurfLight) || tx.value == 0) {
+          bl[0] = bl[1] = bl[2] = 0;
+        } else {
+          float v = (float) tx.value;
+          for (int k = 0; k < 3; k++) bl[k] = v * s.texture_reflectivity[f.texinfo][k];
+        }
+        float color[3] = {0, 0, 0};  // (the reference leaves this uninitialised for an all-black texture)
+        color_normalize(s.reflectivity[p].v, color);
+        for (int k = 0; k < 3; k++) bl[k] *= color[k];
+        s.totallight[p] = s.baselight[p];
+      }
+    }
+  }
+  s.totalarea = totalarea;
+  if (s.params.verbose) printf("%i sqaure feet\n", (int) (totalarea / 64));
+}
+
+void subdivide_patches(Scene &s) {  // patches.c:477-492
+  if (s.params.subdiv < 1) return;
+  int num = s.num_patches();
+  for (int i = 0; i < num; i++) dice_patch(s, i);
+  if (s.params.verbose) printf("%i patches after subdivision\n", s.num_patches());
+  s.bounds.resize((size_t) s.num_patches() * 6);
+  for (int i = 0; i < s.num_patches(); i++) winding_bounds(s.winding[i], &s.bounds[i * 6], &s.bounds[i * 6 + 3]);
+}
+
+// ---------------------------------------------------------------------------
+// CreateDirectLights, lightmap.c:721-838.  Lists are LIFO per cluster.
+void create_direct_lights(Scene &s) {
+  const Bsp &b = s.bsp;
+  const qrad_dleaf_t *leafs = b.as<qrad_dleaf_t>(kLumpLeafs);
+  int nc = b.numclusters();
+  struct L {
+    int cluster, type, style;
+    float intensity, stopdot;
+    Vec3 origin, color, normal;
+  };
+  std::vector<L> made;  // in creation order
+  s.numdlights = 0;
+  for (int i = 0; i < s.num_patches(); i++) {
+    float *tl = s.totallight[i].v;
+    if (tl[0] < 3 && tl[1] < 3 && tl[2] < 3) continue;
+    s.numdlights++;
+    L l{};
+    l.origin = s.origin[i];
+    l.cluster = leafs[b.point_in_leaf(l.origin.v)].cluster;
+    l.type = 0;
+    l.normal = s.normal[i];
+    l.intensity = color_normalize(tl, l.color.v);
+    l.intensity *= s.area[i] * s.params.direct_scale;
+    tl[0] = tl[1] = tl[2] = 0;
+    made.push_back(l);
+  }
+  for (size_t i = 0; i < b.entities.size(); i++) {
+    const Entity &e = b.entities[i];
+    const char *name = e.value("classname");
+    if (strncmp(name, "light", 5)) continue;
+    s.numdlights++;
+    L l{};
+    e.vector("origin", l.origin.v);
+    l.style = (int) e.number("_style");
+    if (!l.style) l.style = (int) e.number("style");
+    if (l.style < 0 || l.style >= 256) l.style = 0;
+    l.cluster = leafs[b.point_in_leaf(l.origin.v)].cluster;
+    float intensity = e.number("light");
+    if (!intensity) intensity = e.number("_light");
+    if (!intensity) intensity = 300;
+    const char *col = e.value("_color");
+    if (col[0] && col[1]) {  // finding F4: the reference reads col[1] of "" (UB); this is the intended test
+      sscanf(col, "%f %f %f", &l.color[0], &l.color[1], &l.color[2]);
+      color_normalize(l.color.v, l.color.v);
+    } else
+      l.color[0] = l.color[1] = l.color[2] = 1.0f;
+    l.intensity = intensity * s.params.entity_scale;
+    l.type = 1;
+    const char *target = e.value("target");
+    if (!strcmp(name, "light_spot") || target[0]) {
+      l.type = 2;
+      l.stopdot = e.number("_cone");
+      if (!l.stopdot) l.stopdot = 10;
+      l.stopdot = (float) cos((double) (l.stopdot / 180) * 3.14159);
+      if (target[0]) {
+        const Entity *e2 = nullptr;
+        for (auto &c : b.entities)
+          if (!strcmp(c.value("targetname"), target)) {
+            e2 = &c;
+            break;
+          }
+        if (!e2)
+          printf("WARNING: light at (%i %i %i) has missing target\n", (int) l.origin[0], (int) l.origin[1], (int) l.origin[2]);
+        else {
+          float dest[3];
+          e2->vector("origin", dest);
+          for (int k = 0; k < 3; k++) l.normal[k] = dest[k] - l.origin[k];
+          normalize(l.normal.v, l.normal.v);
+        }
+      } else {
+        float angle = e.number("angle");
+        if (angle == -1) {
+          l.normal[0] = l.normal[1] = 0;
+          l.normal[2] = 1;
+        } else if (angle == -2) {
+          l.normal[0] = l.normal[1] = 0;
+          l.normal[2] = -1;
+        } else {
+          l.normal[2] = 0;
+          l.normal[0] = (float) cos((double) (angle / 180) * 3.14159);
+          l.normal[1] = (float) sin((double) (angle / 180) * 3.14159);
+        }
+      }
+    }
+    made.push_back(l);
+  }
+  if (s.params.verbose) printf("%i direct lights\n", s.numdlights);
+
+  // flatten: cluster ascending, within a cluster most recently created first
+  s.light_first.assign(nc + 1, 0);
+  int dropped = 0;
+  for (auto &l : made) {
+    if (l.cluster < 0 || l.cluster >= nc) {
+      dropped++;  // the reference indexes directlights[-1] here (out of bounds); such a light can never be gathered
+      continue;
+    }
+    s.light_first[l.cluster + 1]++;
+  }
+  if (dropped) printf("WARNING: %d direct lights sit in solid (cluster -1) and are ignored\n", dropped);
+  for (int c = 0; c < nc; c++) s.light_first[c + 1] += s.light_first[c];
+  int total = s.light_first[nc];
+  s.light_type.assign(total, 0);
+  s.light_style.assign(total, 0);
+  s.light_intensity.assign(total, 0);
+  s.light_stopdot.assign(total, 0);
+  s.light_origin.assign(total, Vec3{{0, 0, 0}});
+  s.light_color.assign(total, Vec3{{0, 0, 0}});
+  s.light_normal.assign(total, Vec3{{0, 0, 0}});
+  std::vector<int> fill(s.light_first.begin(), s.light_first.end() - 1);
+  for (auto it = made.rbegin(); it != made.rend(); ++it) {
+    if (it->cluster < 0 || it->cluster >= nc) continue;
+    int k = fill[it->cluster]++;
+    s.light_type[k] = it->type;
+    s.light_style[k] = it->style;
+    s.light_intensity[k] = it->intensity;
+    s.light_stopdot[k] = it->stopdot;
+    s.light_origin[k] = it->origin;
+    s.light_color[k] = it->color;
+    s.light_normal[k] = it->normal;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Per-face frames: CalcFaceVectors :536-603, CalcFaceExtents :480-528 (as called from
+// BuildFacelights :993-1008), LinkPlaneFaces :42-52, FinalLightFace's vertex bounds :1109-1117.
+void build_face_frames(Scene &s) {
+  const Bsp &b = s.bsp;
+  int nf = b.numfaces();
+  const qrad_dface_t *faces = b.as<qrad_dface_t>(kLumpFaces);
+  const qrad_dplane_t *planes = b.as<qrad_dplane_t>(kLumpPlanes);
+  const qrad_texinfo_t *ti = b.as<qrad_texinfo_t>(kLumpTexinfo);
+  const int32_t *surfedges = b.as<int32_t>(kLumpSurfEdges);
+  const DEdge *edges = b.as<DEdge>(kLumpEdges);
+  const DVertex *verts = b.as<DVertex>(kLumpVertexes);
+  s.face_lit.assign(nf, 0);
+  s.facenormal.assign(nf, Vec3{{0, 0, 0}});
+  s.texorg.assign(nf, Vec3{{0, 0, 0}});
+  s.plane_normal.assign(nf, Vec3{{0, 0, 0}});
+  s.textoworld.assign((size_t) nf * 6, 0);
+  s.exactmins.assign((size_t) nf * 2, 0);
+  s.exactmaxs.assign((size_t) nf * 2, 0);
+  s.face_bounds.assign((size_t) nf * 6, 0);
+  s.minlight.assign(nf, 0);
+  s.texmins.assign((size_t) nf * 2, 0);
+  s.texsize.assign((size_t) nf * 2, 0);
+  s.planelink_head.assign(nf, 0);
+  s.facelinks.assign(nf, 0);
+
+  std::vector<int32_t> planelinks[2];
+  planelinks[0].assign(b.numplanes(), 0);
+  planelinks[1].assign(b.numplanes(), 0);
+  for (int i = 0; i < nf; i++) {
+    int side = faces[i].side ? 1 : 0;
+    s.facelinks[i] = planelinks[side][faces[i].planenum];
+    planelinks[side][faces[i].planenum] = i;
+  }
+
+  for (int fn = 0; fn < nf; fn++) {
+    const qrad_dface_t &f = faces[fn];
+    const qrad_texinfo_t &tex = ti[f.texinfo];
+    s.planelink_head[fn] = planelinks[f.side ? 1 : 0][f.planenum];
+    s.plane_normal[fn] = Vec3{{planes[f.planenum].normal[0], planes[f.planenum].normal[1], planes[f.planenum].normal[2]}};
+    s.minlight[fn] = s.bsp.entities.empty() ? 0.0f : s.bsp.entities[s.face_entity[fn]].number("_minlight") * 128;
+    {
+      float *mn = &s.face_bounds[fn * 6], *mx = mn + 3;
+      mn[0] = mn[1] = mn[2] = 99999;
+      mx[0] = mx[1] = mx[2] = -99999;
+      for (int e = 0; e < f.numedges; e++) {
+        int se = surfedges[f.firstedge + e];
+        const float *v = verts[se >= 0 ? edges[se].v[0] : edges[-se].v[1]].point;
+        for (int k = 0; k < 3; k++) {
+          if (v[k] < mn[k]) mn[k] = v[k];
+          if (v[k] > mx[k]) mx[k] = v[k];
+        }
+      }
+    }
+    if (tex.flags & (kSurfWarp | kSurfSky)) continue;
+    s.face_lit[fn] = 1;
+
+    float facenormal[3], facedist;
+    for (int k = 0; k < 3; k++) facenormal[k] = planes[f.planenum].normal[k];
+    facedist = planes[f.planenum].dist;
+    if (f.side) {
+      for (int k = 0; k < 3; k++) facenormal[k] = 0 - facenormal[k];
+      facedist = -facedist;
+    }
+    for (int k = 0; k < 3; k++) s.facenormal[fn][k] = facenormal[k];
+    const float *modelorg = s.face_offset[fn].v;
+
+    // CalcFaceVectors
+    float worldtotex[2][3], textoworld[2][3], texnormal[3], texorg[3];
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 3; j++) worldtotex[i][j] = tex.vecs[i][j];
+    texnormal[0] = tex.vecs[1][1] * tex.vecs[0][2] - tex.vecs[1][2] * tex.vecs[0][1];
+    texnormal[1] = tex.vecs[1][2] * tex.vecs[0][0] - tex.vecs[1][0] * tex.vecs[0][2];
+    texnormal[2] = tex.vecs[1][0] * tex.vecs[0][1] - tex.vecs[1][1] * tex.vecs[0][0];
+    normalize(texnormal, texnormal);
+    float distscale = dot3(texnormal, facenormal);
+    if (!distscale) {
+      if (s.params.verbose) printf("WARNING: Texture axis perpendicular to face\n");
+      distscale = 1;
+    }
+    if (distscale < 0) {
+      distscale = -distscale;
+      for (int k = 0; k < 3; k++) texnormal[k] = 0 - texnormal[k];
+    }
+    distscale = 1 / distscale;
+    for (int i = 0; i < 2; i++) {
+      float len = (float) length_d(worldtotex[i]);
+      float dist = dot3(worldtotex[i], facenormal);
+      dist *= distscale;
+      vector_ma(worldtotex[i], (double) -dist, texnormal, textoworld[i]);
+      float sc = (1 / len) * (1 / len);
+      for (int k = 0; k < 3; k++) textoworld[i][k] = sc * textoworld[i][k];
+    }
+    for (int i = 0; i < 3; i++) texorg[i] = -tex.vecs[0][3] * textoworld[0][i] - tex.vecs[1][3] * textoworld[1][i];
+    float dist = dot3(texorg, facenormal) - facedist - 1;
+    dist *= distscale;
+    vector_ma(texorg, (double) -dist, texnormal, texorg);
+    for (int k = 0; k < 3; k++) texorg[k] = texorg[k] + modelorg[k];
+    for (int k = 0; k < 3; k++) s.texorg[fn][k] = texorg[k];
+    for (int i = 0; i < 2; i++)
+      for (int k = 0; k < 3; k++) s.textoworld[fn * 6 + i * 3 + k] = textoworld[i][k];
+
+    // CalcFaceExtents
+    float mins[2] = {999999, 999999}, maxs[2] = {-99999, -99999};
+    for (int e = 0; e < f.numedges; e++) {
+      int se = surfedges[f.firstedge + e];
+      const float *vt = verts[se >= 0 ? edges[se].v[0] : edges[-se].v[1]].point;
+      for (int j = 0; j < 2; j++) {
+        float val = dot3(vt, tex.vecs[j]) + tex.vecs[j][3];
+        if (val < mins[j]) mins[j] = val;
+        if (val > maxs[j]) maxs[j] = val;
+      }
+    }
+    int texsize[2] = {0, 0};
+    for (int i = 0; i < 2; i++) {
+      s.exactmins[fn * 2 + i] = mins[i];
+      s.exactmaxs[fn * 2 + i] = maxs[i];
+      float mn = (float) floor((double) (mins[i] / 16));
+      float mx = (float) ceil((double) (maxs[i] / 16));
+      s.texmins[fn * 2 + i] = (int) mn;
+      texsize[i] = (int) (mx - mn);
+      s.texsize[fn * 2 + i] = texsize[i];
+      if (texsize[0] * texsize[1] > (64 * 64 * 4) / 4) fail("Surface to large to map");
+    }
+  }
+}
+
+}  // namespace qrad
