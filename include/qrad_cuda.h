@@ -169,6 +169,8 @@ int  qrad_cuda_upload_patch_light(qrad_cuda_ctx *ctx, const float *totallight, c
 /* facelight[]: luxel_first[F+1]; origins [num_luxels][3]; numstyles[F]; stylenums[F][32];
    samples for style slot s of face f at samples[(slot_first[f]+s) ...] -- see qengine_b200/qrad.py */
 int  qrad_cuda_facelight_layout(qrad_cuda_ctx *ctx, int32_t *luxel_first /*[F+1]*/, int32_t *numstyles /*[F]*/, int32_t *stylenums /*[F][32]*/);
+/* distinct light styles of the map, ascending (ids[0] == 0); these index the style tables below */
+int  qrad_cuda_style_ids(qrad_cuda_ctx *ctx, int32_t *ids /*[256]*/, int32_t *count);
 int  qrad_cuda_download_facelight(qrad_cuda_ctx *ctx, float *origins /*[L][3]*/, int32_t style_slot, float *samples /*[L][3]*/);
 
 #ifdef __cplusplus

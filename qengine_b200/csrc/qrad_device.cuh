@@ -1,0 +1,304 @@
+// Device-side core of libqrad_cuda: context, buffers and the two BSP walkers every
+// kernel uses.  Compiled for sm_100a only, with -fmad=false so that every float and
+// double operation is a separately rounded IEEE op exactly as in the reference's
+// x86-64 SSE build (finding F6: FMA contraction changes bytes).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/qrad_cuda.h"
+
+namespace qrad {
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+[[noreturn]] inline void dfail(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw CudaError(buf);
+}
+#define QCUDA(expr)                                                                                 \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess) ::qrad::dfail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+template <class T> struct DBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DBuf() = default;
+  DBuf(const DBuf &) = delete;
+  DBuf &operator=(const DBuf &) = delete;
+  ~DBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) QCUDA(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void zero(cudaStream_t s) {
+    if (n) QCUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+  }
+  void upload(const T *h, size_t count, cudaStream_t s) {
+    alloc(count);
+    if (count) QCUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T> &h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+  void download(T *h, size_t count, cudaStream_t s) const {
+    if (count) QCUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    QCUDA(cudaStreamSynchronize(s));
+  }
+};
+
+// ---- trace tree ------------------------------------------------------------------
+// One 32-byte record per BSP node, numbered in preorder like MakeTnode (trace.c:47-71).
+// child >= 0: node index.  child < 0: leaf, encoded kLeafFlag | solid << 30 | leaf number.
+struct __align__(16) TNode {
+  float nx, ny, nz, dist;
+  int type, c0, c1, pad;
+};
+constexpr int kLeafFlag = int(0x80000000u);
+constexpr int kSolidBit = 1 << 30;
+constexpr int kLeafMask = 0x3fffffff;
+constexpr int kTraceStack = 64;    // pending far halves; upload rejects deeper trees for the fast kernels
+constexpr int kTraceStackBig = 256;
+
+#ifdef __CUDACC__
+// TestLine_r(0, start, stop), trace.c:92-142, as an explicit-stack walk.  The near half is
+// followed first and the far half (node, stop) is parked; on a pop the new start is the
+// current stop (= the split point), exactly the segments the recursion passes down.
+// Compares: `front >= -ON_EPSILON` with ON_EPSILON the double 0.1 (trace.c:27) is, for a float
+// front, the same predicate as `front > -0.1f`, and `front < ON_EPSILON` the same as
+// `front < 0.1f` (-0.1f < -0.1 and 0.1f > 0.1; checked exhaustively around the constants).
+template <int STACK, bool COUNT>
+__device__ __forceinline__ int test_line(const TNode *__restrict__ nodes, float sx, float sy, float sz, float ex,
+                                         float ey, float ez, unsigned &visits) {
+  float4 stack[STACK];
+  int sp = 0;
+  int node = 0;
+  for (;;) {
+    while (node >= 0) {
+      const float4 pl = __ldg(reinterpret_cast<const float4 *>(nodes + node));
+      const int4 info = __ldg(reinterpret_cast<const int4 *>(nodes + node) + 1);
+      if (COUNT) visits++;
+      float front, back;
+      switch (info.x) {
+        case 0: front = sx - pl.w; back = ex - pl.w; break;
+        case 1: front = sy - pl.w; back = ey - pl.w; break;
+        case 2: front = sz - pl.w; back = ez - pl.w; break;
+        default:
+          front = (sx * pl.x + sy * pl.y + sz * pl.z) - pl.w;
+          back = (ex * pl.x + ey * pl.y + ez * pl.z) - pl.w;
+          break;
+      }
+      if (front > -0.1f && back > -0.1f) {
+        node = info.y;
+        continue;
+      }
+      if (front < 0.1f && back < 0.1f) {
+        node = info.z;
+        continue;
+      }
+      const bool side = front < 0;
+      const float frac = front / (front - back);
+      const float mx = sx + (ex - sx) * frac;
+      const float my = sy + (ey - sy) * frac;
+      const float mz = sz + (ez - sz) * frac;
+      if (sp < STACK) stack[sp] = make_float4(__int_as_float(side ? info.y : info.z), ex, ey, ez);
+      sp++;
+      ex = mx;
+      ey = my;
+      ez = mz;
+      node = side ? info.z : info.y;
+    }
+    if (node & kSolidBit) return 1;
+    if (sp == 0) return 0;
+    sp--;
+    const float4 t = stack[sp < STACK ? sp : STACK - 1];
+    sx = ex;
+    sy = ey;
+    sz = ez;
+    node = __float_as_int(t.x);
+    ex = t.y;
+    ey = t.z;
+    ez = t.w;
+  }
+}
+
+// PointInLeafnum, qrad3.c:131-150: full dot product on every node, `dist > 0` picks child 0.
+__device__ __forceinline__ int point_in_leaf(const TNode *__restrict__ nodes, float x, float y, float z) {
+  int node = 0;
+  while (node >= 0) {
+    const float4 pl = __ldg(reinterpret_cast<const float4 *>(nodes + node));
+    const int4 info = __ldg(reinterpret_cast<const int4 *>(nodes + node) + 1);
+    const float d = (x * pl.x + y * pl.y + z * pl.z) - pl.w;
+    node = d > 0 ? info.y : info.z;
+  }
+  return node & kLeafMask;
+}
+
+// VectorNormalize, mathlib.c:106-122.  (float)sqrt((double)x) == sqrtf(x) and (float)(1.0/(double)x) == 1.0f/x
+// for every float x (53 >= 2*24+2), so the float intrinsics reproduce the reference's double round trip.
+__device__ __forceinline__ float vnormalize(float &x, float &y, float &z) {
+  const float len = __fsqrt_rn(x * x + y * y + z * z);
+  if (len == 0) {
+    x = y = z = 0;
+    return 0;
+  }
+  const float il = __fdiv_rn(1.0f, len);
+  x *= il;
+  y *= il;
+  z *= il;
+  return len;
+}
+#endif  // __CUDACC__
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t s = nullptr;
+  void start(cudaStream_t st) {
+    s = st;
+    if (!a) {
+      QCUDA(cudaEventCreate(&a));
+      QCUDA(cudaEventCreate(&b));
+    }
+    QCUDA(cudaEventRecord(a, s));
+  }
+  float stop() {
+    QCUDA(cudaEventRecord(b, s));
+    QCUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    QCUDA(cudaEventElapsedTime(&ms, a, b));
+    return ms;
+  }
+  ~Timer() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+};
+
+}  // namespace qrad
+
+// The context: everything libqrad_cuda keeps on one GPU between the RadWorld seams.
+struct qrad_cuda_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int rank = 0, world = 1;
+  bool count_nodes = false;
+  qrad_cuda_stats stats{};
+
+  // ---- BSP (qrad_cuda_upload_bsp) ----
+  int numnodes = 0, numleafs = 0, numclusters = 0, tree_depth = 0, pvs_words = 0;
+  bool have_vis = false;
+  qrad::DBuf<qrad::TNode> nodes;
+  qrad::DBuf<int32_t> leaf_contents, leaf_cluster;
+  qrad::DBuf<uint32_t> pvs;            // [numclusters][pvs_words], bit d of row c = cluster d visible from c
+  std::vector<uint32_t> h_pvs;
+
+  // ---- patches, original order (qrad_cuda_upload_patches) ----
+  int N = 0, numfaces_p = 0;
+  std::vector<int32_t> h_cluster;
+  std::vector<uint8_t> h_sky;
+  qrad::DBuf<float4> p_origin_area;    // xyz = origin, w = area
+  qrad::DBuf<float4> p_normal;         // xyz = plane normal
+  qrad::DBuf<float4> p_refl;           // xyz = reflectivity, w = sky flag
+  qrad::DBuf<float> p_baselight, p_totallight, p_samplelight, p_bounds;  // [N][3], [N][3], [N][3], [N][6]
+  qrad::DBuf<int32_t> p_samples, p_face, p_next, face_head, p_cluster;
+
+  // ---- lights ----
+  int numlights = 0, numstyles_map = 1;
+  std::vector<int32_t> h_style_ids;    // distinct light styles ascending, [0] == 0
+  qrad::DBuf<int32_t> light_first, l_type, l_styleslot;
+  qrad::DBuf<float4> l_origin_int;     // xyz origin, w intensity
+  qrad::DBuf<float4> l_color;          // xyz color, w stopdot
+  qrad::DBuf<float4> l_normal;
+
+  // ---- faces ----
+  int F = 0, num_luxels = 0;
+  std::vector<uint8_t> h_lit;
+  std::vector<int32_t> h_luxel_first, h_texsize, h_planelink_head, h_facelinks;
+  std::vector<float> h_face_bounds, h_minlight;
+  qrad::DBuf<uint8_t> f_lit;
+  qrad::DBuf<float> f_normal, f_texorg, f_textoworld, f_exactmins, f_exactmaxs, f_bounds, f_minlight, f_plane_normal;
+  qrad::DBuf<int32_t> f_texmins, f_texsize, f_luxel_first, luxel_face;
+
+  // ---- facelight results (qrad_cuda_build_facelights) ----
+  int fl_numsamples = 1;
+  qrad::DBuf<float> fl_surfpt;         // [numsamples][L][3]; sample 0 = facelight origins
+  qrad::DBuf<float> fl_samples;        // [numstyles_map][L][3]
+  qrad::DBuf<uint32_t> fl_touched;     // [F][numstyles_map] flag: style table exists for the face
+  std::vector<int32_t> h_fl_numstyles, h_fl_stylenums;  // [F], [F][32] (slot indices into h_style_ids)
+  bool facelights_done = false;
+
+  // ---- transfer matrix (qrad_cuda_make_transfers) ----
+  // "slot" order: patches grouped by PVS cluster, each cluster padded to a multiple of 32.
+  int M = 0;                            // number of slots
+  int nc_eff = 0;
+  std::vector<int32_t> h_slot_patch;    // [M] patch or -1
+  std::vector<int32_t> h_patch_slot;    // [N] slot or -1
+  std::vector<int32_t> h_cl_slot_start, h_cl_count, h_slot_cluster;
+  qrad::DBuf<int32_t> slot_patch, patch_slot, slot_cluster;
+  qrad::DBuf<float4> s_origin_area, s_normal;
+  uint64_t bits_words = 0;
+  qrad::DBuf<uint32_t> bits;            // visibility*formfactor>0 bit matrix, rows of source slots
+  qrad::DBuf<float> row_total;          // [M]
+  qrad::DBuf<int32_t> row_count;        // [M] numtransfers of the source in slot s
+  // gather-form matrix, sliced ELL with 32-column slices in slot order
+  bool packed16 = false;
+  int64_t sell_entries = 0;
+  qrad::DBuf<int32_t> col_count;        // [M]
+  qrad::DBuf<int64_t> slice_base;       // [M/32 + 1] entry offsets
+  qrad::DBuf<uint32_t> sell_idx;        // u32 source slot per entry (wide format), or packed {u16 slot, u16 weight}
+  qrad::DBuf<uint16_t> sell_w;          // u16 weight per entry (wide format)
+  // row-major helper lists kept for inspection / download
+  std::vector<int64_t> h_Lptr, h_bits_base;
+  std::vector<int32_t> h_nwords;
+  qrad::DBuf<int64_t> d_Lptr, d_bits_base;
+  qrad::DBuf<int32_t> d_nwords, d_cl_slot_start, d_cl_count;
+  qrad::DBuf<uint32_t> L_slot, L_pos;
+  bool transfers_done = false;
+  int64_t total_transfers = 0;
+
+  // ---- bounce state (slot order) ----
+  qrad::DBuf<float4> rad_a, rad_b;      // radiosity / 0x10000 ("send", qrad3.c:430-431), double buffered
+  qrad::DBuf<float4> s_total;           // totallight per slot
+  qrad::DBuf<float4> s_refl_area;       // xyz reflectivity, w = area (negative area marks sky)
+  qrad::DBuf<float> d_radiosity;        // [N][3] radiosity in patch order (inspection)
+
+  void launch_check(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) qrad::dfail("kernel launch %s failed: %s", what, cudaGetErrorString(e));
+    stats.kernel_launches++;
+  }
+  void sync(const char *what) {
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) qrad::dfail("%s failed: %s", what, cudaGetErrorString(e));
+  }
+};
+
+namespace qrad {
+// implemented in the phase translation units
+void build_facelights_impl(qrad_cuda_ctx *c, int extrasamples, int numbounce);
+void make_transfers_impl(qrad_cuda_ctx *c, int nopvs);
+void bounce_impl(qrad_cuda_ctx *c, int numbounce, float *added_out);
+void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out, int32_t cap, int32_t *size,
+                      int32_t *lightofs, uint8_t *styles);
+void download_transfers_impl(qrad_cuda_ctx *c, int64_t *row_ptr, uint32_t *patch, uint16_t *transfer);
+void test_lines_impl(qrad_cuda_ctx *c, int64_t n, const float *starts, const float *stops, uint8_t *results);
+void point_in_leaf_impl(qrad_cuda_ctx *c, int64_t n, const float *pts, int32_t *out);
+}  // namespace qrad

@@ -1,0 +1,866 @@
+// MakeTransfers (qrad3.c:185-293) and BounceLight (qrad3.c:383-473) on the GPU.
+//
+// Layout ("slot order"): patches are grouped by the PVS cluster of their origin, every
+// cluster padded to a multiple of 32 slots, so one 32-bit word of the visibility matrix
+// = one source patch x 32 consecutive receivers of one cluster.
+//
+//   pass 1  k_visibility   one warp per word: form factor sign tests + TestLine for 32
+//                          receivers of one source (rays batched per source patch, pruned by
+//                          cluster PVS); writes the accept bit  trans > 0  (qrad3.c:216-257).
+//   pass 2  k_row_totals   one warp per source row: walks the row in ascending receiver index
+//                          (the reference's j order) and forms the SERIAL float sum `total`
+//                          (qrad3.c:254) and numtransfers.
+//   pass 3  k_columns      one warp per 32 receivers: walks the potential sources in ascending
+//                          patch index, reads ONE word per source, and emits the quantised
+//                          weights  (int)(trans * 0x10000 / total)  (qrad3.c:283) column by
+//                          column -- the transposed (gather) form ShootLight's scatter needs
+//                          (finding F7), already in the source order the reference adds them.
+//   bounce  k_bounce       one thread per receiver, 128-bit loads of 4 interleaved records,
+//                          serial accumulation in source order, CollectLight fused.
+//
+// Everything is float arithmetic in the reference's operation order; this TU is compiled
+// with -fmad=false.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "qrad_device.cuh"
+
+namespace qrad {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarpsPerBlock = kThreads / 32;
+
+// form factor of source (o, n) towards receiver (po = origin+area, pn): qrad3.c:232-249.
+// Returns trans (0 when rejected); *wants_ray = the reference would call TestLine_r here.
+__device__ __forceinline__ float form_factor_pre(const float4 so, const float4 sn, const float4 po, const float4 pn,
+                                                 float &dist_out, bool &wants_ray) {
+  float dx = po.x - so.x, dy = po.y - so.y, dz = po.z - so.z;
+  const float dist = vnormalize(dx, dy, dz);
+  wants_ray = false;
+  dist_out = dist;
+  if (dist == 0) return 0.f;
+  float scale = dx * sn.x + dy * sn.y + dz * sn.z;
+  scale *= -(dx * pn.x + dy * pn.y + dz * pn.z);
+  if (!(scale > 0)) return 0.f;
+  wants_ray = true;
+  float trans = scale * po.w / (dist * dist);
+  if (trans < 0) trans = 0;
+  return trans;
+}
+
+struct VisArgs {
+  const TNode *nodes;
+  const float4 *s_origin_area, *s_normal;
+  const int32_t *slot_patch;
+  const int64_t *bits_base;      // [nc+1] word offset of the first row of each source cluster
+  const int32_t *nwords;         // [nc]   words per row
+  const int32_t *cl_slot_start;  // [nc]
+  const int32_t *cl_count;       // [nc]
+  const int32_t *vis_ptr;        // [nc+1] CSR of visible receiver clusters per source cluster
+  const int32_t *vis_cluster;    // receiver cluster
+  const int32_t *vis_woff;       // word offset of that cluster inside a row
+  int nc;
+  uint64_t word_begin, word_end;  // this rank's share of the matrix
+  uint32_t *bits;
+  unsigned long long *counters;   // [0] rays, [1] node visits, [2] candidate pairs
+};
+
+template <int STACK, bool COUNT>
+__global__ void __launch_bounds__(kThreads) k_visibility(const VisArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp0 = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const uint64_t nwarps = (uint64_t) gridDim.x * kWarpsPerBlock;
+  unsigned long long rays = 0, pairs = 0;
+  unsigned visits = 0;
+  unsigned long long visits_total = 0;
+  for (uint64_t word = a.word_begin + warp0; word < a.word_end; word += nwarps) {
+    // locate source cluster: last c with bits_base[c] <= word
+    int lo = 0, hi = a.nc;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((uint64_t) a.bits_base[mid] <= word) lo = mid; else hi = mid;
+    }
+    const int c = lo;
+    const int nw = a.nwords[c];
+    const uint64_t rel = word - (uint64_t) a.bits_base[c];
+    const int row = (int) (rel / (uint64_t) nw);
+    const int w = (int) (rel - (uint64_t) row * nw);
+    // receiver cluster: last entry of c's visible list with woff <= w
+    int vlo = a.vis_ptr[c], vhi = a.vis_ptr[c + 1];
+    while (vhi - vlo > 1) {
+      const int mid = (vlo + vhi) >> 1;
+      if (a.vis_woff[mid] <= w) vlo = mid; else vhi = mid;
+    }
+    const int d = a.vis_cluster[vlo];
+    const int sslot = a.cl_slot_start[c] + row;
+    const int rslot = a.cl_slot_start[d] + (w - a.vis_woff[vlo]) * 32 + lane;
+    const bool valid = (w - a.vis_woff[vlo]) * 32 + lane < a.cl_count[d];
+    bool accept = false;
+    if (valid && rslot != sslot) {
+      const float4 so = __ldg(a.s_origin_area + sslot);
+      const float4 sn = __ldg(a.s_normal + sslot);
+      const float4 po = __ldg(a.s_origin_area + rslot);
+      const float4 pn = __ldg(a.s_normal + rslot);
+      float dist;
+      bool wants_ray;
+      const float trans = form_factor_pre(so, sn, po, pn, dist, wants_ray);
+      pairs++;
+      if (wants_ray) {
+        rays++;
+        if (trans > 0) {
+          visits = 0;
+          const int blocked = test_line<STACK, COUNT>(a.nodes, so.x, so.y, so.z, po.x, po.y, po.z, visits);
+          if (COUNT) visits_total += visits;
+          accept = !blocked;
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, accept);
+    if (lane == 0) a.bits[word] = m;
+  }
+  // one atomic per warp per counter
+  for (int o = 16; o; o >>= 1) {
+    rays += __shfl_xor_sync(0xffffffffu, rays, o);
+    pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
+    if (COUNT) visits_total += __shfl_xor_sync(0xffffffffu, visits_total, o);
+  }
+  if (lane == 0) {
+    atomicAdd(a.counters + 0, rays);
+    atomicAdd(a.counters + 2, pairs);
+    if (COUNT) atomicAdd(a.counters + 1, visits_total);
+  }
+}
+
+// Ordered list builder: for each cluster c (one block), all slots j (walking PATCH index ascending)
+// whose cluster is related to c by table[c][cluster(j)] >= 0 (row lists) or table[cluster(j)][c] >= 0
+// (column lists).  out_a = slot of j, out_b = bit position / word address material.
+struct ListArgs {
+  int N, nc;
+  const int32_t *patch_slot;     // [N]
+  const int32_t *slot_cluster;   // [M]
+  const int32_t *woff_table;     // [nc][nc] word offset of receiver cluster d in a row of source cluster c, -1 = not visible
+  const int32_t *cl_slot_start;
+  const int64_t *list_ptr;       // [nc+1]
+  uint32_t *out_slot;
+  uint32_t *out_aux;
+  int transpose;                 // 0: row lists (aux = bit position in the row); 1: column lists (aux unused)
+};
+
+__global__ void __launch_bounds__(1024) k_build_lists(const ListArgs a) {
+  const int c = blockIdx.x;
+  __shared__ int warp_sums[32];
+  __shared__ int64_t base_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_s = a.list_ptr[c];
+  __syncthreads();
+  for (int j0 = 0; j0 < a.N; j0 += blockDim.x) {
+    const int j = j0 + threadIdx.x;
+    bool flag = false;
+    int slot = -1, woff = -1, d = -1;
+    if (j < a.N) {
+      slot = a.patch_slot[j];
+      if (slot >= 0) {
+        d = a.slot_cluster[slot];
+        woff = a.transpose ? a.woff_table[(size_t) d * a.nc + c] : a.woff_table[(size_t) c * a.nc + d];
+        flag = woff >= 0;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) warp_sums[wid] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int k = 0; k < (int) (blockDim.x >> 5); k++) {
+      const int v = warp_sums[k];
+      if (k < wid) before += v;
+      total += v;
+    }
+    if (flag) {
+      const int64_t o = base_s + before + __popc(m & ((1u << lane) - 1));
+      a.out_slot[o] = (uint32_t) slot;
+      if (!a.transpose) a.out_aux[o] = (uint32_t) woff * 32u + (uint32_t) (slot - a.cl_slot_start[d]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) base_s += total;
+    __syncthreads();
+  }
+}
+
+// pass 2: serial row sums in ascending receiver order.
+struct RowArgs {
+  const float4 *s_origin_area, *s_normal;
+  const int32_t *slot_patch, *slot_cluster;
+  const int64_t *bits_base, *Lptr;
+  const int32_t *nwords, *cl_slot_start;
+  const uint32_t *L_slot, *L_pos;
+  const uint32_t *bits;
+  int M;
+  float *row_total;
+  int32_t *row_count;
+  // download mode (reference row format): when out_patch != nullptr, rows are written at row_ptr[patch]
+  const int64_t *row_ptr;
+  uint32_t *out_patch;
+  uint16_t *out_transfer;
+};
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kThreads) k_row_totals(const RowArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int sslot = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (sslot >= a.M) return;
+  const int spatch = a.slot_patch[sslot];
+  if (spatch < 0) return;
+  const int c = a.slot_cluster[sslot];
+  const uint32_t *row = a.bits + a.bits_base[c] + (int64_t) (sslot - a.cl_slot_start[c]) * a.nwords[c];
+  const float4 so = a.s_origin_area[sslot];
+  const float4 sn = a.s_normal[sslot];
+  const int64_t l0 = a.Lptr[c], l1 = a.Lptr[c + 1];
+  float total = 0.f;
+  int count = 0;
+  float rtotal = 0.f;
+  int64_t outp = 0;
+  if (EMIT) {
+    rtotal = a.row_total[sslot];
+    outp = a.row_ptr[spatch];
+  }
+  for (int64_t k0 = l0; k0 < l1; k0 += 32) {
+    const int64_t k = k0 + lane;
+    bool set = false;
+    float trans = 0.f;
+    uint32_t rslot = 0;
+    if (k < l1) {
+      rslot = a.L_slot[k];
+      const uint32_t pos = a.L_pos[k];
+      set = (row[pos >> 5] >> (pos & 31)) & 1u;
+      if (set) {
+        float dist;
+        bool wr;
+        trans = form_factor_pre(so, sn, a.s_origin_area[rslot], a.s_normal[rslot], dist, wr);
+      }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, set);
+    if (EMIT) {
+      if (set) {
+        const int64_t o = outp + __popc(m & ((1u << lane) - 1));
+        a.out_patch[o] = (uint32_t) a.slot_patch[rslot];
+        a.out_transfer[o] = (uint16_t) (int) (trans * 65536.0f / rtotal);
+      }
+      outp += __popc(m);
+    } else {
+      count += __popc(m);
+      while (m) {  // serial float sum in receiver order (qrad3.c:254); uniform across the warp
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        total += __shfl_sync(0xffffffffu, trans, src);
+      }
+    }
+  }
+  if (!EMIT && lane == 0) {
+    a.row_total[sslot] = total;
+    a.row_count[sslot] = count;
+  }
+}
+
+// pass 3: columns.  One warp = 32 receivers (a slice), lane = receiver.
+struct ColArgs {
+  const float4 *s_origin_area, *s_normal;
+  const int32_t *slot_patch, *slot_cluster;
+  const int64_t *bits_base, *Rptr;
+  const int32_t *nwords, *cl_slot_start;
+  const int32_t *woff_table;
+  int nc;
+  const uint32_t *R_slot;
+  const uint32_t *bits;
+  const float *row_total;
+  int M;
+  int32_t *col_count;            // count mode output
+  const int64_t *slice_base;     // fill mode: entry offset per slice
+  uint32_t *sell_idx;
+  uint16_t *sell_w;
+};
+
+template <int MODE>  // 0 = count, 1 = fill wide (u32 + u16), 2 = fill packed16
+__global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int slice = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (slice * 32 >= a.M) return;
+  const int rslot = slice * 32 + lane;
+  const int d = a.slot_cluster[slice * 32];            // all 32 slots of a slice share the cluster
+  const int wslice = (slice * 32 - a.cl_slot_start[d]) >> 5;
+  const bool valid = a.slot_patch[rslot] >= 0;
+  float4 po = make_float4(0, 0, 0, 0), pn = po;
+  if (valid && MODE) {
+    po = a.s_origin_area[rslot];
+    pn = a.s_normal[rslot];
+  }
+  const int64_t r0 = a.Rptr[d], r1 = a.Rptr[d + 1];
+  int cnt = 0;
+  const int64_t base = MODE ? a.slice_base[slice] : 0;
+  for (int64_t k0 = r0; k0 < r1; k0 += 32) {
+    const int64_t k = k0 + lane;
+    uint32_t word = 0, sslot = 0;
+    if (k < r1) {
+      sslot = a.R_slot[k];
+      const int c = a.slot_cluster[sslot];
+      const int woff = a.woff_table[(size_t) c * a.nc + d];
+      word = a.bits[a.bits_base[c] + (int64_t) ((int) sslot - a.cl_slot_start[c]) * a.nwords[c] + woff + wslice];
+    }
+    unsigned nz = __ballot_sync(0xffffffffu, word != 0);
+    while (nz) {
+      const int src = __ffs(nz) - 1;
+      nz &= nz - 1;
+      const uint32_t w = __shfl_sync(0xffffffffu, word, src);
+      const uint32_t ss = __shfl_sync(0xffffffffu, sslot, src);
+      if ((w >> lane) & 1u) {
+        if (MODE) {
+          const float4 so = a.s_origin_area[ss];
+          const float4 sn = a.s_normal[ss];
+          float dist;
+          bool wr;
+          const float trans = form_factor_pre(so, sn, po, pn, dist, wr);
+          const uint32_t itrans = (uint32_t) (int) (trans * 65536.0f / a.row_total[ss]);
+          // sliced-ELL, 4 consecutive entries of one column are contiguous (one 128-bit load in k_bounce)
+          const int64_t o = base + (int64_t) (cnt >> 2) * 128 + lane * 4 + (cnt & 3);
+          if (MODE == 2)
+            a.sell_idx[o] = (ss & 0xffffu) | (itrans << 16);
+          else {
+            a.sell_idx[o] = ss;
+            a.sell_w[o] = (uint16_t) itrans;
+          }
+        }
+        cnt++;
+      }
+    }
+  }
+  if (MODE == 0) a.col_count[rslot] = cnt;
+}
+
+// ---- bounce --------------------------------------------------------------------------------
+struct BounceArgs {
+  const int32_t *col_count;
+  const int64_t *slice_base;
+  const uint32_t *sell_idx;
+  const uint16_t *sell_w;
+  const float4 *send;            // radiosity / 0x10000 per source slot
+  float4 *send_next;
+  float4 *total;                 // totallight per slot
+  const float4 *refl_area;       // xyz reflectivity, w area; w < 0 marks a sky patch
+  float *rad_sum;                // [M] r0 + r1 + r2 of the new radiosity (for `added`), may be null
+  int M;
+};
+
+__device__ __forceinline__ void accum(float &ix, float &iy, float &iz, const float4 s, const float w) {
+  // illumination[j][l] += send[l] * trans->transfer   (qrad3.c:439), mul and add rounded separately
+  ix = ix + s.x * w;
+  iy = iy + s.y * w;
+  iz = iz + s.z * w;
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(kThreads) k_bounce(const BounceArgs a) {
+  const int slot = blockIdx.x * kThreads + threadIdx.x;
+  if (slot >= a.M) return;
+  const int lane = threadIdx.x & 31;
+  const int cnt = a.col_count[slot];
+  const int64_t base = a.slice_base[slot >> 5] + lane * 4;
+  float ix = 0.f, iy = 0.f, iz = 0.f;
+  int k = 0;
+  if (PACKED) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(a.sell_idx + base);
+    for (; k + 4 <= cnt; k += 4, p += 32) {
+      const uint4 e = __ldcs(p);
+      const float4 s0 = __ldg(a.send + (e.x & 0xffffu));
+      const float4 s1 = __ldg(a.send + (e.y & 0xffffu));
+      const float4 s2 = __ldg(a.send + (e.z & 0xffffu));
+      const float4 s3 = __ldg(a.send + (e.w & 0xffffu));
+      accum(ix, iy, iz, s0, (float) (e.x >> 16));
+      accum(ix, iy, iz, s1, (float) (e.y >> 16));
+      accum(ix, iy, iz, s2, (float) (e.z >> 16));
+      accum(ix, iy, iz, s3, (float) (e.w >> 16));
+    }
+    if (k < cnt) {
+      const uint4 e = __ldcs(p);
+      const uint32_t ee[4] = {e.x, e.y, e.z, e.w};
+      for (int q = 0; k + q < cnt; q++) accum(ix, iy, iz, __ldg(a.send + (ee[q] & 0xffffu)), (float) (ee[q] >> 16));
+    }
+  } else {
+    const uint4 *p = reinterpret_cast<const uint4 *>(a.sell_idx + base);
+    const uint2 *pw = reinterpret_cast<const uint2 *>(a.sell_w + base);
+    for (; k + 4 <= cnt; k += 4, p += 32, pw += 32) {
+      const uint4 e = __ldcs(p);
+      const uint2 w = __ldcs(pw);
+      const float4 s0 = __ldg(a.send + e.x);
+      const float4 s1 = __ldg(a.send + e.y);
+      const float4 s2 = __ldg(a.send + e.z);
+      const float4 s3 = __ldg(a.send + e.w);
+      accum(ix, iy, iz, s0, (float) (w.x & 0xffffu));
+      accum(ix, iy, iz, s1, (float) (w.x >> 16));
+      accum(ix, iy, iz, s2, (float) (w.y & 0xffffu));
+      accum(ix, iy, iz, s3, (float) (w.y >> 16));
+    }
+    if (k < cnt) {
+      const uint4 e = __ldcs(p);
+      const uint2 w = __ldcs(pw);
+      const uint32_t ee[4] = {e.x, e.y, e.z, e.w};
+      const uint32_t ww[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
+      for (int q = 0; k + q < cnt; q++) accum(ix, iy, iz, __ldg(a.send + ee[q]), (float) ww[q]);
+    }
+  }
+  // CollectLight, qrad3.c:383-409
+  const float4 ra = a.refl_area[slot];
+  float4 t = a.total[slot];
+  float rx = 0.f, ry = 0.f, rz = 0.f;
+  if (ra.w > 0) {  // not sky (and not a padding slot)
+    t.x += ix / ra.w;
+    t.y += iy / ra.w;
+    t.z += iz / ra.w;
+    rx = ix * ra.x;
+    ry = iy * ra.y;
+    rz = iz * ra.z;
+    a.total[slot] = t;
+  }
+  if (a.rad_sum) a.rad_sum[slot] = rx + ry + rz;
+  a.send_next[slot] = make_float4(rx / 65536.0f, ry / 65536.0f, rz / 65536.0f, 0.f);
+}
+
+// serial float sum of rad_sum over PATCH order (CollectLight's `total`), one warp
+__global__ void k_ordered_sum(const float *__restrict__ v, const int32_t *__restrict__ patch_slot, int n,
+                              float *__restrict__ out) {
+  const int lane = threadIdx.x;
+  float total = 0.f;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    float x = 0.f;
+    bool has = false;
+    if (i < n) {
+      const int s = patch_slot[i];
+      if (s >= 0) {
+        x = v[s];
+        has = true;
+      }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, has);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      total += __shfl_sync(0xffffffffu, x, src);
+    }
+  }
+  if (lane == 0) *out = total;
+}
+
+__global__ void k_init_bounce(int M, const int32_t *__restrict__ slot_patch, const float *__restrict__ samplelight,
+                              const float *__restrict__ totallight, const float4 *__restrict__ p_refl,
+                              const float4 *__restrict__ p_origin_area, float4 *__restrict__ send,
+                              float4 *__restrict__ total, float4 *__restrict__ refl_area) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= M) return;
+  const int p = slot_patch[s];
+  if (p < 0) {
+    send[s] = make_float4(0, 0, 0, 0);
+    total[s] = make_float4(0, 0, 0, 0);
+    refl_area[s] = make_float4(0, 0, 0, -1.f);
+    return;
+  }
+  const float4 r = p_refl[p];
+  const float area = p_origin_area[p].w;
+  // radiosity = samplelight * reflectivity * area   (qrad3.c:455-459), then send = radiosity / 0x10000
+  const float rx = samplelight[p * 3] * r.x * area;
+  const float ry = samplelight[p * 3 + 1] * r.y * area;
+  const float rz = samplelight[p * 3 + 2] * r.z * area;
+  send[s] = make_float4(rx / 65536.0f, ry / 65536.0f, rz / 65536.0f, 0.f);
+  total[s] = make_float4(totallight[p * 3], totallight[p * 3 + 1], totallight[p * 3 + 2], 0.f);
+  refl_area[s] = make_float4(r.x, r.y, r.z, r.w != 0.f ? -area : area);
+}
+
+__global__ void k_finish_bounce(int N, const int32_t *__restrict__ patch_slot, const float4 *__restrict__ total,
+                                const float4 *__restrict__ send, float *__restrict__ totallight,
+                                float *__restrict__ radiosity) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const int s = patch_slot[p];
+  if (s < 0) return;
+  const float4 t = total[s];
+  totallight[p * 3] = t.x;
+  totallight[p * 3 + 1] = t.y;
+  totallight[p * 3 + 2] = t.z;
+  const float4 r = send[s];
+  radiosity[p * 3] = r.x * 65536.0f;
+  radiosity[p * 3 + 1] = r.y * 65536.0f;
+  radiosity[p * 3 + 2] = r.z * 65536.0f;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
+  if (!c->numnodes || !c->N) dfail("make_transfers: BSP and patches must be uploaded first");
+  if (!c->have_vis) dfail("make_transfers: map has no visibility data (the reference forces numbounce = 0)");
+  Timer tall;
+  tall.start(c->stream);
+  const int N = c->N;
+  // ---- host: slot order ----
+  // With -nopvs every patch receives (even those in solid); sources still need a valid cluster
+  // (PvsForOrigin fails for them, qrad3.c:208-209).  That case is one pseudo cluster holding everybody.
+  const int nc = nopvs ? 1 : c->numclusters;
+  if (nc <= 0) dfail("make_transfers: no clusters");
+  if ((int64_t) nc * nc > (int64_t) 1 << 28) dfail("make_transfers: %d clusters exceed the dense PVS table limit", nc);
+  std::vector<int32_t> eff(N);
+  for (int i = 0; i < N; i++) {
+    int cl = c->h_cluster[i];
+    if (cl >= c->numclusters) dfail("patch %d has cluster %d >= numclusters %d", i, cl, c->numclusters);
+    eff[i] = nopvs ? 0 : cl;
+  }
+  c->nc_eff = nc;
+  c->h_cl_count.assign(nc, 0);
+  for (int i = 0; i < N; i++)
+    if (eff[i] >= 0) c->h_cl_count[eff[i]]++;
+  c->h_cl_slot_start.assign(nc + 1, 0);
+  for (int k = 0; k < nc; k++) c->h_cl_slot_start[k + 1] = c->h_cl_slot_start[k] + ((c->h_cl_count[k] + 31) & ~31);
+  const int M = c->h_cl_slot_start[nc];
+  c->M = M;
+  if (M == 0) dfail("make_transfers: no patch lies in a valid cluster");
+  c->h_slot_patch.assign(M, -1);
+  c->h_patch_slot.assign(N, -1);
+  c->h_slot_cluster.assign(M, 0);
+  {
+    std::vector<int32_t> fill(c->h_cl_slot_start.begin(), c->h_cl_slot_start.end() - 1);
+    for (int i = 0; i < N; i++)
+      if (eff[i] >= 0) {
+        int s = fill[eff[i]]++;
+        c->h_slot_patch[s] = i;
+        c->h_patch_slot[i] = s;
+      }
+    for (int k = 0; k < nc; k++)
+      for (int s = c->h_cl_slot_start[k]; s < c->h_cl_slot_start[k + 1]; s++) c->h_slot_cluster[s] = k;
+  }
+  // sources in solid never shoot under -nopvs: remember them so their rows are skipped
+  std::vector<uint8_t> source_ok(M, 0);
+  for (int s = 0; s < M; s++) {
+    int p = c->h_slot_patch[s];
+    source_ok[s] = p >= 0 && c->h_cluster[p] >= 0;
+  }
+  // ---- host: visible cluster lists and row geometry ----
+  std::vector<int32_t> vis_ptr(nc + 1, 0), vis_cluster, vis_woff, woff_table((size_t) nc * nc, -1);
+  c->h_nwords.assign(nc, 0);
+  c->h_bits_base.assign(nc + 1, 0);
+  c->h_Lptr.assign(nc + 1, 0);
+  std::vector<int64_t> Rptr(nc + 1, 0);
+  for (int a = 0; a < nc; a++) {
+    int w = 0;
+    int64_t cand = 0;
+    for (int d = 0; d < nc; d++) {
+      bool vis = nopvs ? true : ((c->h_pvs[(size_t) a * c->pvs_words + (d >> 5)] >> (d & 31)) & 1u);
+      if (!vis || c->h_cl_count[d] == 0) continue;
+      vis_cluster.push_back(d);
+      vis_woff.push_back(w);
+      woff_table[(size_t) a * nc + d] = w;
+      w += (c->h_cl_slot_start[d + 1] - c->h_cl_slot_start[d]) >> 5;
+      cand += c->h_cl_count[d];
+      Rptr[d + 1] += c->h_cl_count[a];
+    }
+    vis_ptr[a + 1] = (int32_t) vis_cluster.size();
+    c->h_nwords[a] = w;
+    c->h_bits_base[a + 1] = c->h_bits_base[a] + (int64_t) c->h_cl_count[a] * w;
+    c->h_Lptr[a + 1] = c->h_Lptr[a] + cand;
+  }
+  for (int d = 0; d < nc; d++) Rptr[d + 1] += Rptr[d];
+  // a cluster that sees nothing would leave a row of zero words; bits_base must stay strictly usable
+  const uint64_t W = (uint64_t) c->h_bits_base[nc];
+  c->bits_words = W;
+  if (c->h_Lptr[nc] >= ((int64_t) 1 << 40)) dfail("make_transfers: candidate lists too large");
+
+  cudaStream_t st = c->stream;
+  c->slot_patch.upload(c->h_slot_patch, st);
+  c->patch_slot.upload(c->h_patch_slot, st);
+  c->slot_cluster.upload(c->h_slot_cluster, st);
+  {
+    std::vector<float4> so(M, make_float4(0, 0, 0, 0)), sn(M, make_float4(0, 0, 0, 0));
+    std::vector<float4> po(N), pn(N);
+    QCUDA(cudaMemcpyAsync(po.data(), c->p_origin_area.p, (size_t) N * 16, cudaMemcpyDeviceToHost, st));
+    QCUDA(cudaMemcpyAsync(pn.data(), c->p_normal.p, (size_t) N * 16, cudaMemcpyDeviceToHost, st));
+    c->sync("make_transfers staging");
+    for (int s = 0; s < M; s++) {
+      int p = c->h_slot_patch[s];
+      if (p >= 0) {
+        so[s] = po[p];
+        sn[s] = pn[p];
+      }
+    }
+    c->s_origin_area.upload(so, st);
+    c->s_normal.upload(sn, st);
+  }
+  DBuf<int32_t> d_vis_ptr, d_vis_cluster, d_vis_woff, d_woff_table;
+  d_vis_ptr.upload(vis_ptr, st);
+  d_vis_cluster.upload(vis_cluster, st);
+  d_vis_woff.upload(vis_woff, st);
+  d_woff_table.upload(woff_table, st);
+  c->d_bits_base.upload(c->h_bits_base, st);
+  c->d_Lptr.upload(c->h_Lptr, st);
+  c->d_nwords.upload(c->h_nwords, st);
+  c->d_cl_slot_start.upload(c->h_cl_slot_start, st);
+  c->d_cl_count.upload(c->h_cl_count, st);
+  DBuf<int64_t> d_Rptr;
+  d_Rptr.upload(Rptr, st);
+  c->bits.alloc((size_t) W + 1);
+  DBuf<unsigned long long> counters;
+  counters.alloc(4);
+  counters.zero(st);
+
+  // ---- pass 1 ----
+  Timer ttrace;
+  ttrace.start(st);
+  if (W) {
+    // rows of patches that sit in solid (only possible under -nopvs) are cleared afterwards
+    VisArgs a;
+    a.nodes = c->nodes.p;
+    a.s_origin_area = c->s_origin_area.p;
+    a.s_normal = c->s_normal.p;
+    a.slot_patch = c->slot_patch.p;
+    a.bits_base = c->d_bits_base.p;
+    a.nwords = c->d_nwords.p;
+    a.cl_slot_start = c->d_cl_slot_start.p;
+    a.cl_count = c->d_cl_count.p;
+    a.vis_ptr = d_vis_ptr.p;
+    a.vis_cluster = d_vis_cluster.p;
+    a.vis_woff = d_vis_woff.p;
+    a.nc = nc;
+    // multi-GPU: each rank traces a contiguous share of the words (rows stay whole per cluster share)
+    const uint64_t per = (W + c->world - 1) / c->world;
+    a.word_begin = std::min<uint64_t>(W, per * c->rank);
+    a.word_end = std::min<uint64_t>(W, per * (c->rank + 1));
+    if (c->world > 1) c->bits.zero(st);
+    a.bits = c->bits.p;
+    a.counters = counters.p;
+    const uint64_t mine = a.word_end - a.word_begin;
+    const uint64_t want_blocks = (mine + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>(want_blocks, (uint64_t) c->sm_count * 8));
+    const bool big = c->tree_depth > kTraceStack;
+    if (c->count_nodes) {
+      if (big) k_visibility<kTraceStackBig, true><<<blocks, kThreads, 0, st>>>(a);
+      else k_visibility<kTraceStack, true><<<blocks, kThreads, 0, st>>>(a);
+    } else {
+      if (big) k_visibility<kTraceStackBig, false><<<blocks, kThreads, 0, st>>>(a);
+      else k_visibility<kTraceStack, false><<<blocks, kThreads, 0, st>>>(a);
+    }
+    c->launch_check("k_visibility");
+  }
+  c->stats.ms_transfers_trace = ttrace.stop();
+  if (nopvs) {
+    // clear rows of sources in solid: they never shoot (qrad3.c:208)
+    for (int s = 0; s < M; s++)
+      if (c->h_slot_patch[s] >= 0 && !source_ok[s])
+        QCUDA(cudaMemsetAsync(c->bits.p + c->h_bits_base[0] + (int64_t) s * c->h_nwords[0], 0, (size_t) c->h_nwords[0] * 4, st));
+  }
+
+  // ---- ordered lists ----
+  c->L_slot.alloc((size_t) c->h_Lptr[nc] + 1);
+  c->L_pos.alloc((size_t) c->h_Lptr[nc] + 1);
+  DBuf<uint32_t> R_slot;
+  R_slot.alloc((size_t) Rptr[nc] + 1);
+  {
+    ListArgs la;
+    la.N = N;
+    la.nc = nc;
+    la.patch_slot = c->patch_slot.p;
+    la.slot_cluster = c->slot_cluster.p;
+    la.woff_table = d_woff_table.p;
+    la.cl_slot_start = c->d_cl_slot_start.p;
+    la.list_ptr = c->d_Lptr.p;
+    la.out_slot = c->L_slot.p;
+    la.out_aux = c->L_pos.p;
+    la.transpose = 0;
+    k_build_lists<<<nc, 1024, 0, st>>>(la);
+    c->launch_check("k_build_lists(rows)");
+    la.list_ptr = d_Rptr.p;
+    la.out_slot = R_slot.p;
+    la.out_aux = nullptr;
+    la.transpose = 1;
+    k_build_lists<<<nc, 1024, 0, st>>>(la);
+    c->launch_check("k_build_lists(cols)");
+  }
+
+  // ---- pass 2 ----
+  c->row_total.alloc((size_t) M);
+  c->row_count.alloc((size_t) M);
+  c->row_total.zero(st);
+  c->row_count.zero(st);
+  {
+    RowArgs ra{};
+    ra.s_origin_area = c->s_origin_area.p;
+    ra.s_normal = c->s_normal.p;
+    ra.slot_patch = c->slot_patch.p;
+    ra.slot_cluster = c->slot_cluster.p;
+    ra.bits_base = c->d_bits_base.p;
+    ra.Lptr = c->d_Lptr.p;
+    ra.nwords = c->d_nwords.p;
+    ra.cl_slot_start = c->d_cl_slot_start.p;
+    ra.L_slot = c->L_slot.p;
+    ra.L_pos = c->L_pos.p;
+    ra.bits = c->bits.p;
+    ra.M = M;
+    ra.row_total = c->row_total.p;
+    ra.row_count = c->row_count.p;
+    k_row_totals<false><<<(M + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(ra);
+    c->launch_check("k_row_totals");
+  }
+
+  // ---- pass 3 ----
+  c->packed16 = M <= 65536;
+  c->col_count.alloc((size_t) M);
+  ColArgs ca{};
+  ca.s_origin_area = c->s_origin_area.p;
+  ca.s_normal = c->s_normal.p;
+  ca.slot_patch = c->slot_patch.p;
+  ca.slot_cluster = c->slot_cluster.p;
+  ca.bits_base = c->d_bits_base.p;
+  ca.Rptr = d_Rptr.p;
+  ca.nwords = c->d_nwords.p;
+  ca.cl_slot_start = c->d_cl_slot_start.p;
+  ca.woff_table = d_woff_table.p;
+  ca.nc = nc;
+  ca.R_slot = R_slot.p;
+  ca.bits = c->bits.p;
+  ca.row_total = c->row_total.p;
+  ca.M = M;
+  ca.col_count = c->col_count.p;
+  const int nslices = M / 32;
+  const int cblocks = (nslices + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  k_columns<0><<<cblocks, kThreads, 0, st>>>(ca);
+  c->launch_check("k_columns<count>");
+  std::vector<int32_t> h_col((size_t) M);
+  c->col_count.download(h_col.data(), (size_t) M, st);
+  std::vector<int64_t> h_slice_base((size_t) nslices + 1, 0);
+  int64_t nnz = 0;
+  for (int s = 0; s < nslices; s++) {
+    int mx = 0;
+    for (int l = 0; l < 32; l++) {
+      mx = std::max(mx, h_col[(size_t) s * 32 + l]);
+      nnz += h_col[(size_t) s * 32 + l];
+    }
+    h_slice_base[s + 1] = h_slice_base[s] + (int64_t) ((mx + 3) & ~3) * 32;
+  }
+  c->sell_entries = h_slice_base[nslices];
+  c->slice_base.upload(h_slice_base, st);
+  c->sell_idx.alloc((size_t) c->sell_entries + 4);
+  c->sell_idx.zero(st);
+  if (!c->packed16) {
+    c->sell_w.alloc((size_t) c->sell_entries + 8);
+    c->sell_w.zero(st);
+  } else
+    c->sell_w.release();
+  ca.slice_base = c->slice_base.p;
+  ca.sell_idx = c->sell_idx.p;
+  ca.sell_w = c->sell_w.p;
+  if (c->packed16) k_columns<2><<<cblocks, kThreads, 0, st>>>(ca);
+  else k_columns<1><<<cblocks, kThreads, 0, st>>>(ca);
+  c->launch_check("k_columns<fill>");
+  c->sync("make_transfers");
+
+  unsigned long long hc[4];
+  counters.download(hc, 4, st);
+  c->stats.rays_transfers = (int64_t) hc[0];
+  c->stats.node_visits += (int64_t) hc[1];
+  c->stats.candidate_pairs = (int64_t) hc[2];
+  c->total_transfers = nnz;
+  c->stats.total_transfers = nnz;
+  c->stats.padded_entries = c->sell_entries;
+  c->stats.transfer_bytes = nnz * (c->packed16 ? 4 : 6);
+  c->transfers_done = true;
+  c->stats.ms_transfers = tall.stop();
+}
+
+// reference row format for parity tests: rows by source patch, receivers ascending
+void download_transfers_impl(qrad_cuda_ctx *c, int64_t *row_ptr, uint32_t *patch, uint16_t *transfer) {
+  const int N = c->N, M = c->M;
+  cudaStream_t st = c->stream;
+  std::vector<int32_t> rc((size_t) M);
+  c->row_count.download(rc.data(), rc.size(), st);
+  row_ptr[0] = 0;
+  for (int i = 0; i < N; i++) row_ptr[i + 1] = row_ptr[i] + (c->h_patch_slot[i] >= 0 ? rc[c->h_patch_slot[i]] : 0);
+  const int64_t nnz = row_ptr[N];
+  DBuf<int64_t> d_row_ptr;
+  d_row_ptr.upload(row_ptr, (size_t) N + 1, st);
+  DBuf<uint32_t> d_patch;
+  DBuf<uint16_t> d_tr;
+  d_patch.alloc((size_t) nnz + 1);
+  d_tr.alloc((size_t) nnz + 1);
+  RowArgs ra{};
+  ra.s_origin_area = c->s_origin_area.p;
+  ra.s_normal = c->s_normal.p;
+  ra.slot_patch = c->slot_patch.p;
+  ra.slot_cluster = c->slot_cluster.p;
+  ra.bits_base = c->d_bits_base.p;
+  ra.Lptr = c->d_Lptr.p;
+  ra.nwords = c->d_nwords.p;
+  ra.cl_slot_start = c->d_cl_slot_start.p;
+  ra.L_slot = c->L_slot.p;
+  ra.L_pos = c->L_pos.p;
+  ra.bits = c->bits.p;
+  ra.M = M;
+  ra.row_total = c->row_total.p;
+  ra.row_count = c->row_count.p;
+  ra.row_ptr = d_row_ptr.p;
+  ra.out_patch = d_patch.p;
+  ra.out_transfer = d_tr.p;
+  k_row_totals<true><<<(M + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(ra);
+  c->launch_check("k_row_totals<emit>");
+  d_patch.download(patch, (size_t) nnz, st);
+  d_tr.download(transfer, (size_t) nnz, st);
+}
+
+// BounceLight, qrad3.c:448-473
+void bounce_impl(qrad_cuda_ctx *c, int numbounce, float *added_out) {
+  if (!c->transfers_done) dfail("bounce: make_transfers has not run");
+  Timer tall;
+  tall.start(c->stream);
+  cudaStream_t st = c->stream;
+  const int M = c->M, N = c->N;
+  c->rad_a.alloc((size_t) M);
+  c->rad_b.alloc((size_t) M);
+  c->s_total.alloc((size_t) M);
+  c->s_refl_area.alloc((size_t) M);
+  k_init_bounce<<<(M + 255) / 256, 256, 0, st>>>(M, c->slot_patch.p, c->p_samplelight.p, c->p_totallight.p, c->p_refl.p,
+                                                 c->p_origin_area.p, c->rad_a.p, c->s_total.p, c->s_refl_area.p);
+  c->launch_check("k_init_bounce");
+  DBuf<float> rad_sum, d_added;
+  if (added_out) {
+    rad_sum.alloc((size_t) M);
+    d_added.alloc((size_t) std::max(numbounce, 1));
+  }
+  BounceArgs a{};
+  a.col_count = c->col_count.p;
+  a.slice_base = c->slice_base.p;
+  a.sell_idx = c->sell_idx.p;
+  a.sell_w = c->sell_w.p;
+  a.total = c->s_total.p;
+  a.refl_area = c->s_refl_area.p;
+  a.rad_sum = added_out ? rad_sum.p : nullptr;
+  a.M = M;
+  float4 *cur = c->rad_a.p, *nxt = c->rad_b.p;
+  Timer tk;
+  float kernel_ms = 0;
+  for (int b = 0; b < numbounce; b++) {
+    a.send = cur;
+    a.send_next = nxt;
+    tk.start(st);
+    if (c->packed16) k_bounce<true><<<(M + kThreads - 1) / kThreads, kThreads, 0, st>>>(a);
+    else k_bounce<false><<<(M + kThreads - 1) / kThreads, kThreads, 0, st>>>(a);
+    c->launch_check("k_bounce");
+    kernel_ms += tk.stop();
+    if (added_out) {
+      k_ordered_sum<<<1, 32, 0, st>>>(rad_sum.p, c->patch_slot.p, N, d_added.p + b);
+      c->launch_check("k_ordered_sum");
+    }
+    std::swap(cur, nxt);
+  }
+  k_finish_bounce<<<(N + 255) / 256, 256, 0, st>>>(N, c->patch_slot.p, c->s_total.p, cur, c->p_totallight.p, c->d_radiosity.p);
+  c->launch_check("k_finish_bounce");
+  if (added_out && numbounce > 0) d_added.download(added_out, (size_t) numbounce, st);
+  c->sync("bounce");
+  c->stats.ms_bounce_kernel = numbounce > 0 ? kernel_ms / numbounce : 0;
+  c->stats.ms_bounce = tall.stop();
+}
+
+}  // namespace qrad

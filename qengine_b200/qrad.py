@@ -347,8 +347,11 @@ class Device:
         L = int(first[-1])
         origins = np.zeros((L, 3), np.float32)
         slots = []
-        maxslots = int(nst.max()) if nf else 0
-        for s in range(max(maxslots, 1)):
+        ids = (C.c_int32 * 256)()
+        nids = C.c_int32()
+        _dck(lib().qrad_cuda_style_ids(self._h, ids, C.byref(nids)))
+        self.style_ids = list(ids)[:nids.value]
+        for s in range(max(nids.value, 1)):
             smp = np.zeros((L, 3), np.float32)
             _dck(lib().qrad_cuda_download_facelight(self._h, _fp(origins), C.c_int32(s), _fp(smp)))
             slots.append(smp)
