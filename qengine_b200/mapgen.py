@@ -127,23 +127,26 @@ def link_assets(dst_root: Path, src_assets: Path) -> Path:
 # ----------------------------------------------------------------------------
 # .map text
 # ----------------------------------------------------------------------------
-def _face(p0, p1, p2, tex, flags=0, value=0) -> str:
+def _face(p0, p1, p2, tex, flags=0, value=0, contents=0) -> str:
     def pt(p):
         return "( %d %d %d )" % p
-    return "%s %s %s %s 0 0 0 1 1 0 %d %d\n" % (pt(p0), pt(p1), pt(p2), tex, flags, value)
+    return "%s %s %s %s 0 0 0 1 1 %d %d %d\n" % (pt(p0), pt(p1), pt(p2), tex, contents, flags, value)
 
 
-def box_brush(x0, y0, z0, x1, y1, z1, tex, top_tex=None, bottom_tex=None, top_light=0, bottom_light=0) -> str:
+def box_brush(x0, y0, z0, x1, y1, z1, tex, top_tex=None, bottom_tex=None, top_light=0, bottom_light=0,
+              contents=0) -> str:
     """Axis-aligned brush; plane point order as written by Quake II editors (cf. assets/maps/sample.map)."""
     top_tex = top_tex or tex
     bottom_tex = bottom_tex or tex
     s = "{\n"
-    s += _face((x0, y0, z0), (x0, y0 + 1, z0), (x0, y0, z0 + 1), tex)
-    s += _face((x1, y1, z1), (x1, y1, z1 + 1), (x1, y1 + 1, z1), tex)
-    s += _face((x0, y0, z0), (x0, y0, z0 + 1), (x0 + 1, y0, z0), tex)
-    s += _face((x1, y1, z1), (x1 + 1, y1, z1), (x1, y1, z1 + 1), tex)
-    s += _face((x1, y1, z1), (x1, y1 + 1, z1), (x1 + 1, y1, z1), top_tex, 1 if top_light else 0, top_light)
-    s += _face((x0, y0, z0), (x0 + 1, y0, z0), (x0, y0 + 1, z0), bottom_tex, 1 if bottom_light else 0, bottom_light)
+    c = contents
+    s += _face((x0, y0, z0), (x0, y0 + 1, z0), (x0, y0, z0 + 1), tex, contents=c)
+    s += _face((x1, y1, z1), (x1, y1, z1 + 1), (x1, y1 + 1, z1), tex, contents=c)
+    s += _face((x0, y0, z0), (x0, y0, z0 + 1), (x0 + 1, y0, z0), tex, contents=c)
+    s += _face((x1, y1, z1), (x1 + 1, y1, z1), (x1, y1, z1 + 1), tex, contents=c)
+    s += _face((x1, y1, z1), (x1, y1 + 1, z1), (x1 + 1, y1, z1), top_tex, 1 if top_light else 0, top_light, contents=c)
+    s += _face((x0, y0, z0), (x0 + 1, y0, z0), (x0, y0 + 1, z0), bottom_tex, 1 if bottom_light else 0, bottom_light,
+               contents=c)
     s += "}\n"
     return s
 

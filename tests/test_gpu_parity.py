@@ -1,0 +1,216 @@
+"""GPU parity tests proper: libqrad_cuda (through its C ABI) against the reference's outputs.
+
+Bar (BASELINE.json north_star): TestLine decisions and transfer counts bit-exact; lighting lump within
++-1 on >= 99.9 % of luxels.  The CUDA path reproduces the reference's float operation order, so these
+tests assert the stronger property the build actually has: byte-identical lumps and whole output files.
+"""
+from __future__ import annotations
+
+import hashlib
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import golden_util as G
+import refdump as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def Q():
+    from qengine_b200 import qrad
+    qrad.lib()
+    return qrad
+
+
+def light(Q, case, tmp_path, count_nodes=False):
+    meta, flags = G.load_case(case)
+    bsp = G.stage_case(case, tmp_path)
+    p = G.params_from_flags(flags)
+    sc = Q.Scene(bsp).prepare(p)
+    dev = Q.Device(0)
+    if count_nodes:
+        dev.set_count_nodes(True)
+    added = Q.rad_world(sc, dev, p)
+    return meta, sc, dev, added, bsp
+
+
+@pytest.mark.parametrize("case", G.CASES)
+def test_lump_identical_to_reference(Q, case, tmp_path):
+    meta, sc, dev, added, bsp = light(Q, case, tmp_path)
+    lump = np.frombuffer(sc.lighting(), np.uint8)
+    want = np.frombuffer((G.GOLDEN / (case + ".lump")).read_bytes(), np.uint8)
+    assert lump.size == want.size == meta["lightdatasize"]
+    d = np.abs(lump.astype(int) - want.astype(int))
+    # tolerance the north star states: +-1 on >= 99.9 % of bytes; maximum deviation reported
+    frac_ok = float((d <= 1).mean()) if d.size else 1.0
+    assert frac_ok >= 0.999, f"only {frac_ok:.5f} within +-1, max deviation {d.max()}"
+    # what this build achieves: no deviation at all
+    assert int(d.max()) == 0, f"{int((d > 0).sum())} bytes differ, max deviation {int(d.max())}"
+    # same `added` energies per bounce (CollectLight's return, qrad3.c:408)
+    assert np.array_equal(added, np.array(meta["added"], np.float32))
+    # whole output file, including dface_t.lightofs/styles and lump order (WriteBSPFile)
+    sc.write(bsp)
+    assert hashlib.md5(bsp.read_bytes()).hexdigest() == meta["file_md5"]
+
+
+@pytest.mark.parametrize("case", ["samplec", "grid2", "grid3_chop16", "hall"])
+def test_testline_decisions(Q, case, tmp_path):
+    meta, flags = G.load_case(case)
+    bsp = G.stage_case(case, tmp_path)
+    sc = Q.Scene(bsp).prepare(G.params_from_flags(flags))
+    dev = Q.Device(0).upload(sc)
+    rays = G.golden_rays(case)
+    got = dev.test_lines(rays["start"], rays["stop"])
+    assert np.array_equal(got != 0, rays["result"] != 0)
+    # direction matters in the reference (epsilon handling): the reverse ray is a separate known answer,
+    # but a ray from a point to itself never hits anything new
+    same = dev.test_lines(rays["start"][:64], rays["start"][:64])
+    leaf = dev.point_in_leaf(rays["start"][:64])
+    assert same.shape == (64,) and leaf.min() >= 0
+
+
+@pytest.mark.parametrize("case", ["samplec", "samplec_extra", "grid2", "grid3_chop16", "hall", "styles"])
+def test_transfer_counts(Q, case, tmp_path):
+    meta, sc, dev, added, _ = light(Q, case, tmp_path)
+    nt = dev.numtransfers()
+    assert np.array_equal(nt, G.golden_numtransfers(case))
+    assert int(nt.sum()) == meta["total_transfer"]
+
+
+def test_transfer_rows_bit_exact(Q, tmp_path):
+    meta, sc, dev, added, _ = light(Q, "samplec", tmp_path)
+    z = np.load(G.GOLDEN / "samplec.transfers.npz")
+    row_ptr, patch, transfer = dev.transfers()
+    assert np.array_equal(np.diff(row_ptr), z["numtransfers"])
+    assert np.array_equal(patch, z["patch"].astype(np.uint32))
+    assert np.array_equal(transfer, z["transfer"])
+    pl = dev.patch_light()
+    assert np.array_equal(pl["totallight"], np.load(G.GOLDEN / "samplec.totallight.npy"))
+    first, nst, sty, origins, slots = dev.facelight()
+    assert np.array_equal(slots[0], np.load(G.GOLDEN / "samplec.facelight0.npy"))
+
+
+def test_row_weights_sum_to_0x10000(Q, tmp_path):
+    """Size-independent property (qrad.h:54-56): every row's u16 weights sum to 0x10000 minus truncation loss."""
+    meta, sc, dev, added, _ = light(Q, "grid3_chop16", tmp_path)
+    row_ptr, patch, transfer = dev.transfers()
+    n = len(row_ptr) - 1
+    sums = np.add.reduceat(np.concatenate([transfer.astype(np.int64), [0]]), row_ptr[:-1])
+    sums[np.diff(row_ptr) == 0] = 0
+    cnt = np.diff(row_ptr)
+    has = cnt > 1   # a single-receiver row stores 65536 as 0 (u16 wrap, qrad3.c:283-285)
+    assert (sums[has] <= 65536).all()
+    assert (sums[has] > 65536 - cnt[has]).all()
+    # receivers ascending and never the source itself
+    for i in range(0, n, max(1, n // 200)):
+        r = patch[row_ptr[i]:row_ptr[i + 1]]
+        assert (np.diff(r.astype(np.int64)) > 0).all()
+        assert i not in r
+
+
+def test_bounce_is_linear_in_power_of_two(Q, tmp_path):
+    """ShootLight/CollectLight are linear; scaling the emitted light by 2 is exact in binary floating point."""
+    meta, flags = G.load_case("grid2")
+    bsp = G.stage_case("grid2", tmp_path)
+    p = G.params_from_flags(flags)
+    sc = Q.Scene(bsp).prepare(p)
+    dev = Q.Device(0).upload(sc)
+    dev.build_facelights(p.extrasamples, p.numbounce)
+    dev.make_transfers(0)
+    base = dev.patch_light()
+    dev.bounce(p.numbounce)
+    t1 = dev.patch_light()["totallight"]
+    dev.upload_patch_light(base["totallight"] * 2, base["samplelight"] * 2, base["samples"])
+    dev.bounce(p.numbounce)
+    t2 = dev.patch_light()["totallight"]
+    assert np.array_equal(t2, t1 * 2)
+
+
+def test_rerun_is_identical(Q, tmp_path):
+    a = light(Q, "grid2", tmp_path / "a")[1].lighting()
+    b = light(Q, "grid2", tmp_path / "b")[1].lighting()
+    assert a == b
+
+
+def test_nopvs_superset(Q, tmp_path):
+    """-nopvs only adds candidates: every PVS-mode transfer is still there and counts never shrink."""
+    meta, flags = G.load_case("samplec")
+    bsp = G.stage_case("samplec", tmp_path)
+    p = G.params_from_flags(flags)
+    sc = Q.Scene(bsp).prepare(p)
+    dev = Q.Device(0).upload(sc)
+    dev.make_transfers(0)
+    a = dev.numtransfers()
+    dev.make_transfers(1)
+    b = dev.numtransfers()
+    assert (b >= a).all()
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref (reference-built harness) not present")
+def test_nopvs_matches_reference(Q, tmp_path):
+    bsp = G.stage_case("samplec", tmp_path)
+    unlit = bsp.read_bytes()
+    R.run_ref_harness(bsp, ["-bounce", "4", "-nopvs"], dumpdir=tmp_path / "dump")
+    want = R.lighting_lump(bsp)
+    cnt, rp, rt = R.read_transfers(tmp_path / "dump" / "transfers.bin")
+    bsp.write_bytes(unlit)
+    p = G.params_from_flags(["-bounce", "4", "-nopvs"])
+    sc = Q.Scene(bsp).prepare(p)
+    dev = Q.Device(0)
+    Q.rad_world(sc, dev, p)
+    assert np.array_equal(dev.numtransfers(), cnt)
+    assert sc.lighting() == want
+
+
+@pytest.mark.skipif(not R.have_ref(), reason="oracle/_ref (reference-built tools) not present")
+def test_fresh_random_map_against_reference(Q, tmp_path):
+    """A map nobody has seen before: generated here, compiled by the reference qbsp3/qvis3, lit by both."""
+    from qengine_b200 import mapgen
+    tools = mapgen.find_map_tools()
+    bsp = mapgen.build_case(tmp_path, "fresh", mapgen.room_grid_map(3, 2, seed=1234, clutter=0.7, lamps=0.5), tools)
+    unlit = bsp.read_bytes()
+    flags = ["-bounce", "5", "-chop", "32", "-extra"]
+    R.run_ref_harness(bsp, flags)
+    want_file = bsp.read_bytes()
+    bsp.write_bytes(unlit)
+    p = G.params_from_flags(flags)
+    sc = Q.Scene(bsp).prepare(p)
+    dev = Q.Device(0)
+    Q.rad_world(sc, dev, p)
+    sc.write(bsp)
+    assert bsp.read_bytes() == want_file
+
+
+def test_cli_drop_in(Q, tmp_path):
+    """The qrad3 executable: same argv as the reference tool, overwrites its input, same bytes out."""
+    from qengine_b200 import build
+    meta, flags = G.load_case("samplec_extra")
+    bsp = G.stage_case("samplec_extra", tmp_path)
+    r = subprocess.run([str(build.EXE), *flags, "-threads", "4", str(bsp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "----- Radiosity ----" in r.stdout and "seconds elapsed" in r.stdout
+    assert hashlib.md5(bsp.read_bytes()).hexdigest() == meta["file_md5"]
+    # usage error like the reference (qrad3.c:608-610): message between the ERROR banner, exit code 1
+    r = subprocess.run([str(build.EXE)], capture_output=True, text=True)
+    assert r.returncode == 1 and "************ ERROR ************" in r.stdout and "usage: qrad" in r.stdout
+
+
+def test_unvised_map_is_direct_only(Q, tmp_path):
+    """No vis data: numbounce forced to 0 and ambient 0.1 (qrad3.c:627-631); GatherSampleLight sees no clusters."""
+    import struct
+    bsp = G.stage_case("samplec", tmp_path)
+    d = bytearray(bsp.read_bytes())
+    struct.pack_into("<ii", d, 8 + 3 * 8, 0, 0)   # empty LUMP_VISIBILITY
+    bsp.write_bytes(bytes(d))
+    p = G.params_from_flags(["-bounce", "8"])
+    sc = Q.Scene(bsp).prepare(p)
+    assert p.numbounce == 0 and abs(p.ambient - 0.1) < 1e-7
+    dev = Q.Device(0)
+    Q.rad_world(sc, dev, p)
+    lump = np.frombuffer(sc.lighting(), np.uint8)
+    assert lump.size == 8928 and (lump == 1).all()
