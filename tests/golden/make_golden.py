@@ -109,8 +109,11 @@ def main():
         info = R.run_ref_harness(staged, flags, dumpdir=dump)
         lump = R.lighting_lump(staged)
         (HERE / (name + ".lump")).write_bytes(lump)
-        rp, _ = R.read_patches(dump / "patches.bin")
-        rp["numtransfers"].astype("<i4").tofile(HERE / (name + ".numtransfers"))
+        if (dump / "transfers.bin").exists():
+            cnt, _, _ = R.read_transfers(dump / "transfers.bin")
+        else:
+            cnt = np.zeros(int(info["num_patches"]), "<i4")
+        cnt.astype("<i4").tofile(HERE / (name + ".numtransfers"))
         rays = R.read_rays(dump / "rays.bin")
         rays[:: max(1, len(rays) // 3000)].tofile(HERE / (name + ".rays"))
         meta = dict(
