@@ -47,7 +47,7 @@ WORKLOADS = {
     "ref_sample_grid6": ("grid6.bsp", ["-bounce", "8", "-chop", "32"],
                          "synthetic 6x6 room grid (~13k patches), -chop 32, 8 bounces (bounded CPU sample)"),
 }
-DEFAULT_WORKLOAD = "c3_grid26"
+DEFAULT_WORKLOAD = "c5_grid16_chop8"
 REF_SAMPLE = "ref_sample_grid6"
 
 
@@ -263,7 +263,7 @@ def main():
         for i in range(1 + max(1, args.steps)):
             barrier()
             t0 = time.perf_counter()
-            Q.rad_world(sc, dev, p)
+            Q.rad_world(sc, dev, p, want_added=False)
             lump = sc.lighting()
             barrier()
             if i:

@@ -358,10 +358,12 @@ class Device:
         return first, nst, sty, origins, slots
 
 
-def rad_world(scene: Scene, dev: Device, params: HostParams):
-    """RadWorld (qrad3.c:494-536) through the C entry point; returns `added` per bounce."""
+def rad_world(scene: Scene, dev: Device, params: HostParams, want_added: bool = True):
+    """RadWorld (qrad3.c:494-536) through the C entry point; returns `added` per bounce.
+
+    want_added=False skips CollectLight's serial energy sum (only printed by `-v` in the reference)."""
     added = np.zeros(max(params.numbounce, 1), np.float32)
-    _hck(lib().qrad_rad_world(scene._h, dev._h, C.byref(params), _fp(added)))
+    _hck(lib().qrad_rad_world(scene._h, dev._h, C.byref(params), _fp(added) if want_added else None))
     dev._n = scene.counts()["num_patches"]
     dev._nf = scene.counts()["numfaces"]
     return added[:max(params.numbounce, 0)]
