@@ -32,6 +32,13 @@ def run(case: str = "samplec") -> None:
             a = np.frombuffer(lump, np.uint8).astype(int)
             b = np.frombuffer(want, np.uint8).astype(int)
             raise AssertionError(f"smoke: lighting lump differs from the golden ({(a != b).sum()} of {a.size} bytes)")
+        # second checker: the plain-C oracle on the same input
+        import sys
+        sys.path.insert(0, str(G.ROOT / "oracle"))
+        import oracle as O
+        o = O.Oracle(bsp, numbounce=p.numbounce, extrasamples=p.extrasamples, subdiv=p.subdiv)
+        olump, _ = o.rad_world()
+        assert olump.tobytes() == lump, "smoke: CUDA lump differs from the C oracle"
         nt = dev.numtransfers()
         assert int(nt.sum()) == meta["total_transfer"], (int(nt.sum()), meta["total_transfer"])
         st = dev.stats()

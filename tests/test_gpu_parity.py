@@ -186,6 +186,33 @@ def test_fresh_random_map_against_reference(Q, tmp_path):
     assert bsp.read_bytes() == want_file
 
 
+@pytest.mark.parametrize("case,flags", [
+    ("grid2", ["-bounce", "3", "-chop", "24", "-extra"]),
+    ("styles", ["-bounce", "2", "-chop", "48", "-ambient", "0.05", "-direct", "1.5", "-entity", "0.7"]),
+    ("samplec", ["-bounce", "5", "-chop", "40", "-scale", "0.8", "-maxlight", "1.2"]),
+])
+def test_new_flags_against_c_oracle(Q, case, flags, tmp_path):
+    """Flag combinations with no golden file: the checker is the plain-C oracle (oracle/qrad_oracle.c, itself pinned
+    to the reference by tests/test_oracle_cpu.py) run on the same seeded input."""
+    import sys
+    sys.path.insert(0, str(G.ROOT / "oracle"))
+    import oracle as O
+    bsp = G.stage_case(case, tmp_path)
+    p = G.params_from_flags(flags)
+    o = O.Oracle(bsp, numbounce=p.numbounce, extrasamples=p.extrasamples, subdiv=p.subdiv, ambient=p.ambient,
+                 maxlight=p.maxlight, lightscale=p.lightscale, direct_scale=p.direct_scale, entity_scale=p.entity_scale)
+    want, want_added = o.rad_world()
+    sc = Q.Scene(bsp).prepare(p)
+    dev = Q.Device(0)
+    dev.set_count_nodes(True)
+    added = Q.rad_world(sc, dev, p)
+    assert sc.lighting() == want.tobytes()
+    assert np.array_equal(added, want_added)
+    assert np.array_equal(dev.numtransfers(), o.patches()["numtransfers"])
+    st = dev.stats()
+    assert (st["rays_direct"], st["rays_transfers"]) == o.ray_counts()   # unit = one root TestLine_r call
+
+
 def test_cli_drop_in(Q, tmp_path):
     """The qrad3 executable: same argv as the reference tool, overwrites its input, same bytes out."""
     from qengine_b200 import build
