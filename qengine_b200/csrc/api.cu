@@ -23,7 +23,7 @@ template <class F> static int guarded(F &&f) {
 // kernels for the query entry points
 // ---------------------------------------------------------------------------
 template <int STACK>
-__global__ void k_test_lines(const TNode *__restrict__ nodes, int64_t n, const float *__restrict__ starts,
+__global__ void k_test_lines(const Tree nodes, int64_t n, const float *__restrict__ starts,
                              const float *__restrict__ stops, uint8_t *__restrict__ out) {
   int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -32,7 +32,7 @@ __global__ void k_test_lines(const TNode *__restrict__ nodes, int64_t n, const f
                                              stops[i * 3 + 1], stops[i * 3 + 2], v);
 }
 
-__global__ void k_point_in_leaf(const TNode *__restrict__ nodes, int64_t n, const float *__restrict__ pts,
+__global__ void k_point_in_leaf(const Tree nodes, int64_t n, const float *__restrict__ pts,
                                 int32_t *__restrict__ out) {
   int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -51,9 +51,9 @@ void test_lines_impl(qrad_cuda_ctx *c, int64_t n, const float *starts, const flo
   dr.alloc((size_t) n);
   int blocks = (int) ((n + 255) / 256);
   if (c->tree_depth <= kTraceStack)
-    k_test_lines<kTraceStack><<<blocks, 256, 0, c->stream>>>(c->nodes.p, n, ds.p, de.p, dr.p);
+    k_test_lines<kTraceStack><<<blocks, 256, 0, c->stream>>>(c->tree(), n, ds.p, de.p, dr.p);
   else
-    k_test_lines<kTraceStackBig><<<blocks, 256, 0, c->stream>>>(c->nodes.p, n, ds.p, de.p, dr.p);
+    k_test_lines<kTraceStackBig><<<blocks, 256, 0, c->stream>>>(c->tree(), n, ds.p, de.p, dr.p);
   c->launch_check("k_test_lines");
   dr.download(results, (size_t) n, c->stream);
 }
@@ -65,7 +65,7 @@ void point_in_leaf_impl(qrad_cuda_ctx *c, int64_t n, const float *pts, int32_t *
   DBuf<int32_t> dr;
   dp.upload(pts, (size_t) n * 3, c->stream);
   dr.alloc((size_t) n);
-  k_point_in_leaf<<<(int) ((n + 255) / 256), 256, 0, c->stream>>>(c->nodes.p, n, dp.p, dr.p);
+  k_point_in_leaf<<<(int) ((n + 255) / 256), 256, 0, c->stream>>>(c->tree(), n, dp.p, dr.p);
   c->launch_check("k_point_in_leaf");
   dr.download(out, (size_t) n, c->stream);
 }
@@ -130,54 +130,59 @@ int qrad_cuda_upload_bsp(qrad_cuda_ctx *c, const qrad_bsp_view *b) {
     t.start(c->stream);
     if (b->numnodes <= 0 || b->numleafs <= 0) dfail("Empty map");
     if (b->numnodes > 65536 || b->numleafs > 65536) dfail("BSP exceeds MAX_MAP_NODES / MAX_MAP_LEAFS");
-    std::vector<TNode> flat((size_t) b->numnodes);
+    std::vector<int4> flat((size_t) b->numnodes);
+    std::vector<float4> normals((size_t) b->numnodes);
     std::vector<int32_t> contents(b->numleafs), cluster(b->numleafs);
     for (int i = 0; i < b->numleafs; i++) {
       contents[i] = b->leafs[i].contents;
       cluster[i] = b->leafs[i].cluster;
     }
-    // preorder numbering with an explicit stack; slot = where to patch the child index
-    struct Item { int dnode, parent_new, which, depth; };
-    std::vector<Item> todo;
-    todo.push_back({0, -1, 0, 1});
-    int next_new = 0, maxdepth = 0;
-    std::vector<uint8_t> seen((size_t) b->numnodes, 0);
-    while (!todo.empty()) {
-      Item it = todo.back();
-      todo.pop_back();
-      if (it.dnode < 0 || it.dnode >= b->numnodes) dfail("node index %d out of range", it.dnode);
-      if (seen[it.dnode]) dfail("BSP node %d reached twice (not a tree)", it.dnode);
-      seen[it.dnode] = 1;
-      if (it.depth > maxdepth) maxdepth = it.depth;
-      int me = next_new++;
-      if (it.parent_new >= 0) (it.which ? flat[it.parent_new].c1 : flat[it.parent_new].c0) = me;
-      const qrad_dnode_t &dn = b->nodes[it.dnode];
+    // breadth-first numbering: queue of (disk node, depth); children get consecutive new indices
+    std::vector<int> order, depth_of, newidx((size_t) b->numnodes, -1);
+    order.push_back(0);
+    depth_of.push_back(1);
+    newidx[0] = 0;
+    int maxdepth = 0;
+    for (size_t q = 0; q < order.size(); q++) {
+      const int dn_i = order[q];
+      if (depth_of[q] > maxdepth) maxdepth = depth_of[q];
+      const qrad_dnode_t &dn = b->nodes[dn_i];
+      for (int k = 0; k < 2; k++) {
+        const int ch = dn.children[k];
+        if (ch < 0) continue;
+        if (ch >= b->numnodes) dfail("node index %d out of range", ch);
+        if (newidx[ch] >= 0) dfail("BSP node %d reached twice (not a tree)", ch);
+        newidx[ch] = (int) order.size();
+        order.push_back(ch);
+        depth_of.push_back(depth_of[q] + 1);
+      }
+    }
+    const int next_new = (int) order.size();
+    for (int me = 0; me < next_new; me++) {
+      const qrad_dnode_t &dn = b->nodes[order[me]];
       if (dn.planenum < 0 || dn.planenum >= b->numplanes) dfail("plane index %d out of range", dn.planenum);
       const qrad_dplane_t &pl = b->planes[dn.planenum];
-      TNode &tn = flat[me];
-      tn.nx = pl.normal[0];
-      tn.ny = pl.normal[1];
-      tn.nz = pl.normal[2];
-      tn.dist = pl.dist;
-      tn.type = pl.type;
-      tn.pad = 0;
-      for (int k = 1; k >= 0; k--) {  // push child 1 first so child 0 is numbered next (preorder)
-        int ch = dn.children[k];
+      int child[2];
+      for (int k = 0; k < 2; k++) {
+        const int ch = dn.children[k];
         if (ch < 0) {
-          int leaf = -ch - 1;
+          const int leaf = -ch - 1;
           if (leaf >= b->numleafs) dfail("leaf index %d out of range", leaf);
-          int enc = kLeafFlag | ((contents[leaf] & 1) ? kSolidBit : 0) | leaf;
-          (k ? tn.c1 : tn.c0) = enc;
-        } else {
-          todo.push_back({ch, me, k, it.depth + 1});
-        }
+          child[k] = kLeafFlag | ((contents[leaf] & 1) ? kSolidBit : 0) | leaf;
+        } else
+          child[k] = newidx[ch];
       }
+      int distbits;
+      memcpy(&distbits, &pl.dist, 4);
+      flat[me] = make_int4(distbits, pl.type, child[0], child[1]);
+      normals[me] = make_float4(pl.normal[0], pl.normal[1], pl.normal[2], pl.dist);
     }
     if (maxdepth > kTraceStackBig) dfail("BSP depth %d exceeds the supported trace stack (%d)", maxdepth, kTraceStackBig);
     c->numnodes = next_new;
     c->numleafs = b->numleafs;
     c->tree_depth = maxdepth;
     c->nodes.upload(flat.data(), (size_t) next_new, c->stream);
+    c->node_normals.upload(normals.data(), (size_t) next_new, c->stream);
     c->leaf_contents.upload(contents, c->stream);
     c->leaf_cluster.upload(cluster, c->stream);
 

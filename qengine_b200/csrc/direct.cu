@@ -13,7 +13,7 @@ namespace {
 __constant__ float c_sampleofs[5][2] = {{0, 0}, {-0.25f, -0.25f}, {0.25f, -0.25f}, {0.25f, 0.25f}, {-0.25f, 0.25f}};
 
 struct FaceArgs {
-  const TNode *nodes;
+  Tree nodes;
   const int32_t *leaf_contents, *leaf_cluster;
   const uint32_t *pvs;
   int pvs_words, numclusters;
@@ -259,7 +259,7 @@ void build_facelights_impl(qrad_cuda_ctx *c, int extrasamples, int numbounce) {
   counters.alloc(2);
   counters.zero(st);
   FaceArgs a{};
-  a.nodes = c->nodes.p;
+  a.nodes = c->tree();
   a.leaf_contents = c->leaf_contents.p;
   a.leaf_cluster = c->leaf_cluster.p;
   a.pvs = c->pvs.p;

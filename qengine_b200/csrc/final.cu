@@ -588,6 +588,13 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
     // (lightmap.c:1187-1189), so those faces are finished here with the same call sequence.
     std::vector<float> lb((size_t) 4 * L * 3 + 1);
     lb_out.download(lb.data(), lb.size(), st);
+    // the reference process never seeds: rand() is glibc's TYPE_3 additive generator from seed 1.  A private
+    // random_r state with the same parameters reproduces it without touching the host program's rand() state.
+    char rstate[128];
+    struct random_data rdata;
+    memset(&rdata, 0, sizeof rdata);
+    memset(rstate, 0, sizeof rstate);
+    initstate_r(1, rstate, sizeof rstate, &rdata);
     for (int f = 0; f < F; f++) {
       if (!c->h_lit[f] || !(c->h_minlight[f] > 0)) continue;
       const float minlight = c->h_minlight[f];
@@ -601,7 +608,11 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
           if (v[2] > mx) mx = v[2];
           float newmax = mx;
           if (newmax < 0) newmax = 0;
-          if (newmax < minlight) newmax = minlight + (rand() % 48);
+          if (newmax < minlight) {
+            int32_t r = 0;
+            random_r(&rdata, &r);
+            newmax = minlight + (r % 48);
+          }
           if (newmax > p->maxlight) newmax = p->maxlight;
           uint8_t *dst = out + lightofs[f] + ((size_t) s * nlux + j) * 3;
           for (int k = 0; k < 3; k++) dst[k] = (uint8_t) (int) (v[k] * newmax / mx);

@@ -65,16 +65,20 @@ template <class T> struct DBuf {
 };
 
 // ---- trace tree ------------------------------------------------------------------
-// One 32-byte record per BSP node, numbered in preorder like MakeTnode (trace.c:47-71).
+// One 16-byte record per BSP node {dist, plane type, child0, child1} so that a node visit is ONE 128-bit
+// load; the plane normal (needed only by non-axial planes in TestLine_r and by PointInLeaf) sits in a
+// separate float4 array.  Nodes are numbered breadth-first: the two children of a node are adjacent
+// (same 32-byte sector) and the top levels occupy the first entries, which k_visibility stages in shared
+// memory.  Layout is free, only results matter (MakeTnode, trace.c:47-71, uses preorder).
 // child >= 0: node index.  child < 0: leaf, encoded kLeafFlag | solid << 30 | leaf number.
-struct __align__(16) TNode {
-  float nx, ny, nz, dist;
-  int type, c0, c1, pad;
+struct Tree {
+  const int4 *nodes;      // x = float bits of dist, y = plane type, z = child 0, w = child 1
+  const float4 *normals;  // xyz = plane normal, w = dist
 };
 constexpr int kLeafFlag = int(0x80000000u);
 constexpr int kSolidBit = 1 << 30;
 constexpr int kLeafMask = 0x3fffffff;
-constexpr int kTraceStack = 64;    // pending far halves; upload rejects deeper trees for the fast kernels
+constexpr int kTraceStack = 64;    // pending far halves; deeper trees use the big-stack instantiation
 constexpr int kTraceStackBig = 256;
 
 #ifdef __CUDACC__
@@ -85,32 +89,33 @@ constexpr int kTraceStackBig = 256;
 // front, the same predicate as `front > -0.1f`, and `front < ON_EPSILON` the same as
 // `front < 0.1f` (-0.1f < -0.1 and 0.1f > 0.1; checked exhaustively around the constants).
 template <int STACK, bool COUNT>
-__device__ __forceinline__ int test_line(const TNode *__restrict__ nodes, float sx, float sy, float sz, float ex,
-                                         float ey, float ez, unsigned &visits) {
+__device__ __forceinline__ int test_line(const Tree tree, float sx, float sy, float sz, float ex, float ey, float ez,
+                                         unsigned &visits) {
   float4 stack[STACK];
   int sp = 0;
   int node = 0;
   for (;;) {
     while (node >= 0) {
-      const float4 pl = __ldg(reinterpret_cast<const float4 *>(nodes + node));
-      const int4 info = __ldg(reinterpret_cast<const int4 *>(nodes + node) + 1);
+      const int4 nd = __ldg(tree.nodes + node);
+      const float dist = __int_as_float(nd.x);
       if (COUNT) visits++;
       float front, back;
-      switch (info.x) {
-        case 0: front = sx - pl.w; back = ex - pl.w; break;
-        case 1: front = sy - pl.w; back = ey - pl.w; break;
-        case 2: front = sz - pl.w; back = ez - pl.w; break;
-        default:
-          front = (sx * pl.x + sy * pl.y + sz * pl.z) - pl.w;
-          back = (ex * pl.x + ey * pl.y + ez * pl.z) - pl.w;
-          break;
+      if (nd.y < 3) {
+        const float s1 = nd.y == 0 ? sx : (nd.y == 1 ? sy : sz);
+        const float e1 = nd.y == 0 ? ex : (nd.y == 1 ? ey : ez);
+        front = s1 - dist;
+        back = e1 - dist;
+      } else {
+        const float4 pl = __ldg(tree.normals + node);
+        front = (sx * pl.x + sy * pl.y + sz * pl.z) - dist;
+        back = (ex * pl.x + ey * pl.y + ez * pl.z) - dist;
       }
       if (front > -0.1f && back > -0.1f) {
-        node = info.y;
+        node = nd.z;
         continue;
       }
       if (front < 0.1f && back < 0.1f) {
-        node = info.z;
+        node = nd.w;
         continue;
       }
       const bool side = front < 0;
@@ -118,12 +123,12 @@ __device__ __forceinline__ int test_line(const TNode *__restrict__ nodes, float 
       const float mx = sx + (ex - sx) * frac;
       const float my = sy + (ey - sy) * frac;
       const float mz = sz + (ez - sz) * frac;
-      if (sp < STACK) stack[sp] = make_float4(__int_as_float(side ? info.y : info.z), ex, ey, ez);
+      if (sp < STACK) stack[sp] = make_float4(__int_as_float(side ? nd.z : nd.w), ex, ey, ez);
       sp++;
       ex = mx;
       ey = my;
       ez = mz;
-      node = side ? info.z : info.y;
+      node = side ? nd.w : nd.z;
     }
     if (node & kSolidBit) return 1;
     if (sp == 0) return 0;
@@ -140,13 +145,13 @@ __device__ __forceinline__ int test_line(const TNode *__restrict__ nodes, float 
 }
 
 // PointInLeafnum, qrad3.c:131-150: full dot product on every node, `dist > 0` picks child 0.
-__device__ __forceinline__ int point_in_leaf(const TNode *__restrict__ nodes, float x, float y, float z) {
+__device__ __forceinline__ int point_in_leaf(const Tree tree, float x, float y, float z) {
   int node = 0;
   while (node >= 0) {
-    const float4 pl = __ldg(reinterpret_cast<const float4 *>(nodes + node));
-    const int4 info = __ldg(reinterpret_cast<const int4 *>(nodes + node) + 1);
+    const float4 pl = __ldg(tree.normals + node);
+    const int4 nd = __ldg(tree.nodes + node);
     const float d = (x * pl.x + y * pl.y + z * pl.z) - pl.w;
-    node = d > 0 ? info.y : info.z;
+    node = d > 0 ? nd.z : nd.w;
   }
   return node & kLeafMask;
 }
@@ -205,7 +210,9 @@ struct qrad_cuda_ctx {
   // ---- BSP (qrad_cuda_upload_bsp) ----
   int numnodes = 0, numleafs = 0, numclusters = 0, tree_depth = 0, pvs_words = 0;
   bool have_vis = false;
-  qrad::DBuf<qrad::TNode> nodes;
+  qrad::DBuf<int4> nodes;
+  qrad::DBuf<float4> node_normals;
+  qrad::Tree tree() const { return qrad::Tree{nodes.p, node_normals.p}; }
   qrad::DBuf<int32_t> leaf_contents, leaf_cluster;
   qrad::DBuf<uint32_t> pvs;            // [numclusters][pvs_words], bit d of row c = cluster d visible from c
   std::vector<uint32_t> h_pvs;

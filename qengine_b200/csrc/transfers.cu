@@ -50,11 +50,13 @@ __device__ __forceinline__ float form_factor_pre(const float4 so, const float4 s
   return trans;
 }
 
+constexpr int kChunkWords = 32;   // one task = one source patch x up to 32 words (1024 receivers)
+
 struct VisArgs {
-  const TNode *nodes;
+  Tree tree;
   const float4 *s_origin_area, *s_normal;
-  const int32_t *slot_patch;
   const int64_t *bits_base;      // [nc+1] word offset of the first row of each source cluster
+  const int64_t *task_base;      // [nc+1] task offset of each source cluster (rows x chunks per row)
   const int32_t *nwords;         // [nc]   words per row
   const int32_t *cl_slot_start;  // [nc]
   const int32_t *cl_count;       // [nc]
@@ -62,65 +64,101 @@ struct VisArgs {
   const int32_t *vis_cluster;    // receiver cluster
   const int32_t *vis_woff;       // word offset of that cluster inside a row
   int nc;
-  uint64_t word_begin, word_end;  // this rank's share of the matrix
+  uint64_t task_begin, task_end;  // this rank's share of the tasks
   uint32_t *bits;
   unsigned long long *counters;   // [0] rays, [1] node visits, [2] candidate pairs
 };
 
+// One warp lights one task: (1) form-factor sign tests for up to 1024 receivers of one source; the pairs the
+// reference would hand to TestLine_r (qrad3.c:244) are compacted into a per-warp queue; (2) the queue is traced
+// 32 rays at a time, every batch starting at the root together (same source, neighbouring receivers: the lanes
+// stay on the same nodes for the top of the tree); (3) accept bits are OR-ed into 32 result words in shared
+// memory and stored with one coalesced write.  Measured alternatives (profiles/README.md): one word per warp
+// without compaction leaves 46 % of the lanes idle; refilling finished lanes from the queue decorrelates the
+// lanes so that every step executes the union of the descend / split / pop paths and is slower.
 template <int STACK, bool COUNT>
 __global__ void __launch_bounds__(kThreads) k_visibility(const VisArgs a) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t warp0 = (uint64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  __shared__ uint16_t s_queue[kWarpsPerBlock][kChunkWords * 32];
+  __shared__ uint32_t s_res[kWarpsPerBlock][kChunkWords];
+  __shared__ int32_t s_wbase[kWarpsPerBlock][kChunkWords];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1;
+  const uint64_t warp0 = (uint64_t) blockIdx.x * kWarpsPerBlock + wid;
   const uint64_t nwarps = (uint64_t) gridDim.x * kWarpsPerBlock;
-  unsigned long long rays = 0, pairs = 0;
-  unsigned visits = 0;
-  unsigned long long visits_total = 0;
-  for (uint64_t word = a.word_begin + warp0; word < a.word_end; word += nwarps) {
-    // locate source cluster: last c with bits_base[c] <= word
+  unsigned long long rays = 0, pairs = 0, visits_total = 0;
+  for (uint64_t task = a.task_begin + warp0; task < a.task_end; task += nwarps) {
+    // ---- decode: source cluster, row, chunk ----
     int lo = 0, hi = a.nc;
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
-      if ((uint64_t) a.bits_base[mid] <= word) lo = mid; else hi = mid;
+      if ((uint64_t) a.task_base[mid] <= task) lo = mid; else hi = mid;
     }
     const int c = lo;
     const int nw = a.nwords[c];
-    const uint64_t rel = word - (uint64_t) a.bits_base[c];
-    const int row = (int) (rel / (uint64_t) nw);
-    const int w = (int) (rel - (uint64_t) row * nw);
-    // receiver cluster: last entry of c's visible list with woff <= w
-    int vlo = a.vis_ptr[c], vhi = a.vis_ptr[c + 1];
-    while (vhi - vlo > 1) {
-      const int mid = (vlo + vhi) >> 1;
-      if (a.vis_woff[mid] <= w) vlo = mid; else vhi = mid;
-    }
-    const int d = a.vis_cluster[vlo];
+    const int cpr = (nw + kChunkWords - 1) / kChunkWords;
+    const uint64_t rel = task - (uint64_t) a.task_base[c];
+    const int row = (int) (rel / (uint64_t) cpr);
+    const int w0 = (int) (rel - (uint64_t) row * cpr) * kChunkWords;
+    const int nwc = min(kChunkWords, nw - w0);
     const int sslot = a.cl_slot_start[c] + row;
-    const int rslot = a.cl_slot_start[d] + (w - a.vis_woff[vlo]) * 32 + lane;
-    const bool valid = (w - a.vis_woff[vlo]) * 32 + lane < a.cl_count[d];
-    bool accept = false;
-    if (valid && rslot != sslot) {
-      const float4 so = __ldg(a.s_origin_area + sslot);
-      const float4 sn = __ldg(a.s_normal + sslot);
-      const float4 po = __ldg(a.s_origin_area + rslot);
-      const float4 pn = __ldg(a.s_normal + rslot);
-      float dist;
-      bool wants_ray;
-      const float trans = form_factor_pre(so, sn, po, pn, dist, wants_ray);
-      pairs++;
-      if (wants_ray) {
-        rays++;
-        if (trans > 0) {
-          visits = 0;
-          const int blocked = test_line<STACK, COUNT>(a.nodes, so.x, so.y, so.z, po.x, po.y, po.z, visits);
-          if (COUNT) visits_total += visits;
-          accept = !blocked;
-        }
+    const float4 so = __ldg(a.s_origin_area + sslot);
+    const float4 sn = __ldg(a.s_normal + sslot);
+    // receiver cluster of the first word: last entry of c's visible list with woff <= w0
+    int v = a.vis_ptr[c];
+    const int vend = a.vis_ptr[c + 1];
+    {
+      int vhi = vend;
+      while (vhi - v > 1) {
+        const int mid = (v + vhi) >> 1;
+        if (a.vis_woff[mid] <= w0) v = mid; else vhi = mid;
       }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, accept);
-    if (lane == 0) a.bits[word] = m;
+    s_res[wid][lane] = 0;
+    // ---- phase 1: cheap tests, compaction ----
+    int n = 0;
+    for (int wi = 0; wi < nwc; wi++) {
+      const int w = w0 + wi;
+      while (v + 1 < vend && a.vis_woff[v + 1] <= w) v++;
+      const int d = a.vis_cluster[v];
+      const int off = (w - a.vis_woff[v]) * 32;
+      const int base = a.cl_slot_start[d] + off;
+      if (lane == 0) s_wbase[wid][wi] = base;
+      const int rslot = base + lane;
+      bool want = false;
+      if (off + lane < a.cl_count[d] && rslot != sslot) {
+        const float4 po = __ldg(a.s_origin_area + rslot);
+        const float4 pn = __ldg(a.s_normal + rslot);
+        float dist;
+        bool wants_ray;
+        const float trans = form_factor_pre(so, sn, po, pn, dist, wants_ray);
+        pairs++;
+        if (wants_ray) {
+          rays++;
+          want = trans > 0;
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, want);
+      if (want) s_queue[wid][n + __popc(m & lt)] = (uint16_t) (wi * 32 + lane);
+      n += __popc(m);
+    }
+    __syncwarp();
+    // ---- phase 2: trace the queue, 32 rays per batch ----
+    for (int base = 0; base < n; base += 32) {
+      const int k = base + lane;
+      if (k < n) {
+        const int cand = s_queue[wid][k];
+        const float4 po = __ldg(a.s_origin_area + s_wbase[wid][cand >> 5] + (cand & 31));
+        unsigned visits = 0;
+        const int blocked = test_line<STACK, COUNT>(a.tree, so.x, so.y, so.z, po.x, po.y, po.z, visits);
+        if (COUNT) visits_total += visits;
+        if (!blocked) atomicOr(&s_res[wid][cand >> 5], 1u << (cand & 31));
+      }
+      __syncwarp();
+    }
+    __syncwarp();
+    if (lane < nwc) a.bits[a.bits_base[c] + (int64_t) row * nw + w0 + lane] = s_res[wid][lane];
+    __syncwarp();
   }
-  // one atomic per warp per counter
   for (int o = 16; o; o >>= 1) {
     rays += __shfl_xor_sync(0xffffffffu, rays, o);
     pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
@@ -546,6 +584,7 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
   c->h_nwords.assign(nc, 0);
   c->h_bits_base.assign(nc + 1, 0);
   c->h_Lptr.assign(nc + 1, 0);
+  std::vector<int64_t> task_base(nc + 1, 0);
   std::vector<int64_t> Rptr(nc + 1, 0);
   for (int a = 0; a < nc; a++) {
     int w = 0;
@@ -563,6 +602,7 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
     vis_ptr[a + 1] = (int32_t) vis_cluster.size();
     c->h_nwords[a] = w;
     c->h_bits_base[a + 1] = c->h_bits_base[a] + (int64_t) c->h_cl_count[a] * w;
+    task_base[a + 1] = task_base[a] + (int64_t) c->h_cl_count[a] * ((w + kChunkWords - 1) / kChunkWords);
     c->h_Lptr[a + 1] = c->h_Lptr[a] + cand;
   }
   for (int d = 0; d < nc; d++) Rptr[d + 1] += Rptr[d];
@@ -601,8 +641,9 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
   c->d_nwords.upload(c->h_nwords, st);
   c->d_cl_slot_start.upload(c->h_cl_slot_start, st);
   c->d_cl_count.upload(c->h_cl_count, st);
-  DBuf<int64_t> d_Rptr;
+  DBuf<int64_t> d_Rptr, d_task_base;
   d_Rptr.upload(Rptr, st);
+  d_task_base.upload(task_base, st);
   c->bits.alloc((size_t) W + 1);
   DBuf<unsigned long long> counters;
   counters.alloc(4);
@@ -614,11 +655,11 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
   if (W) {
     // rows of patches that sit in solid (only possible under -nopvs) are cleared afterwards
     VisArgs a;
-    a.nodes = c->nodes.p;
+    a.tree = c->tree();
     a.s_origin_area = c->s_origin_area.p;
     a.s_normal = c->s_normal.p;
-    a.slot_patch = c->slot_patch.p;
     a.bits_base = c->d_bits_base.p;
+    a.task_base = d_task_base.p;
     a.nwords = c->d_nwords.p;
     a.cl_slot_start = c->d_cl_slot_start.p;
     a.cl_count = c->d_cl_count.p;
@@ -626,14 +667,15 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
     a.vis_cluster = d_vis_cluster.p;
     a.vis_woff = d_vis_woff.p;
     a.nc = nc;
-    // multi-GPU: each rank traces a contiguous share of the words (rows stay whole per cluster share)
-    const uint64_t per = (W + c->world - 1) / c->world;
-    a.word_begin = std::min<uint64_t>(W, per * c->rank);
-    a.word_end = std::min<uint64_t>(W, per * (c->rank + 1));
+    // multi-GPU: each rank traces a contiguous share of the tasks (= a contiguous range of matrix words)
+    const uint64_t T = (uint64_t) task_base[nc];
+    const uint64_t per = (T + c->world - 1) / c->world;
+    a.task_begin = std::min<uint64_t>(T, per * c->rank);
+    a.task_end = std::min<uint64_t>(T, per * (c->rank + 1));
     if (c->world > 1) c->bits.zero(st);
     a.bits = c->bits.p;
     a.counters = counters.p;
-    const uint64_t mine = a.word_end - a.word_begin;
+    const uint64_t mine = a.task_end - a.task_begin;
     const uint64_t want_blocks = (mine + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>(want_blocks, (uint64_t) c->sm_count * 8));
     const bool big = c->tree_depth > kTraceStack;
