@@ -277,11 +277,11 @@ def main():
 
         # ---- roofline of the dominant bandwidth kernel (k_bounce) ----
         peak, peak_src = measured_peak()
-        b = 4 if st["transfer_bytes"] == st["total_transfers"] * 4 else 6
+        b = 4 if st["num_patches"] <= 65535 else 6   # transfer_t is 4 B up to 65 535 patches
         alg_bytes = st["total_transfers"] * b + 64 * st["num_patches"]
         kb_ms = float(np.mean(bounce_ms))
         achieved = alg_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else 0.0
-        stored_bytes = st["padded_entries"] * b
+        stored_bytes = st["transfer_bytes"]
         roofline = {"bound": "hbm", "kernel": "k_bounce", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "stored_bytes_per_launch": stored_bytes,

@@ -122,6 +122,7 @@ typedef struct {
   int64_t total_transfers;    /* nnz of the transfer matrix (total_transfer, qrad3.c:183)         */
   int64_t transfer_bytes;     /* bytes of the gather-form matrix streamed per bounce              */
   int64_t padded_entries;     /* stored entries including slice padding                           */
+  int64_t nonzero_words;      /* (source, 32-receiver slice) pairs with at least one transfer     */
   int32_t num_patches, num_luxels, num_clusters, tree_depth;
   float   ms_upload, ms_facelights, ms_transfers, ms_transfers_trace, ms_bounce, ms_bounce_kernel, ms_final;
   int32_t kernel_launches;    /* kernels launched by this context so far                          */

@@ -265,13 +265,12 @@ struct qrad_cuda_ctx {
   qrad::DBuf<uint32_t> bits;            // visibility*formfactor>0 bit matrix, rows of source slots
   qrad::DBuf<float> row_total;          // [M]
   qrad::DBuf<int32_t> row_count;        // [M] numtransfers of the source in slot s
-  // gather-form matrix, sliced ELL with 32-column slices in slot order
-  bool packed16 = false;
-  int64_t sell_entries = 0;
-  qrad::DBuf<int32_t> col_count;        // [M]
-  qrad::DBuf<int64_t> slice_base;       // [M/32 + 1] entry offsets
-  qrad::DBuf<uint32_t> sell_idx;        // u32 source slot per entry (wide format), or packed {u16 slot, u16 weight}
-  qrad::DBuf<uint16_t> sell_w;          // u16 weight per entry (wide format)
+  // gather-form matrix, "dense slices": see k_columns / k_bounce in transfers.cu
+  int64_t sell_entries = 0;             // list entries over all slices (each slice padded to a multiple of 8)
+  qrad::DBuf<int32_t> slice_len;        // [M/32] list entries of a slice
+  qrad::DBuf<int64_t> slice_base;       // [M/32 + 1] first entry of a slice
+  qrad::DBuf<uint32_t> g_src;           // [entries] source slot
+  qrad::DBuf<uint4> g_w;                // [entries/8][32] 8 u16 weights per lane
   // row-major helper lists kept for inspection / download
   std::vector<int64_t> h_Lptr, h_bits_base;
   std::vector<int32_t> h_nwords;

@@ -301,6 +301,14 @@ __global__ void __launch_bounds__(kThreads) k_row_totals(const RowArgs a) {
 }
 
 // pass 3: columns.  One warp = 32 receivers (a slice), lane = receiver.
+// pass 3 + bounce share the gather-form layout ("dense slices"): for every slice of 32 receivers the list of
+// sources that reach at least one of them (ascending patch index = the order ShootLight adds them), one u32 source
+// slot per list entry and 32 u16 weights per entry (0 = no transfer to that receiver; adding send * 0 leaves the
+// float sum unchanged, and the add is skipped anyway).  Entries are grouped by 8: a lane's 8 weights are 16
+// contiguous bytes (one 128-bit load), a warp reads 512 contiguous bytes per group.  Measured on C5: 18.8 of the
+// 32 receivers of a listed source are hit on average, so this stores 3.6 B per transfer instead of 6 and turns
+// the per-transfer gather of the radiosity vector into one broadcast load per 18.8 transfers (the per-column ELL
+// of the first version was bound by L1 sector lookups at 43 % of HBM peak, profiles/r01c_full_c5_k_bounce.txt).
 struct ColArgs {
   const float4 *s_origin_area, *s_normal;
   const int32_t *slot_patch, *slot_cluster;
@@ -312,13 +320,13 @@ struct ColArgs {
   const uint32_t *bits;
   const float *row_total;
   int M;
-  int32_t *col_count;            // count mode output
-  const int64_t *slice_base;     // fill mode: entry offset per slice
-  uint32_t *sell_idx;
-  uint16_t *sell_w;
+  int32_t *slice_len;            // count mode output: list entries of the slice
+  const int64_t *slice_base;     // fill mode: first entry of the slice (multiple of 8)
+  uint32_t *g_src;               // [entries]      source slot
+  uint4 *g_w;                    // [entries / 8][32] 8 x u16 weights per lane
 };
 
-template <int MODE>  // 0 = count, 1 = fill wide (u32 + u16), 2 = fill packed16
+template <int MODE>  // 0 = count, 1 = fill
 __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
   const int lane = threadIdx.x & 31;
   const int slice = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -333,8 +341,9 @@ __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
     pn = a.s_normal[rslot];
   }
   const int64_t r0 = a.Rptr[d], r1 = a.Rptr[d + 1];
-  int cnt = 0;
+  int n = 0;                                           // list entries so far (uniform)
   const int64_t base = MODE ? a.slice_base[slice] : 0;
+  uint32_t wq[4] = {0, 0, 0, 0};                       // this lane's weights of the current group of 8 entries
   for (int64_t k0 = r0; k0 < r1; k0 += 32) {
     const int64_t k = k0 + lane;
     uint32_t word = 0, sslot = 0;
@@ -345,41 +354,50 @@ __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
       word = a.bits[a.bits_base[c] + (int64_t) ((int) sslot - a.cl_slot_start[c]) * a.nwords[c] + woff + wslice];
     }
     unsigned nz = __ballot_sync(0xffffffffu, word != 0);
+    if (MODE == 0) {
+      n += __popc(nz);
+      continue;
+    }
     while (nz) {
       const int src = __ffs(nz) - 1;
       nz &= nz - 1;
       const uint32_t w = __shfl_sync(0xffffffffu, word, src);
       const uint32_t ss = __shfl_sync(0xffffffffu, sslot, src);
+      uint32_t itrans = 0;
       if ((w >> lane) & 1u) {
-        if (MODE) {
-          const float4 so = a.s_origin_area[ss];
-          const float4 sn = a.s_normal[ss];
-          float dist;
-          bool wr;
-          const float trans = form_factor_pre(so, sn, po, pn, dist, wr);
-          const uint32_t itrans = (uint32_t) (int) (trans * 65536.0f / a.row_total[ss]);
-          // sliced-ELL, 4 consecutive entries of one column are contiguous (one 128-bit load in k_bounce)
-          const int64_t o = base + (int64_t) (cnt >> 2) * 128 + lane * 4 + (cnt & 3);
-          if (MODE == 2)
-            a.sell_idx[o] = (ss & 0xffffu) | (itrans << 16);
-          else {
-            a.sell_idx[o] = ss;
-            a.sell_w[o] = (uint16_t) itrans;
-          }
-        }
-        cnt++;
+        const float4 so = a.s_origin_area[ss];
+        const float4 sn = a.s_normal[ss];
+        float dist;
+        bool wr;
+        const float trans = form_factor_pre(so, sn, po, pn, dist, wr);
+        itrans = (uint32_t) (int) (trans * 65536.0f / a.row_total[ss]) & 0xffffu;   // u16 store wraps (qrad3.c:283-285)
+      }
+      const int q = n & 7;
+      wq[q >> 1] |= itrans << ((q & 1) * 16);
+      if (lane == 0) a.g_src[base + n] = ss;
+      n++;
+      if ((n & 7) == 0) {
+        a.g_w[((base + n) / 8 - 1) * 32 + lane] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+        wq[0] = wq[1] = wq[2] = wq[3] = 0;
       }
     }
   }
-  if (MODE == 0) a.col_count[rslot] = cnt;
+  if (MODE == 0) {
+    if (lane == 0) a.slice_len[slice] = n;
+  } else if (n & 7) {
+    // pad the last group: source slot 0 with zero weights
+    const int pad = 8 - (n & 7);
+    if (lane < pad) a.g_src[base + n + lane] = 0;
+    a.g_w[((base + n) / 8) * 32 + lane] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+  }
 }
 
 // ---- bounce --------------------------------------------------------------------------------
 struct BounceArgs {
-  const int32_t *col_count;
+  const int32_t *slice_len;
   const int64_t *slice_base;
-  const uint32_t *sell_idx;
-  const uint16_t *sell_w;
+  const uint32_t *g_src;
+  const uint4 *g_w;
   const float4 *send;            // radiosity / 0x10000 per source slot
   float4 *send_next;
   float4 *total;                 // totallight per slot
@@ -388,63 +406,69 @@ struct BounceArgs {
   int M;
 };
 
-__device__ __forceinline__ void accum(float &ix, float &iy, float &iz, const float4 s, const float w) {
-  // illumination[j][l] += send[l] * trans->transfer   (qrad3.c:439), mul and add rounded separately
-  ix = ix + s.x * w;
-  iy = iy + s.y * w;
-  iz = iz + s.z * w;
-}
+// (float) w for a u16 w without the quarter-rate I2F: 0x4B000000 | w is the float 2^23 + w, exactly.
+__device__ __forceinline__ float u16_to_float(const uint32_t w) { return __int_as_float(0x4B000000u | w) - 8388608.0f; }
 
-template <bool PACKED>
+// illumination[j][l] += send[l] * trans->transfer   (qrad3.c:439), mul and add rounded separately.
+// A zero weight adds +-0 and leaves the sum unchanged (the sum starts at +0 and never becomes -0).
+#define QRAD_ACCUM(E, W)                                           \
+  do {                                                             \
+    const float fw = u16_to_float(W);                              \
+    const float sx = __shfl_sync(0xffffffffu, cx.x, E);            \
+    const float sy = __shfl_sync(0xffffffffu, cx.y, E);            \
+    const float sz = __shfl_sync(0xffffffffu, cx.z, E);            \
+    ix = ix + sx * fw;                                             \
+    iy = iy + sy * fw;                                             \
+    iz = iz + sz * fw;                                             \
+  } while (0)
+
+// ShootLight (as a gather) + CollectLight.  One warp per slice, lane = receiver; the list is walked in order, so
+// every receiver accumulates its transfers in ascending source order like the reference's serial loop.
+// Per group of 8 list entries: lanes 0-7 fetch the 8 source slots (32 contiguous bytes) and gather the 8 radiosity
+// vectors (one 128-byte wavefront instead of eight 512-byte broadcasts), every lane fetches its 8 weights with one
+// 128-bit load (512 contiguous bytes per warp), the vectors are broadcast with shuffles.  Loads run two groups
+// (slots) / one group (vectors, weights) ahead of the arithmetic.
 __global__ void __launch_bounds__(kThreads) k_bounce(const BounceArgs a) {
-  const int slot = blockIdx.x * kThreads + threadIdx.x;
-  if (slot >= a.M) return;
   const int lane = threadIdx.x & 31;
-  const int cnt = a.col_count[slot];
-  const int64_t base = a.slice_base[slot >> 5] + lane * 4;
+  const int slice = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (slice * 32 >= a.M) return;
+  const int slot = slice * 32 + lane;
+  const int64_t base = a.slice_base[slice];
+  const int groups = (a.slice_len[slice] + 7) >> 3;
+  const uint32_t *ps = a.g_src + base + (lane & 7);
+  const uint4 *pw = a.g_w + (base >> 3) * 32 + lane;
   float ix = 0.f, iy = 0.f, iz = 0.f;
-  int k = 0;
-  if (PACKED) {
-    const uint4 *p = reinterpret_cast<const uint4 *>(a.sell_idx + base);
-    for (; k + 4 <= cnt; k += 4, p += 32) {
-      const uint4 e = __ldcs(p);
-      const float4 s0 = __ldg(a.send + (e.x & 0xffffu));
-      const float4 s1 = __ldg(a.send + (e.y & 0xffffu));
-      const float4 s2 = __ldg(a.send + (e.z & 0xffffu));
-      const float4 s3 = __ldg(a.send + (e.w & 0xffffu));
-      accum(ix, iy, iz, s0, (float) (e.x >> 16));
-      accum(ix, iy, iz, s1, (float) (e.y >> 16));
-      accum(ix, iy, iz, s2, (float) (e.z >> 16));
-      accum(ix, iy, iz, s3, (float) (e.w >> 16));
+  uint32_t nidx = 0;                        // source slot of entry (lane & 7) of the group after next
+  float4 nx = make_float4(0, 0, 0, 0);      // radiosity vector of entry (lane & 7) of the next group
+  uint4 nw = make_uint4(0, 0, 0, 0);        // this lane's weights of the next group
+  const bool feeder = lane < 8;             // lanes 0-7 feed the source slots / radiosity vectors
+  if (groups > 0) {
+    if (feeder) {
+      nx = __ldg(a.send + __ldcs(ps));
+      if (groups > 1) nidx = __ldcs(ps + 8);
     }
-    if (k < cnt) {
-      const uint4 e = __ldcs(p);
-      const uint32_t ee[4] = {e.x, e.y, e.z, e.w};
-      for (int q = 0; k + q < cnt; q++) accum(ix, iy, iz, __ldg(a.send + (ee[q] & 0xffffu)), (float) (ee[q] >> 16));
-    }
-  } else {
-    const uint4 *p = reinterpret_cast<const uint4 *>(a.sell_idx + base);
-    const uint2 *pw = reinterpret_cast<const uint2 *>(a.sell_w + base);
-    for (; k + 4 <= cnt; k += 4, p += 32, pw += 32) {
-      const uint4 e = __ldcs(p);
-      const uint2 w = __ldcs(pw);
-      const float4 s0 = __ldg(a.send + e.x);
-      const float4 s1 = __ldg(a.send + e.y);
-      const float4 s2 = __ldg(a.send + e.z);
-      const float4 s3 = __ldg(a.send + e.w);
-      accum(ix, iy, iz, s0, (float) (w.x & 0xffffu));
-      accum(ix, iy, iz, s1, (float) (w.x >> 16));
-      accum(ix, iy, iz, s2, (float) (w.y & 0xffffu));
-      accum(ix, iy, iz, s3, (float) (w.y >> 16));
-    }
-    if (k < cnt) {
-      const uint4 e = __ldcs(p);
-      const uint2 w = __ldcs(pw);
-      const uint32_t ee[4] = {e.x, e.y, e.z, e.w};
-      const uint32_t ww[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
-      for (int q = 0; k + q < cnt; q++) accum(ix, iy, iz, __ldg(a.send + ee[q]), (float) ww[q]);
-    }
+    nw = __ldcs(pw);
   }
+  for (int g = 0; g < groups; g++) {
+    const float4 cx = nx;
+    const uint4 cw = nw;
+    if (g + 1 < groups) {
+      if (feeder) {
+        nx = __ldg(a.send + nidx);
+        if (g + 2 < groups) nidx = __ldcs(ps + 8 * (g + 2));
+      }
+      nw = __ldcs(pw + 32 * (g + 1));
+    }
+    QRAD_ACCUM(0, cw.x & 0xffffu);
+    QRAD_ACCUM(1, cw.x >> 16);
+    QRAD_ACCUM(2, cw.y & 0xffffu);
+    QRAD_ACCUM(3, cw.y >> 16);
+    QRAD_ACCUM(4, cw.z & 0xffffu);
+    QRAD_ACCUM(5, cw.z >> 16);
+    QRAD_ACCUM(6, cw.w & 0xffffu);
+    QRAD_ACCUM(7, cw.w >> 16);
+  }
+#undef QRAD_ACCUM
   // CollectLight, qrad3.c:383-409
   const float4 ra = a.refl_area[slot];
   float4 t = a.total[slot];
@@ -749,8 +773,8 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
   }
 
   // ---- pass 3 ----
-  c->packed16 = M <= 65536;
-  c->col_count.alloc((size_t) M);
+  const int nslices = M / 32;
+  c->slice_len.alloc((size_t) nslices);
   ColArgs ca{};
   ca.s_origin_area = c->s_origin_area.p;
   ca.s_normal = c->s_normal.p;
@@ -766,38 +790,31 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
   ca.bits = c->bits.p;
   ca.row_total = c->row_total.p;
   ca.M = M;
-  ca.col_count = c->col_count.p;
-  const int nslices = M / 32;
+  ca.slice_len = c->slice_len.p;
   const int cblocks = (nslices + kWarpsPerBlock - 1) / kWarpsPerBlock;
   k_columns<0><<<cblocks, kThreads, 0, st>>>(ca);
   c->launch_check("k_columns<count>");
-  std::vector<int32_t> h_col((size_t) M);
-  c->col_count.download(h_col.data(), (size_t) M, st);
+  std::vector<int32_t> h_len((size_t) nslices);
+  c->slice_len.download(h_len.data(), (size_t) nslices, st);
   std::vector<int64_t> h_slice_base((size_t) nslices + 1, 0);
-  int64_t nnz = 0;
+  int64_t nzw = 0;
   for (int s = 0; s < nslices; s++) {
-    int mx = 0;
-    for (int l = 0; l < 32; l++) {
-      mx = std::max(mx, h_col[(size_t) s * 32 + l]);
-      nnz += h_col[(size_t) s * 32 + l];
-    }
-    h_slice_base[s + 1] = h_slice_base[s] + (int64_t) ((mx + 3) & ~3) * 32;
+    nzw += h_len[s];
+    h_slice_base[s + 1] = h_slice_base[s] + ((h_len[s] + 7) & ~7);
   }
   c->sell_entries = h_slice_base[nslices];
   c->slice_base.upload(h_slice_base, st);
-  c->sell_idx.alloc((size_t) c->sell_entries + 4);
-  c->sell_idx.zero(st);
-  if (!c->packed16) {
-    c->sell_w.alloc((size_t) c->sell_entries + 8);
-    c->sell_w.zero(st);
-  } else
-    c->sell_w.release();
+  c->g_src.alloc((size_t) c->sell_entries + 8);
+  c->g_w.alloc((size_t) (c->sell_entries / 8 + 1) * 32);
   ca.slice_base = c->slice_base.p;
-  ca.sell_idx = c->sell_idx.p;
-  ca.sell_w = c->sell_w.p;
-  if (c->packed16) k_columns<2><<<cblocks, kThreads, 0, st>>>(ca);
-  else k_columns<1><<<cblocks, kThreads, 0, st>>>(ca);
+  ca.g_src = c->g_src.p;
+  ca.g_w = c->g_w.p;
+  k_columns<1><<<cblocks, kThreads, 0, st>>>(ca);
   c->launch_check("k_columns<fill>");
+  std::vector<int32_t> h_rc((size_t) M);
+  c->row_count.download(h_rc.data(), (size_t) M, st);
+  int64_t nnz = 0;
+  for (int s = 0; s < M; s++) nnz += h_rc[s];
   c->sync("make_transfers");
 
   unsigned long long hc[4];
@@ -805,10 +822,11 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
   c->stats.rays_transfers = (int64_t) hc[0];
   c->stats.node_visits += (int64_t) hc[1];
   c->stats.candidate_pairs = (int64_t) hc[2];
+  c->stats.nonzero_words = nzw;
   c->total_transfers = nnz;
   c->stats.total_transfers = nnz;
   c->stats.padded_entries = c->sell_entries;
-  c->stats.transfer_bytes = nnz * (c->packed16 ? 4 : 6);
+  c->stats.transfer_bytes = c->sell_entries * 68;   // stored: u32 source + 32 x u16 weights per list entry
   c->transfers_done = true;
   c->stats.ms_transfers = tall.stop();
 }
@@ -872,10 +890,10 @@ void bounce_impl(qrad_cuda_ctx *c, int numbounce, float *added_out) {
     d_added.alloc((size_t) std::max(numbounce, 1));
   }
   BounceArgs a{};
-  a.col_count = c->col_count.p;
+  a.slice_len = c->slice_len.p;
   a.slice_base = c->slice_base.p;
-  a.sell_idx = c->sell_idx.p;
-  a.sell_w = c->sell_w.p;
+  a.g_src = c->g_src.p;
+  a.g_w = c->g_w.p;
   a.total = c->s_total.p;
   a.refl_area = c->s_refl_area.p;
   a.rad_sum = added_out ? rad_sum.p : nullptr;
@@ -887,8 +905,7 @@ void bounce_impl(qrad_cuda_ctx *c, int numbounce, float *added_out) {
     a.send = cur;
     a.send_next = nxt;
     tk.start(st);
-    if (c->packed16) k_bounce<true><<<(M + kThreads - 1) / kThreads, kThreads, 0, st>>>(a);
-    else k_bounce<false><<<(M + kThreads - 1) / kThreads, kThreads, 0, st>>>(a);
+    k_bounce<<<(M / 32 + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(a);
     c->launch_check("k_bounce");
     kernel_ms += tk.stop();
     if (added_out) {

@@ -62,7 +62,7 @@ class HostParams(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("rays_transfers", C.c_int64), ("rays_direct", C.c_int64), ("node_visits", C.c_int64),
                 ("candidate_pairs", C.c_int64), ("total_transfers", C.c_int64), ("transfer_bytes", C.c_int64),
-                ("padded_entries", C.c_int64),
+                ("padded_entries", C.c_int64), ("nonzero_words", C.c_int64),
                 ("num_patches", C.c_int32), ("num_luxels", C.c_int32), ("num_clusters", C.c_int32),
                 ("tree_depth", C.c_int32),
                 ("ms_upload", C.c_float), ("ms_facelights", C.c_float), ("ms_transfers", C.c_float),
