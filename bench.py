@@ -216,6 +216,8 @@ def main():
             torch.cuda.synchronize()
 
         def device_step():
+            if world > 1:
+                return Q.rad_world_sharded(sc, dev, p, rank, world, upload=False)
             dev.build_facelights(p.extrasamples, p.numbounce)
             dev.make_transfers(p.nopvs)
             dev.bounce(p.numbounce, want_added=False)
@@ -228,27 +230,37 @@ def main():
         barrier()
         launches0 = dev.stats()["kernel_launches"]
         bounce_ms, trace_ms, phase = [], [], []
+        step_wall = []
         with ClockSampler(local_rank) as clk:
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
-            ev0.record()
             for _ in range(args.steps):
+                barrier()
+                ts = time.perf_counter()
                 device_step()
+                barrier()
+                step_wall.append(time.perf_counter() - ts)
                 st = dev.stats()
                 bounce_ms.append(st["ms_bounce_kernel"])
                 trace_ms.append(st["ms_transfers_trace"])
                 phase.append([st["ms_facelights"], st["ms_transfers"], st["ms_bounce"], st["ms_final"]])
-            ev1.record()
             barrier()
             wall = time.perf_counter() - t0
         st = dev.stats()
         launches = st["kernel_launches"] - launches0
-        # the library times each phase with CUDA events on its own stream; the step time is their sum
-        step_ms = float(np.mean([sum(x) for x in phase]))
-        t = torch.tensor([step_ms], device="cuda")
+        # N = 1: the library times each phase with CUDA events on its own stream; the step time is their sum.
+        # N > 1: the exchanges run on torch's NCCL streams between the phases, so the step is timed from barrier +
+        # synchronize to barrier + synchronize and the max over ranks is taken.
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms = float(t.item())
+            step_ms = float(np.mean(step_wall)) * 1e3
+        else:
+            step_ms = float(np.mean([sum(x) for x in phase]))
+        t = torch.tensor([step_ms, float(st["rays_transfers"])], device="cuda", dtype=torch.float64)
+        if world > 1:
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            step_ms = float(tmax[0].item())
+            st["rays_transfers"] = int(t[1].item())     # each rank traced its own granules of the matrix
         rays = st["rays_transfers"] + st["rays_direct"]
         value = rays / (step_ms * 1e-3)
 
@@ -263,7 +275,11 @@ def main():
         for i in range(1 + max(1, args.steps)):
             barrier()
             t0 = time.perf_counter()
-            Q.rad_world(sc, dev, p, want_added=False)
+            if world > 1:
+                data, lightofs, styles = Q.rad_world_sharded(sc, dev, p, rank, world)
+                sc.store_lighting(data, lightofs, styles)
+            else:
+                Q.rad_world(sc, dev, p, want_added=False)
             lump = sc.lighting()
             barrier()
             if i:

@@ -157,6 +157,21 @@ int  qrad_cuda_final_light(qrad_cuda_ctx *ctx, const qrad_final_params *params,
                            uint8_t *dlightdata_out, int32_t lightdata_capacity, int32_t *lightdatasize,
                            int32_t *lightofs_out /*[F]*/, uint8_t *styles_out /*[F][4]*/);
 
+/* ---- multi-GPU (one process per GPU): the phases of make_transfers / bounce with the exchange points exposed.
+   After qrad_cuda_set_shard(rank, world) the host runs, on every rank:
+     make_transfers_phase(0)  ->  all-reduce(sum, u32) of QRAD_XBUF_BITS         (each word is written by one rank)
+     make_transfers_phase(1)  ->  all-gather of QRAD_XBUF_ROW_TOTAL and QRAD_XBUF_ROW_COUNT
+     make_transfers_phase(2)
+     bounce_phase(0); numbounce x { bounce_phase(1) -> all-gather of QRAD_XBUF_RADIOSITY };
+     all-gather of QRAD_XBUF_TOTALLIGHT; bounce_phase(2)
+   (the reference has no multi-process mode; this is the sharding of SURVEY.md section 8e). ---- */
+enum { QRAD_XBUF_BITS = 0, QRAD_XBUF_ROW_TOTAL = 1, QRAD_XBUF_ROW_COUNT = 2, QRAD_XBUF_RADIOSITY = 3, QRAD_XBUF_TOTALLIGHT = 4 };
+int  qrad_cuda_make_transfers_phase(qrad_cuda_ctx *ctx, int nopvs, int phase);
+int  qrad_cuda_bounce_phase(qrad_cuda_ctx *ctx, int phase);
+/* Device pointer and geometry of an exchange buffer: total_bytes of the whole buffer; for the all-gather buffers
+   every rank owns shard_bytes at offset rank * shard_bytes. */
+int  qrad_cuda_exchange_buffer(qrad_cuda_ctx *ctx, int which, void **devptr, int64_t *total_bytes, int64_t *shard_bytes);
+
 /* ---- inspection (parity tests, multi-GPU exchange); not needed by a production host ---- */
 int  qrad_cuda_get_stats(qrad_cuda_ctx *ctx, qrad_cuda_stats *out);
 /* numtransfers per patch (patch->numtransfers). */

@@ -382,6 +382,63 @@ int qrad_cuda_make_transfers(qrad_cuda_ctx *c, int nopvs, int64_t *total_transfe
   });
 }
 
+int qrad_cuda_make_transfers_phase(qrad_cuda_ctx *c, int nopvs, int phase) {
+  return guarded([&] {
+    QCUDA(cudaSetDevice(c->device));
+    if (phase == 0) transfers_trace(c, nopvs);
+    else if (phase == 1) transfers_rows(c);
+    else if (phase == 2) transfers_columns(c);
+    else dfail("make_transfers_phase: bad phase %d", phase);
+  });
+}
+
+int qrad_cuda_bounce_phase(qrad_cuda_ctx *c, int phase) {
+  return guarded([&] {
+    QCUDA(cudaSetDevice(c->device));
+    if (phase == 0) bounce_begin(c, false);
+    else if (phase == 1) {
+      bounce_step(c);
+      c->sync("bounce_step");
+    } else if (phase == 2) bounce_end(c);
+    else dfail("bounce_phase: bad phase %d", phase);
+  });
+}
+
+int qrad_cuda_exchange_buffer(qrad_cuda_ctx *c, int which, void **devptr, int64_t *total_bytes, int64_t *shard_bytes) {
+  return guarded([&] {
+    if (!c->M) dfail("exchange_buffer: make_transfers_phase(0) has not run");
+    switch (which) {
+      case QRAD_XBUF_BITS:
+        *devptr = c->bits.p;
+        *total_bytes = (int64_t) c->bits_words * 4;
+        *shard_bytes = 0;
+        break;
+      case QRAD_XBUF_ROW_TOTAL:
+        *devptr = c->row_total.p;
+        *total_bytes = (int64_t) c->Mpad * 4;
+        *shard_bytes = (int64_t) c->shard_slots * 4;
+        break;
+      case QRAD_XBUF_ROW_COUNT:
+        *devptr = c->row_count.p;
+        *total_bytes = (int64_t) c->Mpad * 4;
+        *shard_bytes = (int64_t) c->shard_slots * 4;
+        break;
+      case QRAD_XBUF_RADIOSITY:
+        *devptr = c->rad_cur;
+        *total_bytes = (int64_t) c->Mpad * 16;
+        *shard_bytes = (int64_t) c->shard_slots * 16;
+        break;
+      case QRAD_XBUF_TOTALLIGHT:
+        *devptr = c->s_total.p;
+        *total_bytes = (int64_t) c->Mpad * 16;
+        *shard_bytes = (int64_t) c->shard_slots * 16;
+        break;
+      default: dfail("exchange_buffer: bad id %d", which);
+    }
+    if (!*devptr) dfail("exchange_buffer %d is not allocated yet", which);
+  });
+}
+
 int qrad_cuda_bounce(qrad_cuda_ctx *c, int numbounce, float *added_out) {
   return guarded([&] {
     QCUDA(cudaSetDevice(c->device));

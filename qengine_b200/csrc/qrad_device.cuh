@@ -279,6 +279,19 @@ struct qrad_cuda_ctx {
   qrad::DBuf<uint32_t> L_slot, L_pos;
   bool transfers_done = false;
   int64_t total_transfers = 0;
+  // state kept between the phases of make_transfers / bounce (multi-GPU hosts exchange in between)
+  int slice_lo = 0, slice_hi = 0;       // this rank's slices (32 slots each)
+  int shard_slots = 0, Mpad = 0;        // slots per shard, world * shard_slots
+  std::vector<int64_t> h_Rptr;
+  qrad::DBuf<int32_t> d_vis_ptr, d_vis_cluster, d_vis_woff, d_woff_table;
+  qrad::DBuf<int64_t> d_Rptr, d_task_base;
+  qrad::DBuf<uint32_t> R_slot;
+  qrad::DBuf<unsigned long long> counters;
+  qrad::DBuf<float> rad_sum;
+  qrad::Timer t_transfers, t_bounce;
+  float4 *rad_cur = nullptr, *rad_nxt = nullptr;
+  float bounce_kernel_ms = 0;
+  int bounce_steps = 0;
 
   // ---- bounce state (slot order) ----
   qrad::DBuf<float4> rad_a, rad_b;      // radiosity / 0x10000 ("send", qrad3.c:430-431), double buffered
@@ -302,6 +315,12 @@ namespace qrad {
 void build_facelights_impl(qrad_cuda_ctx *c, int extrasamples, int numbounce);
 void make_transfers_impl(qrad_cuda_ctx *c, int nopvs);
 void bounce_impl(qrad_cuda_ctx *c, int numbounce, float *added_out);
+void transfers_trace(qrad_cuda_ctx *c, int nopvs);
+void transfers_rows(qrad_cuda_ctx *c);
+void transfers_columns(qrad_cuda_ctx *c);
+void bounce_begin(qrad_cuda_ctx *c, bool want_sum);
+void bounce_step(qrad_cuda_ctx *c);
+void bounce_end(qrad_cuda_ctx *c);
 void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out, int32_t cap, int32_t *size,
                       int32_t *lightofs, uint8_t *styles);
 void download_transfers_impl(qrad_cuda_ctx *c, int64_t *row_ptr, uint32_t *patch, uint16_t *transfer);

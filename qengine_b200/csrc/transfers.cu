@@ -51,6 +51,7 @@ __device__ __forceinline__ float form_factor_pre(const float4 so, const float4 s
 }
 
 constexpr int kChunkWords = 32;   // one task = one source patch x up to 32 words (1024 receivers)
+constexpr int kTaskGranule = 2048;  // multi-GPU: granule g of tasks belongs to rank g % world
 
 struct VisArgs {
   Tree tree;
@@ -64,7 +65,9 @@ struct VisArgs {
   const int32_t *vis_cluster;    // receiver cluster
   const int32_t *vis_woff;       // word offset of that cluster inside a row
   int nc;
-  uint64_t task_begin, task_end;  // this rank's share of the tasks
+  uint64_t num_tasks;             // all tasks
+  uint64_t my_tasks;              // upper bound of this rank's local task index
+  int rank, world;                // tasks are dealt to ranks in granules of kTaskGranule
   uint32_t *bits;
   unsigned long long *counters;   // [0] rays, [1] node visits, [2] candidate pairs
 };
@@ -86,7 +89,9 @@ __global__ void __launch_bounds__(kThreads) k_visibility(const VisArgs a) {
   const uint64_t warp0 = (uint64_t) blockIdx.x * kWarpsPerBlock + wid;
   const uint64_t nwarps = (uint64_t) gridDim.x * kWarpsPerBlock;
   unsigned long long rays = 0, pairs = 0, visits_total = 0;
-  for (uint64_t task = a.task_begin + warp0; task < a.task_end; task += nwarps) {
+  for (uint64_t ltask = warp0; ltask < a.my_tasks; ltask += nwarps) {
+    const uint64_t task = ((ltask / kTaskGranule) * a.world + a.rank) * kTaskGranule + ltask % kTaskGranule;
+    if (task >= a.num_tasks) continue;
     // ---- decode: source cluster, row, chunk ----
     int lo = 0, hi = a.nc;
     while (hi - lo > 1) {
@@ -234,6 +239,7 @@ struct RowArgs {
   const uint32_t *L_slot, *L_pos;
   const uint32_t *bits;
   int M;
+  int slot_lo, slot_hi;          // this rank's rows
   float *row_total;
   int32_t *row_count;
   // download mode (reference row format): when out_patch != nullptr, rows are written at row_ptr[patch]
@@ -245,8 +251,8 @@ struct RowArgs {
 template <bool EMIT>
 __global__ void __launch_bounds__(kThreads) k_row_totals(const RowArgs a) {
   const int lane = threadIdx.x & 31;
-  const int sslot = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (sslot >= a.M) return;
+  const int sslot = a.slot_lo + blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (sslot >= a.slot_hi) return;
   const int spatch = a.slot_patch[sslot];
   if (spatch < 0) return;
   const int c = a.slot_cluster[sslot];
@@ -320,8 +326,9 @@ struct ColArgs {
   const uint32_t *bits;
   const float *row_total;
   int M;
+  int slice_lo, slice_hi;        // this rank's slices
   int32_t *slice_len;            // count mode output: list entries of the slice
-  const int64_t *slice_base;     // fill mode: first entry of the slice (multiple of 8)
+  const int64_t *slice_base;     // fill mode: first entry of the slice (multiple of 32)
   uint32_t *g_src;               // [entries]      source slot
   uint4 *g_w;                    // [entries / 8][32] 8 x u16 weights per lane
 };
@@ -329,8 +336,8 @@ struct ColArgs {
 template <int MODE>  // 0 = count, 1 = fill
 __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
   const int lane = threadIdx.x & 31;
-  const int slice = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (slice * 32 >= a.M) return;
+  const int slice = a.slice_lo + blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (slice >= a.slice_hi) return;
   const int rslot = slice * 32 + lane;
   const int d = a.slot_cluster[slice * 32];            // all 32 slots of a slice share the cluster
   const int wslice = (slice * 32 - a.cl_slot_start[d]) >> 5;
@@ -385,9 +392,7 @@ __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
   if (MODE == 0) {
     if (lane == 0) a.slice_len[slice] = n;
   } else if (n & 7) {
-    // pad the last group: source slot 0 with zero weights
-    const int pad = 8 - (n & 7);
-    if (lane < pad) a.g_src[base + n + lane] = 0;
+    // last, partial group; the rest of the 32-entry batch stays zero (source slot 0, zero weights: buffers are cleared)
     a.g_w[((base + n) / 8) * 32 + lane] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
   }
 }
@@ -404,6 +409,7 @@ struct BounceArgs {
   const float4 *refl_area;       // xyz reflectivity, w area; w < 0 marks a sky patch
   float *rad_sum;                // [M] r0 + r1 + r2 of the new radiosity (for `added`), may be null
   int M;
+  int slice_lo, slice_hi;        // this rank's slices
 };
 
 // (float) w for a u16 w without the quarter-rate I2F: 0x4B000000 | w is the float 2^23 + w, exactly.
@@ -424,49 +430,58 @@ __device__ __forceinline__ float u16_to_float(const uint32_t w) { return __int_a
 
 // ShootLight (as a gather) + CollectLight.  One warp per slice, lane = receiver; the list is walked in order, so
 // every receiver accumulates its transfers in ascending source order like the reference's serial loop.
-// Per group of 8 list entries: lanes 0-7 fetch the 8 source slots (32 contiguous bytes) and gather the 8 radiosity
-// vectors (one 128-byte wavefront instead of eight 512-byte broadcasts), every lane fetches its 8 weights with one
-// 128-bit load (512 contiguous bytes per warp), the vectors are broadcast with shuffles.  Loads run two groups
-// (slots) / one group (vectors, weights) ahead of the arithmetic.
+// The list is consumed in batches of 32 entries (4 groups of 8): lane l fetches source slot l of the batch (one
+// coalesced 128-byte load) and gathers its radiosity vector, every lane fetches its 4 x 8 weights with four 128-bit
+// loads (2 KB contiguous per warp), the vectors are broadcast with shuffles.  Loads run one batch (vectors,
+// weights) / two batches (slots) ahead of the arithmetic: ~2.6 KB in flight per warp, which is what it takes to
+// cover HBM latency at this occupancy (profiles/r01d_full_c5_k_bounce.txt: long-scoreboard bound before).
 __global__ void __launch_bounds__(kThreads) k_bounce(const BounceArgs a) {
   const int lane = threadIdx.x & 31;
-  const int slice = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (slice * 32 >= a.M) return;
+  const int slice = a.slice_lo + blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (slice >= a.slice_hi) return;
   const int slot = slice * 32 + lane;
   const int64_t base = a.slice_base[slice];
-  const int groups = (a.slice_len[slice] + 7) >> 3;
-  const uint32_t *ps = a.g_src + base + (lane & 7);
+  const int batches = (a.slice_len[slice] + 31) >> 5;
+  const uint32_t *ps = a.g_src + base + lane;
   const uint4 *pw = a.g_w + (base >> 3) * 32 + lane;
   float ix = 0.f, iy = 0.f, iz = 0.f;
-  uint32_t nidx = 0;                        // source slot of entry (lane & 7) of the group after next
-  float4 nx = make_float4(0, 0, 0, 0);      // radiosity vector of entry (lane & 7) of the next group
-  uint4 nw = make_uint4(0, 0, 0, 0);        // this lane's weights of the next group
-  const bool feeder = lane < 8;             // lanes 0-7 feed the source slots / radiosity vectors
-  if (groups > 0) {
-    if (feeder) {
-      nx = __ldg(a.send + __ldcs(ps));
-      if (groups > 1) nidx = __ldcs(ps + 8);
-    }
-    nw = __ldcs(pw);
+  uint32_t nidx = 0;                        // source slot of entry `lane` of the batch after next
+  float4 nx = make_float4(0, 0, 0, 0);      // radiosity vector of entry `lane` of the next batch
+  uint4 nw0 = make_uint4(0, 0, 0, 0), nw1 = nw0, nw2 = nw0, nw3 = nw0;   // this lane's weights of the next batch
+  if (batches > 0) {
+    nx = __ldg(a.send + __ldcs(ps));
+    nw0 = __ldcs(pw);
+    nw1 = __ldcs(pw + 32);
+    nw2 = __ldcs(pw + 64);
+    nw3 = __ldcs(pw + 96);
+    if (batches > 1) nidx = __ldcs(ps + 32);
   }
-  for (int g = 0; g < groups; g++) {
+  for (int b = 0; b < batches; b++) {
     const float4 cx = nx;
-    const uint4 cw = nw;
-    if (g + 1 < groups) {
-      if (feeder) {
-        nx = __ldg(a.send + nidx);
-        if (g + 2 < groups) nidx = __ldcs(ps + 8 * (g + 2));
-      }
-      nw = __ldcs(pw + 32 * (g + 1));
+    const uint4 cw0 = nw0, cw1 = nw1, cw2 = nw2, cw3 = nw3;
+    if (b + 1 < batches) {
+      nx = __ldg(a.send + nidx);
+      const uint4 *q = pw + 128 * (b + 1);
+      nw0 = __ldcs(q);
+      nw1 = __ldcs(q + 32);
+      nw2 = __ldcs(q + 64);
+      nw3 = __ldcs(q + 96);
+      if (b + 2 < batches) nidx = __ldcs(ps + 32 * (b + 2));
     }
-    QRAD_ACCUM(0, cw.x & 0xffffu);
-    QRAD_ACCUM(1, cw.x >> 16);
-    QRAD_ACCUM(2, cw.y & 0xffffu);
-    QRAD_ACCUM(3, cw.y >> 16);
-    QRAD_ACCUM(4, cw.z & 0xffffu);
-    QRAD_ACCUM(5, cw.z >> 16);
-    QRAD_ACCUM(6, cw.w & 0xffffu);
-    QRAD_ACCUM(7, cw.w >> 16);
+#define QRAD_GROUP(G, CW)                 \
+  QRAD_ACCUM(G * 8 + 0, CW.x & 0xffffu);  \
+  QRAD_ACCUM(G * 8 + 1, CW.x >> 16);      \
+  QRAD_ACCUM(G * 8 + 2, CW.y & 0xffffu);  \
+  QRAD_ACCUM(G * 8 + 3, CW.y >> 16);      \
+  QRAD_ACCUM(G * 8 + 4, CW.z & 0xffffu);  \
+  QRAD_ACCUM(G * 8 + 5, CW.z >> 16);      \
+  QRAD_ACCUM(G * 8 + 6, CW.w & 0xffffu);  \
+  QRAD_ACCUM(G * 8 + 7, CW.w >> 16)
+    QRAD_GROUP(0, cw0);
+    QRAD_GROUP(1, cw1);
+    QRAD_GROUP(2, cw2);
+    QRAD_GROUP(3, cw3);
+#undef QRAD_GROUP
   }
 #undef QRAD_ACCUM
   // CollectLight, qrad3.c:383-409
@@ -556,11 +571,12 @@ __global__ void k_finish_bounce(int N, const int32_t *__restrict__ patch_slot, c
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
+// phase 0: slot order, row geometry, pass 1 (this rank's granules of tasks)
+void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   if (!c->numnodes || !c->N) dfail("make_transfers: BSP and patches must be uploaded first");
   if (!c->have_vis) dfail("make_transfers: map has no visibility data (the reference forces numbounce = 0)");
-  Timer tall;
-  tall.start(c->stream);
+  c->t_transfers.start(c->stream);
+  c->transfers_done = false;
   const int N = c->N;
   // ---- host: slot order ----
   // With -nopvs every patch receives (even those in solid); sources still need a valid cluster
@@ -582,6 +598,13 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
   for (int k = 0; k < nc; k++) c->h_cl_slot_start[k + 1] = c->h_cl_slot_start[k] + ((c->h_cl_count[k] + 31) & ~31);
   const int M = c->h_cl_slot_start[nc];
   c->M = M;
+  {  // shards of slots for passes 2, 3 and the bounces: equal runs of whole slices
+    const int nsl = M / 32, per = (nsl + c->world - 1) / c->world;
+    c->slice_lo = std::min(nsl, per * c->rank);
+    c->slice_hi = std::min(nsl, per * (c->rank + 1));
+    c->shard_slots = per * 32;
+    c->Mpad = c->shard_slots * c->world;
+  }
   if (M == 0) dfail("make_transfers: no patch lies in a valid cluster");
   c->h_slot_patch.assign(M, -1);
   c->h_patch_slot.assign(N, -1);
@@ -655,23 +678,21 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
     c->s_origin_area.upload(so, st);
     c->s_normal.upload(sn, st);
   }
-  DBuf<int32_t> d_vis_ptr, d_vis_cluster, d_vis_woff, d_woff_table;
-  d_vis_ptr.upload(vis_ptr, st);
-  d_vis_cluster.upload(vis_cluster, st);
-  d_vis_woff.upload(vis_woff, st);
-  d_woff_table.upload(woff_table, st);
+  c->d_vis_ptr.upload(vis_ptr, st);
+  c->d_vis_cluster.upload(vis_cluster, st);
+  c->d_vis_woff.upload(vis_woff, st);
+  c->d_woff_table.upload(woff_table, st);
   c->d_bits_base.upload(c->h_bits_base, st);
   c->d_Lptr.upload(c->h_Lptr, st);
   c->d_nwords.upload(c->h_nwords, st);
   c->d_cl_slot_start.upload(c->h_cl_slot_start, st);
   c->d_cl_count.upload(c->h_cl_count, st);
-  DBuf<int64_t> d_Rptr, d_task_base;
-  d_Rptr.upload(Rptr, st);
-  d_task_base.upload(task_base, st);
+  c->h_Rptr = Rptr;
+  c->d_Rptr.upload(Rptr, st);
+  c->d_task_base.upload(task_base, st);
   c->bits.alloc((size_t) W + 1);
-  DBuf<unsigned long long> counters;
-  counters.alloc(4);
-  counters.zero(st);
+  c->counters.alloc(4);
+  c->counters.zero(st);
 
   // ---- pass 1 ----
   Timer ttrace;
@@ -683,23 +704,27 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
     a.s_origin_area = c->s_origin_area.p;
     a.s_normal = c->s_normal.p;
     a.bits_base = c->d_bits_base.p;
-    a.task_base = d_task_base.p;
+    a.task_base = c->d_task_base.p;
     a.nwords = c->d_nwords.p;
     a.cl_slot_start = c->d_cl_slot_start.p;
     a.cl_count = c->d_cl_count.p;
-    a.vis_ptr = d_vis_ptr.p;
-    a.vis_cluster = d_vis_cluster.p;
-    a.vis_woff = d_vis_woff.p;
+    a.vis_ptr = c->d_vis_ptr.p;
+    a.vis_cluster = c->d_vis_cluster.p;
+    a.vis_woff = c->d_vis_woff.p;
     a.nc = nc;
-    // multi-GPU: each rank traces a contiguous share of the tasks (= a contiguous range of matrix words)
+    // multi-GPU: tasks are dealt to the ranks in granules; words of other ranks stay zero so that the exchange
+    // is one sum all-reduce of the matrix (each word is written by exactly one rank)
     const uint64_t T = (uint64_t) task_base[nc];
-    const uint64_t per = (T + c->world - 1) / c->world;
-    a.task_begin = std::min<uint64_t>(T, per * c->rank);
-    a.task_end = std::min<uint64_t>(T, per * (c->rank + 1));
+    const uint64_t granules = (T + kTaskGranule - 1) / kTaskGranule;
+    const uint64_t mine_g = granules / c->world + ((granules % c->world) > (uint64_t) c->rank ? 1 : 0);
+    a.num_tasks = T;
+    a.my_tasks = mine_g * kTaskGranule;
+    a.rank = c->rank;
+    a.world = c->world;
     if (c->world > 1) c->bits.zero(st);
     a.bits = c->bits.p;
-    a.counters = counters.p;
-    const uint64_t mine = a.task_end - a.task_begin;
+    a.counters = c->counters.p;
+    const uint64_t mine = a.my_tasks;
     const uint64_t want_blocks = (mine + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>(want_blocks, (uint64_t) c->sm_count * 8));
     const bool big = c->tree_depth > kTraceStack;
@@ -720,18 +745,24 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
         QCUDA(cudaMemsetAsync(c->bits.p + c->h_bits_base[0] + (int64_t) s * c->h_nwords[0], 0, (size_t) c->h_nwords[0] * 4, st));
   }
 
+  c->sync("make_transfers pass 1");
+}
+
+// phase 1: ordered lists + pass 2 (row totals of this rank's slots).  Needs the complete bit matrix.
+void transfers_rows(qrad_cuda_ctx *c) {
+  cudaStream_t st = c->stream;
+  const int N = c->N, M = c->M, nc = c->nc_eff;
   // ---- ordered lists ----
   c->L_slot.alloc((size_t) c->h_Lptr[nc] + 1);
   c->L_pos.alloc((size_t) c->h_Lptr[nc] + 1);
-  DBuf<uint32_t> R_slot;
-  R_slot.alloc((size_t) Rptr[nc] + 1);
+  c->R_slot.alloc((size_t) c->h_Rptr[nc] + 1);
   {
     ListArgs la;
     la.N = N;
     la.nc = nc;
     la.patch_slot = c->patch_slot.p;
     la.slot_cluster = c->slot_cluster.p;
-    la.woff_table = d_woff_table.p;
+    la.woff_table = c->d_woff_table.p;
     la.cl_slot_start = c->d_cl_slot_start.p;
     la.list_ptr = c->d_Lptr.p;
     la.out_slot = c->L_slot.p;
@@ -739,8 +770,8 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
     la.transpose = 0;
     k_build_lists<<<nc, 1024, 0, st>>>(la);
     c->launch_check("k_build_lists(rows)");
-    la.list_ptr = d_Rptr.p;
-    la.out_slot = R_slot.p;
+    la.list_ptr = c->d_Rptr.p;
+    la.out_slot = c->R_slot.p;
     la.out_aux = nullptr;
     la.transpose = 1;
     k_build_lists<<<nc, 1024, 0, st>>>(la);
@@ -748,8 +779,8 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
   }
 
   // ---- pass 2 ----
-  c->row_total.alloc((size_t) M);
-  c->row_count.alloc((size_t) M);
+  c->row_total.alloc((size_t) c->Mpad);
+  c->row_count.alloc((size_t) c->Mpad);
   c->row_total.zero(st);
   c->row_count.zero(st);
   {
@@ -766,32 +797,45 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
     ra.L_pos = c->L_pos.p;
     ra.bits = c->bits.p;
     ra.M = M;
+    ra.slot_lo = c->slice_lo * 32;
+    ra.slot_hi = c->slice_hi * 32;
     ra.row_total = c->row_total.p;
     ra.row_count = c->row_count.p;
-    k_row_totals<false><<<(M + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(ra);
-    c->launch_check("k_row_totals");
+    const int rows = ra.slot_hi - ra.slot_lo;
+    if (rows > 0) {
+      k_row_totals<false><<<(rows + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(ra);
+      c->launch_check("k_row_totals");
+    }
   }
+  c->sync("make_transfers pass 2");
+}
 
-  // ---- pass 3 ----
+// phase 2: pass 3 (gather lists of this rank's slices).  Needs the row totals of every source.
+void transfers_columns(qrad_cuda_ctx *c) {
+  cudaStream_t st = c->stream;
+  const int M = c->M, nc = c->nc_eff;
   const int nslices = M / 32;
   c->slice_len.alloc((size_t) nslices);
+  c->slice_len.zero(st);
   ColArgs ca{};
   ca.s_origin_area = c->s_origin_area.p;
   ca.s_normal = c->s_normal.p;
   ca.slot_patch = c->slot_patch.p;
   ca.slot_cluster = c->slot_cluster.p;
   ca.bits_base = c->d_bits_base.p;
-  ca.Rptr = d_Rptr.p;
+  ca.Rptr = c->d_Rptr.p;
   ca.nwords = c->d_nwords.p;
   ca.cl_slot_start = c->d_cl_slot_start.p;
-  ca.woff_table = d_woff_table.p;
+  ca.woff_table = c->d_woff_table.p;
   ca.nc = nc;
-  ca.R_slot = R_slot.p;
+  ca.R_slot = c->R_slot.p;
   ca.bits = c->bits.p;
   ca.row_total = c->row_total.p;
   ca.M = M;
+  ca.slice_lo = c->slice_lo;
+  ca.slice_hi = c->slice_hi;
   ca.slice_len = c->slice_len.p;
-  const int cblocks = (nslices + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int cblocks = std::max(1, (c->slice_hi - c->slice_lo + kWarpsPerBlock - 1) / kWarpsPerBlock);
   k_columns<0><<<cblocks, kThreads, 0, st>>>(ca);
   c->launch_check("k_columns<count>");
   std::vector<int32_t> h_len((size_t) nslices);
@@ -800,12 +844,14 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
   int64_t nzw = 0;
   for (int s = 0; s < nslices; s++) {
     nzw += h_len[s];
-    h_slice_base[s + 1] = h_slice_base[s] + ((h_len[s] + 7) & ~7);
+    h_slice_base[s + 1] = h_slice_base[s] + ((h_len[s] + 31) & ~31);
   }
   c->sell_entries = h_slice_base[nslices];
   c->slice_base.upload(h_slice_base, st);
-  c->g_src.alloc((size_t) c->sell_entries + 8);
-  c->g_w.alloc((size_t) (c->sell_entries / 8 + 1) * 32);
+  c->g_src.alloc((size_t) c->sell_entries + 32);
+  c->g_w.alloc((size_t) (c->sell_entries / 8 + 4) * 32);
+  c->g_src.zero(st);
+  c->g_w.zero(st);
   ca.slice_base = c->slice_base.p;
   ca.g_src = c->g_src.p;
   ca.g_w = c->g_w.p;
@@ -816,9 +862,10 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
   int64_t nnz = 0;
   for (int s = 0; s < M; s++) nnz += h_rc[s];
   c->sync("make_transfers");
+  c->R_slot.release();
 
   unsigned long long hc[4];
-  counters.download(hc, 4, st);
+  c->counters.download(hc, 4, st);
   c->stats.rays_transfers = (int64_t) hc[0];
   c->stats.node_visits += (int64_t) hc[1];
   c->stats.candidate_pairs = (int64_t) hc[2];
@@ -828,7 +875,14 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
   c->stats.padded_entries = c->sell_entries;
   c->stats.transfer_bytes = c->sell_entries * 68;   // stored: u32 source + 32 x u16 weights per list entry
   c->transfers_done = true;
-  c->stats.ms_transfers = tall.stop();
+  c->stats.ms_transfers = c->t_transfers.stop();
+}
+
+void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
+  if (c->world > 1) dfail("make_transfers: this context is a shard (%d/%d); use qrad_cuda_make_transfers_phase and exchange", c->rank, c->world);
+  transfers_trace(c, nopvs);
+  transfers_rows(c);
+  transfers_columns(c);
 }
 
 // reference row format for parity tests: rows by source patch, receivers ascending
@@ -859,6 +913,8 @@ void download_transfers_impl(qrad_cuda_ctx *c, int64_t *row_ptr, uint32_t *patch
   ra.L_pos = c->L_pos.p;
   ra.bits = c->bits.p;
   ra.M = M;
+  ra.slot_lo = 0;
+  ra.slot_hi = M;
   ra.row_total = c->row_total.p;
   ra.row_count = c->row_count.p;
   ra.row_ptr = d_row_ptr.p;
@@ -870,25 +926,35 @@ void download_transfers_impl(qrad_cuda_ctx *c, int64_t *row_ptr, uint32_t *patch
   d_tr.download(transfer, (size_t) nnz, st);
 }
 
-// BounceLight, qrad3.c:448-473
-void bounce_impl(qrad_cuda_ctx *c, int numbounce, float *added_out) {
+// BounceLight, qrad3.c:448-473, in three parts so that a multi-GPU host can all-gather the radiosity vector
+// between bounces: begin (radiosity = samplelight * reflectivity * area), step (one ShootLight + CollectLight
+// over this rank's slices), end (totallight back to patch order).
+void bounce_begin(qrad_cuda_ctx *c, bool want_sum) {
   if (!c->transfers_done) dfail("bounce: make_transfers has not run");
-  Timer tall;
-  tall.start(c->stream);
+  c->t_bounce.start(c->stream);
   cudaStream_t st = c->stream;
-  const int M = c->M, N = c->N;
-  c->rad_a.alloc((size_t) M);
-  c->rad_b.alloc((size_t) M);
-  c->s_total.alloc((size_t) M);
-  c->s_refl_area.alloc((size_t) M);
+  const int M = c->M;
+  c->rad_a.alloc((size_t) c->Mpad);
+  c->rad_b.alloc((size_t) c->Mpad);
+  c->s_total.alloc((size_t) c->Mpad);
+  c->s_refl_area.alloc((size_t) c->Mpad);
+  c->rad_a.zero(st);
+  c->rad_b.zero(st);
+  c->s_total.zero(st);
   k_init_bounce<<<(M + 255) / 256, 256, 0, st>>>(M, c->slot_patch.p, c->p_samplelight.p, c->p_totallight.p, c->p_refl.p,
                                                  c->p_origin_area.p, c->rad_a.p, c->s_total.p, c->s_refl_area.p);
   c->launch_check("k_init_bounce");
-  DBuf<float> rad_sum, d_added;
-  if (added_out) {
-    rad_sum.alloc((size_t) M);
-    d_added.alloc((size_t) std::max(numbounce, 1));
-  }
+  if (want_sum) c->rad_sum.alloc((size_t) c->Mpad);
+  else c->rad_sum.release();
+  c->rad_cur = c->rad_a.p;
+  c->rad_nxt = c->rad_b.p;
+  c->bounce_kernel_ms = 0;
+  c->bounce_steps = 0;
+  c->sync("bounce_begin");
+}
+
+void bounce_step(qrad_cuda_ctx *c) {
+  cudaStream_t st = c->stream;
   BounceArgs a{};
   a.slice_len = c->slice_len.p;
   a.slice_base = c->slice_base.p;
@@ -896,30 +962,46 @@ void bounce_impl(qrad_cuda_ctx *c, int numbounce, float *added_out) {
   a.g_w = c->g_w.p;
   a.total = c->s_total.p;
   a.refl_area = c->s_refl_area.p;
-  a.rad_sum = added_out ? rad_sum.p : nullptr;
-  a.M = M;
-  float4 *cur = c->rad_a.p, *nxt = c->rad_b.p;
+  a.rad_sum = c->rad_sum.p;
+  a.M = c->M;
+  a.slice_lo = c->slice_lo;
+  a.slice_hi = c->slice_hi;
+  a.send = c->rad_cur;
+  a.send_next = c->rad_nxt;
+  const int blocks = std::max(1, (c->slice_hi - c->slice_lo + kWarpsPerBlock - 1) / kWarpsPerBlock);
   Timer tk;
-  float kernel_ms = 0;
+  tk.start(st);
+  k_bounce<<<blocks, kThreads, 0, st>>>(a);
+  c->launch_check("k_bounce");
+  c->bounce_kernel_ms += tk.stop();
+  c->bounce_steps++;
+  std::swap(c->rad_cur, c->rad_nxt);   // rad_cur now holds the new radiosity (this rank's slots)
+}
+
+void bounce_end(qrad_cuda_ctx *c) {
+  cudaStream_t st = c->stream;
+  k_finish_bounce<<<(c->N + 255) / 256, 256, 0, st>>>(c->N, c->patch_slot.p, c->s_total.p, c->rad_cur, c->p_totallight.p,
+                                                      c->d_radiosity.p);
+  c->launch_check("k_finish_bounce");
+  c->sync("bounce");
+  c->stats.ms_bounce_kernel = c->bounce_steps > 0 ? c->bounce_kernel_ms / c->bounce_steps : 0;
+  c->stats.ms_bounce = c->t_bounce.stop();
+}
+
+void bounce_impl(qrad_cuda_ctx *c, int numbounce, float *added_out) {
+  if (c->world > 1) dfail("bounce: this context is a shard (%d/%d); use qrad_cuda_bounce_phase and exchange", c->rank, c->world);
+  bounce_begin(c, added_out != nullptr);
+  DBuf<float> d_added;
+  if (added_out) d_added.alloc((size_t) std::max(numbounce, 1));
   for (int b = 0; b < numbounce; b++) {
-    a.send = cur;
-    a.send_next = nxt;
-    tk.start(st);
-    k_bounce<<<(M / 32 + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(a);
-    c->launch_check("k_bounce");
-    kernel_ms += tk.stop();
+    bounce_step(c);
     if (added_out) {
-      k_ordered_sum<<<1, 32, 0, st>>>(rad_sum.p, c->patch_slot.p, N, d_added.p + b);
+      k_ordered_sum<<<1, 32, 0, c->stream>>>(c->rad_sum.p, c->patch_slot.p, c->N, d_added.p + b);
       c->launch_check("k_ordered_sum");
     }
-    std::swap(cur, nxt);
   }
-  k_finish_bounce<<<(N + 255) / 256, 256, 0, st>>>(N, c->patch_slot.p, c->s_total.p, cur, c->p_totallight.p, c->d_radiosity.p);
-  c->launch_check("k_finish_bounce");
-  if (added_out && numbounce > 0) d_added.download(added_out, (size_t) numbounce, st);
-  c->sync("bounce");
-  c->stats.ms_bounce_kernel = numbounce > 0 ? kernel_ms / numbounce : 0;
-  c->stats.ms_bounce = tall.stop();
+  if (added_out && numbounce > 0) d_added.download(added_out, (size_t) numbounce, c->stream);
+  bounce_end(c);
 }
 
 }  // namespace qrad

@@ -369,6 +369,63 @@ def rad_world(scene: Scene, dev: Device, params: HostParams, want_added: bool = 
     return added[:max(params.numbounce, 0)]
 
 
+XBUF_BITS, XBUF_ROW_TOTAL, XBUF_ROW_COUNT, XBUF_RADIOSITY, XBUF_TOTALLIGHT = range(5)
+
+
+class _DevArray:
+    """Zero-copy view of a library-owned device buffer for torch (CUDA array interface v2)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def exchange_tensor(dev: Device, which: int, dtype_str: str):
+    """torch tensor over one of the exchange buffers (include/qrad_cuda.h, QRAD_XBUF_*) + elements per shard."""
+    import torch
+    ptr = C.c_void_p()
+    total = C.c_int64()
+    shard = C.c_int64()
+    _dck(lib().qrad_cuda_exchange_buffer(dev._h, C.c_int(which), C.byref(ptr), C.byref(total), C.byref(shard)))
+    t = torch.as_tensor(_DevArray(ptr.value, total.value // 4, dtype_str), device="cuda")
+    return t, shard.value // 4
+
+
+def rad_world_sharded(scene: Scene, dev: Device, params: HostParams, rank: int, world: int, upload: bool = True):
+    """RadWorld (qrad3.c:494-536) with the source rows / receiver slices sharded over `world` ranks, one process
+    per GPU, exchanges over torch.distributed (NCCL over NVLink): one sum all-reduce of the visibility bit matrix,
+    all-gathers of the row totals, one all-gather of the radiosity vector per bounce.
+    Direct lighting and FinalLightFace are replicated (together ~1 % of the work).  Returns (lump, lightofs, styles)."""
+    import torch
+    import torch.distributed as dist
+    L = lib()
+    dev.set_shard(rank, world)
+    if upload:
+        dev.upload(scene)
+    dev.build_facelights(params.extrasamples, params.numbounce)
+
+    def gather_in_place(which, typestr):
+        t, shard = exchange_tensor(dev, which, typestr)
+        dist.all_gather_into_tensor(t, t[rank * shard:(rank + 1) * shard])
+        torch.cuda.synchronize()
+
+    if params.numbounce > 0:
+        _dck(L.qrad_cuda_make_transfers_phase(dev._h, C.c_int(params.nopvs), C.c_int(0)))
+        bits, _ = exchange_tensor(dev, XBUF_BITS, "<i4")
+        dist.all_reduce(bits)          # every word is written by exactly one rank, the others hold 0
+        torch.cuda.synchronize()
+        _dck(L.qrad_cuda_make_transfers_phase(dev._h, C.c_int(params.nopvs), C.c_int(1)))
+        gather_in_place(XBUF_ROW_TOTAL, "<f4")
+        gather_in_place(XBUF_ROW_COUNT, "<i4")
+        _dck(L.qrad_cuda_make_transfers_phase(dev._h, C.c_int(params.nopvs), C.c_int(2)))
+        _dck(L.qrad_cuda_bounce_phase(dev._h, C.c_int(0)))
+        for _ in range(params.numbounce):
+            _dck(L.qrad_cuda_bounce_phase(dev._h, C.c_int(1)))
+            gather_in_place(XBUF_RADIOSITY, "<f4")
+        gather_in_place(XBUF_TOTALLIGHT, "<f4")
+        _dck(L.qrad_cuda_bounce_phase(dev._h, C.c_int(2)))
+    return dev.final_light(params.ambient, params.maxlight, params.lightscale, params.subdiv, params.numbounce)
+
+
 def qrad3(argv) -> int:
     """The drop-in command line (same flags as the reference qrad3), in-process."""
     args = [b"qrad3"] + [str(a).encode() for a in argv]

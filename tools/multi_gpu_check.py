@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check (run under torchrun, one rank per GPU): the sharded RadWorld must write the same
+lighting lump as the reference on every rank.  usage:
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py
+"""
+import os
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+import golden_util as G  # noqa: E402
+from qengine_b200 import qrad as Q  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+for case in sys.argv[1:] or ["samplec", "grid2", "grid3_chop16", "hall", "styles"]:
+    meta, flags = G.load_case(case)
+    with tempfile.TemporaryDirectory() as tmp:
+        bsp = G.stage_case(case, Path(tmp))
+        p = G.params_from_flags(flags)
+        sc = Q.Scene(bsp).prepare(p)
+        dev = Q.Device(local)
+        data, lightofs, styles = Q.rad_world_sharded(sc, dev, p, rank, world)
+        want = np.frombuffer((G.GOLDEN / (case + ".lump")).read_bytes(), np.uint8)
+        same = data.size == want.size and bool((data == want).all())
+        nt = dev.numtransfers()
+        same_nt = bool(np.array_equal(nt, G.golden_numtransfers(case)))
+        print(f"rank {rank}/{world} {case}: lump identical={same} numtransfers identical={same_nt}", flush=True)
+        ok &= same and same_nt
+t = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("MULTI_GPU_CHECK", "PASS" if t.item() == 1 else "FAIL", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if t.item() == 1 else 1)
