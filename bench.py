@@ -294,14 +294,19 @@ def main():
         # ---- roofline of the dominant bandwidth kernel (k_bounce) ----
         peak, peak_src = measured_peak()
         b = 4 if st["num_patches"] <= 65535 else 6   # transfer_t is 4 B up to 65 535 patches
-        alg_bytes = st["total_transfers"] * b + 64 * st["num_patches"]
+        # per GPU: a launch of k_bounce processes this rank's share of the matrix (1/world of the slices)
+        alg_bytes = (st["total_transfers"] * b + 64 * st["num_patches"]) / world
         kb_ms = float(np.mean(bounce_ms))
         achieved = alg_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else 0.0
-        stored_bytes = st["transfer_bytes"]
+        stored_bytes = st["transfer_bytes"]     # what this rank's launch actually streams (dense-slice format)
         roofline = {"bound": "hbm", "kernel": "k_bounce", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "stored_bytes_per_launch": stored_bytes,
-                    "ms_per_launch": kb_ms, "launches_per_step": p.numbounce}
+                    "stored_gbs": stored_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else 0.0,
+                    "stored_frac": stored_bytes / (kb_ms * 1e-3) / 1e9 / peak if kb_ms > 0 else 0.0,
+                    "note": "achieved = algorithmic bytes (nnz*b + 64*N, SURVEY 8d) / CUDA-event time; the stored layout "
+                            "is 3.6 B per transfer on this map, so stored_frac is the real HBM utilisation",
+                    "ms_per_launch": kb_ms, "launches_per_step": p.numbounce, "per_gpu": world > 1}
         prof = ROOT / "profiles" / "bounce_traffic.json"
         if prof.exists():
             try:

@@ -241,3 +241,15 @@ def test_unvised_map_is_direct_only(Q, tmp_path):
     Q.rad_world(sc, dev, p)
     lump = np.frombuffer(sc.lighting(), np.uint8)
     assert lump.size == 8928 and (lump == 1).all()
+
+
+def test_two_gpu_sharded_parity(Q):
+    """Sharded RadWorld (one process per GPU, NCCL) writes the reference's bytes on every rank."""
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(G.ROOT / "tools" / "multi_gpu_check.py"),
+                        "samplec", "grid2", "styles"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MULTI_GPU_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
