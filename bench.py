@@ -325,7 +325,9 @@ def main():
                        "parallelism": f"rows x{world}"},
             "s_per_map": step_ms * 1e-3,
             "phase_ms": dict(zip(["facelights", "transfers", "bounce", "final"], [float(x) for x in np.mean(phase, axis=0)])),
+            "exchange_ms": getattr(dev, "exchange_ms", None),
             "trace_kernel_ms": float(np.mean(trace_ms)),
+            "transfers_breakdown_ms": {k: st[k] for k in ("ms_tr_setup", "ms_transfers_trace", "ms_tr_lists", "ms_tr_rows", "ms_tr_columns")},
             "trace_rays_per_s": st["rays_transfers"] / (float(np.mean(trace_ms)) * 1e-3) if np.mean(trace_ms) > 0 else None,
             "bounce_gbs": achieved,
             "wall_s_per_step": wall / args.steps,

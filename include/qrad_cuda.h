@@ -126,6 +126,8 @@ typedef struct {
   int32_t num_patches, num_luxels, num_clusters, tree_depth;
   float   ms_upload, ms_facelights, ms_transfers, ms_transfers_trace, ms_bounce, ms_bounce_kernel, ms_final;
   int32_t kernel_launches;    /* kernels launched by this context so far                          */
+  /* wall-clock breakdown of make_transfers on the host thread (ms): slot order + uploads, ordered lists, pass 2, pass 3 */
+  float   ms_tr_setup, ms_tr_lists, ms_tr_rows, ms_tr_columns;
 } qrad_cuda_stats;
 
 int  qrad_cuda_abi_version(void);

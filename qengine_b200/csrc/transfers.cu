@@ -21,6 +21,7 @@
 // Everything is float arithmetic in the reference's operation order; this TU is compiled
 // with -fmad=false.
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <numeric>
 
@@ -576,6 +577,7 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   if (!c->numnodes || !c->N) dfail("make_transfers: BSP and patches must be uploaded first");
   if (!c->have_vis) dfail("make_transfers: map has no visibility data (the reference forces numbounce = 0)");
   c->t_transfers.start(c->stream);
+  const auto wall0 = std::chrono::steady_clock::now();
   c->transfers_done = false;
   const int N = c->N;
   // ---- host: slot order ----
@@ -694,6 +696,8 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   c->counters.alloc(4);
   c->counters.zero(st);
 
+  c->sync("make_transfers uploads");
+  c->stats.ms_tr_setup = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   // ---- pass 1 ----
   Timer ttrace;
   ttrace.start(st);
@@ -751,6 +755,7 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
 // phase 1: ordered lists + pass 2 (row totals of this rank's slots).  Needs the complete bit matrix.
 void transfers_rows(qrad_cuda_ctx *c) {
   cudaStream_t st = c->stream;
+  auto wall0 = std::chrono::steady_clock::now();
   const int N = c->N, M = c->M, nc = c->nc_eff;
   // ---- ordered lists ----
   c->L_slot.alloc((size_t) c->h_Lptr[nc] + 1);
@@ -778,6 +783,9 @@ void transfers_rows(qrad_cuda_ctx *c) {
     c->launch_check("k_build_lists(cols)");
   }
 
+  c->sync("make_transfers lists");
+  c->stats.ms_tr_lists = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+  wall0 = std::chrono::steady_clock::now();
   // ---- pass 2 ----
   c->row_total.alloc((size_t) c->Mpad);
   c->row_count.alloc((size_t) c->Mpad);
@@ -808,11 +816,13 @@ void transfers_rows(qrad_cuda_ctx *c) {
     }
   }
   c->sync("make_transfers pass 2");
+  c->stats.ms_tr_rows = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
 }
 
 // phase 2: pass 3 (gather lists of this rank's slices).  Needs the row totals of every source.
 void transfers_columns(qrad_cuda_ctx *c) {
   cudaStream_t st = c->stream;
+  const auto wall0 = std::chrono::steady_clock::now();
   const int M = c->M, nc = c->nc_eff;
   const int nslices = M / 32;
   c->slice_len.alloc((size_t) nslices);
@@ -875,6 +885,7 @@ void transfers_columns(qrad_cuda_ctx *c) {
   c->stats.padded_entries = c->sell_entries;
   c->stats.transfer_bytes = c->sell_entries * 68;   // stored: u32 source + 32 x u16 weights per list entry
   c->transfers_done = true;
+  c->stats.ms_tr_columns = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   c->stats.ms_transfers = c->t_transfers.stop();
 }
 

@@ -67,7 +67,9 @@ class Stats(C.Structure):
                 ("tree_depth", C.c_int32),
                 ("ms_upload", C.c_float), ("ms_facelights", C.c_float), ("ms_transfers", C.c_float),
                 ("ms_transfers_trace", C.c_float), ("ms_bounce", C.c_float), ("ms_bounce_kernel", C.c_float),
-                ("ms_final", C.c_float), ("kernel_launches", C.c_int32)]
+                ("ms_final", C.c_float), ("kernel_launches", C.c_int32),
+                ("ms_tr_setup", C.c_float), ("ms_tr_lists", C.c_float), ("ms_tr_rows", C.c_float),
+                ("ms_tr_columns", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -395,24 +397,30 @@ def rad_world_sharded(scene: Scene, dev: Device, params: HostParams, rank: int, 
     per GPU, exchanges over torch.distributed (NCCL over NVLink): one sum all-reduce of the visibility bit matrix,
     all-gathers of the row totals, one all-gather of the radiosity vector per bounce.
     Direct lighting and FinalLightFace are replicated (together ~1 % of the work).  Returns (lump, lightofs, styles)."""
+    import time
     import torch
     import torch.distributed as dist
     L = lib()
+    xt = {"bits_allreduce_ms": 0.0, "allgather_ms": 0.0}
     dev.set_shard(rank, world)
     if upload:
         dev.upload(scene)
     dev.build_facelights(params.extrasamples, params.numbounce)
 
     def gather_in_place(which, typestr):
+        t0 = time.perf_counter()
         t, shard = exchange_tensor(dev, which, typestr)
         dist.all_gather_into_tensor(t, t[rank * shard:(rank + 1) * shard])
         torch.cuda.synchronize()
+        xt["allgather_ms"] += (time.perf_counter() - t0) * 1e3
 
     if params.numbounce > 0:
         _dck(L.qrad_cuda_make_transfers_phase(dev._h, C.c_int(params.nopvs), C.c_int(0)))
+        t0 = time.perf_counter()
         bits, _ = exchange_tensor(dev, XBUF_BITS, "<i4")
         dist.all_reduce(bits)          # every word is written by exactly one rank, the others hold 0
         torch.cuda.synchronize()
+        xt["bits_allreduce_ms"] = (time.perf_counter() - t0) * 1e3
         _dck(L.qrad_cuda_make_transfers_phase(dev._h, C.c_int(params.nopvs), C.c_int(1)))
         gather_in_place(XBUF_ROW_TOTAL, "<f4")
         gather_in_place(XBUF_ROW_COUNT, "<i4")
@@ -423,6 +431,7 @@ def rad_world_sharded(scene: Scene, dev: Device, params: HostParams, rank: int, 
             gather_in_place(XBUF_RADIOSITY, "<f4")
         gather_in_place(XBUF_TOTALLIGHT, "<f4")
         _dck(L.qrad_cuda_bounce_phase(dev._h, C.c_int(2)))
+    dev.exchange_ms = xt
     return dev.final_light(params.ambient, params.maxlight, params.lightscale, params.subdiv, params.numbounce)
 
 
