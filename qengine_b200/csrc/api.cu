@@ -177,6 +177,40 @@ int qrad_cuda_upload_bsp(qrad_cuda_ctx *c, const qrad_bsp_view *b) {
       flat[me] = make_int4(distbits, pl.type, child[0], child[1]);
       normals[me] = make_float4(pl.normal[0], pl.normal[1], pl.normal[2], pl.dist);
     }
+    // root -> leaf paths (for reaches_leaf): parent links in the new numbering, then one record list per leaf
+    {
+      std::vector<int> parent((size_t) next_new, -1), pside((size_t) next_new, 0);
+      std::vector<int> lparent((size_t) b->numleafs, -1), lside((size_t) b->numleafs, 0);
+      for (int me = 0; me < next_new; me++) {
+        const int ch[2] = {flat[me].z, flat[me].w};
+        for (int k = 0; k < 2; k++) {
+          if (ch[k] >= 0) {
+            parent[ch[k]] = me;
+            pside[ch[k]] = k;
+          } else {
+            lparent[ch[k] & kLeafMask] = me;
+            lside[ch[k] & kLeafMask] = k;
+          }
+        }
+      }
+      std::vector<int32_t> first((size_t) b->numleafs + 1, 0);
+      std::vector<int4> recs;
+      std::vector<int4> tmp;
+      for (int l = 0; l < b->numleafs; l++) {
+        tmp.clear();
+        int node = lparent[l], sd = lside[l];
+        while (node >= 0) {
+          tmp.push_back(make_int4(flat[node].x, flat[node].y | (sd << 8), node, 0));
+          sd = pside[node];
+          node = parent[node];
+        }
+        recs.insert(recs.end(), tmp.rbegin(), tmp.rend());
+        first[l + 1] = (int32_t) recs.size();
+      }
+      if (recs.empty()) recs.push_back(make_int4(0, 0, 0, 0));
+      c->leaf_path.upload(recs, c->stream);
+      c->leaf_path_first.upload(first, c->stream);
+    }
     if (maxdepth > kTraceStackBig) dfail("BSP depth %d exceeds the supported trace stack (%d)", maxdepth, kTraceStackBig);
     c->numnodes = next_new;
     c->numleafs = b->numleafs;

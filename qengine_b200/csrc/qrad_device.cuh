@@ -88,9 +88,10 @@ constexpr int kTraceStackBig = 256;
 // Compares: `front >= -ON_EPSILON` with ON_EPSILON the double 0.1 (trace.c:27) is, for a float
 // front, the same predicate as `front > -0.1f`, and `front < ON_EPSILON` the same as
 // `front < 0.1f` (-0.1f < -0.1 and 0.1f > 0.1; checked exhaustively around the constants).
+// Returns 0 (clear) or 1 (blocked); *blocker, when given, receives the solid leaf that ended the walk.
 template <int STACK, bool COUNT>
 __device__ __forceinline__ int test_line(const Tree tree, float sx, float sy, float sz, float ex, float ey, float ez,
-                                         unsigned &visits) {
+                                         unsigned &visits, int *blocker = nullptr) {
   float4 stack[STACK];
   int sp = 0;
   int node = 0;
@@ -130,7 +131,10 @@ __device__ __forceinline__ int test_line(const Tree tree, float sx, float sy, fl
       ez = mz;
       node = side ? nd.w : nd.z;
     }
-    if (node & kSolidBit) return 1;
+    if (node & kSolidBit) {
+      if (blocker) *blocker = node & kLeafMask;
+      return 1;
+    }
     if (sp == 0) return 0;
     sp--;
     const float4 t = stack[sp < STACK ? sp : STACK - 1];
@@ -142,6 +146,52 @@ __device__ __forceinline__ int test_line(const Tree tree, float sx, float sy, fl
     ey = t.z;
     ez = t.w;
   }
+}
+
+// Does TestLine_r(0, start, stop) reach leaf X?  The segment TestLine_r hands to a child depends only on the
+// ancestors of that child (trace.c:124-141), so walking the root -> X path with the same three-way test and the same
+// clipping arithmetic decides it exactly, without a stack and without visiting any sibling subtree.  `path` holds,
+// root first, one record per ancestor: x = float bits of dist, y = plane type | (side of X's subtree) << 8,
+// z = node index (for the normal of a non-axial plane).  Since TestLine_r's result is the OR over all reachable
+// leaves, "a SOLID leaf is reachable" proves the ray blocked; callers use the leaf that blocked a neighbouring ray
+// as the guess and fall back to the full walk when the guess is not reached.
+template <bool COUNT>
+__device__ __forceinline__ bool reaches_leaf(const Tree tree, const int4 *__restrict__ path, const int len, float sx,
+                                             float sy, float sz, float ex, float ey, float ez, unsigned &visits) {
+  for (int i = 0; i < len; i++) {
+    const int4 nd = __ldg(path + i);
+    const float dist = __int_as_float(nd.x);
+    const int type = nd.y & 0xff, want = nd.y >> 8;
+    if (COUNT) visits++;
+    float front, back;
+    if (type < 3) {
+      const float s1 = type == 0 ? sx : (type == 1 ? sy : sz);
+      const float e1 = type == 0 ? ex : (type == 1 ? ey : ez);
+      front = s1 - dist;
+      back = e1 - dist;
+    } else {
+      const float4 pl = __ldg(tree.normals + nd.z);
+      front = (sx * pl.x + sy * pl.y + sz * pl.z) - dist;
+      back = (ex * pl.x + ey * pl.y + ez * pl.z) - dist;
+    }
+    if (front > -0.1f && back > -0.1f) {
+      if (want != 0) return false;
+    } else if (front < 0.1f && back < 0.1f) {
+      if (want != 1) return false;
+    } else {
+      const int side = front < 0 ? 1 : 0;
+      const float frac = front / (front - back);
+      const float mx = sx + (ex - sx) * frac;
+      const float my = sy + (ey - sy) * frac;
+      const float mz = sz + (ez - sz) * frac;
+      if (want == side) {  // near half: (start, mid)
+        ex = mx; ey = my; ez = mz;
+      } else {             // far half: (mid, stop)
+        sx = mx; sy = my; sz = mz;
+      }
+    }
+  }
+  return true;
 }
 
 // PointInLeafnum, qrad3.c:131-150: full dot product on every node, `dist > 0` picks child 0.
@@ -212,6 +262,8 @@ struct qrad_cuda_ctx {
   bool have_vis = false;
   qrad::DBuf<int4> nodes;
   qrad::DBuf<float4> node_normals;
+  qrad::DBuf<int4> leaf_path;           // root -> leaf ancestor records of every leaf, see reaches_leaf()
+  qrad::DBuf<int32_t> leaf_path_first;  // [numleafs + 1]
   qrad::Tree tree() const { return qrad::Tree{nodes.p, node_normals.p}; }
   qrad::DBuf<int32_t> leaf_contents, leaf_cluster;
   qrad::DBuf<uint32_t> pvs;            // [numclusters][pvs_words], bit d of row c = cluster d visible from c
@@ -277,6 +329,8 @@ struct qrad_cuda_ctx {
   qrad::DBuf<int64_t> d_Lptr, d_bits_base;
   qrad::DBuf<int32_t> d_nwords, d_cl_slot_start, d_cl_count;
   qrad::DBuf<uint32_t> L_slot, L_pos;
+  qrad::DBuf<uint4> L_sum;              // per 32-entry chunk of a row list: row words / masks it can touch
+  qrad::DBuf<int64_t> d_chunk_base;
   bool transfers_done = false;
   int64_t total_transfers = 0;
   // state kept between the phases of make_transfers / bounce (multi-GPU hosts exchange in between)
@@ -286,6 +340,7 @@ struct qrad_cuda_ctx {
   qrad::DBuf<int32_t> d_vis_ptr, d_vis_cluster, d_vis_woff, d_woff_table;
   qrad::DBuf<int64_t> d_Rptr, d_task_base;
   qrad::DBuf<uint32_t> R_slot;
+  qrad::DBuf<int64_t> R_addr;
   qrad::DBuf<unsigned long long> counters;
   qrad::DBuf<float> rad_sum;
   qrad::Timer t_transfers, t_bounce;

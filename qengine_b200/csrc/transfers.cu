@@ -52,10 +52,13 @@ __device__ __forceinline__ float form_factor_pre(const float4 so, const float4 s
 }
 
 constexpr int kChunkWords = 32;   // one task = one source patch x up to 32 words (1024 receivers)
+constexpr int kTaskRun = 8;         // consecutive tasks handled by one warp (its blocker guesses stay warm)
 constexpr int kTaskGranule = 2048;  // multi-GPU: granule g of tasks belongs to rank g % world
 
 struct VisArgs {
   Tree tree;
+  const int4 *leaf_path;          // root -> leaf ancestor records (reaches_leaf)
+  const int32_t *leaf_path_first;
   const float4 *s_origin_area, *s_normal;
   const int64_t *bits_base;      // [nc+1] word offset of the first row of each source cluster
   const int64_t *task_base;      // [nc+1] task offset of each source cluster (rows x chunks per row)
@@ -74,23 +77,30 @@ struct VisArgs {
 };
 
 // One warp lights one task: (1) form-factor sign tests for up to 1024 receivers of one source; the pairs the
-// reference would hand to TestLine_r (qrad3.c:244) are compacted into a per-warp queue; (2) the queue is traced
-// 32 rays at a time, every batch starting at the root together (same source, neighbouring receivers: the lanes
-// stay on the same nodes for the top of the tree); (3) accept bits are OR-ed into 32 result words in shared
-// memory and stored with one coalesced write.  Measured alternatives (profiles/README.md): one word per warp
-// without compaction leaves 46 % of the lanes idle; refilling finished lanes from the queue decorrelates the
-// lanes so that every step executes the union of the descend / split / pop paths and is slower.
+// reference would hand to TestLine_r (qrad3.c:244) are compacted into a per-warp queue; (2) the queue is consumed 32
+// rays at a time.  95 % of these rays are blocked, and 98.6 % of the blocked ones by the same solid leaf as the
+// previous blocked ray of the same source (measured on C5 with the CPU oracle), so every lane first asks whether the
+// leaf that blocked its previous ray is reached (reaches_leaf: one root -> leaf path, no stack); rays that are not
+// settled that way collect in a second queue and take the full TestLine walk in full batches, which also refreshes
+// the guesses; (3) accept bits are OR-ed into 32 result words in shared memory and stored with one coalesced write.
+// Measured alternatives (profiles/README.md): one word per warp without compaction leaves 46 % of the lanes idle;
+// refilling finished lanes from the queue decorrelates the lanes and is slower.
 template <int STACK, bool COUNT>
 __global__ void __launch_bounds__(kThreads) k_visibility(const VisArgs a) {
   __shared__ uint16_t s_queue[kWarpsPerBlock][kChunkWords * 32];
   __shared__ uint32_t s_res[kWarpsPerBlock][kChunkWords];
   __shared__ int32_t s_wbase[kWarpsPerBlock][kChunkWords];
+  __shared__ uint16_t s_fb[kWarpsPerBlock][64];     // rays whose guess failed: receiver index | lane << 10
+  __shared__ int32_t s_guess[kWarpsPerBlock][32];   // per lane: solid leaf that blocked its last fully traced ray
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1;
   const uint64_t warp0 = (uint64_t) blockIdx.x * kWarpsPerBlock + wid;
   const uint64_t nwarps = (uint64_t) gridDim.x * kWarpsPerBlock;
-  unsigned long long rays = 0, pairs = 0, visits_total = 0;
-  for (uint64_t ltask = warp0; ltask < a.my_tasks; ltask += nwarps) {
+  unsigned long long rays = 0, pairs = 0, visits_total = 0, fallbacks = 0;
+  s_guess[wid][lane] = -1;
+  __syncwarp();
+  for (uint64_t lrun = warp0 * kTaskRun; lrun < a.my_tasks; lrun += nwarps * kTaskRun)
+  for (uint64_t ltask = lrun; ltask < lrun + kTaskRun && ltask < a.my_tasks; ltask++) {
     const uint64_t task = ((ltask / kTaskGranule) * a.world + a.rank) * kTaskGranule + ltask % kTaskGranule;
     if (task >= a.num_tasks) continue;
     // ---- decode: source cluster, row, chunk ----
@@ -148,19 +158,55 @@ __global__ void __launch_bounds__(kThreads) k_visibility(const VisArgs a) {
       n += __popc(m);
     }
     __syncwarp();
-    // ---- phase 2: trace the queue, 32 rays per batch ----
-    for (int base = 0; base < n; base += 32) {
-      const int k = base + lane;
-      if (k < n) {
-        const int cand = s_queue[wid][k];
+    // ---- phase 2: guess walks, full walks for the rest ----
+    int fbn = 0;
+    // full TestLine for the first `cnt` entries of the fallback queue
+    auto full_batch = [&](const int cnt) {
+      if (lane < cnt) {
+        const int e = s_fb[wid][lane];
+        const int cand = e & 1023;
         const float4 po = __ldg(a.s_origin_area + s_wbase[wid][cand >> 5] + (cand & 31));
         unsigned visits = 0;
-        const int blocked = test_line<STACK, COUNT>(a.tree, so.x, so.y, so.z, po.x, po.y, po.z, visits);
+        int leaf = -1;
+        const int blocked = test_line<STACK, COUNT>(a.tree, so.x, so.y, so.z, po.x, po.y, po.z, visits, &leaf);
         if (COUNT) visits_total += visits;
         if (!blocked) atomicOr(&s_res[wid][cand >> 5], 1u << (cand & 31));
+        else s_guess[wid][e >> 10] = leaf;
       }
       __syncwarp();
+    };
+    for (int base = 0; base < n; base += 32) {
+      const int k = base + lane;
+      bool miss = false;
+      int cand = 0;
+      if (k < n) {
+        cand = s_queue[wid][k];
+        const int g = s_guess[wid][lane];
+        miss = true;
+        if (g >= 0) {
+          const float4 po = __ldg(a.s_origin_area + s_wbase[wid][cand >> 5] + (cand & 31));
+          const int p0 = __ldg(a.leaf_path_first + g), p1 = __ldg(a.leaf_path_first + g + 1);
+          unsigned visits = 0;
+          miss = !reaches_leaf<COUNT>(a.tree, a.leaf_path + p0, p1 - p0, so.x, so.y, so.z, po.x, po.y, po.z, visits);
+          if (COUNT) visits_total += visits;
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, miss);
+      if (COUNT && miss) fallbacks++;
+      if (miss) s_fb[wid][fbn + __popc(m & lt)] = (uint16_t) (cand | (lane << 10));
+      fbn += __popc(m);
+      __syncwarp();
+      if (fbn >= 32) {
+        full_batch(32);
+        uint16_t t = 0;
+        if (lane < fbn - 32) t = s_fb[wid][32 + lane];
+        __syncwarp();
+        if (lane < fbn - 32) s_fb[wid][lane] = t;
+        fbn -= 32;
+        __syncwarp();
+      }
     }
+    if (fbn > 0) full_batch(fbn);
     __syncwarp();
     if (lane < nwc) a.bits[a.bits_base[c] + (int64_t) row * nw + w0 + lane] = s_res[wid][lane];
     __syncwarp();
@@ -169,11 +215,13 @@ __global__ void __launch_bounds__(kThreads) k_visibility(const VisArgs a) {
     rays += __shfl_xor_sync(0xffffffffu, rays, o);
     pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
     if (COUNT) visits_total += __shfl_xor_sync(0xffffffffu, visits_total, o);
+    if (COUNT) fallbacks += __shfl_xor_sync(0xffffffffu, fallbacks, o);
   }
   if (lane == 0) {
     atomicAdd(a.counters + 0, rays);
     atomicAdd(a.counters + 2, pairs);
     if (COUNT) atomicAdd(a.counters + 1, visits_total);
+    if (COUNT) atomicAdd(a.counters + 3, fallbacks);
   }
 }
 
@@ -189,7 +237,10 @@ struct ListArgs {
   const int64_t *list_ptr;       // [nc+1]
   uint32_t *out_slot;
   uint32_t *out_aux;
-  int transpose;                 // 0: row lists (aux = bit position in the row); 1: column lists (aux unused)
+  int transpose;                 // 0: row lists (aux = bit position in the row); 1: column lists (addr = word address)
+  const int64_t *bits_base;      // column lists: geometry of the bit matrix
+  const int32_t *nwords;
+  int64_t *out_addr;             // column lists: word of (source row, first slice of the receiver cluster)
 };
 
 __global__ void __launch_bounds__(1024) k_build_lists(const ListArgs a) {
@@ -224,11 +275,44 @@ __global__ void __launch_bounds__(1024) k_build_lists(const ListArgs a) {
       const int64_t o = base_s + before + __popc(m & ((1u << lane) - 1));
       a.out_slot[o] = (uint32_t) slot;
       if (!a.transpose) a.out_aux[o] = (uint32_t) woff * 32u + (uint32_t) (slot - a.cl_slot_start[d]);
+      else a.out_addr[o] = a.bits_base[d] + (int64_t) (slot - a.cl_slot_start[d]) * a.nwords[d] + woff;
     }
     __syncthreads();
     if (threadIdx.x == 0) base_s += total;
     __syncthreads();
   }
+}
+
+// Summaries of the row lists: which row words a 32-entry chunk can touch (entries that are neighbours in patch order
+// are mostly neighbours in slot order too, so a chunk usually lies inside one or two words).
+__global__ void __launch_bounds__(kThreads) k_list_summaries(int nc, const int64_t *__restrict__ Lptr,
+                                                             const int64_t *__restrict__ chunk_base,
+                                                             const uint32_t *__restrict__ L_pos, uint4 *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = (int64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (chunk >= chunk_base[nc]) return;
+  int lo = 0, hi = nc;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (chunk_base[mid] <= chunk) lo = mid; else hi = mid;
+  }
+  const int64_t k = Lptr[lo] + ((chunk - chunk_base[lo]) << 5) + lane;
+  const bool have = k < Lptr[lo + 1];
+  const uint32_t pos = have ? L_pos[k] : 0;
+  const uint32_t word = pos >> 5, bit = have ? 1u << (pos & 31) : 0u;
+  const unsigned hm = __ballot_sync(0xffffffffu, have);   // lane 0 always has an entry
+  const uint32_t w0 = __shfl_sync(0xffffffffu, word, 0);
+  const uint32_t m0 = __reduce_or_sync(0xffffffffu, (have && word == w0) ? bit : 0u);
+  const unsigned rest = __ballot_sync(0xffffffffu, have && word != w0);
+  uint32_t w1 = 0xffffffffu, m1 = 0;
+  bool complex_chunk = false;
+  if (rest) {
+    w1 = __shfl_sync(0xffffffffu, word, __ffs(rest) - 1);
+    m1 = __reduce_or_sync(0xffffffffu, (have && word == w1) ? bit : 0u);
+    complex_chunk = __ballot_sync(0xffffffffu, have && word != w0 && word != w1) != 0;
+  }
+  (void) hm;
+  if (lane == 0) out[chunk] = complex_chunk ? make_uint4(0xffffffffu, 0, 0, 0) : make_uint4(w0, m0, w1, m1);
 }
 
 // pass 2: serial row sums in ascending receiver order.
@@ -238,6 +322,8 @@ struct RowArgs {
   const int64_t *bits_base, *Lptr;
   const int32_t *nwords, *cl_slot_start;
   const uint32_t *L_slot, *L_pos;
+  const uint4 *L_sum;            // per 32-entry chunk of a list: {word0, mask0, word1, mask1} it can touch
+  const int64_t *chunk_base;     // [nc+1] first chunk of each cluster's list
   const uint32_t *bits;
   int M;
   int slot_lo, slot_hi;          // this rank's rows
@@ -269,35 +355,54 @@ __global__ void __launch_bounds__(kThreads) k_row_totals(const RowArgs a) {
     rtotal = a.row_total[sslot];
     outp = a.row_ptr[spatch];
   }
-  for (int64_t k0 = l0; k0 < l1; k0 += 32) {
-    const int64_t k = k0 + lane;
-    bool set = false;
-    float trans = 0.f;
-    uint32_t rslot = 0;
-    if (k < l1) {
-      rslot = a.L_slot[k];
-      const uint32_t pos = a.L_pos[k];
-      set = (row[pos >> 5] >> (pos & 31)) & 1u;
-      if (set) {
-        float dist;
-        bool wr;
-        trans = form_factor_pre(so, sn, a.s_origin_area[rslot], a.s_normal[rslot], dist, wr);
+  // The list has ~40 candidates per accepted receiver.  Each 32-entry chunk has a precomputed summary of the (at
+  // most two) row words it can touch, so 32 chunks are ruled out per step with one masked test per lane and only
+  // chunks holding an accept bit take the ordered walk below (the order of the float sum is untouched).
+  const int64_t nchunks = (l1 - l0 + 31) >> 5;
+  const uint4 *sum = a.L_sum + a.chunk_base[c];
+  for (int64_t g0 = 0; g0 < nchunks; g0 += 32) {
+    bool live = false;
+    if (g0 + lane < nchunks) {
+      const uint4 sm = __ldg(sum + g0 + lane);
+      if (sm.x == 0xffffffffu) live = true;  // touches more than two words: always walk it
+      else {
+        live = (row[sm.x] & sm.y) != 0;
+        if (!live && sm.z != 0xffffffffu) live = (row[sm.z] & sm.w) != 0;
       }
     }
-    unsigned m = __ballot_sync(0xffffffffu, set);
-    if (EMIT) {
-      if (set) {
-        const int64_t o = outp + __popc(m & ((1u << lane) - 1));
-        a.out_patch[o] = (uint32_t) a.slot_patch[rslot];
-        a.out_transfer[o] = (uint16_t) (int) (trans * 65536.0f / rtotal);
+    unsigned lm = __ballot_sync(0xffffffffu, live);
+    while (lm) {
+      const int ci = __ffs(lm) - 1;
+      lm &= lm - 1;
+      const int64_t k = l0 + ((g0 + ci) << 5) + lane;
+      bool set = false;
+      float trans = 0.f;
+      uint32_t rslot = 0;
+      if (k < l1) {
+        rslot = a.L_slot[k];
+        const uint32_t pos = a.L_pos[k];
+        set = (row[pos >> 5] >> (pos & 31)) & 1u;
+        if (set) {
+          float dist;
+          bool wr;
+          trans = form_factor_pre(so, sn, a.s_origin_area[rslot], a.s_normal[rslot], dist, wr);
+        }
       }
-      outp += __popc(m);
-    } else {
-      count += __popc(m);
-      while (m) {  // serial float sum in receiver order (qrad3.c:254); uniform across the warp
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        total += __shfl_sync(0xffffffffu, trans, src);
+      unsigned m = __ballot_sync(0xffffffffu, set);
+      if (EMIT) {
+        if (set) {
+          const int64_t o = outp + __popc(m & ((1u << lane) - 1));
+          a.out_patch[o] = (uint32_t) a.slot_patch[rslot];
+          a.out_transfer[o] = (uint16_t) (int) (trans * 65536.0f / rtotal);
+        }
+        outp += __popc(m);
+      } else {
+        count += __popc(m);
+        while (m) {  // serial float sum in receiver order (qrad3.c:254); uniform across the warp
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          total += __shfl_sync(0xffffffffu, trans, src);
+        }
       }
     }
   }
@@ -324,6 +429,7 @@ struct ColArgs {
   const int32_t *woff_table;
   int nc;
   const uint32_t *R_slot;
+  const int64_t *R_addr;         // word address of (source row, first slice of this receiver cluster)
   const uint32_t *bits;
   const float *row_total;
   int M;
@@ -356,10 +462,8 @@ __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
     const int64_t k = k0 + lane;
     uint32_t word = 0, sslot = 0;
     if (k < r1) {
-      sslot = a.R_slot[k];
-      const int c = a.slot_cluster[sslot];
-      const int woff = a.woff_table[(size_t) c * a.nc + d];
-      word = a.bits[a.bits_base[c] + (int64_t) ((int) sslot - a.cl_slot_start[c]) * a.nwords[c] + woff + wslice];
+      if (MODE) sslot = a.R_slot[k];
+      word = a.bits[a.R_addr[k] + wslice];
     }
     unsigned nz = __ballot_sync(0xffffffffu, word != 0);
     if (MODE == 0) {
@@ -705,6 +809,8 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
     // rows of patches that sit in solid (only possible under -nopvs) are cleared afterwards
     VisArgs a;
     a.tree = c->tree();
+    a.leaf_path = c->leaf_path.p;
+    a.leaf_path_first = c->leaf_path_first.p;
     a.s_origin_area = c->s_origin_area.p;
     a.s_normal = c->s_normal.p;
     a.bits_base = c->d_bits_base.p;
@@ -729,7 +835,7 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
     a.bits = c->bits.p;
     a.counters = c->counters.p;
     const uint64_t mine = a.my_tasks;
-    const uint64_t want_blocks = (mine + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const uint64_t want_blocks = (mine / kTaskRun + kWarpsPerBlock) / kWarpsPerBlock;
     const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>(want_blocks, (uint64_t) c->sm_count * 8));
     const bool big = c->tree_depth > kTraceStack;
     if (c->count_nodes) {
@@ -773,16 +879,35 @@ void transfers_rows(qrad_cuda_ctx *c) {
     la.out_slot = c->L_slot.p;
     la.out_aux = c->L_pos.p;
     la.transpose = 0;
+    la.bits_base = nullptr;
+    la.nwords = nullptr;
+    la.out_addr = nullptr;
     k_build_lists<<<nc, 1024, 0, st>>>(la);
     c->launch_check("k_build_lists(rows)");
     la.list_ptr = c->d_Rptr.p;
     la.out_slot = c->R_slot.p;
     la.out_aux = nullptr;
     la.transpose = 1;
+    la.bits_base = c->d_bits_base.p;
+    la.nwords = c->d_nwords.p;
+    c->R_addr.alloc((size_t) c->h_Rptr[nc] + 1);
+    la.out_addr = c->R_addr.p;
     k_build_lists<<<nc, 1024, 0, st>>>(la);
     c->launch_check("k_build_lists(cols)");
   }
 
+  {
+    std::vector<int64_t> chunk_base((size_t) nc + 1, 0);
+    for (int k = 0; k < nc; k++) chunk_base[k + 1] = chunk_base[k] + ((c->h_Lptr[k + 1] - c->h_Lptr[k] + 31) >> 5);
+    c->d_chunk_base.upload(chunk_base, st);
+    c->L_sum.alloc((size_t) chunk_base[nc] + 1);
+    const int64_t nch = chunk_base[nc];
+    if (nch > 0) {
+      k_list_summaries<<<(unsigned) ((nch + kWarpsPerBlock - 1) / kWarpsPerBlock), kThreads, 0, st>>>(
+          nc, c->d_Lptr.p, c->d_chunk_base.p, c->L_pos.p, c->L_sum.p);
+      c->launch_check("k_list_summaries");
+    }
+  }
   c->sync("make_transfers lists");
   c->stats.ms_tr_lists = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   wall0 = std::chrono::steady_clock::now();
@@ -803,6 +928,8 @@ void transfers_rows(qrad_cuda_ctx *c) {
     ra.cl_slot_start = c->d_cl_slot_start.p;
     ra.L_slot = c->L_slot.p;
     ra.L_pos = c->L_pos.p;
+    ra.L_sum = c->L_sum.p;
+    ra.chunk_base = c->d_chunk_base.p;
     ra.bits = c->bits.p;
     ra.M = M;
     ra.slot_lo = c->slice_lo * 32;
@@ -839,6 +966,7 @@ void transfers_columns(qrad_cuda_ctx *c) {
   ca.woff_table = c->d_woff_table.p;
   ca.nc = nc;
   ca.R_slot = c->R_slot.p;
+  ca.R_addr = c->R_addr.p;
   ca.bits = c->bits.p;
   ca.row_total = c->row_total.p;
   ca.M = M;
@@ -873,12 +1001,14 @@ void transfers_columns(qrad_cuda_ctx *c) {
   for (int s = 0; s < M; s++) nnz += h_rc[s];
   c->sync("make_transfers");
   c->R_slot.release();
+  c->R_addr.release();
 
   unsigned long long hc[4];
   c->counters.download(hc, 4, st);
   c->stats.rays_transfers = (int64_t) hc[0];
   c->stats.node_visits += (int64_t) hc[1];
   c->stats.candidate_pairs = (int64_t) hc[2];
+  c->stats.full_walks = (int64_t) hc[3];
   c->stats.nonzero_words = nzw;
   c->total_transfers = nnz;
   c->stats.total_transfers = nnz;
@@ -922,6 +1052,8 @@ void download_transfers_impl(qrad_cuda_ctx *c, int64_t *row_ptr, uint32_t *patch
   ra.cl_slot_start = c->d_cl_slot_start.p;
   ra.L_slot = c->L_slot.p;
   ra.L_pos = c->L_pos.p;
+  ra.L_sum = c->L_sum.p;
+  ra.chunk_base = c->d_chunk_base.p;
   ra.bits = c->bits.p;
   ra.M = M;
   ra.slot_lo = 0;
