@@ -38,10 +38,12 @@ MAPS = ROOT / "bench_maps"
 
 # name -> (bsp file, qrad3 flags, description)
 WORKLOADS = {
-    "c3_grid26": ("grid26.bsp", ["-bounce", "8", "-chop", "32"],
-                  "synthetic 26x26 room grid (~20k faces / ~250k patches), -chop 32, 8 bounces [BASELINE configs[2]]"),
+    "c3_grid14": ("grid14r512.bsp", ["-bounce", "8", "-chop", "32"],
+                  "synthetic 14x14 grid of 512-unit rooms (~19k faces / ~200k patches), -chop 32, 8 bounces [BASELINE configs[2]]"),
     "c5_grid16_chop8": ("grid16c128.bsp", ["-bounce", "16", "-chop", "8"],
                         "synthetic 16x16 room grid, qbsp3 -chop 128, qrad3 -chop 8 (~1M patches), 16 bounces [configs[4]]"),
+    "c4_hall2000": ("hall2000.bsp", ["-bounce", "0", "-extra"],
+                    "synthetic direct-light stress hall: 2 000 light / light_spot entities, -extra, direct only [configs[3]]"),
     "probe_grid10": ("grid10.bsp", ["-bounce", "8", "-chop", "32"],
                      "synthetic 10x10 room grid (~37k patches), -chop 32, 8 bounces"),
     "ref_sample_grid6": ("grid6.bsp", ["-bounce", "8", "-chop", "32"],

@@ -331,6 +331,10 @@ int qrad_cuda_upload_lights(qrad_cuda_ctx *c, const qrad_lights_view *l) {
     std::vector<int32_t> first(l->light_first, l->light_first + l->numclusters + 1);
     if (first.empty()) first.push_back(0);
     c->light_first.upload(first, c->stream);
+    std::vector<int32_t> lcl((size_t) n);
+    for (int cl = 0; cl < l->numclusters; cl++)
+      for (int k = first[cl]; k < first[cl + 1]; k++) lcl[k] = cl;
+    c->l_cluster.upload(lcl, c->stream);
     c->l_type.upload(l->type, (size_t) n, c->stream);
     c->l_styleslot.upload(slot, c->stream);
     c->l_origin_int.upload(pack4(l->origin, l->intensity, n), c->stream);

@@ -3,6 +3,7 @@
 // Float / double mix and operation order follow the reference;
 // compiled with -fmad=false.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "qrad_device.cuh"
@@ -23,7 +24,8 @@ struct FaceArgs {
   int L, numsamples;
   float *surfpt;                 // [numsamples][L][3]
   // lights
-  const int32_t *light_first, *l_type, *l_styleslot;
+  const int32_t *light_first, *l_type, *l_styleslot, *l_cluster;
+  int numlights;
   const float4 *l_origin_int, *l_color, *l_normal;
   int numstyles;
   float *samples;                // [numstyles][L][3]
@@ -186,6 +188,133 @@ __global__ void __launch_bounds__(128) k_gather(const FaceArgs a) {
   }
 }
 
+// Warp-cooperative GatherSampleLight: one warp per luxel.  The lights a sample sees are, in the reference's order
+// (clusters ascending, each cluster's list in order), exactly the flattened light array restricted to the clusters
+// of the sample's PVS; the warp compacts those light indices into a small queue and evaluates 32 of them at a time
+// (same sample point: the shadow rays of a batch share their origin and walk the top of the tree together).  The
+// contributions are then folded into the style tables in queue order by all lanes redundantly, which keeps the
+// serial chain of rounded double multiply-adds of the reference.
+template <int STACK, bool COUNT>
+__global__ void __launch_bounds__(128) k_gather_warp(const FaceArgs a) {
+  __shared__ int32_t s_q[4][64];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1;
+  const int lux = blockIdx.x * 4 + wid;
+  unsigned long long rays = 0, visits_total = 0;
+  if (lux < a.L) {
+    const int f = a.luxel_face[lux];
+    const float nx = a.f_normal[f * 3], ny = a.f_normal[f * 3 + 1], nz = a.f_normal[f * 3 + 2];
+    const float lightscale = a.numsamples == 5 ? (float) (1.0 / 5) : 1.0f;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;  // style slot 0 (style 0), identical in every lane
+    for (int smp = 0; smp < a.numsamples; smp++) {
+      const float *pos = a.surfpt + ((size_t) smp * a.L + lux) * 3;
+      const float px = pos[0], py = pos[1], pz = pos[2];
+      const int leaf = point_in_leaf(a.nodes, px, py, pz);
+      const int cluster = a.leaf_cluster[leaf];
+      if (cluster < 0) continue;  // PvsForOrigin fails in solid, qrad3.c:171-172
+      const uint32_t *row = a.pvs + (size_t) cluster * a.pvs_words;
+      // evaluate the first `cnt` lights of the queue, then fold their contributions in order
+      auto batch = [&](const int cnt) {
+        bool contrib = false;
+        float scale = 0.f;
+        int l = 0;
+        if (lane < cnt) {
+          l = s_q[wid][lane];
+          const float4 lo = __ldg(a.l_origin_int + l);
+          float dx = lo.x - px, dy = lo.y - py, dz = lo.z - pz;
+          const float dist = vnormalize(dx, dy, dz);
+          const float dot = dx * nx + dy * ny + dz * nz;
+          bool pass = !((double) dot <= 0.001);  // behind sample surface
+          if (pass) {
+            const int type = a.l_type[l];
+            if (type == 1) {
+              scale = (lo.w - dist) * dot;
+            } else {
+              const float4 ln = __ldg(a.l_normal + l);
+              const float dot2 = -(dx * ln.x + dy * ln.y + dz * ln.z);
+              if (type == 0) {
+                if ((double) dot2 <= 0.001) pass = false;  // behind light surface
+                else scale = (lo.w / (dist * dist)) * dot * dot2;
+              } else {
+                if (dot2 <= __ldg(a.l_color + l).w) pass = false;  // outside light cone
+                else scale = (lo.w - dist) * dot;
+              }
+            }
+          }
+          if (pass) {
+            rays++;  // the reference traces before it looks at scale (lightmap.c:898-902)
+            if (scale > 0) {
+              unsigned v = 0;
+              const int blocked = test_line<STACK, COUNT>(a.nodes, px, py, pz, lo.x, lo.y, lo.z, v);
+              if (COUNT) visits_total += v;
+              contrib = !blocked;
+            }
+          }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, contrib);
+        const float scaled = scale * lightscale;  // VectorMA(dest, scale * lightscale, color, dest)
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const double sc = (double) __shfl_sync(0xffffffffu, scaled, src);
+          const int ll = __shfl_sync(0xffffffffu, l, src);
+          const float4 col = __ldg(a.l_color + ll);
+          const int slot = __ldg(a.l_styleslot + ll);
+          if (slot == 0) {
+            acc0 = (float) ((double) acc0 + sc * (double) col.x);
+            acc1 = (float) ((double) acc1 + sc * (double) col.y);
+            acc2 = (float) ((double) acc2 + sc * (double) col.z);
+          } else if (lane == 0) {
+            float *dst = a.samples + ((size_t) slot * a.L + lux) * 3;
+            dst[0] = (float) ((double) dst[0] + sc * (double) col.x);
+            dst[1] = (float) ((double) dst[1] + sc * (double) col.y);
+            dst[2] = (float) ((double) dst[2] + sc * (double) col.z);
+            a.touched[(size_t) f * a.numstyles + slot] = 1u;
+          }
+        }
+        __syncwarp();
+      };
+      int qn = 0;
+      for (int lb = 0; lb < a.numlights; lb += 32) {
+        const int l = lb + lane;
+        bool vis = false;
+        if (l < a.numlights) {
+          const int cl = __ldg(a.l_cluster + l);
+          vis = (__ldg(row + (cl >> 5)) >> (cl & 31)) & 1u;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, vis);
+        if (vis) s_q[wid][qn + __popc(m & lt)] = l;
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) {
+          batch(32);
+          int t = 0;
+          if (lane < qn - 32) t = s_q[wid][32 + lane];
+          __syncwarp();
+          if (lane < qn - 32) s_q[wid][lane] = t;
+          qn -= 32;
+          __syncwarp();
+        }
+      }
+      if (qn > 0) batch(qn);
+    }
+    if (lane == 0) {
+      float *dst = a.samples + (size_t) lux * 3;
+      dst[0] = acc0;
+      dst[1] = acc1;
+      dst[2] = acc2;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    rays += __shfl_xor_sync(0xffffffffu, rays, o);
+    if (COUNT) visits_total += __shfl_xor_sync(0xffffffffu, visits_total, o);
+  }
+  if (lane == 0) {
+    if (rays) atomicAdd(a.counters + 0, rays);
+    if (COUNT && visits_total) atomicAdd(a.counters + 1, visits_total);
+  }
+}
+
 // AddSampleToPatch + the averaging loop, lightmap.c:932-958, 1028-1034: one thread per patch walks
 // the luxels of its face in order, so samplelight is the same serial float sum.
 __global__ void k_add_samples(int N, const int32_t *__restrict__ p_face, const float *__restrict__ p_bounds,
@@ -280,6 +409,8 @@ void build_facelights_impl(qrad_cuda_ctx *c, int extrasamples, int numbounce) {
   a.light_first = c->light_first.p;
   a.l_type = c->l_type.p;
   a.l_styleslot = c->l_styleslot.p;
+  a.l_cluster = c->l_cluster.p;
+  a.numlights = c->numlights;
   a.l_origin_int = c->l_origin_int.p;
   a.l_color = c->l_color.p;
   a.l_normal = c->l_normal.p;
@@ -305,8 +436,15 @@ void build_facelights_impl(qrad_cuda_ctx *c, int extrasamples, int numbounce) {
     c->launch_check("k_calc_points");
     // an un-vised map has dvis->numclusters == 0: GatherSampleLight's loop never runs (appendix C)
     if (c->numclusters > 0 && c->numlights > 0) {
-      QRAD_LAUNCH2(k_gather, gb);
-      c->launch_check("k_gather");
+      // many lights per luxel: one warp per luxel (coherent shadow rays); few: one thread per luxel
+      const bool warp_mode = getenv("QRAD_GATHER_THREAD") == nullptr && c->numlights >= 64;
+      if (warp_mode) {
+        QRAD_LAUNCH2(k_gather_warp, (L + 3) / 4);
+        c->launch_check("k_gather_warp");
+      } else {
+        QRAD_LAUNCH2(k_gather, gb);
+        c->launch_check("k_gather");
+      }
     }
 #undef QRAD_LAUNCH2
     if (numbounce > 0) {

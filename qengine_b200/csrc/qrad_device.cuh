@@ -282,7 +282,7 @@ struct qrad_cuda_ctx {
   // ---- lights ----
   int numlights = 0, numstyles_map = 1;
   std::vector<int32_t> h_style_ids;    // distinct light styles ascending, [0] == 0
-  qrad::DBuf<int32_t> light_first, l_type, l_styleslot;
+  qrad::DBuf<int32_t> light_first, l_type, l_styleslot, l_cluster;
   qrad::DBuf<float4> l_origin_int;     // xyz origin, w intensity
   qrad::DBuf<float4> l_color;          // xyz color, w stopdot
   qrad::DBuf<float4> l_normal;
