@@ -38,8 +38,9 @@ MAPS = ROOT / "bench_maps"
 
 # name -> (bsp file, qrad3 flags, description)
 WORKLOADS = {
-    "c3_grid14": ("grid14r512.bsp", ["-bounce", "8", "-chop", "32"],
-                  "synthetic 14x14 grid of 512-unit rooms (~19k faces / ~200k patches), -chop 32, 8 bounces [BASELINE configs[2]]"),
+    "c3_grid13": ("grid13r512.bsp", ["-bounce", "8", "-chop", "32"],
+                  "synthetic 13x13 grid of 512-unit rooms (~8k faces / ~150k patches; 14x14 exceeds MAX_MAP_LIGHTING), "
+                  "-chop 32, 8 bounces [BASELINE configs[2]]"),
     "c5_grid16_chop8": ("grid16c128.bsp", ["-bounce", "16", "-chop", "8"],
                         "synthetic 16x16 room grid, qbsp3 -chop 128, qrad3 -chop 8 (~1M patches), 16 bounces [configs[4]]"),
     "c4_hall2000": ("hall2000.bsp", ["-bounce", "0", "-extra"],
@@ -221,8 +222,9 @@ def main():
             if world > 1:
                 return Q.rad_world_sharded(sc, dev, p, rank, world, upload=False)
             dev.build_facelights(p.extrasamples, p.numbounce)
-            dev.make_transfers(p.nopvs)
-            dev.bounce(p.numbounce, want_added=False)
+            if p.numbounce > 0:
+                dev.make_transfers(p.nopvs)
+                dev.bounce(p.numbounce, want_added=False)
             return dev.final_light(p.ambient, p.maxlight, p.lightscale, p.subdiv, p.numbounce)
 
         # ---- device-resident value ----

@@ -20,7 +20,7 @@ from qengine_b200 import mapgen  # noqa: E402
 
 # name: (grid n, seed, qbsp3 -chop[, room size])
 SPECS = {
-    "grid14r512": (14, 4, None, 512),  # BASELINE configs[2]: ~19k faces / ~200k patches at qrad3 -chop 32
+    "grid13r512": (13, 4, None, 512),  # BASELINE configs[2]: ~8k faces / ~150k patches at qrad3 -chop 32 (lump < 2 MB)
     "grid6": (6, 1, None),
     "grid10": (10, 1, None),
     "grid26": (26, 1, None),        # BASELINE configs[2]: ~20k faces / ~250k patches at qrad3 -chop 32
