@@ -528,9 +528,10 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
 
   const int blocks = std::max(1, std::min((F + kWarps - 1) / kWarps, c->sm_count * 2));
   const size_t nw = (size_t) blocks * kWarps;
-  DBuf<uint16_t> matrix_pool, ep0, ep1, tedges, stack;
-  DBuf<int16_t> etri;
-  DBuf<float4> pts_pool, eplane;
+  // scratch pools live in the context so that repeated calls reuse the allocations
+  DBuf<uint16_t> &matrix_pool = c->fin_matrix, &ep0 = c->fin_ep0, &ep1 = c->fin_ep1, &tedges = c->fin_tedges, &stack = c->fin_stack;
+  DBuf<int16_t> &etri = c->fin_etri;
+  DBuf<float4> &pts_pool = c->fin_pts, &eplane = c->fin_eplane;
   matrix_pool.alloc(nw * pmax * pmax);
   pts_pool.alloc(nw * pmax);
   eplane.alloc(nw * (kMaxTriEdges + 2));

@@ -33,9 +33,11 @@ struct CudaError : std::runtime_error {
     if (e__ != cudaSuccess) ::qrad::dfail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// Device buffer.  alloc() keeps the allocation when it is already large enough: a host that lights map after map
+// (or a benchmark that repeats a step) does not pay cudaMalloc/cudaFree of multi-GB buffers every time.
 template <class T> struct DBuf {
   T *p = nullptr;
-  size_t n = 0;
+  size_t n = 0, cap = 0;
   DBuf() = default;
   DBuf(const DBuf &) = delete;
   DBuf &operator=(const DBuf &) = delete;
@@ -43,12 +45,17 @@ template <class T> struct DBuf {
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
-    n = 0;
+    n = cap = 0;
   }
   void alloc(size_t count) {
-    release();
+    if (count > cap || (cap > (size_t) 1 << 20 && count < cap / 4)) {
+      release();
+      if (count) {
+        QCUDA(cudaMalloc(&p, count * sizeof(T)));
+        cap = count;
+      }
+    }
     n = count;
-    if (count) QCUDA(cudaMalloc(&p, count * sizeof(T)));
   }
   void zero(cudaStream_t s) {
     if (n) QCUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
@@ -347,6 +354,11 @@ struct qrad_cuda_ctx {
   float4 *rad_cur = nullptr, *rad_nxt = nullptr;
   float bounce_kernel_ms = 0;
   int bounce_steps = 0;
+
+  // ---- FinalLightFace scratch (per resident warp) ----
+  qrad::DBuf<uint16_t> fin_matrix, fin_ep0, fin_ep1, fin_tedges, fin_stack;
+  qrad::DBuf<int16_t> fin_etri;
+  qrad::DBuf<float4> fin_pts, fin_eplane;
 
   // ---- bounce state (slot order) ----
   qrad::DBuf<float4> rad_a, rad_b;      // radiosity / 0x10000 ("send", qrad3.c:430-431), double buffered

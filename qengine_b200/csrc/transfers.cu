@@ -237,6 +237,7 @@ struct ListArgs {
   const int64_t *list_ptr;       // [nc+1]
   uint32_t *out_slot;
   uint32_t *out_aux;
+  int c_first;                   // first cluster handled by this launch (blockIdx.x is relative to it)
   int transpose;                 // 0: row lists (aux = bit position in the row); 1: column lists (addr = word address)
   const int64_t *bits_base;      // column lists: geometry of the bit matrix
   const int32_t *nwords;
@@ -244,7 +245,7 @@ struct ListArgs {
 };
 
 __global__ void __launch_bounds__(1024) k_build_lists(const ListArgs a) {
-  const int c = blockIdx.x;
+  const int c = a.c_first + blockIdx.x;
   __shared__ int warp_sums[32];
   __shared__ int64_t base_s;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -287,10 +288,11 @@ __global__ void __launch_bounds__(1024) k_build_lists(const ListArgs a) {
 // are mostly neighbours in slot order too, so a chunk usually lies inside one or two words).
 __global__ void __launch_bounds__(kThreads) k_list_summaries(int nc, const int64_t *__restrict__ Lptr,
                                                              const int64_t *__restrict__ chunk_base,
-                                                             const uint32_t *__restrict__ L_pos, uint4 *__restrict__ out) {
+                                                             const uint32_t *__restrict__ L_pos, uint4 *__restrict__ out,
+                                                             const int64_t chunk_lo, const int64_t chunk_hi) {
   const int lane = threadIdx.x & 31;
-  const int64_t chunk = (int64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (chunk >= chunk_base[nc]) return;
+  const int64_t chunk = chunk_lo + (int64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (chunk >= chunk_hi) return;
   int lo = 0, hi = nc;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -882,7 +884,12 @@ void transfers_rows(qrad_cuda_ctx *c) {
     la.bits_base = nullptr;
     la.nwords = nullptr;
     la.out_addr = nullptr;
-    k_build_lists<<<nc, 1024, 0, st>>>(la);
+    // only the clusters this rank's slots belong to (all of them on one GPU)
+    const int c_lo = c->slice_hi > c->slice_lo ? c->h_slot_cluster[(size_t) c->slice_lo * 32] : 0;
+    const int c_hi = c->slice_hi > c->slice_lo ? c->h_slot_cluster[(size_t) c->slice_hi * 32 - 1] : -1;
+    const int c_n = c_hi - c_lo + 1;
+    la.c_first = c_lo;
+    if (c_n > 0) k_build_lists<<<c_n, 1024, 0, st>>>(la);
     c->launch_check("k_build_lists(rows)");
     la.list_ptr = c->d_Rptr.p;
     la.out_slot = c->R_slot.p;
@@ -892,7 +899,7 @@ void transfers_rows(qrad_cuda_ctx *c) {
     la.nwords = c->d_nwords.p;
     c->R_addr.alloc((size_t) c->h_Rptr[nc] + 1);
     la.out_addr = c->R_addr.p;
-    k_build_lists<<<nc, 1024, 0, st>>>(la);
+    if (c_n > 0) k_build_lists<<<c_n, 1024, 0, st>>>(la);
     c->launch_check("k_build_lists(cols)");
   }
 
@@ -901,10 +908,12 @@ void transfers_rows(qrad_cuda_ctx *c) {
     for (int k = 0; k < nc; k++) chunk_base[k + 1] = chunk_base[k] + ((c->h_Lptr[k + 1] - c->h_Lptr[k] + 31) >> 5);
     c->d_chunk_base.upload(chunk_base, st);
     c->L_sum.alloc((size_t) chunk_base[nc] + 1);
-    const int64_t nch = chunk_base[nc];
-    if (nch > 0) {
-      k_list_summaries<<<(unsigned) ((nch + kWarpsPerBlock - 1) / kWarpsPerBlock), kThreads, 0, st>>>(
-          nc, c->d_Lptr.p, c->d_chunk_base.p, c->L_pos.p, c->L_sum.p);
+    const int c_lo = c->slice_hi > c->slice_lo ? c->h_slot_cluster[(size_t) c->slice_lo * 32] : 0;
+    const int c_hi = c->slice_hi > c->slice_lo ? c->h_slot_cluster[(size_t) c->slice_hi * 32 - 1] : -1;
+    const int64_t ch_lo = chunk_base[c_lo], ch_hi = c_hi >= c_lo ? chunk_base[c_hi + 1] : chunk_base[c_lo];
+    if (ch_hi > ch_lo) {
+      k_list_summaries<<<(unsigned) ((ch_hi - ch_lo + kWarpsPerBlock - 1) / kWarpsPerBlock), kThreads, 0, st>>>(
+          nc, c->d_Lptr.p, c->d_chunk_base.p, c->L_pos.p, c->L_sum.p, ch_lo, ch_hi);
       c->launch_check("k_list_summaries");
     }
   }
@@ -1000,8 +1009,6 @@ void transfers_columns(qrad_cuda_ctx *c) {
   int64_t nnz = 0;
   for (int s = 0; s < M; s++) nnz += h_rc[s];
   c->sync("make_transfers");
-  c->R_slot.release();
-  c->R_addr.release();
 
   unsigned long long hc[4];
   c->counters.download(hc, 4, st);
@@ -1028,6 +1035,7 @@ void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
 
 // reference row format for parity tests: rows by source patch, receivers ascending
 void download_transfers_impl(qrad_cuda_ctx *c, int64_t *row_ptr, uint32_t *patch, uint16_t *transfer) {
+  if (c->world > 1) dfail("download_transfers: not available on a shard (row lists exist only for this rank's clusters)");
   const int N = c->N, M = c->M;
   cudaStream_t st = c->stream;
   std::vector<int32_t> rc((size_t) M);
