@@ -276,7 +276,7 @@ def main():
                + lv.numlights * (4 * 4 + 36) + (lv.numclusters + 1) * 4
                + fv.numfaces * (1 + 12 * 3 + 24 + 8 * 4 + 24 + 4 * 3))
         e2e_times = []
-        for i in range(1 + max(1, args.steps)):
+        for i in range(1 + max(1, min(args.steps, 3))):   # 1 untimed + up to 3 timed end-to-end maps
             barrier()
             t0 = time.perf_counter()
             if world > 1:

@@ -86,7 +86,7 @@ struct VisArgs {
 // Measured alternatives (profiles/README.md): one word per warp without compaction leaves 46 % of the lanes idle;
 // refilling finished lanes from the queue decorrelates the lanes and is slower.
 template <int STACK, bool COUNT>
-__global__ void __launch_bounds__(kThreads) k_visibility(const VisArgs a) {
+__global__ void __launch_bounds__(kThreads, 5) k_visibility(const VisArgs a) {
   __shared__ uint16_t s_queue[kWarpsPerBlock][kChunkWords * 32];
   __shared__ uint32_t s_res[kWarpsPerBlock][kChunkWords];
   __shared__ int32_t s_wbase[kWarpsPerBlock][kChunkWords];
