@@ -45,6 +45,8 @@ CASES = {
     "grid3_chop16": ("grid3", None, ["-bounce", "4", "-chop", "16", "-extra"]),
     "hall": ("hall", None, ["-bounce", "2", "-extra"]),
     "styles": ("styles", None, ["-bounce", "3", "-ambient", "0.02", "-scale", "1.5", "-maxlight", "1.6"]),
+    "manystyles": ("manystyles", None, ["-bounce", "2", "-chop", "48"]),
+    "nolights": ("nolights", None, ["-bounce", "2"]),
 }
 
 
@@ -70,7 +72,29 @@ def styles_map_text() -> str:
     return txt + extra
 
 
+def manystyles_map_text() -> str:
+    """One room lit by seven lights with seven different styles: faces collect more than MAXLIGHTMAPS (4) styles
+    (lightmap.c:1088 reserves space for all of them, :1152-1156 writes four)."""
+    txt = mapgen.room_grid_map(1, 1, seed=11, clutter=1.0)
+    extra = ""
+    for k, sty in enumerate([1, 2, 3, 5, 8, 13, 31]):
+        extra += ('{\n"classname" "light"\n"origin" "%d %d %d"\n"light" "%d"\n"_color" "1 %g %g"\n"style" "%d"\n}\n'
+                  % (-90 + 30 * k, 60 - 20 * k, 20, 150 + 20 * k, 0.5 + 0.05 * k, 1.0 - 0.1 * k, sty))
+    return txt + extra
+
+
+def nolights_map_text() -> str:
+    """A sealed room with no light entity and no emissive surface: everything clamps to the floor value 1."""
+    txt = mapgen.room_grid_map(1, 1, seed=12)
+    i = txt.index('{\n"classname" "light"')
+    return txt[:i]
+
+
 def map_text(kind: str) -> str:
+    if kind == "manystyles":
+        return manystyles_map_text()
+    if kind == "nolights":
+        return nolights_map_text()
     if kind == "sample":
         return sample_map_text()
     if kind == "grid2":
