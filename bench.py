@@ -43,6 +43,8 @@ WORKLOADS = {
                   "-chop 32, 8 bounces [BASELINE configs[2]]"),
     "c5_grid16_chop8": ("grid16c128.bsp", ["-bounce", "16", "-chop", "8"],
                         "synthetic 16x16 room grid, qbsp3 -chop 128, qrad3 -chop 8 (~1M patches), 16 bounces [configs[4]]"),
+    "c5_chop16": ("grid16c128.bsp", ["-bounce", "16", "-chop", "16"],
+                  "the C5 map at -chop 16 (~250k patches): profiling stand-in whose kernels fit an ncu replay"),
     "c4_hall2000": ("hall2000.bsp", ["-bounce", "0", "-extra"],
                     "synthetic direct-light stress hall: 2 000 light / light_spot entities, -extra, direct only [configs[3]]"),
     "probe_grid10": ("grid10.bsp", ["-bounce", "8", "-chop", "32"],
