@@ -89,6 +89,16 @@ constexpr int kTraceStack = 64;    // pending far halves; deeper trees use the b
 constexpr int kTraceStackBig = 256;
 
 #ifdef __CUDACC__
+// Distances of both segment ends to a NON-axial plane (trace.c:119-121).  Kept out of line on purpose: when it is
+// inlined ptxas if-converts it and every node visit issues the (predicated-off) dot products and the normal load
+// even on maps whose planes are all axial -- 10 % of k_visibility's instructions in profiles/r01f_full_c5chop16.txt.
+static __device__ __noinline__ float2 nonaxial_dists(const float4 *__restrict__ normals, const int node, const float dist,
+                                              const float sx, const float sy, const float sz, const float ex,
+                                              const float ey, const float ez) {
+  const float4 pl = __ldg(normals + node);
+  return make_float2((sx * pl.x + sy * pl.y + sz * pl.z) - dist, (ex * pl.x + ey * pl.y + ez * pl.z) - dist);
+}
+
 // TestLine_r(0, start, stop), trace.c:92-142, as an explicit-stack walk.  The near half is
 // followed first and the far half (node, stop) is parked; on a pop the new start is the
 // current stop (= the split point), exactly the segments the recursion passes down.
@@ -114,9 +124,9 @@ __device__ __forceinline__ int test_line(const Tree tree, float sx, float sy, fl
         front = s1 - dist;
         back = e1 - dist;
       } else {
-        const float4 pl = __ldg(tree.normals + node);
-        front = (sx * pl.x + sy * pl.y + sz * pl.z) - dist;
-        back = (ex * pl.x + ey * pl.y + ez * pl.z) - dist;
+        const float2 fb = nonaxial_dists(tree.normals, node, dist, sx, sy, sz, ex, ey, ez);
+        front = fb.x;
+        back = fb.y;
       }
       if (front > -0.1f && back > -0.1f) {
         node = nd.z;
@@ -177,9 +187,9 @@ __device__ __forceinline__ bool reaches_leaf(const Tree tree, const int4 *__rest
       front = s1 - dist;
       back = e1 - dist;
     } else {
-      const float4 pl = __ldg(tree.normals + nd.z);
-      front = (sx * pl.x + sy * pl.y + sz * pl.z) - dist;
-      back = (ex * pl.x + ey * pl.y + ez * pl.z) - dist;
+      const float2 fb = nonaxial_dists(tree.normals, nd.z, dist, sx, sy, sz, ex, ey, ez);
+      front = fb.x;
+      back = fb.y;
     }
     if (front > -0.1f && back > -0.1f) {
       if (want != 0) return false;
