@@ -129,6 +129,7 @@ typedef struct {
   /* wall-clock breakdown of make_transfers on the host thread (ms): slot order + uploads, ordered lists, pass 2, pass 3 */
   float   ms_tr_setup, ms_tr_lists, ms_tr_rows, ms_tr_columns;
   int64_t full_walks;         /* MakeTransfers rays that needed the full TestLine walk (counted with node counting on) */
+  int64_t box_pruned_rays;    /* MakeTransfers rays settled by a whole-word box proof (counted with node counting on)  */
 } qrad_cuda_stats;
 
 int  qrad_cuda_abi_version(void);

@@ -211,6 +211,77 @@ __device__ __forceinline__ bool reaches_leaf(const Tree tree, const int4 *__rest
   return true;
 }
 
+// reaches_leaf for a whole BOX of end points at once: returns true only if, for EVERY end point e inside
+// [mn, mx], TestLine_r(0, s, e) provably reaches leaf X.  Interval version of the walk above:
+//  * the start / end of the clipped segment are kept as axis-aligned intervals that contain the reference's float
+//    values for every e in the box.  `coordinate - dist` is one correctly rounded subtraction, monotone in the
+//    coordinate, so evaluating it at the interval ends bounds front / back exactly;
+//  * a node is passed only when the interval ends show that every e takes the same branch of trace.c:124-141
+//    (first test, second test, or split with the same `side`) and that branch leads towards X;
+//  * at a split, frac = front / (front - back) is monotone in front and in back on the sign pattern at hand, and
+//    mid = start + (stop - start) * frac is a convex combination, monotone in start and stop, so its range follows
+//    from the interval ends; frac is widened by 1e-5 and mid by 0.02 units, an order of magnitude more than the float
+//    rounding of those three operations at world coordinates (|x| <= 8192, ulp <= 0.001);
+//  * non-axial planes are not handled (returns false = "do not know").
+// A `true` answer for a SOLID leaf X therefore proves every ray into the box blocked; `false` proves nothing and the
+// rays are tested one by one.
+__device__ __forceinline__ bool box_reaches_leaf(const int4 *__restrict__ path, const int len, const float4 s,
+                                                 const float4 mn, const float4 mx) {
+  float slo[3] = {s.x, s.y, s.z}, shi[3] = {s.x, s.y, s.z};
+  float elo[3] = {mn.x, mn.y, mn.z}, ehi[3] = {mx.x, mx.y, mx.z};
+  for (int i = 0; i < len; i++) {
+    const int4 nd = __ldg(path + i);
+    const float dist = __int_as_float(nd.x);
+    const int type = nd.y & 0xff, want = nd.y >> 8;
+    if (type >= 3) return false;
+    const float f_lo = (type == 0 ? slo[0] : (type == 1 ? slo[1] : slo[2])) - dist;
+    const float f_hi = (type == 0 ? shi[0] : (type == 1 ? shi[1] : shi[2])) - dist;
+    const float b_lo = (type == 0 ? elo[0] : (type == 1 ? elo[1] : elo[2])) - dist;
+    const float b_hi = (type == 0 ? ehi[0] : (type == 1 ? ehi[1] : ehi[2])) - dist;
+    if (f_lo > -0.1f && b_lo > -0.1f) {  // every e: first test true -> child 0
+      if (want != 0) return false;
+      continue;
+    }
+    if ((!(f_hi > -0.1f) || !(b_hi > -0.1f)) && f_hi < 0.1f && b_hi < 0.1f) {  // every e: first false, second true
+      if (want != 1) return false;
+      continue;
+    }
+    int side;
+    if (!(f_lo < 0.1f) && !(b_hi > -0.1f)) side = 0;        // every e: front >= 0.1, back <= -0.1: split, side 0
+    else if (!(f_hi > -0.1f) && !(b_lo < 0.1f)) side = 1;   // every e: front <= -0.1, back >= 0.1: split, side 1
+    else return false;
+    float fr_lo, fr_hi;
+    if (side == 0) {
+      fr_lo = f_lo / (f_lo - b_lo);
+      fr_hi = f_hi / (f_hi - b_hi);
+    } else {
+      fr_lo = f_hi / (f_hi - b_hi);
+      fr_hi = f_lo / (f_lo - b_lo);
+    }
+    fr_lo = fmaxf(fr_lo - 1e-5f, 0.f);
+    fr_hi = fminf(fr_hi + 1e-5f, 1.f);
+    float mlo[3], mhi[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float c1 = slo[k] + (elo[k] - slo[k]) * fr_lo, c2 = slo[k] + (elo[k] - slo[k]) * fr_hi;
+      const float d1 = shi[k] + (ehi[k] - shi[k]) * fr_lo, d2 = shi[k] + (ehi[k] - shi[k]) * fr_hi;
+      mlo[k] = fminf(c1, c2) - 0.02f;
+      mhi[k] = fmaxf(d1, d2) + 0.02f;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      if (want == side) {  // near half: (start, mid)
+        elo[k] = mlo[k];
+        ehi[k] = mhi[k];
+      } else {             // far half: (mid, stop)
+        slo[k] = mlo[k];
+        shi[k] = mhi[k];
+      }
+    }
+  }
+  return true;
+}
+
 // PointInLeafnum, qrad3.c:131-150: full dot product on every node, `dist > 0` picks child 0.
 __device__ __forceinline__ int point_in_leaf(const Tree tree, float x, float y, float z) {
   int node = 0;
@@ -329,7 +400,7 @@ struct qrad_cuda_ctx {
   std::vector<int32_t> h_patch_slot;    // [N] slot or -1
   std::vector<int32_t> h_cl_slot_start, h_cl_count, h_slot_cluster;
   qrad::DBuf<int32_t> slot_patch, patch_slot, slot_cluster;
-  qrad::DBuf<float4> s_origin_area, s_normal;
+  qrad::DBuf<float4> s_origin_area, s_normal, wbox_min, wbox_max;
   uint64_t bits_words = 0;
   qrad::DBuf<uint32_t> bits;            // visibility*formfactor>0 bit matrix, rows of source slots
   qrad::DBuf<float> row_total;          // [M]

@@ -52,13 +52,14 @@ __device__ __forceinline__ float form_factor_pre(const float4 so, const float4 s
 }
 
 constexpr int kChunkWords = 32;   // one task = one source patch x up to 32 words (1024 receivers)
-constexpr int kTaskRun = 8;         // consecutive tasks handled by one warp (its blocker guesses stay warm)
+constexpr int kTaskRun = 128;       // consecutive tasks (same receivers, neighbouring sources) handled by one warp
 constexpr int kTaskGranule = 2048;  // multi-GPU: granule g of tasks belongs to rank g % world
 
 struct VisArgs {
   Tree tree;
   const int4 *leaf_path;          // root -> leaf ancestor records (reaches_leaf)
   const int32_t *leaf_path_first;
+  const float4 *wbox_min, *wbox_max;  // [M/32] bounding box of the patch origins of each 32-slot word
   const float4 *s_origin_area, *s_normal;
   const int64_t *bits_base;      // [nc+1] word offset of the first row of each source cluster
   const int64_t *task_base;      // [nc+1] task offset of each source cluster (rows x chunks per row)
@@ -76,34 +77,41 @@ struct VisArgs {
   unsigned long long *counters;   // [0] rays, [1] node visits, [2] candidate pairs
 };
 
-// One warp lights one task: (1) form-factor sign tests for up to 1024 receivers of one source; the pairs the
-// reference would hand to TestLine_r (qrad3.c:244) are compacted into a per-warp queue; (2) the queue is consumed 32
-// rays at a time.  95 % of these rays are blocked, and 98.6 % of the blocked ones by the same solid leaf as the
-// previous blocked ray of the same source (measured on C5 with the CPU oracle), so every lane first asks whether the
-// leaf that blocked its previous ray is reached (reaches_leaf: one root -> leaf path, no stack); rays that are not
-// settled that way collect in a second queue and take the full TestLine walk in full batches, which also refreshes
-// the guesses; (3) accept bits are OR-ed into 32 result words in shared memory and stored with one coalesced write.
+// One warp lights one task = one source patch x one chunk of <= 32 words (1024 receivers).  Tasks are numbered
+// chunk-major inside a source cluster, so the consecutive tasks a warp takes are the SAME receivers seen from
+// neighbouring source patches; what blocked a receiver last time is an excellent guess for this time
+// (measured with the CPU oracle on C5: 95 % of the rays are blocked, 94-99 % of those by the leaf that blocked the
+// same receiver from the previous source, and a single leaf blocks a whole word for about half of the words).
+//   (1) lane w looks up word w of the chunk and runs the interval walk box_reaches_leaf() for the bounding box of its
+//       32 receivers with the word's last blocker: a proven word needs no ray at all;
+//   (2) form-factor sign tests for all receivers (they define which pairs the reference would hand to TestLine_r,
+//       qrad3.c:244, and are counted as rays either way); pairs of unproven words are compacted into a queue;
+//   (3) the queue is consumed 32 rays at a time: reaches_leaf() with the receiver's last blocker (one root -> leaf
+//       path, no stack); rays that are not settled collect in a second queue and take the full TestLine walk in full
+//       batches, which refreshes the guesses;
+//   (4) accept bits are OR-ed into 32 result words in shared memory and stored with one coalesced write.
 // Measured alternatives (profiles/README.md): one word per warp without compaction leaves 46 % of the lanes idle;
 // refilling finished lanes from the queue decorrelates the lanes and is slower.
 template <int STACK, bool COUNT>
-__global__ void __launch_bounds__(kThreads, 5) k_visibility(const VisArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
   __shared__ uint16_t s_queue[kWarpsPerBlock][kChunkWords * 32];
+  __shared__ uint16_t s_rguess[kWarpsPerBlock][kChunkWords * 32];  // per receiver of the chunk: last blocker leaf
+  __shared__ uint16_t s_wguess[kWarpsPerBlock][kChunkWords];       // per word: last blocker leaf seen in it
   __shared__ uint32_t s_res[kWarpsPerBlock][kChunkWords];
-  __shared__ int32_t s_wbase[kWarpsPerBlock][kChunkWords];
-  __shared__ uint16_t s_fb[kWarpsPerBlock][64];     // rays whose guess failed: receiver index | lane << 10
-  __shared__ int32_t s_guess[kWarpsPerBlock][32];   // per lane: solid leaf that blocked its last fully traced ray
+  __shared__ int32_t s_wbase[kWarpsPerBlock][kChunkWords];         // first receiver slot of the word
+  __shared__ int32_t s_wcnt[kWarpsPerBlock][kChunkWords];          // valid receivers in the word
+  __shared__ uint16_t s_fb[kWarpsPerBlock][64];                    // rays whose guess failed (receiver index)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1;
   const uint64_t warp0 = (uint64_t) blockIdx.x * kWarpsPerBlock + wid;
   const uint64_t nwarps = (uint64_t) gridDim.x * kWarpsPerBlock;
-  unsigned long long rays = 0, pairs = 0, visits_total = 0, fallbacks = 0;
-  s_guess[wid][lane] = -1;
-  __syncwarp();
+  unsigned long long rays = 0, pairs = 0, visits_total = 0, fallbacks = 0, boxed = 0;
+  int guess_c = -1, guess_w0 = -1;   // which (source cluster, chunk) the guesses belong to
   for (uint64_t lrun = warp0 * kTaskRun; lrun < a.my_tasks; lrun += nwarps * kTaskRun)
   for (uint64_t ltask = lrun; ltask < lrun + kTaskRun && ltask < a.my_tasks; ltask++) {
     const uint64_t task = ((ltask / kTaskGranule) * a.world + a.rank) * kTaskGranule + ltask % kTaskGranule;
     if (task >= a.num_tasks) continue;
-    // ---- decode: source cluster, row, chunk ----
+    // ---- decode: source cluster, chunk, row (chunk-major) ----
     int lo = 0, hi = a.nc;
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
@@ -111,37 +119,50 @@ __global__ void __launch_bounds__(kThreads, 5) k_visibility(const VisArgs a) {
     }
     const int c = lo;
     const int nw = a.nwords[c];
-    const int cpr = (nw + kChunkWords - 1) / kChunkWords;
+    const int rows = a.cl_count[c];
     const uint64_t rel = task - (uint64_t) a.task_base[c];
-    const int row = (int) (rel / (uint64_t) cpr);
-    const int w0 = (int) (rel - (uint64_t) row * cpr) * kChunkWords;
+    const int chunk = (int) (rel / (uint64_t) rows);
+    const int row = (int) (rel - (uint64_t) chunk * rows);
+    const int w0 = chunk * kChunkWords;
     const int nwc = min(kChunkWords, nw - w0);
     const int sslot = a.cl_slot_start[c] + row;
     const float4 so = __ldg(a.s_origin_area + sslot);
     const float4 sn = __ldg(a.s_normal + sslot);
-    // receiver cluster of the first word: last entry of c's visible list with woff <= w0
-    int v = a.vis_ptr[c];
-    const int vend = a.vis_ptr[c + 1];
-    {
-      int vhi = vend;
-      while (vhi - v > 1) {
-        const int mid = (v + vhi) >> 1;
-        if (a.vis_woff[mid] <= w0) v = mid; else vhi = mid;
-      }
+    if (c != guess_c || w0 != guess_w0) {   // new receivers: forget the guesses
+      guess_c = c;
+      guess_w0 = w0;
+      for (int k = lane; k < kChunkWords * 32; k += 32) s_rguess[wid][k] = 0xffffu;
+      s_wguess[wid][lane] = 0xffffu;
     }
     s_res[wid][lane] = 0;
-    // ---- phase 1: cheap tests, compaction ----
-    int n = 0;
-    for (int wi = 0; wi < nwc; wi++) {
-      const int w = w0 + wi;
-      while (v + 1 < vend && a.vis_woff[v + 1] <= w) v++;
+    // ---- (1) per word: receiver slots, box test ----
+    bool proven = false;
+    if (lane < nwc) {
+      const int w = w0 + lane;
+      int v = a.vis_ptr[c], vhi = a.vis_ptr[c + 1];
+      while (vhi - v > 1) {  // last entry of c's visible list with woff <= w
+        const int mid = (v + vhi) >> 1;
+        if (a.vis_woff[mid] <= w) v = mid; else vhi = mid;
+      }
       const int d = a.vis_cluster[v];
       const int off = (w - a.vis_woff[v]) * 32;
       const int base = a.cl_slot_start[d] + off;
-      if (lane == 0) s_wbase[wid][wi] = base;
-      const int rslot = base + lane;
+      s_wbase[wid][lane] = base;
+      s_wcnt[wid][lane] = min(32, a.cl_count[d] - off);
+      const int g = s_wguess[wid][lane];
+      if (g != 0xffff) {
+        const int p0 = __ldg(a.leaf_path_first + g), p1 = __ldg(a.leaf_path_first + g + 1);
+        proven = box_reaches_leaf(a.leaf_path + p0, p1 - p0, so, __ldg(a.wbox_min + (base >> 5)), __ldg(a.wbox_max + (base >> 5)));
+      }
+    }
+    const unsigned proven_mask = __ballot_sync(0xffffffffu, proven);
+    __syncwarp();
+    // ---- (2) cheap tests, compaction ----
+    int n = 0;
+    for (int wi = 0; wi < nwc; wi++) {
+      const int rslot = s_wbase[wid][wi] + lane;
       bool want = false;
-      if (off + lane < a.cl_count[d] && rslot != sslot) {
+      if (lane < s_wcnt[wid][wi] && rslot != sslot) {
         const float4 po = __ldg(a.s_origin_area + rslot);
         const float4 pn = __ldg(a.s_normal + rslot);
         float dist;
@@ -150,7 +171,8 @@ __global__ void __launch_bounds__(kThreads, 5) k_visibility(const VisArgs a) {
         pairs++;
         if (wants_ray) {
           rays++;
-          want = trans > 0;
+          want = trans > 0 && !((proven_mask >> wi) & 1u);
+          if (COUNT && trans > 0 && !want) boxed++;
         }
       }
       const unsigned m = __ballot_sync(0xffffffffu, want);
@@ -158,20 +180,21 @@ __global__ void __launch_bounds__(kThreads, 5) k_visibility(const VisArgs a) {
       n += __popc(m);
     }
     __syncwarp();
-    // ---- phase 2: guess walks, full walks for the rest ----
+    // ---- (3) guess walks, full walks for the rest ----
     int fbn = 0;
-    // full TestLine for the first `cnt` entries of the fallback queue
-    auto full_batch = [&](const int cnt) {
+    auto full_batch = [&](const int cnt) {  // full TestLine for the first `cnt` entries of the fallback queue
       if (lane < cnt) {
-        const int e = s_fb[wid][lane];
-        const int cand = e & 1023;
+        const int cand = s_fb[wid][lane];
         const float4 po = __ldg(a.s_origin_area + s_wbase[wid][cand >> 5] + (cand & 31));
         unsigned visits = 0;
         int leaf = -1;
         const int blocked = test_line<STACK, COUNT>(a.tree, so.x, so.y, so.z, po.x, po.y, po.z, visits, &leaf);
         if (COUNT) visits_total += visits;
         if (!blocked) atomicOr(&s_res[wid][cand >> 5], 1u << (cand & 31));
-        else s_guess[wid][e >> 10] = leaf;
+        else if (leaf < 0xffff) {
+          s_rguess[wid][cand] = (uint16_t) leaf;
+          s_wguess[wid][cand >> 5] = (uint16_t) leaf;
+        }
       }
       __syncwarp();
     };
@@ -181,9 +204,9 @@ __global__ void __launch_bounds__(kThreads, 5) k_visibility(const VisArgs a) {
       int cand = 0;
       if (k < n) {
         cand = s_queue[wid][k];
-        const int g = s_guess[wid][lane];
+        const int g = s_rguess[wid][cand];
         miss = true;
-        if (g >= 0) {
+        if (g != 0xffff) {
           const float4 po = __ldg(a.s_origin_area + s_wbase[wid][cand >> 5] + (cand & 31));
           const int p0 = __ldg(a.leaf_path_first + g), p1 = __ldg(a.leaf_path_first + g + 1);
           unsigned visits = 0;
@@ -193,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, 5) k_visibility(const VisArgs a) {
       }
       const unsigned m = __ballot_sync(0xffffffffu, miss);
       if (COUNT && miss) fallbacks++;
-      if (miss) s_fb[wid][fbn + __popc(m & lt)] = (uint16_t) (cand | (lane << 10));
+      if (miss) s_fb[wid][fbn + __popc(m & lt)] = (uint16_t) cand;
       fbn += __popc(m);
       __syncwarp();
       if (fbn >= 32) {
@@ -216,12 +239,14 @@ __global__ void __launch_bounds__(kThreads, 5) k_visibility(const VisArgs a) {
     pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
     if (COUNT) visits_total += __shfl_xor_sync(0xffffffffu, visits_total, o);
     if (COUNT) fallbacks += __shfl_xor_sync(0xffffffffu, fallbacks, o);
+    if (COUNT) boxed += __shfl_xor_sync(0xffffffffu, boxed, o);
   }
   if (lane == 0) {
     atomicAdd(a.counters + 0, rays);
     atomicAdd(a.counters + 2, pairs);
     if (COUNT) atomicAdd(a.counters + 1, visits_total);
     if (COUNT) atomicAdd(a.counters + 3, fallbacks);
+    if (COUNT) atomicAdd(a.counters + 4, boxed);
   }
 }
 
@@ -785,6 +810,15 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
     }
     c->s_origin_area.upload(so, st);
     c->s_normal.upload(sn, st);
+    std::vector<float4> bmn((size_t) M / 32, make_float4(3e38f, 3e38f, 3e38f, 0)), bmx((size_t) M / 32, make_float4(-3e38f, -3e38f, -3e38f, 0));
+    for (int s = 0; s < M; s++) {
+      if (c->h_slot_patch[s] < 0) continue;
+      float4 &lo4 = bmn[s >> 5], &hi4 = bmx[s >> 5];
+      lo4.x = std::min(lo4.x, so[s].x); lo4.y = std::min(lo4.y, so[s].y); lo4.z = std::min(lo4.z, so[s].z);
+      hi4.x = std::max(hi4.x, so[s].x); hi4.y = std::max(hi4.y, so[s].y); hi4.z = std::max(hi4.z, so[s].z);
+    }
+    c->wbox_min.upload(bmn, st);
+    c->wbox_max.upload(bmx, st);
   }
   c->d_vis_ptr.upload(vis_ptr, st);
   c->d_vis_cluster.upload(vis_cluster, st);
@@ -799,7 +833,7 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   c->d_Rptr.upload(Rptr, st);
   c->d_task_base.upload(task_base, st);
   c->bits.alloc((size_t) W + 1);
-  c->counters.alloc(4);
+  c->counters.alloc(8);
   c->counters.zero(st);
 
   c->sync("make_transfers uploads");
@@ -813,6 +847,8 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
     a.tree = c->tree();
     a.leaf_path = c->leaf_path.p;
     a.leaf_path_first = c->leaf_path_first.p;
+    a.wbox_min = c->wbox_min.p;
+    a.wbox_max = c->wbox_max.p;
     a.s_origin_area = c->s_origin_area.p;
     a.s_normal = c->s_normal.p;
     a.bits_base = c->d_bits_base.p;
@@ -1010,12 +1046,13 @@ void transfers_columns(qrad_cuda_ctx *c) {
   for (int s = 0; s < M; s++) nnz += h_rc[s];
   c->sync("make_transfers");
 
-  unsigned long long hc[4];
-  c->counters.download(hc, 4, st);
+  unsigned long long hc[8];
+  c->counters.download(hc, 8, st);
   c->stats.rays_transfers = (int64_t) hc[0];
   c->stats.node_visits += (int64_t) hc[1];
   c->stats.candidate_pairs = (int64_t) hc[2];
   c->stats.full_walks = (int64_t) hc[3];
+  c->stats.box_pruned_rays = (int64_t) hc[4];
   c->stats.nonzero_words = nzw;
   c->total_transfers = nnz;
   c->stats.total_transfers = nnz;

@@ -69,7 +69,7 @@ class Stats(C.Structure):
                 ("ms_transfers_trace", C.c_float), ("ms_bounce", C.c_float), ("ms_bounce_kernel", C.c_float),
                 ("ms_final", C.c_float), ("kernel_launches", C.c_int32),
                 ("ms_tr_setup", C.c_float), ("ms_tr_lists", C.c_float), ("ms_tr_rows", C.c_float),
-                ("ms_tr_columns", C.c_float), ("full_walks", C.c_int64)]
+                ("ms_tr_columns", C.c_float), ("full_walks", C.c_int64), ("box_pruned_rays", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

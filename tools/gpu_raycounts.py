@@ -25,6 +25,6 @@ for name in sys.argv[1:]:
         Q.rad_world(sc, dev, p)
         st = dev.stats()
         out[name] = {k: st[k] for k in ("rays_transfers", "rays_direct", "node_visits", "candidate_pairs",
-                                        "total_transfers", "num_patches", "num_luxels", "padded_entries")}
+                                        "total_transfers", "num_patches", "num_luxels", "padded_entries", "full_walks", "box_pruned_rays")}
         print(name, json.dumps(st), file=sys.stderr)
 print(json.dumps(out, indent=1))
