@@ -286,8 +286,10 @@ int qrad_cuda_upload_patches(qrad_cuda_ctx *c, const qrad_patches_view *p) {
       if (p->face[i] < 0 || p->face[i] >= p->numfaces) dfail("patch %d has bad face %d", i, p->face[i]);
       if (p->next[i] < -1 || p->next[i] >= n) dfail("patch %d has bad next %d", i, p->next[i]);
     }
-    c->p_origin_area.upload(pack4(p->origin, p->area, n), c->stream);
-    c->p_normal.upload(pack4(p->normal, nullptr, n), c->stream);
+    c->h_origin_area = pack4(p->origin, p->area, n);
+    c->h_normal = pack4(p->normal, nullptr, n);
+    c->p_origin_area.upload(c->h_origin_area, c->stream);
+    c->p_normal.upload(c->h_normal, c->stream);
     std::vector<float> skyf(n);
     for (int i = 0; i < n; i++) skyf[i] = p->sky[i] ? 1.f : 0.f;
     c->p_refl.upload(pack4(p->reflectivity, skyf.data(), n), c->stream);

@@ -361,6 +361,7 @@ struct qrad_cuda_ctx {
   int N = 0, numfaces_p = 0;
   std::vector<int32_t> h_cluster;
   std::vector<uint8_t> h_sky;
+  std::vector<float4> h_origin_area, h_normal;
   qrad::DBuf<float4> p_origin_area;    // xyz = origin, w = area
   qrad::DBuf<float4> p_normal;         // xyz = plane normal
   qrad::DBuf<float4> p_refl;           // xyz = reflectivity, w = sky flag

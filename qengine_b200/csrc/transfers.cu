@@ -797,10 +797,7 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   c->slot_cluster.upload(c->h_slot_cluster, st);
   {
     std::vector<float4> so(M, make_float4(0, 0, 0, 0)), sn(M, make_float4(0, 0, 0, 0));
-    std::vector<float4> po(N), pn(N);
-    QCUDA(cudaMemcpyAsync(po.data(), c->p_origin_area.p, (size_t) N * 16, cudaMemcpyDeviceToHost, st));
-    QCUDA(cudaMemcpyAsync(pn.data(), c->p_normal.p, (size_t) N * 16, cudaMemcpyDeviceToHost, st));
-    c->sync("make_transfers staging");
+    const std::vector<float4> &po = c->h_origin_area, &pn = c->h_normal;   // host copies kept by upload_patches
     for (int s = 0; s < M; s++) {
       int p = c->h_slot_patch[s];
       if (p >= 0) {
