@@ -121,8 +121,9 @@ int qrad_cuda_set_count_nodes(qrad_cuda_ctx *c, int enable) {
   return 0;
 }
 
-// Flatten dnodes/dplanes/dleafs into the trace tree (MakeTnodes, trace.c:47-88) and expand the RLE PVS
-// rows (DecompressVis, bspfile.c:129-154) once, so kernels test a cluster bit with one load.
+// Flatten dnodes/dplanes/dleafs into the trace tree (MakeTnodes, trace.c:47-88; breadth-first here), record the
+// root -> leaf ancestor paths, and expand the RLE PVS rows (DecompressVis, bspfile.c:129-154) once, so kernels
+// test a cluster bit with one load.
 int qrad_cuda_upload_bsp(qrad_cuda_ctx *c, const qrad_bsp_view *b) {
   return guarded([&] {
     QCUDA(cudaSetDevice(c->device));

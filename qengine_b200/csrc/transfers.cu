@@ -4,26 +4,29 @@
 // cluster padded to a multiple of 32 slots, so one 32-bit word of the visibility matrix
 // = one source patch x 32 consecutive receivers of one cluster.
 //
-//   pass 1  k_visibility   one warp per word: form factor sign tests + TestLine for 32
-//                          receivers of one source (rays batched per source patch, pruned by
-//                          cluster PVS); writes the accept bit  trans > 0  (qrad3.c:216-257).
+//   pass 1  k_visibility   one warp per task (1 source x <= 1024 receivers, PVS pruning is structural):
+//                          whole-word interval proofs, form factor sign tests, blocker-guess walks, full
+//                          TestLine for the rest; writes the accept bit  trans > 0  (qrad3.c:216-257).
 //   pass 2  k_row_totals   one warp per source row: walks the row in ascending receiver index
 //                          (the reference's j order) and forms the SERIAL float sum `total`
 //                          (qrad3.c:254) and numtransfers.
-//   pass 3  k_columns      one warp per 32 receivers: walks the potential sources in ascending
-//                          patch index, reads ONE word per source, and emits the quantised
-//                          weights  (int)(trans * 0x10000 / total)  (qrad3.c:283) column by
-//                          column -- the transposed (gather) form ShootLight's scatter needs
-//                          (finding F7), already in the source order the reference adds them.
-//   bounce  k_bounce       one thread per receiver, 128-bit loads of 4 interleaved records,
-//                          serial accumulation in source order, CollectLight fused.
+//   pass 3  k_columns      one warp per 32 receivers (slice): walks the potential sources in ascending
+//                          patch index, reads ONE word per source, and emits the quantised weights
+//                          (int)(trans * 0x10000 / total)  (qrad3.c:283) as "dense slice" lists -- the
+//                          transposed (gather) form ShootLight's scatter needs (finding F7), already in
+//                          the source order the reference adds them.
+//   bounce  k_bounce       one warp per slice, lane = receiver, 128-bit loads of 8 weights per lane,
+//                          radiosity vectors broadcast by shuffles, serial accumulation in source order,
+//                          CollectLight fused.
+//
+// Multi-GPU: every phase takes this rank's share (task granules / slices); the host exchanges in between
+// (qrad_cuda_make_transfers_phase, qrad_cuda_bounce_phase, qrad_cuda_exchange_buffer).
 //
 // Everything is float arithmetic in the reference's operation order; this TU is compiled
 // with -fmad=false.
 #include <algorithm>
 #include <chrono>
 #include <cstring>
-#include <numeric>
 
 #include "qrad_device.cuh"
 
