@@ -151,6 +151,37 @@ def box_brush(x0, y0, z0, x1, y1, z1, tex, top_tex=None, bottom_tex=None, top_li
     return s
 
 
+def _plane(a, u, v, tex, flags=0, value=0) -> str:
+    """Face through point a whose outward normal is cross(u, v) (Quake II order: normal = cross(p0 - p1, p2 - p1))."""
+    p0 = (a[0] + u[0], a[1] + u[1], a[2] + u[2])
+    p2 = (a[0] + v[0], a[1] + v[1], a[2] + v[2])
+    return _face(p0, a, p2, tex, flags, value)
+
+
+def diamond_pillar(cx, cy, r, z0, z1, tex) -> str:
+    """Vertical pillar whose four walls are 45-degree (non-axial, PLANE_ANYX/ANYY) planes."""
+    s = "{\n"
+    s += _plane((cx + r, cy, z0), (0, 0, 1), (1, -1, 0), tex)     # normal ( 1,  1, 0)
+    s += _plane((cx - r, cy, z0), (0, 0, 1), (-1, 1, 0), tex)     # normal (-1, -1, 0)
+    s += _plane((cx + r, cy, z0), (0, 0, 1), (-1, -1, 0), tex)    # normal ( 1, -1, 0)
+    s += _plane((cx - r, cy, z0), (0, 0, 1), (1, 1, 0), tex)      # normal (-1,  1, 0)
+    s += _face((cx, cy, z1), (cx, cy + 1, z1), (cx + 1, cy, z1), tex)
+    s += _face((cx, cy, z0), (cx + 1, cy, z0), (cx, cy + 1, z0), tex)
+    return s + "}\n"
+
+
+def ramp_brush(x0, y0, z0, x1, y1, h0, h1, tex, top_flags=0) -> str:
+    """Box footprint [x0,x1]x[y0,y1] from z0 up to a sloped top (z0+h0 at x0, z0+h1 at x1): a PLANE_ANYZ plane."""
+    s = "{\n"
+    s += _face((x0, y0, z0), (x0, y0 + 1, z0), (x0, y0, z0 + 1), tex)
+    s += _face((x1, y1, z0), (x1, y1, z0 + 1), (x1, y1 + 1, z0), tex)
+    s += _face((x0, y0, z0), (x0, y0, z0 + 1), (x0 + 1, y0, z0), tex)
+    s += _face((x1, y1, z0), (x1 + 1, y1, z0), (x1, y1, z0 + 1), tex)
+    s += _plane((x0, y0, z0 + h0), (x1 - x0, 0, h1 - h0), (0, 1, 0), tex, top_flags)
+    s += _face((x0, y0, z0), (x0 + 1, y0, z0), (x0, y0 + 1, z0), tex)
+    return s + "}\n"
+
+
 def _light_entity(rng, x, y, z, spot=False) -> str:
     col = tuple(round(rng.uniform(0.5, 1.0), 3) for _ in range(3))
     s = '{\n"classname" "%s"\n' % ("light_spot" if spot else "light")

@@ -47,6 +47,7 @@ CASES = {
     "styles": ("styles", None, ["-bounce", "3", "-ambient", "0.02", "-scale", "1.5", "-maxlight", "1.6"]),
     "manystyles": ("manystyles", None, ["-bounce", "2", "-chop", "48"]),
     "nolights": ("nolights", None, ["-bounce", "2"]),
+    "angled": ("angled", None, ["-bounce", "4", "-chop", "24", "-extra"]),
 }
 
 
@@ -90,7 +91,26 @@ def nolights_map_text() -> str:
     return txt[:i]
 
 
+def angled_map_text() -> str:
+    """2x2 rooms with non-axial geometry (45-degree pillars, ramps: PLANE_ANYX/ANYY/ANYZ nodes in the trace tree),
+    a sky panel (SURF_SKY: patches that never collect, qrad3.c:393-397) and a warp surface (SURF_WARP: unlit face,
+    lightmap.c:981)."""
+    txt = mapgen.room_grid_map(2, 2, seed=21, clutter=0.3, lamps=0.5)
+    head, tail = txt.split('}\n{\n"classname" "info_player_start"', 1)
+    extra = ""
+    # room pitch is 272; rooms are centred on (+-136, +-136) around the origin-shifted grid, z from -64 to 64
+    for (cx, cy) in [(-200, -200), (120, -176), (-120, 152), (200, 200)]:
+        extra += mapgen.diamond_pillar(cx, cy, 32, -64, 32, mapgen.TEX_WALL)
+    extra += mapgen.ramp_brush(-232, -120, -64, -168, -56, 8, 40, mapgen.TEX_FLOOR)
+    extra += mapgen.ramp_brush(40, 40, -64, 136, 104, 48, 8, mapgen.TEX_FLOOR, top_flags=8)       # SURF_WARP top
+    extra += mapgen.box_brush(64, -232, 56, 128, -168, 64, mapgen.TEX_WALL, bottom_tex=mapgen.TEX_CEIL)
+    extra = extra.replace("b200/ceil 0 0 0 1 1 0 0 0", "b200/ceil 0 0 0 1 1 0 4 0", 1)            # SURF_SKY panel
+    return head + extra + '}\n{\n"classname" "info_player_start"' + tail
+
+
 def map_text(kind: str) -> str:
+    if kind == "angled":
+        return angled_map_text()
     if kind == "manystyles":
         return manystyles_map_text()
     if kind == "nolights":

@@ -9,7 +9,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
 GOLDEN = ROOT / "tests" / "golden"
-CASES = ["samplec", "samplec_extra", "samplec_direct", "grid2", "grid3_chop16", "hall", "styles", "manystyles", "nolights"]
+CASES = ["samplec", "samplec_extra", "samplec_direct", "grid2", "grid3_chop16", "hall", "styles", "manystyles", "nolights", "angled"]
 
 RAY_DTYPE = np.dtype([("start", "<f4", 3), ("stop", "<f4", 3), ("result", "<i4")])
 

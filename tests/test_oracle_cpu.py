@@ -34,7 +34,7 @@ def make(case, tmp_path):
     return meta, O.Oracle(bsp, **kw)
 
 
-@pytest.mark.parametrize("case", ["samplec", "samplec_extra", "samplec_direct", "grid2", "styles", "manystyles", "nolights"])
+@pytest.mark.parametrize("case", ["samplec", "samplec_extra", "samplec_direct", "grid2", "styles", "manystyles", "nolights", "angled"])
 def test_oracle_reproduces_reference_lump(case, tmp_path):
     meta, o = make(case, tmp_path)
     lump, added = o.rad_world()
