@@ -448,8 +448,10 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
   // plane groups: the chain FinalLightFace walks from planelinks[side][planenum] (lightmap.c:1123); it stops
   // at face index 0, so face 0 never contributes (appendix C)
   std::vector<int32_t> group_of_face(F, -1), group_first{0}, group_patch;
-  DBuf<int32_t> d_group_of_face, d_group_first, d_group_patch, tri_count, tri_points;
-  DBuf<int64_t> d_tri_first;
+  // device buffers live in the context so that repeated calls reuse the allocations
+  DBuf<int32_t> &d_group_of_face = c->fin_i32[0], &d_group_first = c->fin_i32[1], &d_group_patch = c->fin_i32[2],
+                &tri_count = c->fin_i32[3], &tri_points = c->fin_i32[4];
+  DBuf<int64_t> &d_tri_first = c->fin_i64;
   std::vector<int32_t> h_tri_count(F, 0);
   std::vector<int64_t> h_tri_first(F + 1, 0);
   int pmax = 1;
@@ -511,16 +513,16 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
   }
 
   // face style slots
-  DBuf<int32_t> d_numstyles, d_styleslot, d_lightofs;
+  DBuf<int32_t> &d_numstyles = c->fin_i32[5], &d_styleslot = c->fin_i32[6], &d_lightofs = c->fin_i32[7];
   d_numstyles.upload(c->h_fl_numstyles, st);
   d_styleslot.upload(c->h_fl_stylenums, st);
   d_lightofs.upload(lightofs, st);
-  DBuf<uint8_t> d_out;
+  DBuf<uint8_t> &d_out = c->fin_out;
   d_out.alloc((size_t) total + 4);
   d_out.zero(st);
-  DBuf<float> lb_out;
+  DBuf<float> &lb_out = c->fin_lb;
   if (any_minlight) lb_out.alloc((size_t) 4 * L * 3 + 1);
-  DBuf<int> d_err, d_counter;
+  DBuf<int32_t> &d_err = c->fin_i32[8], &d_counter = c->fin_i32[9];
   d_err.alloc(1);
   d_err.zero(st);
   d_counter.alloc(1);

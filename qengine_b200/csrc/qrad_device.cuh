@@ -412,6 +412,7 @@ struct qrad_cuda_ctx {
   qrad::DBuf<int64_t> slice_base;       // [M/32 + 1] first entry of a slice
   qrad::DBuf<uint32_t> g_src;           // [entries] source slot
   qrad::DBuf<uint4> g_w;                // [entries/8][32] 8 u16 weights per lane
+  qrad::DBuf<int32_t> col_blk_slice0, col_blk_n;   // k_columns block table
   // row-major helper lists kept for inspection / download
   std::vector<int64_t> h_Lptr, h_bits_base;
   std::vector<int32_t> h_nwords;
@@ -441,6 +442,10 @@ struct qrad_cuda_ctx {
   qrad::DBuf<uint16_t> fin_matrix, fin_ep0, fin_ep1, fin_tedges, fin_stack;
   qrad::DBuf<int16_t> fin_etri;
   qrad::DBuf<float4> fin_pts, fin_eplane;
+  qrad::DBuf<int32_t> fin_i32[10];
+  qrad::DBuf<int64_t> fin_i64;
+  qrad::DBuf<uint8_t> fin_out;
+  qrad::DBuf<float> fin_lb;
 
   // ---- bounce state (slot order) ----
   qrad::DBuf<float4> rad_a, rad_b;      // radiosity / 0x10000 ("send", qrad3.c:430-431), double buffered

@@ -56,7 +56,7 @@ __device__ __forceinline__ float form_factor_pre(const float4 so, const float4 s
 
 constexpr int kChunkWords = 32;   // one task = one source patch x up to 32 words (1024 receivers)
 constexpr int kTaskRun = 128;       // consecutive tasks (same receivers, neighbouring sources) handled by one warp
-constexpr int kTaskGranule = 2048;  // multi-GPU: granule g of tasks belongs to rank g % world
+constexpr int kTaskGranule = 512;   // multi-GPU: granule g of tasks belongs to rank g % world
 
 struct VisArgs {
   Tree tree;
@@ -463,7 +463,8 @@ struct ColArgs {
   const uint32_t *bits;
   const float *row_total;
   int M;
-  int slice_lo, slice_hi;        // this rank's slices
+  const int32_t *blk_slice0;     // per block: first slice (8 consecutive slices of ONE cluster per block)
+  const int32_t *blk_n;          // per block: slices in use (1..8)
   int32_t *slice_len;            // count mode output: list entries of the slice
   const int64_t *slice_base;     // fill mode: first entry of the slice (multiple of 32)
   uint32_t *g_src;               // [entries]      source slot
@@ -472,13 +473,17 @@ struct ColArgs {
 
 template <int MODE>  // 0 = count, 1 = fill
 __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
+  // The 8 warps of a block own 8 neighbouring slices of one cluster and step through the cluster's source list
+  // together (__syncthreads per 32 sources): the words they fetch for one source share a 32-byte sector, so it is
+  // fetched from HBM once instead of once per slice (ncu before: DRAM read = 25x the bit matrix, r01g_full_c5chop16).
   const int lane = threadIdx.x & 31;
-  const int slice = a.slice_lo + blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (slice >= a.slice_hi) return;
+  const int slice0 = a.blk_slice0[blockIdx.x];
+  const bool active = (int) (threadIdx.x >> 5) < a.blk_n[blockIdx.x];
+  const int slice = slice0 + (active ? (int) (threadIdx.x >> 5) : 0);
   const int rslot = slice * 32 + lane;
-  const int d = a.slot_cluster[slice * 32];            // all 32 slots of a slice share the cluster
+  const int d = a.slot_cluster[slice0 * 32];           // all slots of the block share the cluster
   const int wslice = (slice * 32 - a.cl_slot_start[d]) >> 5;
-  const bool valid = a.slot_patch[rslot] >= 0;
+  const bool valid = active && a.slot_patch[rslot] >= 0;
   float4 po = make_float4(0, 0, 0, 0), pn = po;
   if (valid && MODE) {
     po = a.s_origin_area[rslot];
@@ -489,9 +494,10 @@ __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
   const int64_t base = MODE ? a.slice_base[slice] : 0;
   uint32_t wq[4] = {0, 0, 0, 0};                       // this lane's weights of the current group of 8 entries
   for (int64_t k0 = r0; k0 < r1; k0 += 32) {
+    __syncthreads();
     const int64_t k = k0 + lane;
     uint32_t word = 0, sslot = 0;
-    if (k < r1) {
+    if (k < r1 && active) {
       if (MODE) sslot = a.R_slot[k];
       word = a.bits[a.R_addr[k] + wslice];
     }
@@ -524,6 +530,7 @@ __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
       }
     }
   }
+  if (!active) return;
   if (MODE == 0) {
     if (lane == 0) a.slice_len[slice] = n;
   } else if (n & 7) {
@@ -547,32 +554,34 @@ struct BounceArgs {
   int slice_lo, slice_hi;        // this rank's slices
 };
 
-// (float) w for a u16 w without the quarter-rate I2F: 0x4B000000 | w is the float 2^23 + w, exactly.
-__device__ __forceinline__ float u16_to_float(const uint32_t w) { return __int_as_float(0x4B000000u | w) - 8388608.0f; }
-
-// illumination[j][l] += send[l] * trans->transfer   (qrad3.c:439), mul and add rounded separately.
-// A zero weight adds +-0 and leaves the sum unchanged (the sum starts at +0 and never becomes -0).
-#define QRAD_ACCUM(E, W)                                           \
-  do {                                                             \
-    const float fw = u16_to_float(W);                              \
-    const float sx = __shfl_sync(0xffffffffu, cx.x, E);            \
-    const float sy = __shfl_sync(0xffffffffu, cx.y, E);            \
-    const float sz = __shfl_sync(0xffffffffu, cx.z, E);            \
-    ix = ix + sx * fw;                                             \
-    iy = iy + sy * fw;                                             \
-    iz = iz + sz * fw;                                             \
-  } while (0)
+// (float) lo16(W), (float) hi16(W) without the quarter-rate I2F: 0x4B000000 | w is the float 2^23 + w, exactly, so one
+// byte permute per half and ONE packed subtraction give both weights of a 32-bit word.
+__device__ __forceinline__ float2 u16x2_to_float2(const uint32_t w) {
+  const float2 m = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)),
+                               __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)));
+  return __fadd2_rn(m, make_float2(-8388608.0f, -8388608.0f));
+}
 
 // ShootLight (as a gather) + CollectLight.  One warp per slice, lane = receiver; the list is walked in order, so
-// every receiver accumulates its transfers in ascending source order like the reference's serial loop.
+// every receiver accumulates its transfers in ascending source order like the reference's serial loop:
+// illumination[j][l] += send[l] * trans->transfer (qrad3.c:439), mul and add rounded separately.  A zero weight adds
+// +-0 and leaves the sum unchanged (the sum starts at +0 and never becomes -0).
 // The list is consumed in batches of 32 entries (4 groups of 8): lane l fetches source slot l of the batch (one
 // coalesced 128-byte load) and gathers its radiosity vector, every lane fetches its 4 x 8 weights with four 128-bit
-// loads (2 KB contiguous per warp), the vectors are broadcast with shuffles.  Loads run one batch (vectors,
-// weights) / two batches (slots) ahead of the arithmetic: ~2.6 KB in flight per warp, which is what it takes to
-// cover HBM latency at this occupancy (profiles/r01d_full_c5_k_bounce.txt: long-scoreboard bound before).
+// loads (2 KB contiguous per warp).  Loads run one batch (vectors, weights) / two batches (slots) ahead of the
+// arithmetic: ~2.6 KB in flight per warp, which is what it takes to cover HBM latency at this occupancy
+// (profiles/r01d_full_c5_k_bounce.txt: long-scoreboard bound before).
+// Instruction diet (the r01g kernel issued 12 instructions per list entry -- 3 shuffles, 3 unpack/convert, 3 FMUL,
+// 3 FADD -- and sat at 58 % of the issue rate with HBM at 54 %, profiles/r01g_full_c5_k_bounce.txt): the 32 vectors of
+// a batch are parked in shared memory as {x0 x1 y0 y1 | z0 z1} per PAIR of entries, so a pair costs two broadcast
+// loads, two byte permutes + one packed subtract for its two weights, three packed multiplies (sm_100 FMUL2: both
+// entries of a channel at once) and six scalar adds, which keep the serial order: 7 instructions per entry.
+// (Packed adds are not used: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false,
+// which would change the rounding; build.py checks that this kernel's SASS holds no FFMA.)
 __global__ void __launch_bounds__(kThreads) k_bounce(const BounceArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int slice = a.slice_lo + blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  __shared__ __align__(16) float s_vec[kWarpsPerBlock][2][16 * 8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int slice = a.slice_lo + blockIdx.x * kWarpsPerBlock + wid;
   if (slice >= a.slice_hi) return;
   const int slot = slice * 32 + lane;
   const int64_t base = a.slice_base[slice];
@@ -582,43 +591,67 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const BounceArgs a) {
   float ix = 0.f, iy = 0.f, iz = 0.f;
   uint32_t nidx = 0;                        // source slot of entry `lane` of the batch after next
   float4 nx = make_float4(0, 0, 0, 0);      // radiosity vector of entry `lane` of the next batch
-  uint4 nw0 = make_uint4(0, 0, 0, 0), nw1 = nw0, nw2 = nw0, nw3 = nw0;   // this lane's weights of the next batch
+  // this lane's weights of the current / next batch: two register sets that swap roles every batch (no copies)
+  uint4 wa0 = make_uint4(0, 0, 0, 0), wa1 = wa0, wa2 = wa0, wa3 = wa0, wb0 = wa0, wb1 = wa0, wb2 = wa0, wb3 = wa0;
   if (batches > 0) {
     nx = __ldg(a.send + __ldcs(ps));
-    nw0 = __ldcs(pw);
-    nw1 = __ldcs(pw + 32);
-    nw2 = __ldcs(pw + 64);
-    nw3 = __ldcs(pw + 96);
+    wa0 = __ldcs(pw);
+    wa1 = __ldcs(pw + 32);
+    wa2 = __ldcs(pw + 64);
+    wa3 = __ldcs(pw + 96);
     if (batches > 1) nidx = __ldcs(ps + 32);
   }
-  for (int b = 0; b < batches; b++) {
-    const float4 cx = nx;
-    const uint4 cw0 = nw0, cw1 = nw1, cw2 = nw2, cw3 = nw3;
-    if (b + 1 < batches) {
-      nx = __ldg(a.send + nidx);
-      const uint4 *q = pw + 128 * (b + 1);
-      nw0 = __ldcs(q);
-      nw1 = __ldcs(q + 32);
-      nw2 = __ldcs(q + 64);
-      nw3 = __ldcs(q + 96);
-      if (b + 2 < batches) nidx = __ldcs(ps + 32 * (b + 2));
-    }
-#define QRAD_GROUP(G, CW)                 \
-  QRAD_ACCUM(G * 8 + 0, CW.x & 0xffffu);  \
-  QRAD_ACCUM(G * 8 + 1, CW.x >> 16);      \
-  QRAD_ACCUM(G * 8 + 2, CW.y & 0xffffu);  \
-  QRAD_ACCUM(G * 8 + 3, CW.y >> 16);      \
-  QRAD_ACCUM(G * 8 + 4, CW.z & 0xffffu);  \
-  QRAD_ACCUM(G * 8 + 5, CW.z >> 16);      \
-  QRAD_ACCUM(G * 8 + 6, CW.w & 0xffffu);  \
-  QRAD_ACCUM(G * 8 + 7, CW.w >> 16)
-    QRAD_GROUP(0, cw0);
-    QRAD_GROUP(1, cw1);
-    QRAD_GROUP(2, cw2);
-    QRAD_GROUP(3, cw3);
-#undef QRAD_GROUP
+  const int park = (lane >> 1) * 8 + (lane & 1);
+#define QRAD_PAIR(P, W)                                                              \
+  do {                                                                               \
+    const float4 xy = *reinterpret_cast<const float4 *>(sv + (P) * 8);               \
+    const float2 zz = *reinterpret_cast<const float2 *>(sv + (P) * 8 + 4);           \
+    const float2 fw = u16x2_to_float2(W);                                            \
+    const float2 px = __fmul2_rn(make_float2(xy.x, xy.y), fw);                       \
+    const float2 py = __fmul2_rn(make_float2(xy.z, xy.w), fw);                       \
+    const float2 pz = __fmul2_rn(zz, fw);                                            \
+    ix = ix + px.x;                                                                  \
+    iy = iy + py.x;                                                                  \
+    iz = iz + pz.x;                                                                  \
+    ix = ix + px.y;                                                                  \
+    iy = iy + py.y;                                                                  \
+    iz = iz + pz.y;                                                                  \
+  } while (0)
+#define QRAD_GROUP(G, CW)         \
+  QRAD_PAIR(G * 4 + 0, CW.x);     \
+  QRAD_PAIR(G * 4 + 1, CW.y);     \
+  QRAD_PAIR(G * 4 + 2, CW.z);     \
+  QRAD_PAIR(G * 4 + 3, CW.w)
+// batch B: park the vectors (double buffered: the other half may still be read by slower lanes), start the loads of
+// batch B + 1 into the N registers, then consume the C registers
+#define QRAD_BATCH(B, C0, C1, C2, C3, N0, N1, N2, N3)          \
+  do {                                                         \
+    float *sv = s_vec[wid][(B) & 1];                           \
+    sv[park] = nx.x;                                           \
+    sv[park + 2] = nx.y;                                       \
+    sv[park + 4] = nx.z;                                       \
+    __syncwarp();                                              \
+    if ((B) + 1 < batches) {                                   \
+      nx = __ldg(a.send + nidx);                               \
+      const uint4 *q = pw + 128 * ((B) + 1);                   \
+      N0 = __ldcs(q);                                          \
+      N1 = __ldcs(q + 32);                                     \
+      N2 = __ldcs(q + 64);                                     \
+      N3 = __ldcs(q + 96);                                     \
+      if ((B) + 2 < batches) nidx = __ldcs(ps + 32 * ((B) + 2)); \
+    }                                                          \
+    QRAD_GROUP(0, C0);                                         \
+    QRAD_GROUP(1, C1);                                         \
+    QRAD_GROUP(2, C2);                                         \
+    QRAD_GROUP(3, C3);                                         \
+  } while (0)
+  for (int b = 0; b < batches; b += 2) {
+    QRAD_BATCH(b, wa0, wa1, wa2, wa3, wb0, wb1, wb2, wb3);
+    if (b + 1 < batches) QRAD_BATCH(b + 1, wb0, wb1, wb2, wb3, wa0, wa1, wa2, wa3);
   }
-#undef QRAD_ACCUM
+#undef QRAD_BATCH
+#undef QRAD_GROUP
+#undef QRAD_PAIR
   // CollectLight, qrad3.c:383-409
   const float4 ra = a.refl_area[slot];
   float4 t = a.total[slot];
@@ -1015,11 +1048,23 @@ void transfers_columns(qrad_cuda_ctx *c) {
   ca.bits = c->bits.p;
   ca.row_total = c->row_total.p;
   ca.M = M;
-  ca.slice_lo = c->slice_lo;
-  ca.slice_hi = c->slice_hi;
+  // blocks: runs of up to 8 consecutive slices that lie in one cluster and in this rank's range
+  std::vector<int32_t> blk_slice0, blk_n;
+  for (int s = c->slice_lo; s < c->slice_hi;) {
+    const int cl = c->h_slot_cluster[(size_t) s * 32];
+    const int cl_end = c->h_cl_slot_start[cl + 1] / 32;
+    const int e = std::min(std::min(s + kWarpsPerBlock, cl_end), c->slice_hi);
+    blk_slice0.push_back(s);
+    blk_n.push_back(e - s);
+    s = e;
+  }
+  const int cblocks = (int) blk_slice0.size();
+  c->col_blk_slice0.upload(blk_slice0, st);
+  c->col_blk_n.upload(blk_n, st);
+  ca.blk_slice0 = c->col_blk_slice0.p;
+  ca.blk_n = c->col_blk_n.p;
   ca.slice_len = c->slice_len.p;
-  const int cblocks = std::max(1, (c->slice_hi - c->slice_lo + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  k_columns<0><<<cblocks, kThreads, 0, st>>>(ca);
+  if (cblocks > 0) k_columns<0><<<cblocks, kThreads, 0, st>>>(ca);
   c->launch_check("k_columns<count>");
   std::vector<int32_t> h_len((size_t) nslices);
   c->slice_len.download(h_len.data(), (size_t) nslices, st);
@@ -1038,7 +1083,7 @@ void transfers_columns(qrad_cuda_ctx *c) {
   ca.slice_base = c->slice_base.p;
   ca.g_src = c->g_src.p;
   ca.g_w = c->g_w.p;
-  k_columns<1><<<cblocks, kThreads, 0, st>>>(ca);
+  if (cblocks > 0) k_columns<1><<<cblocks, kThreads, 0, st>>>(ca);
   c->launch_check("k_columns<fill>");
   std::vector<int32_t> h_rc((size_t) M);
   c->row_count.download(h_rc.data(), (size_t) M, st);

@@ -1,13 +1,13 @@
 """Shard geometry of the multi-GPU path (mirrors qengine_b200/csrc/transfers.cu; one process per GPU).
 
-* pass 1 (visibility): tasks are dealt in granules of TASK_GRANULE, granule g belongs to rank g % world; every word
+* pass 1 (visibility): tasks are dealt in granules of TASK_GRANULE (512), granule g belongs to rank g % world; every word
   of the bit matrix is therefore written by exactly one rank and the exchange is one sum all-reduce.
 * passes 2/3 and the bounces: whole 32-slot slices in `world` equal contiguous runs; exchange buffers are padded to
   world * shard so that all-gathers use equal shards.
 """
 from __future__ import annotations
 
-TASK_GRANULE = 2048
+TASK_GRANULE = 512
 
 
 def task_owner(task: int, world: int) -> int:
