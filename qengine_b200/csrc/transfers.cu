@@ -552,6 +552,9 @@ struct BounceArgs {
   float *rad_sum;                // [M] r0 + r1 + r2 of the new radiosity (for `added`), may be null
   int M;
   int slice_lo, slice_hi;        // this rank's slices
+  const int32_t *order;          // this rank's slices, longest list first
+  int32_t *next;                 // [2] work counters: launch `parity` draws from next[parity] and clears the other
+  int parity;
 };
 
 // (float) lo16(W), (float) hi16(W) without the quarter-rate I2F: 0x4B000000 | w is the float 2^23 + w, exactly, so one
@@ -562,111 +565,148 @@ __device__ __forceinline__ float2 u16x2_to_float2(const uint32_t w) {
   return __fadd2_rn(m, make_float2(-8388608.0f, -8388608.0f));
 }
 
+// Streaming (evict-first) / read-only loads of k_bounce's prefetch stage.
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_vec_f4(const float4 *p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 // ShootLight (as a gather) + CollectLight.  One warp per slice, lane = receiver; the list is walked in order, so
 // every receiver accumulates its transfers in ascending source order like the reference's serial loop:
 // illumination[j][l] += send[l] * trans->transfer (qrad3.c:439), mul and add rounded separately.  A zero weight adds
 // +-0 and leaves the sum unchanged (the sum starts at +0 and never becomes -0).
 // The list is consumed in batches of 32 entries (4 groups of 8): lane l fetches source slot l of the batch (one
 // coalesced 128-byte load) and gathers its radiosity vector, every lane fetches its 4 x 8 weights with four 128-bit
-// loads (2 KB contiguous per warp).  Loads run one batch (vectors, weights) / two batches (slots) ahead of the
-// arithmetic: ~2.6 KB in flight per warp, which is what it takes to cover HBM latency at this occupancy
-// (profiles/r01d_full_c5_k_bounce.txt: long-scoreboard bound before).
+// loads (2 KB contiguous per warp).  The loads of batch b + 1 are written ahead of the arithmetic of batch b, but ptxas
+// places them at the end of the batch and keeps ONE set of weight registers: 48 registers, 40 resident warps per SM,
+// and it is the other warps that cover the HBM latency (measured: 3.2 ms per bounce on C5 = 6.26 TB/s of stored
+// matrix, 96 % of the measured copy bandwidth; the 78-register version with both sets live ran at 4.9 ms).
+// The prefetch is unconditional: g_src / g_w are padded by two batches / one batch and hold valid slots.
 // Instruction diet (the r01g kernel issued 12 instructions per list entry -- 3 shuffles, 3 unpack/convert, 3 FMUL,
 // 3 FADD -- and sat at 58 % of the issue rate with HBM at 54 %, profiles/r01g_full_c5_k_bounce.txt): the 32 vectors of
-// a batch are parked in shared memory as {x0 x1 y0 y1 | z0 z1} per PAIR of entries, so a pair costs two broadcast
-// loads, two byte permutes + one packed subtract for its two weights, three packed multiplies (sm_100 FMUL2: both
-// entries of a channel at once) and six scalar adds, which keep the serial order: 7 instructions per entry.
-// (Packed adds are not used: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false,
-// which would change the rounding; build.py checks that this kernel's SASS holds no FFMA.)
+// a batch are parked in shared memory channel-major (x[32] y[32] z[32], conflict-free stores), so FOUR entries cost
+// three broadcast 128-bit loads, four byte permutes + two packed subtracts for their weights, six packed multiplies
+// (sm_100 FMUL2: two entries of a channel at once) and twelve scalar adds, which keep the serial order: 6.75
+// instructions per entry.  (Packed adds are not used: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even
+// under -fmad=false, which would change the rounding.)
+// Slices are handed out longest-first from a work counter (persistent warps): with one block per 8 consecutive
+// slices only 16 of 24 resident warps were alive on average (profiles/r01i_full_c5_k_bounce.txt).
 __global__ void __launch_bounds__(kThreads) k_bounce(const BounceArgs a) {
-  __shared__ __align__(16) float s_vec[kWarpsPerBlock][2][16 * 8];
+  __shared__ __align__(16) float s_vec[kWarpsPerBlock][2][3 * 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int slice = a.slice_lo + blockIdx.x * kWarpsPerBlock + wid;
-  if (slice >= a.slice_hi) return;
-  const int slot = slice * 32 + lane;
-  const int64_t base = a.slice_base[slice];
-  const int batches = (a.slice_len[slice] + 31) >> 5;
-  const uint32_t *ps = a.g_src + base + lane;
-  const uint4 *pw = a.g_w + (base >> 3) * 32 + lane;
-  float ix = 0.f, iy = 0.f, iz = 0.f;
-  uint32_t nidx = 0;                        // source slot of entry `lane` of the batch after next
-  float4 nx = make_float4(0, 0, 0, 0);      // radiosity vector of entry `lane` of the next batch
-  // this lane's weights of the current / next batch: two register sets that swap roles every batch (no copies)
-  uint4 wa0 = make_uint4(0, 0, 0, 0), wa1 = wa0, wa2 = wa0, wa3 = wa0, wb0 = wa0, wb1 = wa0, wb2 = wa0, wb3 = wa0;
-  if (batches > 0) {
-    nx = __ldg(a.send + __ldcs(ps));
-    wa0 = __ldcs(pw);
-    wa1 = __ldcs(pw + 32);
-    wa2 = __ldcs(pw + 64);
-    wa3 = __ldcs(pw + 96);
-    if (batches > 1) nidx = __ldcs(ps + 32);
-  }
-  const int park = (lane >> 1) * 8 + (lane & 1);
-#define QRAD_PAIR(P, W)                                                              \
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.next[a.parity ^ 1] = 0;
+  const int nslices = a.slice_hi - a.slice_lo;
+  for (;;) {
+    int k = 0;
+    if (lane == 0) k = atomicAdd(a.next + a.parity, 1);
+    k = __shfl_sync(0xffffffffu, k, 0);     // also: every lane is done with the previous slice's shared memory
+    if (k >= nslices) break;
+    const int slice = a.order[k];
+    const int slot = slice * 32 + lane;
+    const int64_t base = a.slice_base[slice];
+    const int batches = (a.slice_len[slice] + 31) >> 5;
+    const uint32_t *ps = a.g_src + base + lane;
+    const uint4 *pw = a.g_w + (base >> 3) * 32 + lane;
+    float ix = 0.f, iy = 0.f, iz = 0.f;
+    uint32_t nidx = 0;                        // source slot of entry `lane` of the batch after next
+    float4 nx = make_float4(0, 0, 0, 0);      // radiosity vector of entry `lane` of the next batch
+    // this lane's weights of the current / next batch: two register sets that swap roles every batch (no copies)
+    uint4 wa0 = make_uint4(0, 0, 0, 0), wa1 = wa0, wa2 = wa0, wa3 = wa0, wb0 = wa0, wb1 = wa0, wb2 = wa0, wb3 = wa0;
+    if (batches > 0) {
+      nx = __ldg(a.send + __ldcs(ps));
+      wa0 = __ldcs(pw);
+      wa1 = __ldcs(pw + 32);
+      wa2 = __ldcs(pw + 64);
+      wa3 = __ldcs(pw + 96);
+      nidx = __ldcs(ps + 32);
+    }
+// entries 4Q .. 4Q+3 of the batch: W0 holds the weights of the first two, W1 of the last two
+#define QRAD_QUAD(Q, W0, W1)                                                         \
   do {                                                                               \
-    const float4 xy = *reinterpret_cast<const float4 *>(sv + (P) * 8);               \
-    const float2 zz = *reinterpret_cast<const float2 *>(sv + (P) * 8 + 4);           \
-    const float2 fw = u16x2_to_float2(W);                                            \
-    const float2 px = __fmul2_rn(make_float2(xy.x, xy.y), fw);                       \
-    const float2 py = __fmul2_rn(make_float2(xy.z, xy.w), fw);                       \
-    const float2 pz = __fmul2_rn(zz, fw);                                            \
-    ix = ix + px.x;                                                                  \
-    iy = iy + py.x;                                                                  \
-    iz = iz + pz.x;                                                                  \
-    ix = ix + px.y;                                                                  \
-    iy = iy + py.y;                                                                  \
-    iz = iz + pz.y;                                                                  \
+    const float4 vx = *reinterpret_cast<const float4 *>(sv + (Q) * 4);               \
+    const float4 vy = *reinterpret_cast<const float4 *>(sv + 32 + (Q) * 4);          \
+    const float4 vz = *reinterpret_cast<const float4 *>(sv + 64 + (Q) * 4);          \
+    const float2 f0 = u16x2_to_float2(W0), f1 = u16x2_to_float2(W1);                 \
+    const float2 px0 = __fmul2_rn(make_float2(vx.x, vx.y), f0);                      \
+    const float2 py0 = __fmul2_rn(make_float2(vy.x, vy.y), f0);                      \
+    const float2 pz0 = __fmul2_rn(make_float2(vz.x, vz.y), f0);                      \
+    const float2 px1 = __fmul2_rn(make_float2(vx.z, vx.w), f1);                      \
+    const float2 py1 = __fmul2_rn(make_float2(vy.z, vy.w), f1);                      \
+    const float2 pz1 = __fmul2_rn(make_float2(vz.z, vz.w), f1);                      \
+    ix = ix + px0.x;                                                                 \
+    iy = iy + py0.x;                                                                 \
+    iz = iz + pz0.x;                                                                 \
+    ix = ix + px0.y;                                                                 \
+    iy = iy + py0.y;                                                                 \
+    iz = iz + pz0.y;                                                                 \
+    ix = ix + px1.x;                                                                 \
+    iy = iy + py1.x;                                                                 \
+    iz = iz + pz1.x;                                                                 \
+    ix = ix + px1.y;                                                                 \
+    iy = iy + py1.y;                                                                 \
+    iz = iz + pz1.y;                                                                 \
   } while (0)
-#define QRAD_GROUP(G, CW)         \
-  QRAD_PAIR(G * 4 + 0, CW.x);     \
-  QRAD_PAIR(G * 4 + 1, CW.y);     \
-  QRAD_PAIR(G * 4 + 2, CW.z);     \
-  QRAD_PAIR(G * 4 + 3, CW.w)
 // batch B: park the vectors (double buffered: the other half may still be read by slower lanes), start the loads of
 // batch B + 1 into the N registers, then consume the C registers
-#define QRAD_BATCH(B, C0, C1, C2, C3, N0, N1, N2, N3)          \
-  do {                                                         \
-    float *sv = s_vec[wid][(B) & 1];                           \
-    sv[park] = nx.x;                                           \
-    sv[park + 2] = nx.y;                                       \
-    sv[park + 4] = nx.z;                                       \
-    __syncwarp();                                              \
-    if ((B) + 1 < batches) {                                   \
-      nx = __ldg(a.send + nidx);                               \
-      const uint4 *q = pw + 128 * ((B) + 1);                   \
-      N0 = __ldcs(q);                                          \
-      N1 = __ldcs(q + 32);                                     \
-      N2 = __ldcs(q + 64);                                     \
-      N3 = __ldcs(q + 96);                                     \
-      if ((B) + 2 < batches) nidx = __ldcs(ps + 32 * ((B) + 2)); \
-    }                                                          \
-    QRAD_GROUP(0, C0);                                         \
-    QRAD_GROUP(1, C1);                                         \
-    QRAD_GROUP(2, C2);                                         \
-    QRAD_GROUP(3, C3);                                         \
+#define QRAD_BATCH(B, C0, C1, C2, C3, N0, N1, N2, N3)            \
+  do {                                                           \
+    float *sv = s_vec[wid][(B) & 1];                             \
+    sv[lane] = nx.x;                                             \
+    sv[32 + lane] = nx.y;                                        \
+    sv[64 + lane] = nx.z;                                        \
+    __syncwarp();                                                \
+    /* unconditional: the buffers are padded by two batches and hold valid slots */ \
+    nx = ld_vec_f4(a.send + nidx);                               \
+    {                                                            \
+      const uint4 *q = pw + 128 * ((B) + 1);                     \
+      N0 = ld_stream_u4(q);                                      \
+      N1 = ld_stream_u4(q + 32);                                 \
+      N2 = ld_stream_u4(q + 64);                                 \
+      N3 = ld_stream_u4(q + 96);                                 \
+      nidx = ld_stream_u32(ps + 32 * ((B) + 2));                 \
+    }                                                            \
+    QRAD_QUAD(0, C0.x, C0.y);                                    \
+    QRAD_QUAD(1, C0.z, C0.w);                                    \
+    QRAD_QUAD(2, C1.x, C1.y);                                    \
+    QRAD_QUAD(3, C1.z, C1.w);                                    \
+    QRAD_QUAD(4, C2.x, C2.y);                                    \
+    QRAD_QUAD(5, C2.z, C2.w);                                    \
+    QRAD_QUAD(6, C3.x, C3.y);                                    \
+    QRAD_QUAD(7, C3.z, C3.w);                                    \
   } while (0)
-  for (int b = 0; b < batches; b += 2) {
-    QRAD_BATCH(b, wa0, wa1, wa2, wa3, wb0, wb1, wb2, wb3);
-    if (b + 1 < batches) QRAD_BATCH(b + 1, wb0, wb1, wb2, wb3, wa0, wa1, wa2, wa3);
-  }
+    for (int b = 0; b < batches; b += 2) {
+      QRAD_BATCH(b, wa0, wa1, wa2, wa3, wb0, wb1, wb2, wb3);
+      if (b + 1 < batches) QRAD_BATCH(b + 1, wb0, wb1, wb2, wb3, wa0, wa1, wa2, wa3);
+    }
 #undef QRAD_BATCH
-#undef QRAD_GROUP
-#undef QRAD_PAIR
-  // CollectLight, qrad3.c:383-409
-  const float4 ra = a.refl_area[slot];
-  float4 t = a.total[slot];
-  float rx = 0.f, ry = 0.f, rz = 0.f;
-  if (ra.w > 0) {  // not sky (and not a padding slot)
-    t.x += ix / ra.w;
-    t.y += iy / ra.w;
-    t.z += iz / ra.w;
-    rx = ix * ra.x;
-    ry = iy * ra.y;
-    rz = iz * ra.z;
-    a.total[slot] = t;
+#undef QRAD_QUAD
+    // CollectLight, qrad3.c:383-409
+    const float4 ra = a.refl_area[slot];
+    float4 t = a.total[slot];
+    float rx = 0.f, ry = 0.f, rz = 0.f;
+    if (ra.w > 0) {  // not sky (and not a padding slot)
+      t.x += ix / ra.w;
+      t.y += iy / ra.w;
+      t.z += iz / ra.w;
+      rx = ix * ra.x;
+      ry = iy * ra.y;
+      rz = iz * ra.z;
+      a.total[slot] = t;
+    }
+    if (a.rad_sum) a.rad_sum[slot] = rx + ry + rz;
+    a.send_next[slot] = make_float4(rx / 65536.0f, ry / 65536.0f, rz / 65536.0f, 0.f);
   }
-  if (a.rad_sum) a.rad_sum[slot] = rx + ry + rz;
-  a.send_next[slot] = make_float4(rx / 65536.0f, ry / 65536.0f, rz / 65536.0f, 0.f);
 }
 
 // serial float sum of rad_sum over PATCH order (CollectLight's `total`), one warp
@@ -1076,8 +1116,16 @@ void transfers_columns(qrad_cuda_ctx *c) {
   }
   c->sell_entries = h_slice_base[nslices];
   c->slice_base.upload(h_slice_base, st);
-  c->g_src.alloc((size_t) c->sell_entries + 32);
-  c->g_w.alloc((size_t) (c->sell_entries / 8 + 4) * 32);
+  {  // k_bounce hands this rank's slices to its warps longest list first
+    std::vector<int32_t> order;
+    for (int s = c->slice_lo; s < c->slice_hi; s++) order.push_back(s);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return h_len[x] > h_len[y]; });
+    if (order.empty()) order.push_back(0);
+    c->slice_order.upload(order, st);
+  }
+  // k_bounce prefetches without bounds checks: slots two batches, weights one batch past the end of a list
+  c->g_src.alloc((size_t) c->sell_entries + 96);
+  c->g_w.alloc((size_t) (c->sell_entries / 8 + 8) * 32);
   c->g_src.zero(st);
   c->g_w.zero(st);
   ca.slice_base = c->slice_base.p;
@@ -1183,6 +1231,13 @@ void bounce_begin(qrad_cuda_ctx *c, bool want_sum) {
   c->rad_nxt = c->rad_b.p;
   c->bounce_kernel_ms = 0;
   c->bounce_steps = 0;
+  c->bounce_next.alloc(2);
+  c->bounce_next.zero(st);
+  if (c->bounce_blocks_per_sm == 0) {
+    int per_sm = 0;
+    QCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce, kThreads, 0));
+    c->bounce_blocks_per_sm = std::max(1, per_sm);
+  }
   c->sync("bounce_begin");
 }
 
@@ -1201,7 +1256,12 @@ void bounce_step(qrad_cuda_ctx *c) {
   a.slice_hi = c->slice_hi;
   a.send = c->rad_cur;
   a.send_next = c->rad_nxt;
-  const int blocks = std::max(1, (c->slice_hi - c->slice_lo + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  a.order = c->slice_order.p;
+  a.next = c->bounce_next.p;
+  a.parity = c->bounce_steps & 1;
+  // persistent warps: as many blocks as fit on the chip, slices are drawn from the work counter
+  const int want = std::max(1, (c->slice_hi - c->slice_lo + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  const int blocks = std::min(want, c->sm_count * c->bounce_blocks_per_sm);
   Timer tk;
   tk.start(st);
   k_bounce<<<blocks, kThreads, 0, st>>>(a);
