@@ -208,7 +208,7 @@ int qrad_cuda_upload_bsp(qrad_cuda_ctx *c, const qrad_bsp_view *b) {
         recs.insert(recs.end(), tmp.rbegin(), tmp.rend());
         first[l + 1] = (int32_t) recs.size();
       }
-      if (recs.empty()) recs.push_back(make_int4(0, 0, 0, 0));
+      for (int k = 0; k < 4; k++) recs.push_back(make_int4(0, 0, 0, 0));   // the walkers fetch records four at a time
       c->leaf_path.upload(recs, c->stream);
       c->leaf_path_first.upload(first, c->stream);
     }

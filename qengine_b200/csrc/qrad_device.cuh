@@ -99,6 +99,18 @@ static __device__ __noinline__ float2 nonaxial_dists(const float4 *__restrict__ 
   return make_float2((sx * pl.x + sy * pl.y + sz * pl.z) - dist, (ex * pl.x + ey * pl.y + ez * pl.z) - dist);
 }
 
+// Coordinate `type` (0, 1, 2) of a point, as two selects.  Written in PTX on purpose: from the C ternaries ptxas builds
+// a three-way branch, and since neighbouring lanes walk different paths every node visit then diverges by plane axis
+// (profiles/r01g_full_c5chop16.txt: 25.4 of 32 lanes active, the ALU pipe the busiest at 58 %).
+__device__ __forceinline__ float axis_pick(const int type, const float x, const float y, const float z) {
+  float r;
+  asm("{\n\t.reg .pred p0, p1;\n\t.reg .f32 t;\n\t"
+      "setp.eq.s32 p0, %1, 0;\n\tsetp.eq.s32 p1, %1, 1;\n\t"
+      "selp.f32 t, %3, %4, p1;\n\tselp.f32 %0, %2, t, p0;\n\t}"
+      : "=f"(r) : "r"(type), "f"(x), "f"(y), "f"(z));
+  return r;
+}
+
 // TestLine_r(0, start, stop), trace.c:92-142, as an explicit-stack walk.  The near half is
 // followed first and the far half (node, stop) is parked; on a pop the new start is the
 // current stop (= the split point), exactly the segments the recursion passes down.
@@ -119,10 +131,8 @@ __device__ __forceinline__ int test_line(const Tree tree, float sx, float sy, fl
       if (COUNT) visits++;
       float front, back;
       if (nd.y < 3) {
-        const float s1 = nd.y == 0 ? sx : (nd.y == 1 ? sy : sz);
-        const float e1 = nd.y == 0 ? ex : (nd.y == 1 ? ey : ez);
-        front = s1 - dist;
-        back = e1 - dist;
+        front = axis_pick(nd.y, sx, sy, sz) - dist;
+        back = axis_pick(nd.y, ex, ey, ez) - dist;
       } else {
         const float2 fb = nonaxial_dists(tree.normals, node, dist, sx, sy, sz, ex, ey, ez);
         front = fb.x;
@@ -172,42 +182,55 @@ __device__ __forceinline__ int test_line(const Tree tree, float sx, float sy, fl
 // z = node index (for the normal of a non-axial plane).  Since TestLine_r's result is the OR over all reachable
 // leaves, "a SOLID leaf is reachable" proves the ray blocked; callers use the leaf that blocked a neighbouring ray
 // as the guess and fall back to the full walk when the guess is not reached.
+// The records of a path are fetched four at a time (the array is padded by four records): the loads do not depend
+// on the walk, so one L1 round trip is paid per four ancestors instead of per ancestor -- k_visibility is bound by
+// exactly this dependent-latency chain (profiles/r01g_full_c5chop16.txt: 10.5 cycles per issued instruction per warp).
 template <bool COUNT>
 __device__ __forceinline__ bool reaches_leaf(const Tree tree, const int4 *__restrict__ path, const int len, float sx,
                                              float sy, float sz, float ex, float ey, float ez, unsigned &visits) {
-  for (int i = 0; i < len; i++) {
-    const int4 nd = __ldg(path + i);
-    const float dist = __int_as_float(nd.x);
-    const int type = nd.y & 0xff, want = nd.y >> 8;
-    if (COUNT) visits++;
-    float front, back;
-    if (type < 3) {
-      const float s1 = type == 0 ? sx : (type == 1 ? sy : sz);
-      const float e1 = type == 0 ? ex : (type == 1 ? ey : ez);
-      front = s1 - dist;
-      back = e1 - dist;
-    } else {
-      const float2 fb = nonaxial_dists(tree.normals, nd.z, dist, sx, sy, sz, ex, ey, ez);
-      front = fb.x;
-      back = fb.y;
-    }
-    if (front > -0.1f && back > -0.1f) {
-      if (want != 0) return false;
-    } else if (front < 0.1f && back < 0.1f) {
-      if (want != 1) return false;
-    } else {
-      const int side = front < 0 ? 1 : 0;
-      const float frac = front / (front - back);
-      const float mx = sx + (ex - sx) * frac;
-      const float my = sy + (ey - sy) * frac;
-      const float mz = sz + (ez - sz) * frac;
-      if (want == side) {  // near half: (start, mid)
-        ex = mx; ey = my; ez = mz;
-      } else {             // far half: (mid, stop)
-        sx = mx; sy = my; sz = mz;
-      }
-    }
+#define QRAD_PATH_STEP(ND)                                                                               \
+  do {                                                                                                   \
+    const int4 nd = ND;                                                                                  \
+    const float dist = __int_as_float(nd.x);                                                             \
+    const int type = nd.y & 0xff, want = nd.y >> 8;                                                      \
+    if (COUNT) visits++;                                                                                 \
+    float front, back;                                                                                   \
+    if (type < 3) {                                                                                      \
+      front = axis_pick(type, sx, sy, sz) - dist;                                                        \
+      back = axis_pick(type, ex, ey, ez) - dist;                                                         \
+    } else {                                                                                             \
+      const float2 fb = nonaxial_dists(tree.normals, nd.z, dist, sx, sy, sz, ex, ey, ez);                \
+      front = fb.x;                                                                                      \
+      back = fb.y;                                                                                       \
+    }                                                                                                    \
+    if (front > -0.1f && back > -0.1f) {                                                                 \
+      if (want != 0) return false;                                                                       \
+    } else if (front < 0.1f && back < 0.1f) {                                                            \
+      if (want != 1) return false;                                                                       \
+    } else {                                                                                             \
+      const int side = front < 0 ? 1 : 0;                                                                \
+      const float frac = front / (front - back);                                                         \
+      const float mx = sx + (ex - sx) * frac;                                                            \
+      const float my = sy + (ey - sy) * frac;                                                            \
+      const float mz = sz + (ez - sz) * frac;                                                            \
+      if (want == side) { /* near half: (start, mid) */                                                  \
+        ex = mx; ey = my; ez = mz;                                                                       \
+      } else {            /* far half: (mid, stop) */                                                    \
+        sx = mx; sy = my; sz = mz;                                                                       \
+      }                                                                                                  \
+    }                                                                                                    \
+  } while (0)
+  for (int i = 0; i < len; i += 4) {
+    const int4 r0 = __ldg(path + i), r1 = __ldg(path + i + 1), r2 = __ldg(path + i + 2), r3 = __ldg(path + i + 3);
+    QRAD_PATH_STEP(r0);
+    if (i + 1 >= len) break;
+    QRAD_PATH_STEP(r1);
+    if (i + 2 >= len) break;
+    QRAD_PATH_STEP(r2);
+    if (i + 3 >= len) break;
+    QRAD_PATH_STEP(r3);
   }
+#undef QRAD_PATH_STEP
   return true;
 }
 
@@ -234,10 +257,10 @@ __device__ __forceinline__ bool box_reaches_leaf(const int4 *__restrict__ path, 
     const float dist = __int_as_float(nd.x);
     const int type = nd.y & 0xff, want = nd.y >> 8;
     if (type >= 3) return false;
-    const float f_lo = (type == 0 ? slo[0] : (type == 1 ? slo[1] : slo[2])) - dist;
-    const float f_hi = (type == 0 ? shi[0] : (type == 1 ? shi[1] : shi[2])) - dist;
-    const float b_lo = (type == 0 ? elo[0] : (type == 1 ? elo[1] : elo[2])) - dist;
-    const float b_hi = (type == 0 ? ehi[0] : (type == 1 ? ehi[1] : ehi[2])) - dist;
+    const float f_lo = axis_pick(type, slo[0], slo[1], slo[2]) - dist;
+    const float f_hi = axis_pick(type, shi[0], shi[1], shi[2]) - dist;
+    const float b_lo = axis_pick(type, elo[0], elo[1], elo[2]) - dist;
+    const float b_hi = axis_pick(type, ehi[0], ehi[1], ehi[2]) - dist;
     if (f_lo > -0.1f && b_lo > -0.1f) {  // every e: first test true -> child 0
       if (want != 0) return false;
       continue;
