@@ -185,9 +185,35 @@ __device__ __forceinline__ int test_line(const Tree tree, float sx, float sy, fl
 // The records of a path are fetched four at a time (the array is padded by four records): the loads do not depend
 // on the walk, so one L1 round trip is paid per four ancestors instead of per ancestor -- k_visibility is bound by
 // exactly this dependent-latency chain (profiles/r01g_full_c5chop16.txt: 10.5 cycles per issued instruction per warp).
+// `first` / `splits` (optional) come from a failed box_reaches_leaf() of the same leaf for a box that holds this end
+// point: the interval walk proved that the ray passes the ancestors [0, first) towards X, unclipped except at the
+// ancestors in `splits`, where it is split with the near/far half leading on.  Those splits are replayed with the
+// exact arithmetic (no three-way test needed), the other ancestors of the prefix are skipped, and the normal walk
+// starts at ancestor `first`.
 template <bool COUNT>
 __device__ __forceinline__ bool reaches_leaf(const Tree tree, const int4 *__restrict__ path, const int len, float sx,
-                                             float sy, float sz, float ex, float ey, float ez, unsigned &visits) {
+                                             float sy, float sz, float ex, float ey, float ez, unsigned &visits,
+                                             const int first = 0, unsigned long long splits = 0) {
+  while (splits) {
+    const int i = __ffsll((long long) splits) - 1;
+    splits &= splits - 1;
+    const int4 nd = __ldg(path + i);
+    const float dist = __int_as_float(nd.x);
+    const int type = nd.y & 0xff, want = nd.y >> 8;   // box walks stop at non-axial planes: type < 3 here
+    if (COUNT) visits++;
+    const float front = axis_pick(type, sx, sy, sz) - dist;
+    const float back = axis_pick(type, ex, ey, ez) - dist;
+    const int side = front < 0 ? 1 : 0;
+    const float frac = front / (front - back);
+    const float mx = sx + (ex - sx) * frac;
+    const float my = sy + (ey - sy) * frac;
+    const float mz = sz + (ez - sz) * frac;
+    if (want == side) {
+      ex = mx; ey = my; ez = mz;
+    } else {
+      sx = mx; sy = my; sz = mz;
+    }
+  }
 #define QRAD_PATH_STEP(ND)                                                                               \
   do {                                                                                                   \
     const int4 nd = ND;                                                                                  \
@@ -220,7 +246,7 @@ __device__ __forceinline__ bool reaches_leaf(const Tree tree, const int4 *__rest
       }                                                                                                  \
     }                                                                                                    \
   } while (0)
-  for (int i = 0; i < len; i += 4) {
+  for (int i = first; i < len; i += 4) {
     const int4 r0 = __ldg(path + i), r1 = __ldg(path + i + 1), r2 = __ldg(path + i + 2), r3 = __ldg(path + i + 3);
     QRAD_PATH_STEP(r0);
     if (i + 1 >= len) break;
@@ -248,31 +274,53 @@ __device__ __forceinline__ bool reaches_leaf(const Tree tree, const int4 *__rest
 //  * non-axial planes are not handled (returns false = "do not know").
 // A `true` answer for a SOLID leaf X therefore proves every ray into the box blocked; `false` proves nothing and the
 // rays are tested one by one.
-__device__ __forceinline__ bool box_reaches_leaf(const int4 *__restrict__ path, const int len, const float4 s,
-                                                 const float4 mn, const float4 mx) {
+//
+// Result: kBoxProven; kBoxElsewhere = every ray of the box provably leaves the path to X at ancestor `first` (so X is
+// reached by none of them); kBoxUnknown = the rays part ways (or meet a non-axial plane) at ancestor `first`.  In the
+// last two cases `splits` has bit i set for every ancestor i < first at which all rays are split; reaches_leaf() uses
+// (first, splits) to skip the proven prefix ray by ray.  Paths deeper than 64 report first = 0.
+enum { kBoxUnknown = 0, kBoxProven = 1, kBoxElsewhere = 2 };
+__device__ __forceinline__ int box_reaches_leaf(const int4 *__restrict__ path, const int len, const float4 s,
+                                                const float4 mn, const float4 mx, int &first, unsigned long long &splits) {
+  first = 0;
+  splits = 0;
+  const bool track = len <= 64;
   float slo[3] = {s.x, s.y, s.z}, shi[3] = {s.x, s.y, s.z};
   float elo[3] = {mn.x, mn.y, mn.z}, ehi[3] = {mx.x, mx.y, mx.z};
   for (int i = 0; i < len; i++) {
     const int4 nd = __ldg(path + i);
     const float dist = __int_as_float(nd.x);
     const int type = nd.y & 0xff, want = nd.y >> 8;
-    if (type >= 3) return false;
+    if (type >= 3) {
+      if (track) first = i; else splits = 0;
+      return kBoxUnknown;
+    }
     const float f_lo = axis_pick(type, slo[0], slo[1], slo[2]) - dist;
     const float f_hi = axis_pick(type, shi[0], shi[1], shi[2]) - dist;
     const float b_lo = axis_pick(type, elo[0], elo[1], elo[2]) - dist;
     const float b_hi = axis_pick(type, ehi[0], ehi[1], ehi[2]) - dist;
     if (f_lo > -0.1f && b_lo > -0.1f) {  // every e: first test true -> child 0
-      if (want != 0) return false;
+      if (want != 0) {
+        if (track) first = i; else splits = 0;
+        return kBoxElsewhere;
+      }
       continue;
     }
     if ((!(f_hi > -0.1f) || !(b_hi > -0.1f)) && f_hi < 0.1f && b_hi < 0.1f) {  // every e: first false, second true
-      if (want != 1) return false;
+      if (want != 1) {
+        if (track) first = i; else splits = 0;
+        return kBoxElsewhere;
+      }
       continue;
     }
     int side;
     if (!(f_lo < 0.1f) && !(b_hi > -0.1f)) side = 0;        // every e: front >= 0.1, back <= -0.1: split, side 0
     else if (!(f_hi > -0.1f) && !(b_lo < 0.1f)) side = 1;   // every e: front <= -0.1, back >= 0.1: split, side 1
-    else return false;
+    else {
+      if (track) first = i; else splits = 0;
+      return kBoxUnknown;
+    }
+    splits |= 1ull << (i & 63);
     float fr_lo, fr_hi;
     if (side == 0) {
       fr_lo = f_lo / (f_lo - b_lo);
@@ -302,7 +350,7 @@ __device__ __forceinline__ bool box_reaches_leaf(const int4 *__restrict__ path, 
       }
     }
   }
-  return true;
+  return kBoxProven;
 }
 
 // PointInLeafnum, qrad3.c:131-150: full dot product on every node, `dist > 0` picks child 0.

@@ -104,12 +104,18 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
   __shared__ int32_t s_wbase[kWarpsPerBlock][kChunkWords];         // first receiver slot of the word
   __shared__ int32_t s_wcnt[kWarpsPerBlock][kChunkWords];          // valid receivers in the word
   __shared__ uint16_t s_fb[kWarpsPerBlock][64];                    // rays whose guess failed (receiver index)
+  // what the word's box walk learned when it did not prove the word (see box_reaches_leaf): the leaf it was run for,
+  // the first ancestor not passed by all rays (0x80 | .. = all rays leave the path there) and the splits before it
+  __shared__ uint16_t s_bleaf[kWarpsPerBlock][kChunkWords];
+  __shared__ uint8_t s_bfirst[kWarpsPerBlock][kChunkWords];
+  __shared__ unsigned long long s_bsplits[kWarpsPerBlock][kChunkWords];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1;
   const uint64_t warp0 = (uint64_t) blockIdx.x * kWarpsPerBlock + wid;
   const uint64_t nwarps = (uint64_t) gridDim.x * kWarpsPerBlock;
   unsigned long long rays = 0, pairs = 0, visits_total = 0, fallbacks = 0, boxed = 0;
   int guess_c = -1, guess_w0 = -1;   // which (source cluster, chunk) the guesses belong to
+  long long tk0 = 0, tk_box = 0, tk_pairs = 0, tk_guess = 0, tk_full = 0, tk_misc = 0;   // COUNT: warp cycles per phase
   for (uint64_t lrun = warp0 * kTaskRun; lrun < a.my_tasks; lrun += nwarps * kTaskRun)
   for (uint64_t ltask = lrun; ltask < lrun + kTaskRun && ltask < a.my_tasks; ltask++) {
     const uint64_t task = ((ltask / kTaskGranule) * a.world + a.rank) * kTaskGranule + ltask % kTaskGranule;
@@ -138,6 +144,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
       s_wguess[wid][lane] = 0xffffu;
     }
     s_res[wid][lane] = 0;
+    if (COUNT) { const long long t = clock64(); if (tk0) tk_misc += t - tk0; tk0 = t; }
     // ---- (1) per word: receiver slots, box test ----
     bool proven = false;
     if (lane < nwc) {
@@ -153,21 +160,33 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
       s_wbase[wid][lane] = base;
       s_wcnt[wid][lane] = min(32, a.cl_count[d] - off);
       const int g = s_wguess[wid][lane];
+      s_bleaf[wid][lane] = 0xffffu;
       if (g != 0xffff) {
         const int p0 = __ldg(a.leaf_path_first + g), p1 = __ldg(a.leaf_path_first + g + 1);
-        proven = box_reaches_leaf(a.leaf_path + p0, p1 - p0, so, __ldg(a.wbox_min + (base >> 5)), __ldg(a.wbox_max + (base >> 5)));
+        int first;
+        unsigned long long splits;
+        const int r = box_reaches_leaf(a.leaf_path + p0, p1 - p0, so, __ldg(a.wbox_min + (base >> 5)),
+                                       __ldg(a.wbox_max + (base >> 5)), first, splits);
+        proven = r == kBoxProven;
+        if (!proven) {
+          s_bleaf[wid][lane] = (uint16_t) g;
+          s_bfirst[wid][lane] = (uint8_t) (first | (r == kBoxElsewhere ? 0x80 : 0));
+          s_bsplits[wid][lane] = splits;
+        }
       }
     }
     const unsigned proven_mask = __ballot_sync(0xffffffffu, proven);
     __syncwarp();
+    if (COUNT) { const long long t = clock64(); tk_box += t - tk0; tk0 = t; }
     // ---- (2) cheap tests, compaction ----
     int n = 0;
     for (int wi = 0; wi < nwc; wi++) {
       const int rslot = s_wbase[wid][wi] + lane;
       bool want = false;
       if (lane < s_wcnt[wid][wi] && rslot != sslot) {
-        const float4 po = __ldg(a.s_origin_area + rslot);
-        const float4 pn = __ldg(a.s_normal + rslot);
+        // receivers stream through (32 KB per task and warp): keep them out of L1, which holds the tree and the paths
+        const float4 po = __ldcg(a.s_origin_area + rslot);
+        const float4 pn = __ldcg(a.s_normal + rslot);
         float dist;
         bool wants_ray;
         const float trans = form_factor_pre(so, sn, po, pn, dist, wants_ray);
@@ -183,12 +202,15 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
       n += __popc(m);
     }
     __syncwarp();
+    if (COUNT) { const long long t = clock64(); tk_pairs += t - tk0; tk0 = t; }
     // ---- (3) guess walks, full walks for the rest ----
     int fbn = 0;
     auto full_batch = [&](const int cnt) {  // full TestLine for the first `cnt` entries of the fallback queue
+      long long tf0 = 0;
+      if (COUNT) tf0 = clock64();
       if (lane < cnt) {
         const int cand = s_fb[wid][lane];
-        const float4 po = __ldg(a.s_origin_area + s_wbase[wid][cand >> 5] + (cand & 31));
+        const float4 po = __ldcg(a.s_origin_area + s_wbase[wid][cand >> 5] + (cand & 31));
         unsigned visits = 0;
         int leaf = -1;
         const int blocked = test_line<STACK, COUNT>(a.tree, so.x, so.y, so.z, po.x, po.y, po.z, visits, &leaf);
@@ -200,6 +222,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
         }
       }
       __syncwarp();
+      if (COUNT) tk_full += clock64() - tf0;
     };
     for (int base = 0; base < n; base += 32) {
       const int k = base + lane;
@@ -209,11 +232,18 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
         cand = s_queue[wid][k];
         const int g = s_rguess[wid][cand];
         miss = true;
-        if (g != 0xffff) {
-          const float4 po = __ldg(a.s_origin_area + s_wbase[wid][cand >> 5] + (cand & 31));
+        int first = 0;
+        unsigned long long splits = 0;
+        if (g != 0xffff && g == s_bleaf[wid][cand >> 5]) {   // the word's box walk was about this very leaf
+          first = s_bfirst[wid][cand >> 5];
+          splits = s_bsplits[wid][cand >> 5];
+        }
+        if (g != 0xffff && !(first & 0x80)) {   // 0x80: no ray into this word reaches g; straight to the full walk
+          const float4 po = __ldcg(a.s_origin_area + s_wbase[wid][cand >> 5] + (cand & 31));
           const int p0 = __ldg(a.leaf_path_first + g), p1 = __ldg(a.leaf_path_first + g + 1);
           unsigned visits = 0;
-          miss = !reaches_leaf<COUNT>(a.tree, a.leaf_path + p0, p1 - p0, so.x, so.y, so.z, po.x, po.y, po.z, visits);
+          miss = !reaches_leaf<COUNT>(a.tree, a.leaf_path + p0, p1 - p0, so.x, so.y, so.z, po.x, po.y, po.z, visits,
+                                      first, splits);
           if (COUNT) visits_total += visits;
         }
       }
@@ -234,6 +264,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
     }
     if (fbn > 0) full_batch(fbn);
     __syncwarp();
+    if (COUNT) { const long long t = clock64(); tk_guess += t - tk0; tk0 = t; }
     if (lane < nwc) a.bits[a.bits_base[c] + (int64_t) row * nw + w0 + lane] = s_res[wid][lane];
     __syncwarp();
   }
@@ -250,6 +281,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
     if (COUNT) atomicAdd(a.counters + 1, visits_total);
     if (COUNT) atomicAdd(a.counters + 3, fallbacks);
     if (COUNT) atomicAdd(a.counters + 4, boxed);
+    if (COUNT) {
+      atomicAdd(a.counters + 8, (unsigned long long) tk_box);
+      atomicAdd(a.counters + 9, (unsigned long long) tk_pairs);
+      atomicAdd(a.counters + 10, (unsigned long long) (tk_guess - tk_full));
+      atomicAdd(a.counters + 11, (unsigned long long) tk_full);
+      atomicAdd(a.counters + 12, (unsigned long long) tk_misc);
+    }
   }
 }
 
@@ -906,7 +944,7 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   c->d_Rptr.upload(Rptr, st);
   c->d_task_base.upload(task_base, st);
   c->bits.alloc((size_t) W + 1);
-  c->counters.alloc(8);
+  c->counters.alloc(16);
   c->counters.zero(st);
 
   c->sync("make_transfers uploads");
@@ -1139,8 +1177,14 @@ void transfers_columns(qrad_cuda_ctx *c) {
   for (int s = 0; s < M; s++) nnz += h_rc[s];
   c->sync("make_transfers");
 
-  unsigned long long hc[8];
-  c->counters.download(hc, 8, st);
+  unsigned long long hc[16];
+  c->counters.download(hc, 16, st);
+  if (c->count_nodes) {   // warp cycles per phase of k_visibility (tools/gpu_raycounts.py)
+    const double tot = (double) (hc[8] + hc[9] + hc[10] + hc[11] + hc[12]);
+    if (tot > 0)
+      fprintf(stderr, "k_visibility warp cycles: box walks %.1f %%, pair tests %.1f %%, guess walks %.1f %%, full walks %.1f %%, "
+              "task set-up / stores %.1f %%\n", 100 * hc[8] / tot, 100 * hc[9] / tot, 100 * hc[10] / tot, 100 * hc[11] / tot, 100 * hc[12] / tot);
+  }
   c->stats.rays_transfers = (int64_t) hc[0];
   c->stats.node_visits += (int64_t) hc[1];
   c->stats.candidate_pairs = (int64_t) hc[2];
