@@ -180,13 +180,22 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
     if (COUNT) { const long long t = clock64(); tk_box += t - tk0; tk0 = t; }
     // ---- (2) cheap tests, compaction ----
     int n = 0;
+    // receivers stream through (32 KB per task and warp): they bypass L1, which holds the tree and the paths, and the
+    // next word's 32 receivers are requested before this word's are tested (an L2 round trip per word otherwise)
+    float4 po_n = make_float4(0, 0, 0, 0), pn_n = po_n;
+    if (nwc > 0) {
+      po_n = __ldcg(a.s_origin_area + s_wbase[wid][0] + lane);
+      pn_n = __ldcg(a.s_normal + s_wbase[wid][0] + lane);
+    }
     for (int wi = 0; wi < nwc; wi++) {
       const int rslot = s_wbase[wid][wi] + lane;
+      const float4 po = po_n, pn = pn_n;
+      if (wi + 1 < nwc) {   // slots are padded to whole words: every lane has a valid address
+        po_n = __ldcg(a.s_origin_area + s_wbase[wid][wi + 1] + lane);
+        pn_n = __ldcg(a.s_normal + s_wbase[wid][wi + 1] + lane);
+      }
       bool want = false;
       if (lane < s_wcnt[wid][wi] && rslot != sslot) {
-        // receivers stream through (32 KB per task and warp): keep them out of L1, which holds the tree and the paths
-        const float4 po = __ldcg(a.s_origin_area + rslot);
-        const float4 pn = __ldcg(a.s_normal + rslot);
         float dist;
         bool wants_ray;
         const float trans = form_factor_pre(so, sn, po, pn, dist, wants_ray);
