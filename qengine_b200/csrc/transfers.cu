@@ -359,8 +359,10 @@ __global__ void __launch_bounds__(1024) k_build_lists(const ListArgs a) {
   }
 }
 
-// Summaries of the row lists: which row words a 32-entry chunk can touch (entries that are neighbours in patch order
-// are mostly neighbours in slot order too, so a chunk usually lies inside one or two words).
+// Summaries of the row lists: which row words a 32-entry chunk can touch, as up to four {word, mask} pairs in two
+// uint4 (entries that are neighbours in patch order are neighbours in slot order as long as they lie in one cluster, so
+// a chunk usually lies inside one or two words, three or four where the list moves on to another cluster).
+// out[2 * chunk].x == 0xffffffff marks a chunk with more than four words; an unused pair has word 0xffffffff.
 __global__ void __launch_bounds__(kThreads) k_list_summaries(int nc, const int64_t *__restrict__ Lptr,
                                                              const int64_t *__restrict__ chunk_base,
                                                              const uint32_t *__restrict__ L_pos, uint4 *__restrict__ out,
@@ -377,19 +379,22 @@ __global__ void __launch_bounds__(kThreads) k_list_summaries(int nc, const int64
   const bool have = k < Lptr[lo + 1];
   const uint32_t pos = have ? L_pos[k] : 0;
   const uint32_t word = pos >> 5, bit = have ? 1u << (pos & 31) : 0u;
-  const unsigned hm = __ballot_sync(0xffffffffu, have);   // lane 0 always has an entry
-  const uint32_t w0 = __shfl_sync(0xffffffffu, word, 0);
-  const uint32_t m0 = __reduce_or_sync(0xffffffffu, (have && word == w0) ? bit : 0u);
-  const unsigned rest = __ballot_sync(0xffffffffu, have && word != w0);
-  uint32_t w1 = 0xffffffffu, m1 = 0;
-  bool complex_chunk = false;
-  if (rest) {
-    w1 = __shfl_sync(0xffffffffu, word, __ffs(rest) - 1);
-    m1 = __reduce_or_sync(0xffffffffu, (have && word == w1) ? bit : 0u);
-    complex_chunk = __ballot_sync(0xffffffffu, have && word != w0 && word != w1) != 0;
+  uint32_t w[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}, m[4] = {0, 0, 0, 0};
+  bool left = have;   // lane 0 always has an entry
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const unsigned rest = __ballot_sync(0xffffffffu, left);
+    if (rest) {
+      w[t] = __shfl_sync(0xffffffffu, word, __ffs(rest) - 1);
+      m[t] = __reduce_or_sync(0xffffffffu, (left && word == w[t]) ? bit : 0u);
+      left = left && word != w[t];
+    }
   }
-  (void) hm;
-  if (lane == 0) out[chunk] = complex_chunk ? make_uint4(0xffffffffu, 0, 0, 0) : make_uint4(w0, m0, w1, m1);
+  const bool complex_chunk = __ballot_sync(0xffffffffu, left) != 0;
+  if (lane == 0) {
+    out[2 * chunk] = complex_chunk ? make_uint4(0xffffffffu, 0, 0, 0) : make_uint4(w[0], m[0], w[1], m[1]);
+    out[2 * chunk + 1] = make_uint4(w[2], m[2], w[3], m[3]);
+  }
 }
 
 // pass 2: serial row sums in ascending receiver order.
@@ -436,15 +441,20 @@ __global__ void __launch_bounds__(kThreads) k_row_totals(const RowArgs a) {
   // most two) row words it can touch, so 32 chunks are ruled out per step with one masked test per lane and only
   // chunks holding an accept bit take the ordered walk below (the order of the float sum is untouched).
   const int64_t nchunks = (l1 - l0 + 31) >> 5;
-  const uint4 *sum = a.L_sum + a.chunk_base[c];
+  const uint4 *sum = a.L_sum + 2 * a.chunk_base[c];
   for (int64_t g0 = 0; g0 < nchunks; g0 += 32) {
     bool live = false;
     if (g0 + lane < nchunks) {
-      const uint4 sm = __ldg(sum + g0 + lane);
-      if (sm.x == 0xffffffffu) live = true;  // touches more than two words: always walk it
+      const uint4 sm = __ldg(sum + 2 * (g0 + lane));
+      if (sm.x == 0xffffffffu) live = true;  // touches more than four words: always walk it
       else {
         live = (row[sm.x] & sm.y) != 0;
-        if (!live && sm.z != 0xffffffffu) live = (row[sm.z] & sm.w) != 0;
+        if (!live && sm.z != 0xffffffffu) {
+          live = (row[sm.z] & sm.w) != 0;
+          const uint4 sn2 = __ldg(sum + 2 * (g0 + lane) + 1);
+          if (!live && sn2.x != 0xffffffffu) live = (row[sn2.x] & sn2.y) != 0;
+          if (!live && sn2.z != 0xffffffffu) live = (row[sn2.z] & sn2.w) != 0;
+        }
       }
     }
     unsigned lm = __ballot_sync(0xffffffffu, live);
@@ -484,6 +494,97 @@ __global__ void __launch_bounds__(kThreads) k_row_totals(const RowArgs a) {
     }
   }
   if (!EMIT && lane == 0) {
+    a.row_total[sslot] = total;
+    a.row_count[sslot] = count;
+  }
+}
+
+// pass 2, lane = row: one warp sums 32 consecutive source rows of one cluster at once.  The rows share the cluster's
+// candidate list, and neighbouring sources accept nearly the same receivers, so the warp walks the list once, skips a
+// 32-candidate chunk when none of its 32 rows has an accept bit in it, and otherwise visits only the candidates some
+// row accepts: their receiver is staged in shared memory and every lane that accepts it adds its own form factor to
+// its own serial sum (qrad3.c:254) -- the sums of 32 rows advance together instead of one shuffle + add per transfer
+// with 31 lanes looking on (k_row_totals, kept for the download path: 206 ms on C5 against ~40 ms here).
+__global__ void __launch_bounds__(kThreads) k_row_totals32(const RowArgs a) {
+  __shared__ float4 s_po[kWarpsPerBlock][32], s_pn[kWarpsPerBlock][32];
+  __shared__ uint32_t s_pos[kWarpsPerBlock][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int sslot0 = a.slot_lo + (blockIdx.x * kWarpsPerBlock + wid) * 32;
+  if (sslot0 >= a.slot_hi) return;
+  const int sslot = sslot0 + lane;
+  const int c = a.slot_cluster[sslot0];              // a 32-slot slice lies in one cluster
+  const bool live_row = a.slot_patch[sslot] >= 0;
+  const uint32_t *row = a.bits + a.bits_base[c] + (int64_t) (sslot - a.cl_slot_start[c]) * a.nwords[c];
+  const float4 so = a.s_origin_area[sslot];
+  const float4 sn = a.s_normal[sslot];
+  const int64_t l0 = a.Lptr[c], l1 = a.Lptr[c + 1];
+  const int64_t nchunks = (l1 - l0 + 31) >> 5;
+  const uint4 *sum = a.L_sum + 2 * a.chunk_base[c];
+  float total = 0.f;
+  int count = 0;
+  uint4 sa_n = make_uint4(0, 0, 0, 0), sb_n = sa_n;
+  if (nchunks > 0) {
+    sa_n = __ldg(sum);
+    sb_n = __ldg(sum + 1);
+  }
+  for (int64_t g = 0; g < nchunks; g++) {
+    const uint4 sa = sa_n, sb = sb_n;
+    if (g + 1 < nchunks) {
+      sa_n = __ldg(sum + 2 * (g + 1));
+      sb_n = __ldg(sum + 2 * (g + 1) + 1);
+    }
+    const bool cx = sa.x == 0xffffffffu;             // chunk touches more than four row words
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;         // this row's accept bits in the chunk's words
+    if (!cx) {
+      if (live_row) {
+        a0 = row[sa.x] & sa.y;
+        if (sa.z != 0xffffffffu) a1 = row[sa.z] & sa.w;
+        if (sb.x != 0xffffffffu) a2 = row[sb.x] & sb.y;
+        if (sb.z != 0xffffffffu) a3 = row[sb.z] & sb.w;
+      }
+      if (!__any_sync(0xffffffffu, (a0 | a1 | a2 | a3) != 0)) continue;
+    }
+    // stage the chunk's candidates: lane k holds candidate k; s_pos = which of the four words << 5 | bit
+    const int64_t k = l0 + (g << 5) + lane;
+    const bool have = k < l1;
+    const uint32_t rslot = have ? a.L_slot[k] : 0u;
+    const uint32_t pos = have ? a.L_pos[k] : 0u;
+    const uint32_t w = pos >> 5;
+    const uint32_t t = w == sa.x ? 0u : (w == sa.z ? 1u : (w == sb.x ? 2u : 3u));
+    __syncwarp();
+    s_pos[wid][lane] = cx ? pos : (t << 5 | (pos & 31));
+    s_po[wid][lane] = a.s_origin_area[rslot];
+    s_pn[wid][lane] = a.s_normal[rslot];
+    __syncwarp();
+    // candidates accepted by at least one of the 32 rows
+    unsigned hot;
+    if (!cx) {
+      const uint32_t u0 = __reduce_or_sync(0xffffffffu, a0), u1 = __reduce_or_sync(0xffffffffu, a1);
+      const uint32_t u2 = __reduce_or_sync(0xffffffffu, a2), u3 = __reduce_or_sync(0xffffffffu, a3);
+      const uint32_t u = t == 0 ? u0 : (t == 1 ? u1 : (t == 2 ? u2 : u3));
+      hot = __ballot_sync(0xffffffffu, have && ((u >> (pos & 31)) & 1u));
+    } else
+      hot = __ballot_sync(0xffffffffu, have);
+    while (hot) {
+      const int kk = __ffs(hot) - 1;
+      hot &= hot - 1;
+      const uint32_t pk = s_pos[wid][kk];   // the same for every lane
+      uint32_t word;
+      if (!cx) {
+        const uint32_t tk = pk >> 5;
+        word = tk == 0 ? a0 : (tk == 1 ? a1 : (tk == 2 ? a2 : a3));
+      } else
+        word = live_row ? row[pk >> 5] : 0u;
+      if ((word >> (pk & 31)) & 1u) {
+        float dist;
+        bool wr;
+        const float trans = form_factor_pre(so, sn, s_po[wid][kk], s_pn[wid][kk], dist, wr);
+        total += trans;
+        count++;
+      }
+    }
+  }
+  if (live_row) {
     a.row_total[sslot] = total;
     a.row_count[sslot] = count;
   }
@@ -1063,7 +1164,7 @@ void transfers_rows(qrad_cuda_ctx *c) {
     std::vector<int64_t> chunk_base((size_t) nc + 1, 0);
     for (int k = 0; k < nc; k++) chunk_base[k + 1] = chunk_base[k] + ((c->h_Lptr[k + 1] - c->h_Lptr[k] + 31) >> 5);
     c->d_chunk_base.upload(chunk_base, st);
-    c->L_sum.alloc((size_t) chunk_base[nc] + 1);
+    c->L_sum.alloc((size_t) 2 * chunk_base[nc] + 2);
     const int c_lo = c->slice_hi > c->slice_lo ? c->h_slot_cluster[(size_t) c->slice_lo * 32] : 0;
     const int c_hi = c->slice_hi > c->slice_lo ? c->h_slot_cluster[(size_t) c->slice_hi * 32 - 1] : -1;
     const int64_t ch_lo = chunk_base[c_lo], ch_hi = c_hi >= c_lo ? chunk_base[c_hi + 1] : chunk_base[c_lo];
@@ -1101,10 +1202,10 @@ void transfers_rows(qrad_cuda_ctx *c) {
     ra.slot_hi = c->slice_hi * 32;
     ra.row_total = c->row_total.p;
     ra.row_count = c->row_count.p;
-    const int rows = ra.slot_hi - ra.slot_lo;
+    const int rows = ra.slot_hi - ra.slot_lo;   // whole 32-slot slices
     if (rows > 0) {
-      k_row_totals<false><<<(rows + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(ra);
-      c->launch_check("k_row_totals");
+      k_row_totals32<<<(rows / 32 + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(ra);
+      c->launch_check("k_row_totals32");
     }
   }
   c->sync("make_transfers pass 2");
