@@ -611,49 +611,101 @@ struct ColArgs {
   const uint32_t *bits;
   const float *row_total;
   int M;
-  const int32_t *blk_slice0;     // per block: first slice (8 consecutive slices of ONE cluster per block)
-  const int32_t *blk_n;          // per block: slices in use (1..8)
+  const int32_t *blk_slice0;     // k_columns, per block: first slice (up to 8 consecutive slices of ONE cluster)
+  const int32_t *blk_n;          // per block: slices (1..8)
   int32_t *slice_len;            // count mode output: list entries of the slice
   const int64_t *slice_base;     // fill mode: first entry of the slice (multiple of 32)
   uint32_t *g_src;               // [entries]      source slot
   uint4 *g_w;                    // [entries / 8][32] 8 x u16 weights per lane
 };
 
-template <int MODE>  // 0 = count, 1 = fill
+// pass 3a: list lengths.  One block per receiver cluster, lane = SOURCE: per batch of 32 sources a lane reads the
+// words of its source row for up to 32 slices of the cluster back to back (consecutive sectors of one row, used
+// completely) and the warp counts the non-zero words per slice with one ballot each; lane j keeps the count of slice
+// j; the 8 warps of the block take every 8th batch.  Measured on C5 (profiles/r01k_full_c5_columns.txt): counting with
+// one word per lane and slice reads the 26.7 GB matrix ten times over from HBM.
+__global__ void __launch_bounds__(kThreads) k_column_counts(const ColArgs a, const int c_first, const int slice_lo,
+                                                            const int slice_hi) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int d = c_first + blockIdx.x;
+  const int cs0 = a.cl_slot_start[d] >> 5, cs1 = a.cl_slot_start[d + 1] >> 5;   // the cluster's slices
+  const int s_lo = max(cs0, slice_lo), s_hi = min(cs1, slice_hi);               // ... that belong to this rank
+  const int64_t r0 = a.Rptr[d], r1 = a.Rptr[d + 1];
+  constexpr int64_t kStep = 32 * kWarpsPerBlock;
+  for (int p0 = s_lo; p0 < s_hi; p0 += 32) {             // passes of 32 slices (one for all but huge clusters)
+    const int np = min(32, s_hi - p0);
+    const int woff = p0 - cs0;
+    int mycnt = 0;
+    const int64_t first = r0 + wid * 32 + lane;
+    int64_t addr_n = first < r1 ? a.R_addr[first] : -1;
+    for (int64_t k = first; k - lane < r1; k += kStep) {   // k - lane is warp-uniform
+      const int64_t addr = addr_n;
+      addr_n = k + kStep < r1 ? a.R_addr[k + kStep] : -1;
+      for (int j0 = 0; j0 < np; j0 += 8) {
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) w[j] = (addr >= 0 && j0 + j < np) ? __ldcs(a.bits + addr + woff + j0 + j) : 0u;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int cnt = __popc(__ballot_sync(0xffffffffu, w[j] != 0));
+          if (lane == j0 + j) mycnt += cnt;
+        }
+      }
+    }
+    if (lane < np && mycnt) atomicAdd(a.slice_len + p0 + lane, mycnt);
+  }
+}
+
+// pass 3b: the lists.  One warp per slice, lane = receiver; the 8 warps of a block own 8 neighbouring slices of one
+// cluster and walk the cluster's source list together, re-aligned by a barrier every 16 batches of 32 sources, so
+// that the words they fetch for one source (one 32-byte sector) come from HBM once and are then served by L1 -- a
+// warp per slice on its own reads the matrix 25 times over (profiles/r01k_full_c5_columns.txt: 661 GB, HBM-bound),
+// and a barrier per batch makes every warp wait for the one with the most entries.
+// Sources are taken 32 at a time: lane k fetches the word of source k (addresses and words are requested two / one
+// batch ahead); when some word is non-zero the sources that own one are staged in shared memory (origin, normal, row
+// total: one gather per batch instead of a dependent L2 round trip per list entry), and the warp then emits the
+// entries in source order.
 __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
-  // The 8 warps of a block own 8 neighbouring slices of one cluster and step through the cluster's source list
-  // together (__syncthreads per 32 sources): the words they fetch for one source share a 32-byte sector, so it is
-  // fetched from HBM once instead of once per slice (ncu before: DRAM read = 25x the bit matrix, r01g_full_c5chop16).
-  const int lane = threadIdx.x & 31;
+  __shared__ float4 s_so[kWarpsPerBlock][32], s_sn[kWarpsPerBlock][32];
+  __shared__ float s_rt[kWarpsPerBlock][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int slice0 = a.blk_slice0[blockIdx.x];
-  const bool active = (int) (threadIdx.x >> 5) < a.blk_n[blockIdx.x];
-  const int slice = slice0 + (active ? (int) (threadIdx.x >> 5) : 0);
+  const bool active = wid < a.blk_n[blockIdx.x];
+  const int slice = slice0 + (active ? wid : 0);
   const int rslot = slice * 32 + lane;
   const int d = a.slot_cluster[slice0 * 32];           // all slots of the block share the cluster
   const int wslice = (slice * 32 - a.cl_slot_start[d]) >> 5;
   const bool valid = active && a.slot_patch[rslot] >= 0;
   float4 po = make_float4(0, 0, 0, 0), pn = po;
-  if (valid && MODE) {
+  if (valid) {
     po = a.s_origin_area[rslot];
     pn = a.s_normal[rslot];
   }
   const int64_t r0 = a.Rptr[d], r1 = a.Rptr[d + 1];
   int n = 0;                                           // list entries so far (uniform)
-  const int64_t base = MODE ? a.slice_base[slice] : 0;
+  const int64_t base = a.slice_base[slice];
   uint32_t wq[4] = {0, 0, 0, 0};                       // this lane's weights of the current group of 8 entries
-  for (int64_t k0 = r0; k0 < r1; k0 += 32) {
-    __syncthreads();
-    const int64_t k = k0 + lane;
-    uint32_t word = 0, sslot = 0;
-    if (k < r1 && active) {
-      if (MODE) sslot = a.R_slot[k];
-      word = a.bits[a.R_addr[k] + wslice];
-    }
+  // pipeline: addresses two batches ahead, words one batch ahead
+  int64_t addr_n = (active && r0 + lane < r1) ? a.R_addr[r0 + lane] : -1;
+  uint32_t word_n = addr_n >= 0 ? a.bits[addr_n + wslice] : 0u;
+  addr_n = (active && r0 + 32 + lane < r1) ? a.R_addr[r0 + 32 + lane] : -1;
+  int batch = 0;
+  for (int64_t k0 = r0; k0 < r1; k0 += 32, batch++) {
+    if ((batch & 15) == 0) __syncthreads();
+    const uint32_t word = word_n;
+    word_n = addr_n >= 0 ? a.bits[addr_n + wslice] : 0u;
+    addr_n = (active && k0 + 64 + lane < r1) ? a.R_addr[k0 + 64 + lane] : -1;
     unsigned nz = __ballot_sync(0xffffffffu, word != 0);
-    if (MODE == 0) {
-      n += __popc(nz);
-      continue;
+    if (nz == 0) continue;
+    uint32_t sslot = 0;
+    __syncwarp();
+    if (word != 0) {
+      sslot = a.R_slot[k0 + lane];
+      s_so[wid][lane] = a.s_origin_area[sslot];
+      s_sn[wid][lane] = a.s_normal[sslot];
+      s_rt[wid][lane] = a.row_total[sslot];
     }
+    __syncwarp();
     while (nz) {
       const int src = __ffs(nz) - 1;
       nz &= nz - 1;
@@ -661,12 +713,10 @@ __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
       const uint32_t ss = __shfl_sync(0xffffffffu, sslot, src);
       uint32_t itrans = 0;
       if ((w >> lane) & 1u) {
-        const float4 so = a.s_origin_area[ss];
-        const float4 sn = a.s_normal[ss];
         float dist;
         bool wr;
-        const float trans = form_factor_pre(so, sn, po, pn, dist, wr);
-        itrans = (uint32_t) (int) (trans * 65536.0f / a.row_total[ss]) & 0xffffu;   // u16 store wraps (qrad3.c:283-285)
+        const float trans = form_factor_pre(s_so[wid][src], s_sn[wid][src], po, pn, dist, wr);
+        itrans = (uint32_t) (int) (trans * 65536.0f / s_rt[wid][src]) & 0xffffu;   // u16 store wraps (qrad3.c:283-285)
       }
       const int q = n & 7;
       wq[q >> 1] |= itrans << ((q & 1) * 16);
@@ -678,10 +728,7 @@ __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
       }
     }
   }
-  if (!active) return;
-  if (MODE == 0) {
-    if (lane == 0) a.slice_len[slice] = n;
-  } else if (n & 7) {
+  if (active && (n & 7)) {
     // last, partial group; the rest of the 32-entry batch stays zero (source slot 0, zero weights: buffers are cleared)
     a.g_w[((base + n) / 8) * 32 + lane] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
   }
@@ -1252,8 +1299,11 @@ void transfers_columns(qrad_cuda_ctx *c) {
   ca.blk_slice0 = c->col_blk_slice0.p;
   ca.blk_n = c->col_blk_n.p;
   ca.slice_len = c->slice_len.p;
-  if (cblocks > 0) k_columns<0><<<cblocks, kThreads, 0, st>>>(ca);
-  c->launch_check("k_columns<count>");
+  if (c->slice_hi > c->slice_lo) {   // slice_len was cleared above
+    const int c_lo = c->h_slot_cluster[(size_t) c->slice_lo * 32], c_hi = c->h_slot_cluster[(size_t) c->slice_hi * 32 - 1];
+    k_column_counts<<<c_hi - c_lo + 1, kThreads, 0, st>>>(ca, c_lo, c->slice_lo, c->slice_hi);
+  }
+  c->launch_check("k_column_counts");
   std::vector<int32_t> h_len((size_t) nslices);
   c->slice_len.download(h_len.data(), (size_t) nslices, st);
   std::vector<int64_t> h_slice_base((size_t) nslices + 1, 0);
@@ -1279,8 +1329,8 @@ void transfers_columns(qrad_cuda_ctx *c) {
   ca.slice_base = c->slice_base.p;
   ca.g_src = c->g_src.p;
   ca.g_w = c->g_w.p;
-  if (cblocks > 0) k_columns<1><<<cblocks, kThreads, 0, st>>>(ca);
-  c->launch_check("k_columns<fill>");
+  if (cblocks > 0) k_columns<<<cblocks, kThreads, 0, st>>>(ca);
+  c->launch_check("k_columns");
   std::vector<int32_t> h_rc((size_t) M);
   c->row_count.download(h_rc.data(), (size_t) M, st);
   int64_t nnz = 0;
