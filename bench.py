@@ -310,8 +310,12 @@ def main():
                     "algorithmic_bytes_per_launch": alg_bytes, "stored_bytes_per_launch": stored_bytes,
                     "stored_gbs": stored_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else 0.0,
                     "stored_frac": stored_bytes / (kb_ms * 1e-3) / 1e9 / peak if kb_ms > 0 else 0.0,
-                    "note": "achieved = algorithmic bytes (nnz*b + 64*N, SURVEY 8d) / CUDA-event time; the stored layout "
-                            "is 3.6 B per transfer on this map, so stored_frac is the real HBM utilisation",
+                    "note": "achieved = algorithmic bytes (nnz*b + 64*N, SURVEY 8d) / CUDA-event time of k_bounce. The "
+                            "stored dense-slice layout is smaller than the algorithmic record (3.6 B against 6 B per "
+                            "transfer on C5), so frac can exceed 1; stored_frac = bytes the launch really streams / time "
+                            "/ peak is the HBM utilisation, and traffic is ncu's DRAM bytes of one launch. The step "
+                            "is dominated by k_visibility (trace_kernel_ms), which is instruction-issue bound, not "
+                            "HBM bound: see trace_rays_per_s and profiles/",
                     "ms_per_launch": kb_ms, "launches_per_step": p.numbounce, "per_gpu": world > 1}
         prof = ROOT / "profiles" / "bounce_traffic.json"
         if prof.exists():

@@ -7,17 +7,18 @@
 //   pass 1  k_visibility   one warp per task (1 source x <= 1024 receivers, PVS pruning is structural):
 //                          whole-word interval proofs, form factor sign tests, blocker-guess walks, full
 //                          TestLine for the rest; writes the accept bit  trans > 0  (qrad3.c:216-257).
-//   pass 2  k_row_totals   one warp per source row: walks the row in ascending receiver index
-//                          (the reference's j order) and forms the SERIAL float sum `total`
-//                          (qrad3.c:254) and numtransfers.
-//   pass 3  k_columns      one warp per 32 receivers (slice): walks the potential sources in ascending
+//   pass 2  k_row_totals32 one warp per 32 source rows of a cluster, lane = row: walks the shared candidate list in
+//                          ascending receiver index (the reference's j order); every lane forms the SERIAL float
+//                          sum `total` (qrad3.c:254) and numtransfers of its own row.
+//   pass 3  k_column_counts / k_columns
+//                          one warp per 32 receivers (slice): walks the potential sources in ascending
 //                          patch index, reads ONE word per source, and emits the quantised weights
 //                          (int)(trans * 0x10000 / total)  (qrad3.c:283) as "dense slice" lists -- the
 //                          transposed (gather) form ShootLight's scatter needs (finding F7), already in
 //                          the source order the reference adds them.
-//   bounce  k_bounce       one warp per slice, lane = receiver, 128-bit loads of 8 weights per lane,
-//                          radiosity vectors broadcast by shuffles, serial accumulation in source order,
-//                          CollectLight fused.
+//   bounce  k_bounce       persistent warps, one slice at a time, lane = receiver, 128-bit loads of 8 weights per
+//                          lane, radiosity vectors broadcast from shared memory, packed multiplies, serial
+//                          accumulation in source order, CollectLight fused.
 //
 // Multi-GPU: every phase takes this rank's share (task granules / slices); the host exchanges in between
 // (qrad_cuda_make_transfers_phase, qrad_cuda_bounce_phase, qrad_cuda_exchange_buffer).
