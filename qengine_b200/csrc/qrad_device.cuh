@@ -486,7 +486,7 @@ struct qrad_cuda_ctx {
   qrad::DBuf<int32_t> col_blk_slice0, col_blk_n;   // k_columns block table
   qrad::DBuf<int32_t> slice_order;      // this rank's slices, longest list first (k_bounce work order)
   qrad::DBuf<int32_t> bounce_next;      // [2] k_bounce work counters
-  int bounce_blocks_per_sm = 0;
+  int bounce_blocks_per_sm = 0, bounce_regs_blocks_per_sm = 0;
   // row-major helper lists kept for inspection / download
   std::vector<int64_t> h_Lptr, h_bits_base;
   std::vector<int32_t> h_nwords;

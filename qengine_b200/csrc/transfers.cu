@@ -27,6 +27,7 @@
 // with -fmad=false.
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include "qrad_device.cuh"
@@ -778,27 +779,174 @@ __device__ __forceinline__ float4 ld_vec_f4(const float4 *p) {
   return v;
 }
 
+// ---- bulk-copy ring of k_bounce (sm_90+ PTX: cp.async.bulk + mbarrier complete_tx) ----
+constexpr int kBounceStages = 3;                    // batches resident per warp: one in use, two in flight
+constexpr int kBounceStageBytes = 2048 + 128;       // 32 entries: 32 lanes x 4 x 16 B of weights, 32 source slots
+constexpr int kBounceWarpBytes = 7424;              // stages + parked vectors (2 x 96 floats) + mbarriers, 128-aligned
+constexpr int kBounceVecOfs = kBounceStages * kBounceStageBytes;
+constexpr int kBounceBarOfs = kBounceVecOfs + 2 * 96 * 4;
+static_assert(kBounceBarOfs + kBounceStages * 8 <= kBounceWarpBytes, "k_bounce shared memory layout");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(const uint32_t bar, const uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(const uint32_t bar, const uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(const uint32_t dst, const void *src, const uint32_t bytes, const uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t parity) {
+  uint32_t ok = 0;
+  for (unsigned spins = 0; !ok; spins++) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (spins > (1u << 28)) __trap();   // a copy that never lands is a bug: fail loudly instead of hanging the GPU
+  }
+}
+
 // ShootLight (as a gather) + CollectLight.  One warp per slice, lane = receiver; the list is walked in order, so
 // every receiver accumulates its transfers in ascending source order like the reference's serial loop:
 // illumination[j][l] += send[l] * trans->transfer (qrad3.c:439), mul and add rounded separately.  A zero weight adds
 // +-0 and leaves the sum unchanged (the sum starts at +0 and never becomes -0).
-// The list is consumed in batches of 32 entries (4 groups of 8): lane l fetches source slot l of the batch (one
-// coalesced 128-byte load) and gathers its radiosity vector, every lane fetches its 4 x 8 weights with four 128-bit
-// loads (2 KB contiguous per warp).  The loads of batch b + 1 are written ahead of the arithmetic of batch b, but ptxas
-// places them at the end of the batch and keeps ONE set of weight registers: 48 registers, 40 resident warps per SM,
-// and it is the other warps that cover the HBM latency (measured: 3.2 ms per bounce on C5 = 6.26 TB/s of stored
-// matrix, 96 % of the measured copy bandwidth; the 78-register version with both sets live ran at 4.9 ms).
-// The prefetch is unconditional: g_src / g_w are padded by two batches / one batch and hold valid slots.
-// Instruction diet (the r01g kernel issued 12 instructions per list entry -- 3 shuffles, 3 unpack/convert, 3 FMUL,
-// 3 FADD -- and sat at 58 % of the issue rate with HBM at 54 %, profiles/r01g_full_c5_k_bounce.txt): the 32 vectors of
-// a batch are parked in shared memory channel-major (x[32] y[32] z[32], conflict-free stores), so FOUR entries cost
-// three broadcast 128-bit loads, four byte permutes + two packed subtracts for their weights, six packed multiplies
-// (sm_100 FMUL2: two entries of a channel at once) and twelve scalar adds, which keep the serial order: 6.75
-// instructions per entry.  (Packed adds are not used: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even
-// under -fmad=false, which would change the rounding.)
+// Data movement: the list is consumed in batches of 32 entries = 2 KB of weights + 128 B of source slots, contiguous
+// in HBM.  Each warp owns a ring of three batch buffers in shared memory; lane 0 refills a buffer with two bulk async
+// copies (cp.async.bulk, completion counted on an mbarrier) as soon as the warp has consumed it, so two batches are
+// always in flight per warp without holding a register, and the radiosity vectors of the next batch are gathered while
+// the current one is summed.  This matters when a GPU has few slices (8-GPU shard: 3 900 slices on 148 SMs): the
+// kernel then lasts as long as its longest list, i.e. as fast as ONE warp can stream (the register-prefetch version
+// took 2.0 ms for 2.5 GB per GPU at 8 GPUs because ptxas sinks the loads next to their use).
+// Arithmetic (the r01g kernel issued 12 instructions per list entry -- 3 shuffles, 3 unpack/convert, 3 FMUL, 3 FADD --
+// and sat at 58 % of the issue rate with HBM at 54 %, profiles/r01g_full_c5_k_bounce.txt): the 32 vectors of a batch
+// are parked in shared memory channel-major (x[32] y[32] z[32], conflict-free stores), so FOUR entries cost three
+// broadcast 128-bit loads, four byte permutes + two packed subtracts for their weights, six packed multiplies (sm_100
+// FMUL2: two entries of a channel at once) and twelve scalar adds, which keep the serial order: 6.75 instructions per
+// entry.  (Packed adds are not used: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under
+// -fmad=false, which would change the rounding.)
 // Slices are handed out longest-first from a work counter (persistent warps): with one block per 8 consecutive
 // slices only 16 of 24 resident warps were alive on average (profiles/r01i_full_c5_k_bounce.txt).
 __global__ void __launch_bounds__(kThreads) k_bounce(const BounceArgs a) {
+  extern __shared__ __align__(128) unsigned char s_bounce[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned char *const wbase = s_bounce + wid * kBounceWarpBytes;
+  float *const s_vec = reinterpret_cast<float *>(wbase + kBounceVecOfs);
+  const uint32_t stage0 = smem_u32(wbase), bar0 = stage0 + kBounceBarOfs;
+  if (lane == 0) {
+    for (int s = 0; s < kBounceStages; s++) mbar_init(bar0 + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.next[a.parity ^ 1] = 0;
+  const int nslices = a.slice_hi - a.slice_lo;
+  uint32_t gb = 0;   // batches this warp has consumed so far: batch gb + i lives in buffer (gb + i) % stages
+  for (;;) {
+    int k = 0;
+    if (lane == 0) k = atomicAdd(a.next + a.parity, 1);
+    k = __shfl_sync(0xffffffffu, k, 0);     // also: every lane is done with the previous slice's shared memory
+    if (k >= nslices) break;
+    const int slice = a.order[k];
+    const int slot = slice * 32 + lane;
+    const int64_t base = a.slice_base[slice];
+    const int batches = (a.slice_len[slice] + 31) >> 5;
+    const uint32_t *const ps = a.g_src + base;
+    const uint4 *const pw = a.g_w + (base >> 3) * 32;
+    auto issue = [&](const int i) {   // lane 0: start the copies of batch i of this slice
+      const uint32_t s = (gb + (uint32_t) i) % kBounceStages;
+      const uint32_t dst = stage0 + s * kBounceStageBytes, bar = bar0 + 8 * s;
+      mbar_expect_tx(bar, kBounceStageBytes);
+      bulk_g2s(dst, pw + (int64_t) i * 128, 2048, bar);
+      bulk_g2s(dst + 2048, ps + (int64_t) i * 32, 128, bar);
+    };
+    auto arrived = [&](const int i) {   // wait for batch i and return this lane's source slot of it
+      const uint32_t u = gb + (uint32_t) i, s = u % kBounceStages;
+      mbar_wait(bar0 + 8 * s, (u / kBounceStages) & 1u);
+      return *reinterpret_cast<const uint32_t *>(wbase + s * kBounceStageBytes + 2048 + lane * 4);
+    };
+    if (lane == 0)
+      for (int i = 0; i < kBounceStages && i < batches; i++) issue(i);
+    float ix = 0.f, iy = 0.f, iz = 0.f;
+    float4 nx = make_float4(0, 0, 0, 0);      // radiosity vector of entry `lane` of the next batch
+    if (batches > 0) nx = __ldg(a.send + arrived(0));
+// entries 4Q .. 4Q+3 of the batch: W0 holds the weights of the first two, W1 of the last two
+#define QRAD_QUAD(Q, W0, W1)                                                         \
+  do {                                                                               \
+    const float4 vx = *reinterpret_cast<const float4 *>(sv + (Q) * 4);               \
+    const float4 vy = *reinterpret_cast<const float4 *>(sv + 32 + (Q) * 4);          \
+    const float4 vz = *reinterpret_cast<const float4 *>(sv + 64 + (Q) * 4);          \
+    const float2 f0 = u16x2_to_float2(W0), f1 = u16x2_to_float2(W1);                 \
+    const float2 px0 = __fmul2_rn(make_float2(vx.x, vx.y), f0);                      \
+    const float2 py0 = __fmul2_rn(make_float2(vy.x, vy.y), f0);                      \
+    const float2 pz0 = __fmul2_rn(make_float2(vz.x, vz.y), f0);                      \
+    const float2 px1 = __fmul2_rn(make_float2(vx.z, vx.w), f1);                      \
+    const float2 py1 = __fmul2_rn(make_float2(vy.z, vy.w), f1);                      \
+    const float2 pz1 = __fmul2_rn(make_float2(vz.z, vz.w), f1);                      \
+    ix = ix + px0.x;                                                                 \
+    iy = iy + py0.x;                                                                 \
+    iz = iz + pz0.x;                                                                 \
+    ix = ix + px0.y;                                                                 \
+    iy = iy + py0.y;                                                                 \
+    iz = iz + pz0.y;                                                                 \
+    ix = ix + px1.x;                                                                 \
+    iy = iy + py1.x;                                                                 \
+    iz = iz + pz1.x;                                                                 \
+    ix = ix + px1.y;                                                                 \
+    iy = iy + py1.y;                                                                 \
+    iz = iz + pz1.y;                                                                 \
+  } while (0)
+    for (int b = 0; b < batches; b++) {
+      // park the vectors of batch b (double buffered: the other half may still be read by slower lanes)
+      float *const sv = s_vec + (b & 1) * 96;
+      sv[lane] = nx.x;
+      sv[32 + lane] = nx.y;
+      sv[64 + lane] = nx.z;
+      __syncwarp();
+      if (b + 1 < batches) nx = __ldg(a.send + arrived(b + 1));   // gather one batch ahead
+      const uint4 *const cw = reinterpret_cast<const uint4 *>(wbase + ((gb + (uint32_t) b) % kBounceStages) * kBounceStageBytes) + lane;
+      const uint4 c0 = cw[0], c1 = cw[32], c2 = cw[64], c3 = cw[96];
+      QRAD_QUAD(0, c0.x, c0.y);
+      QRAD_QUAD(1, c0.z, c0.w);
+      QRAD_QUAD(2, c1.x, c1.y);
+      QRAD_QUAD(3, c1.z, c1.w);
+      QRAD_QUAD(4, c2.x, c2.y);
+      QRAD_QUAD(5, c2.z, c2.w);
+      QRAD_QUAD(6, c3.x, c3.y);
+      QRAD_QUAD(7, c3.z, c3.w);
+      __syncwarp();   // every lane holds its weights of batch b in registers: the buffer may be refilled
+      if (lane == 0 && b + kBounceStages < batches) issue(b + kBounceStages);
+    }
+#undef QRAD_QUAD
+    gb += (uint32_t) batches;
+    // CollectLight, qrad3.c:383-409
+    const float4 ra = a.refl_area[slot];
+    float4 t = a.total[slot];
+    float rx = 0.f, ry = 0.f, rz = 0.f;
+    if (ra.w > 0) {  // not sky (and not a padding slot)
+      t.x += ix / ra.w;
+      t.y += iy / ra.w;
+      t.z += iz / ra.w;
+      rx = ix * ra.x;
+      ry = iy * ra.y;
+      rz = iz * ra.z;
+      a.total[slot] = t;
+    }
+    if (a.rad_sum) a.rad_sum[slot] = rx + ry + rz;
+    a.send_next[slot] = make_float4(rx / 65536.0f, ry / 65536.0f, rz / 65536.0f, 0.f);
+  }
+}
+
+// k_bounce with register prefetch instead of the bulk-copy ring: same arithmetic, same order; the weights of the next
+// batch are ordinary 128-bit streaming loads.  ptxas places them at the end of the batch and keeps ONE set of weight
+// registers (48 registers, 40 resident warps per SM), so it is the other warps that cover the HBM latency: the
+// faster kernel when a GPU has many slices per resident warp (one B200, C5: 3.2 ms per bounce = 6.26 TB/s of stored
+// matrix against 3.5 ms with the ring), the slower one when it has few (2 GPUs: 2.6 ms against 2.2 ms; 8 GPUs: 2.0 ms
+// for an eighth of the matrix).  bounce_step() picks by slices per resident warp.
+// The prefetch is unconditional: g_src / g_w are padded by two batches / one batch and hold valid slots.
+__global__ void __launch_bounds__(kThreads) k_bounce_regs(const BounceArgs a) {
   __shared__ __align__(16) float s_vec[kWarpsPerBlock][2][3 * 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (blockIdx.x == 0 && threadIdx.x == 0) a.next[a.parity ^ 1] = 0;
@@ -1440,8 +1588,11 @@ void bounce_begin(qrad_cuda_ctx *c, bool want_sum) {
   c->bounce_next.zero(st);
   if (c->bounce_blocks_per_sm == 0) {
     int per_sm = 0;
-    QCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce, kThreads, 0));
+    QCUDA(cudaFuncSetAttribute(k_bounce, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarpsPerBlock * kBounceWarpBytes));
+    QCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce, kThreads, kWarpsPerBlock * kBounceWarpBytes));
     c->bounce_blocks_per_sm = std::max(1, per_sm);
+    QCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce_regs, kThreads, 0));
+    c->bounce_regs_blocks_per_sm = std::max(1, per_sm);
   }
   c->sync("bounce_begin");
 }
@@ -1466,10 +1617,13 @@ void bounce_step(qrad_cuda_ctx *c) {
   a.parity = c->bounce_steps & 1;
   // persistent warps: as many blocks as fit on the chip, slices are drawn from the work counter
   const int want = std::max(1, (c->slice_hi - c->slice_lo + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  const int blocks = std::min(want, c->sm_count * c->bounce_blocks_per_sm);
   Timer tk;
   tk.start(st);
-  k_bounce<<<blocks, kThreads, 0, st>>>(a);
+  // few slices per resident warp: the launch lasts as long as ONE warp needs for the longest list -> bulk-copy ring
+  bool ring = (int64_t) (c->slice_hi - c->slice_lo) < (int64_t) 4 * c->sm_count * 40;
+  if (const char *force = getenv("QRAD_BOUNCE_KERNEL")) ring = strcmp(force, "regs") != 0;   // tests cover both
+  if (ring) k_bounce<<<std::min(want, c->sm_count * c->bounce_blocks_per_sm), kThreads, kWarpsPerBlock * kBounceWarpBytes, st>>>(a);
+  else k_bounce_regs<<<std::min(want, c->sm_count * c->bounce_regs_blocks_per_sm), kThreads, 0, st>>>(a);
   c->launch_check("k_bounce");
   c->bounce_kernel_ms += tk.stop();
   c->bounce_steps++;

@@ -58,6 +58,17 @@ def test_lump_identical_to_reference(Q, case, tmp_path):
     assert hashlib.md5(bsp.read_bytes()).hexdigest() == meta["file_md5"]
 
 
+@pytest.mark.parametrize("kernel", ["regs", "ring"])
+@pytest.mark.parametrize("case", ["samplec", "grid3_chop16", "manystyles"])
+def test_both_bounce_kernels(Q, case, kernel, tmp_path, monkeypatch):
+    """BounceLight has two kernels (register prefetch for many slices per warp, bulk-copy ring for few); the library
+    picks by problem size, QRAD_BOUNCE_KERNEL forces one.  Both must give the reference's bytes and energies."""
+    monkeypatch.setenv("QRAD_BOUNCE_KERNEL", kernel)
+    meta, sc, dev, added, bsp = light(Q, case, tmp_path)
+    assert sc.lighting() == (G.GOLDEN / (case + ".lump")).read_bytes()
+    assert np.array_equal(added, np.array(meta["added"], np.float32))
+
+
 @pytest.mark.parametrize("case", ["samplec", "grid2", "grid3_chop16", "hall"])
 def test_testline_decisions(Q, case, tmp_path):
     meta, flags = G.load_case(case)
