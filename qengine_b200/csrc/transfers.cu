@@ -27,6 +27,7 @@
 // with -fmad=false.
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cstdlib>
 #include <cstring>
 
@@ -752,6 +753,7 @@ struct BounceArgs {
   const int32_t *order;          // this rank's slices, longest list first
   int32_t *next;                 // [2] work counters: launch `parity` draws from next[parity] and clears the other
   int parity;
+  int slice_cut;                 // tools/bounce_shard_probe.py: slices >= slice_cut are skipped (INT_MAX otherwise)
 };
 
 // (float) lo16(W), (float) hi16(W) without the quarter-rate I2F: 0x4B000000 | w is the float 2^23 + w, exactly, so one
@@ -780,9 +782,9 @@ __device__ __forceinline__ float4 ld_vec_f4(const float4 *p) {
 }
 
 // ---- bulk-copy ring of k_bounce (sm_90+ PTX: cp.async.bulk + mbarrier complete_tx) ----
-constexpr int kBounceStages = 3;                    // batches resident per warp: one in use, two in flight
+constexpr int kBounceStages = 4;                    // batches resident per warp: one in use, three in flight
 constexpr int kBounceStageBytes = 2048 + 128;       // 32 entries: 32 lanes x 4 x 16 B of weights, 32 source slots
-constexpr int kBounceWarpBytes = 7424;              // stages + parked vectors (2 x 96 floats) + mbarriers, 128-aligned
+constexpr int kBounceWarpBytes = 9600;              // stages + parked vectors (2 x 96 floats) + mbarriers, 128-aligned
 constexpr int kBounceVecOfs = kBounceStages * kBounceStageBytes;
 constexpr int kBounceBarOfs = kBounceVecOfs + 2 * 96 * 4;
 static_assert(kBounceBarOfs + kBounceStages * 8 <= kBounceWarpBytes, "k_bounce shared memory layout");
@@ -850,6 +852,7 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const BounceArgs a) {
     k = __shfl_sync(0xffffffffu, k, 0);     // also: every lane is done with the previous slice's shared memory
     if (k >= nslices) break;
     const int slice = a.order[k];
+    if (slice >= a.slice_cut) continue;
     const int slot = slice * 32 + lane;
     const int64_t base = a.slice_base[slice];
     const int batches = (a.slice_len[slice] + 31) >> 5;
@@ -870,8 +873,11 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const BounceArgs a) {
     if (lane == 0)
       for (int i = 0; i < kBounceStages && i < batches; i++) issue(i);
     float ix = 0.f, iy = 0.f, iz = 0.f;
-    float4 nx = make_float4(0, 0, 0, 0);      // radiosity vector of entry `lane` of the next batch
+    // radiosity vectors of entry `lane` of the next two batches: gathered two batches ahead, so that a warp that has
+    // an SM to itself does not wait for an L2 round trip per batch
+    float4 nx = make_float4(0, 0, 0, 0), nx2 = nx;
     if (batches > 0) nx = __ldg(a.send + arrived(0));
+    if (batches > 1) nx2 = __ldg(a.send + arrived(1));
 // entries 4Q .. 4Q+3 of the batch: W0 holds the weights of the first two, W1 of the last two
 #define QRAD_QUAD(Q, W0, W1)                                                         \
   do {                                                                               \
@@ -905,7 +911,8 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const BounceArgs a) {
       sv[32 + lane] = nx.y;
       sv[64 + lane] = nx.z;
       __syncwarp();
-      if (b + 1 < batches) nx = __ldg(a.send + arrived(b + 1));   // gather one batch ahead
+      nx = nx2;
+      if (b + 2 < batches) nx2 = __ldg(a.send + arrived(b + 2));
       const uint4 *const cw = reinterpret_cast<const uint4 *>(wbase + ((gb + (uint32_t) b) % kBounceStages) * kBounceStageBytes) + lane;
       const uint4 c0 = cw[0], c1 = cw[32], c2 = cw[64], c3 = cw[96];
       QRAD_QUAD(0, c0.x, c0.y);
@@ -957,6 +964,7 @@ __global__ void __launch_bounds__(kThreads) k_bounce_regs(const BounceArgs a) {
     k = __shfl_sync(0xffffffffu, k, 0);     // also: every lane is done with the previous slice's shared memory
     if (k >= nslices) break;
     const int slice = a.order[k];
+    if (slice >= a.slice_cut) continue;
     const int slot = slice * 32 + lane;
     const int64_t base = a.slice_base[slice];
     const int batches = (a.slice_len[slice] + 31) >> 5;
@@ -1462,6 +1470,15 @@ void transfers_columns(qrad_cuda_ctx *c) {
     h_slice_base[s + 1] = h_slice_base[s] + ((h_len[s] + 31) & ~31);
   }
   c->sell_entries = h_slice_base[nslices];
+  if (getenv("QRAD_DEBUG_SLICES")) {   // list length statistics for tools/bounce_shard_probe.py
+    int mx = 0, mx8 = 0;
+    for (int s = 0; s < nslices; s++) {
+      mx = std::max(mx, h_len[s]);
+      if (s < nslices / 8) mx8 = std::max(mx8, h_len[s]);
+    }
+    fprintf(stderr, "slices %d, list entries: mean %.0f, longest %d, longest in the first eighth %d\n", nslices,
+            nslices ? (double) nzw / nslices : 0.0, mx, mx8);
+  }
   c->slice_base.upload(h_slice_base, st);
   {  // k_bounce hands this rank's slices to its warps longest list first
     std::vector<int32_t> order;
@@ -1615,12 +1632,18 @@ void bounce_step(qrad_cuda_ctx *c) {
   a.order = c->slice_order.p;
   a.next = c->bounce_next.p;
   a.parity = c->bounce_steps & 1;
+  a.slice_cut = INT_MAX;
+  int nsl = c->slice_hi - c->slice_lo;
+  if (const char *f = getenv("QRAD_DEBUG_BOUNCE_SHARD")) {   // time the launch an n-GPU shard would see, on one GPU
+    nsl = std::max(1, (int) (nsl * atof(f)));
+    a.slice_cut = c->slice_lo + nsl;
+  }
   // persistent warps: as many blocks as fit on the chip, slices are drawn from the work counter
   const int want = std::max(1, (c->slice_hi - c->slice_lo + kWarpsPerBlock - 1) / kWarpsPerBlock);
   Timer tk;
   tk.start(st);
   // few slices per resident warp: the launch lasts as long as ONE warp needs for the longest list -> bulk-copy ring
-  bool ring = (int64_t) (c->slice_hi - c->slice_lo) < (int64_t) 4 * c->sm_count * 40;
+  bool ring = (int64_t) nsl < (int64_t) 4 * c->sm_count * 40;
   if (const char *force = getenv("QRAD_BOUNCE_KERNEL")) ring = strcmp(force, "regs") != 0;   // tests cover both
   if (ring) k_bounce<<<std::min(want, c->sm_count * c->bounce_blocks_per_sm), kThreads, kWarpsPerBlock * kBounceWarpBytes, st>>>(a);
   else k_bounce_regs<<<std::min(want, c->sm_count * c->bounce_regs_blocks_per_sm), kThreads, 0, st>>>(a);
