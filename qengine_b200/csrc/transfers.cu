@@ -904,28 +904,36 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const BounceArgs a) {
     iy = iy + py1.y;                                                                 \
     iz = iz + pz1.y;                                                                 \
   } while (0)
-    for (int b = 0; b < batches; b++) {
-      // park the vectors of batch b (double buffered: the other half may still be read by slower lanes)
-      float *const sv = s_vec + (b & 1) * 96;
-      sv[lane] = nx.x;
-      sv[32 + lane] = nx.y;
-      sv[64 + lane] = nx.z;
-      __syncwarp();
-      nx = nx2;
-      if (b + 2 < batches) nx2 = __ldg(a.send + arrived(b + 2));
-      const uint4 *const cw = reinterpret_cast<const uint4 *>(wbase + ((gb + (uint32_t) b) % kBounceStages) * kBounceStageBytes) + lane;
-      const uint4 c0 = cw[0], c1 = cw[32], c2 = cw[64], c3 = cw[96];
-      QRAD_QUAD(0, c0.x, c0.y);
-      QRAD_QUAD(1, c0.z, c0.w);
-      QRAD_QUAD(2, c1.x, c1.y);
-      QRAD_QUAD(3, c1.z, c1.w);
-      QRAD_QUAD(4, c2.x, c2.y);
-      QRAD_QUAD(5, c2.z, c2.w);
-      QRAD_QUAD(6, c3.x, c3.y);
-      QRAD_QUAD(7, c3.z, c3.w);
-      __syncwarp();   // every lane holds its weights of batch b in registers: the buffer may be refilled
-      if (lane == 0 && b + kBounceStages < batches) issue(b + kBounceStages);
+// batch B: park its vectors V (double buffered: the other half may still be read by slower lanes), gather those of
+// batch B + 2 into the same registers, consume the weights, hand the buffer back.  Two register sets alternate, so no
+// instruction touches a gathered vector before it is parked (a register copy would wait for the load).
+#define QRAD_BATCH(B, V)                                                                                              \
+  do {                                                                                                                \
+    float *const sv = s_vec + ((B) & 1) * 96;                                                                         \
+    sv[lane] = V.x;                                                                                                   \
+    sv[32 + lane] = V.y;                                                                                              \
+    sv[64 + lane] = V.z;                                                                                              \
+    __syncwarp();                                                                                                     \
+    if ((B) + 2 < batches) V = __ldg(a.send + arrived((B) + 2));                                                      \
+    const uint4 *const cw =                                                                                           \
+        reinterpret_cast<const uint4 *>(wbase + ((gb + (uint32_t) (B)) % kBounceStages) * kBounceStageBytes) + lane;  \
+    const uint4 c0 = cw[0], c1 = cw[32], c2 = cw[64], c3 = cw[96];                                                    \
+    QRAD_QUAD(0, c0.x, c0.y);                                                                                         \
+    QRAD_QUAD(1, c0.z, c0.w);                                                                                         \
+    QRAD_QUAD(2, c1.x, c1.y);                                                                                         \
+    QRAD_QUAD(3, c1.z, c1.w);                                                                                         \
+    QRAD_QUAD(4, c2.x, c2.y);                                                                                         \
+    QRAD_QUAD(5, c2.z, c2.w);                                                                                         \
+    QRAD_QUAD(6, c3.x, c3.y);                                                                                         \
+    QRAD_QUAD(7, c3.z, c3.w);                                                                                         \
+    __syncwarp(); /* every lane holds its weights of batch B in registers: the buffer may be refilled */              \
+    if (lane == 0 && (B) + kBounceStages < batches) issue((B) + kBounceStages);                                       \
+  } while (0)
+    for (int b = 0; b < batches; b += 2) {
+      QRAD_BATCH(b, nx);
+      if (b + 1 < batches) QRAD_BATCH(b + 1, nx2);
     }
+#undef QRAD_BATCH
 #undef QRAD_QUAD
     gb += (uint32_t) batches;
     // CollectLight, qrad3.c:383-409

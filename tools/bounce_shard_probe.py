@@ -28,8 +28,10 @@ with tempfile.TemporaryDirectory() as tmp:
     os.environ["QRAD_DEBUG_SLICES"] = "1"
     dev.make_transfers(p.nopvs)
     full = dev.stats()["transfer_bytes"]
-    for frac in (1.0, 0.125, 0.01):
-        for kernel in ("regs", "ring"):
+    fracs = [float(x) for x in os.environ.get("PROBE_SHARDS", "1,0.5,0.25,0.125,0.01").split(",")]
+    kernels = os.environ.get("PROBE_KERNELS", "regs,ring").split(",")
+    for frac in fracs:
+        for kernel in kernels:
             os.environ["QRAD_DEBUG_BOUNCE_SHARD"] = str(frac)
             os.environ["QRAD_BOUNCE_KERNEL"] = kernel
             dev.bounce(4, want_added=False)
