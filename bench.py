@@ -296,6 +296,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
         d2h = len(lump) + counts["numfaces"] * 8
+        import hashlib
+        lump_md5 = hashlib.md5(bytes(lump)).hexdigest()   # the same at every GPU count: sharding changes no byte
 
         # ---- roofline of the dominant bandwidth kernel (k_bounce) ----
         peak, peak_src = measured_peak()
@@ -332,6 +334,7 @@ def main():
                        "faces": counts["numfaces"], "luxels": st["num_luxels"], "clusters": st["num_clusters"],
                        "transfers_nnz": st["total_transfers"], "rays_per_step": rays,
                        "l2_policy": "inputs larger than L2 / every phase recomputed each step",
+                       "lump_bytes": len(lump), "lump_md5": lump_md5,
                        "parallelism": f"rows x{world}"},
             "s_per_map": step_ms * 1e-3,
             "phase_ms": dict(zip(["facelights", "transfers", "bounce", "final"], [float(x) for x in np.mean(phase, axis=0)])),
