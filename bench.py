@@ -2,23 +2,27 @@
 """Benchmark of the qrad3 hot path (BASELINE.json metric) -- see DESIGN.md "Measurement".
 
 One step = lighting one map: BuildFacelights + MakeTransfers + BounceLight + FinalLightFace.
-  value  : visibility + shadow rays per second of the device phases, inputs already resident in HBM
-           (BSP, patches, lights, faces uploaded before the timed region).  Maps are larger than L2 in
-           their transfer matrix; nothing is cached between steps (every step recomputes all phases).
-  e2e    : the same metric through the public C entry point qrad_rad_world() with HOST buffers: the
-           timed region contains every host->device upload and the device->host lump read-back.
-  roofline: the BounceLight gather SpMV (k_bounce), algorithmic bytes = nnz*b + 64*N per bounce
-            over its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline / --impl reference: the reference qrad3 (oracle/_ref, compiled from /root/reference)
-           on a bounded sample of the same generator family, 1 host core (the reference has no Linux
-           threading: SURVEY.md finding F2).
+  value   : visibility + shadow rays per second over the device phases, inputs already resident in HBM
+            (BSP, patches, lights, faces uploaded before the timed region).  Nothing is cached between steps
+            (every step recomputes all phases) and the transfer matrix is far larger than L2.
+  e2e     : the same metric through the drop-in's own call sequence with HOST buffers and FILES: the timed region is
+            qrad_host_load (LoadBSPFile + ParseEntities + CalcTextureReflectivity) + qrad_host_prepare (MakePatches,
+            SubdividePatches, CreateDirectLights) + qrad_rad_world (every upload, all device phases, lump read-back)
+            + qrad_host_write (WriteBSPFile) -- what `qrad3 map.bsp` does; bytes are counted by the library.
+  roofline: the BounceLight gather SpMV (k_bounce), the one HBM-bound kernel of the path, CUDA-event timed; plus
+            `roofline_visibility` for k_visibility, the kernel that is ~90 % of the step and is bound by instruction
+            issue, not by memory.
+  cpu_baseline / --impl reference: the REFERENCE's own MakeTransfers / BuildFacelights (oracle/_ref/ref_harness_big:
+            the reference translation units with the 65 000-patch limit lifted, byte-identical on every golden) on a
+            deterministic sample of the rows / faces of THE SAME MAP, 1 host core (the reference has no Linux
+            threading: SURVEY.md finding F2); rays are counted by the harness itself.
 
 Launch:  python bench.py [--gpus N --steps K --warmup W] ; N > 1 under torchrun (one rank per GPU).
 """
 from __future__ import annotations
 
 import argparse
-import gzip
+import hashlib
 import json
 import os
 import shutil
@@ -31,43 +35,11 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, str(ROOT / "tests"))
+
+from qengine_b200.workloads import DEFAULT_WORKLOAD, WORKLOADS, stage_workload  # noqa: E402
 
 METRIC = "qrad3 s/map; visibility+shadow rays/s; BounceLight SpMV GB/s vs HBM peak"
-MAPS = ROOT / "bench_maps"
-
-# name -> (bsp file, qrad3 flags, description)
-WORKLOADS = {
-    "c3_grid13": ("grid13r512.bsp", ["-bounce", "8", "-chop", "32"],
-                  "synthetic 13x13 grid of 512-unit rooms (~8k faces / ~150k patches; 14x14 exceeds MAX_MAP_LIGHTING), "
-                  "-chop 32, 8 bounces [BASELINE configs[2]]"),
-    "c5_grid16_chop8": ("grid16c128.bsp", ["-bounce", "16", "-chop", "8"],
-                        "synthetic 16x16 room grid, qbsp3 -chop 128, qrad3 -chop 8 (~1M patches), 16 bounces [configs[4]]"),
-    "c5_chop16": ("grid16c128.bsp", ["-bounce", "16", "-chop", "16"],
-                  "the C5 map at -chop 16 (~250k patches): profiling stand-in whose kernels fit an ncu replay"),
-    "c4_hall2000": ("hall2000.bsp", ["-bounce", "0", "-extra"],
-                    "synthetic direct-light stress hall: 2 000 light / light_spot entities, -extra, direct only [configs[3]]"),
-    "probe_grid10": ("grid10.bsp", ["-bounce", "8", "-chop", "32"],
-                     "synthetic 10x10 room grid (~37k patches), -chop 32, 8 bounces"),
-    "ref_sample_grid6": ("grid6.bsp", ["-bounce", "8", "-chop", "32"],
-                         "synthetic 6x6 room grid (~13k patches), -chop 32, 8 bounces (bounded CPU sample)"),
-}
-DEFAULT_WORKLOAD = "c5_grid16_chop8"
-REF_SAMPLE = "ref_sample_grid6"
-
-
-def stage_workload(name: str, tmp: Path) -> Path:
-    """Unpack bench_maps/<bsp>.gz into tmp/assets/maps with the synthetic palette/textures beside it."""
-    from qengine_b200 import mapgen
-    bspname, _, _ = WORKLOADS[name]
-    assets = mapgen.write_assets(tmp)
-    dst = assets / "maps" / bspname
-    src = MAPS / (bspname + ".gz")
-    if not src.exists():
-        raise SystemExit(f"{src} is missing (tools/build_bench_maps.py builds it with the reference qbsp3/qvis3)")
-    with gzip.open(src, "rb") as f, open(dst, "wb") as g:
-        shutil.copyfileobj(f, g)
-    return dst
+REF_HARNESS = ROOT / "oracle" / "_ref" / "ref_harness_big"
 
 
 class ClockSampler:
@@ -117,8 +89,7 @@ class ClockSampler:
             except (ValueError, IndexError):
                 pass
         sm.sort()
-        # median over samples under load (upper half of the samples)
-        load = sm[len(sm) // 2:] if sm else []
+        load = sm[len(sm) // 2:] if sm else []   # median over the samples under load (upper half)
         med = load[len(load) // 2] if load else None
         return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -133,28 +104,59 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def run_reference_cpu(workload: str, steps: int, warmup: int):
-    """Time the reference qrad3 (oracle/_ref/ref_harness, built from /root/reference) on one host core."""
-    import refdump as R
-    if not R.have_ref():
+def run_reference_cpu(workload: str, steps: int):
+    """The reference's own MakeTransfers + BuildFacelights on a deterministic sample of the SAME map (1 host core).
+    Step s lights the rows i = s mod stride and the faces f = s mod stride, so `steps` steps touch disjoint samples.
+    Returns None when oracle/_ref is not on this box."""
+    if not REF_HARNESS.exists():
         return None
     _, flags, desc = WORKLOADS[workload]
-    times, info = [], None
     with tempfile.TemporaryDirectory() as tmp:
         bsp = stage_workload(workload, Path(tmp))
-        unlit = bsp.read_bytes()
-        for i in range(warmup + steps):
-            bsp.write_bytes(unlit)
-            t0 = time.perf_counter()
-            info = R.run_ref_harness(bsp, flags)
-            dt = time.perf_counter() - t0
-            if i >= warmup:
-                times.append(dt)
-    rc = MAPS / "raycounts.json"
-    rays = json.loads(rc.read_text()).get(workload) if rc.exists() else None
-    if rays is None:
-        return None
-    return dict(times=times, info=info, rays=rays, desc=desc, flags=flags)
+        # stride 0 = the harness's automatic choice: ceil(num_patches / 128), about 128 rows (a few seconds) per step
+        cmd = [str(REF_HARNESS), *flags, "-benchsteps", str(steps), "-rows", "0:0", str(bsp)]
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=3000)
+        wall = time.perf_counter() - t0
+    if r.returncode:
+        raise RuntimeError("reference harness failed: " + r.stdout[-1000:] + r.stderr[-500:])
+    rows = [json.loads(l[8:]) for l in r.stdout.splitlines() if l.startswith("REFSTEP ")]
+    return dict(steps=rows, stride=rows[0]["stride"], desc=desc, flags=flags, wall=wall)
+
+
+def reference_summary(r, use):
+    """Aggregate the harness's REFSTEP lines `use` (a slice) into the bench fields."""
+    st = r["steps"][use]
+    secs = sum(s["facelights_s"] + s["transfers_s"] for s in st)
+    rays = sum(s["rays_direct"] + s["rays_transfers"] for s in st)
+    n = len(st)
+    s0 = st[0]
+    stride = r["stride"]
+    sample = (f"reference MakeTransfers + BuildFacelights on 1/{stride} of the rows and faces of the same map per step "
+              f"({s0['rows']} of {s0['num_patches']} rows, {s0['faces']} of {s0['numfaces']} faces; step s takes i = s mod "
+              f"{stride}); {rays // n} rays and {secs / n:.2f} s per step; BounceLight / FinalLightFace (about 2 % of the "
+              f"reference's time) are not sampled; 1 core (the reference is single-threaded on Linux)")
+    return dict(value=rays / secs, ms_per_step=secs / n * 1e3, sample=sample, rays_per_step=rays / n,
+                s_per_map_extrapolated=s0["setup_s"] + secs / n * stride,
+                phases_s={"setup_s": s0["setup_s"], "facelights_s_sample": sum(s["facelights_s"] for s in st) / n,
+                          "transfers_s_sample": sum(s["transfers_s"] for s in st) / n})
+
+
+def visibility_issue_block(workload, trace_ms, rays):
+    """k_visibility is bound by instruction issue (the tree is L1/L2 resident).  The issue rate comes from
+    the committed ncu capture of the same kernel (profiles/visibility_issue.json); the time and rays are live."""
+    out = {"bound": "issue", "kernel": "k_visibility", "ms_per_launch": trace_ms,
+           "rays_per_s": rays / (trace_ms * 1e-3) if trace_ms > 0 else None, "unit": "thread-instructions/clk/SM"}
+    p = ROOT / "profiles" / "visibility_issue.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            out.update({"achieved": d["warp_inst_per_clk_per_sm"] * d["lanes_active"], "peak": 4.0 * 32,
+                        "frac": d["warp_inst_per_clk_per_sm"] * d["lanes_active"] / 128.0,
+                        "source": d.get("source"), "measured_on": d.get("workload")})
+        except Exception:
+            pass
+    return out
 
 
 def main():
@@ -170,26 +172,26 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _, flags, desc = WORKLOADS[args.workload]
+    workload_name = f"{args.workload}: {desc}"
 
     if args.impl == "reference":
         if rank != 0:
             return
-        r = run_reference_cpu(REF_SAMPLE, max(1, args.steps), 0)
+        steps, warm = max(1, args.steps), max(0, args.warmup)
+        r = run_reference_cpu(args.workload, steps + warm)
         if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference build) not present on this box"}))
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_harness_big (reference build) not present on this box"}))
             return
-        dt = sum(r["times"]) / len(r["times"])
-        rays = r["rays"]["rays_transfers"] + r["rays"]["rays_direct"]
-        val = rays / dt
-        sample = f"{REF_SAMPLE}: {r['desc']}; {r['info']['num_patches']} patches, {rays} rays, {dt:.2f} s per step"
+        s = reference_summary(r, slice(warm, None))
         line = {
-            "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": len(r["times"]), "warmup": 0,
-            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOADS[args.workload][2], "reference_sample": sample},
-            "s_per_map": dt,
-            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": 1, "kind": "reference", "sample": sample},
-            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "metric": METRIC, "value": s["value"], "unit": "rays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": s["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name, "flags": " ".join(flags), "sampled": True},
+            "s_per_map_extrapolated": s["s_per_map_extrapolated"], "rays_per_step": s["rays_per_step"],
+            "cpu_baseline": {"value": s["value"], "unit": "rays/s", "cores": 1, "kind": "reference", "sample": s["sample"]},
+            "e2e": {"value": s["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line))
         return
@@ -203,17 +205,21 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
 
-    _, flags, desc = WORKLOADS[args.workload]
-    import golden_util as G
-    p = G.params_from_flags(flags)
+    p = Q.params_from_flags(flags)
     tmp = Path(tempfile.mkdtemp(prefix="qrad_bench_"))
     try:
         bsp = stage_workload(args.workload, tmp)
-        sc = Q.Scene(bsp).prepare(p)
+        unlit = bsp.read_bytes()
+        t0 = time.perf_counter()
+        sc = Q.Scene(bsp)
+        load_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        sc.prepare(p)
+        prepare_s = time.perf_counter() - t0
         counts = sc.counts()
         dev = Q.Device(local_rank)
         if world > 1:
-            dev.set_shard(rank, world)
+            Q.join_communicator(dev, rank, world)
 
         def barrier():
             if world > 1:
@@ -221,8 +227,6 @@ def main():
             torch.cuda.synchronize()
 
         def device_step():
-            if world > 1:
-                return Q.rad_world_sharded(sc, dev, p, rank, world, upload=False)
             dev.build_facelights(p.extrasamples, p.numbounce)
             if p.numbounce > 0:
                 dev.make_transfers(p.nopvs)
@@ -235,8 +239,7 @@ def main():
             device_step()
         barrier()
         launches0 = dev.stats()["kernel_launches"]
-        bounce_ms, trace_ms, phase = [], [], []
-        step_wall = []
+        bounce_ms, trace_ms, phase, step_wall = [], [], [], []
         with ClockSampler(local_rank) as clk:
             t0 = time.perf_counter()
             for _ in range(args.steps):
@@ -254,114 +257,107 @@ def main():
         st = dev.stats()
         launches = st["kernel_launches"] - launches0
         # N = 1: the library times each phase with CUDA events on its own stream; the step time is their sum.
-        # N > 1: the exchanges run on torch's NCCL streams between the phases, so the step is timed from barrier +
-        # synchronize to barrier + synchronize and the max over ranks is taken.
-        if world > 1:
-            step_ms = float(np.mean(step_wall)) * 1e3
-        else:
-            step_ms = float(np.mean([sum(x) for x in phase]))
-        t = torch.tensor([step_ms, float(st["rays_transfers"])], device="cuda", dtype=torch.float64)
+        # N > 1: the exchanges (NCCL, inside the library) overlap phases, so the step is timed from barrier + synchronize
+        # to barrier + synchronize and the max over ranks is taken.
+        step_ms = float(np.mean(step_wall)) * 1e3 if world > 1 else float(np.mean([sum(x) for x in phase]))
+        t = torch.tensor([step_ms, float(st["rays_transfers"]), float(st["rays_direct"])], device="cuda", dtype=torch.float64)
         if world > 1:
             tmax = t.clone()
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             step_ms = float(tmax[0].item())
-            st["rays_transfers"] = int(t[1].item())     # each rank traced its own granules of the matrix
+            st["rays_transfers"] = int(t[1].item())     # each rank traced its own rows / lit its own faces
+            st["rays_direct"] = int(t[2].item())
         rays = st["rays_transfers"] + st["rays_direct"]
         value = rays / (step_ms * 1e-3)
 
-        # ---- end to end through qrad_rad_world (uploads + lump read-back inside the timed region) ----
-        _, pv, lv, fv = sc.views()
-        bv = sc.views()[0]
-        h2d = (bv.numplanes * 20 + bv.numnodes * 28 + bv.numleafs * 28 + bv.visdatasize
-               + pv.num_patches * (12 * 5 + 4 * 4 + 1 + 24) + pv.numfaces * 4
-               + lv.numlights * (4 * 4 + 36) + (lv.numclusters + 1) * 4
-               + fv.numfaces * (1 + 12 * 3 + 24 + 8 * 4 + 24 + 4 * 3))
-        e2e_times = []
-        for i in range(1 + max(1, min(args.steps, 3))):   # 1 untimed + up to 3 timed end-to-end maps
+        # ---- end to end: what `qrad3 map.bsp` does, files and host buffers, every copy inside the timed region ----
+        e2e_times, e2e_parts, h2d, d2h = [], [], 0, 0
+        for i in range(1 + max(1, min(args.steps, 3))):   # 1 untimed + up to 3 timed maps
+            bsp.write_bytes(unlit)   # every rank lights its own staged copy; rank 0 writes the result
             barrier()
+            s0 = dev.stats()
             t0 = time.perf_counter()
-            if world > 1:
-                data, lightofs, styles = Q.rad_world_sharded(sc, dev, p, rank, world)
-                sc.store_lighting(data, lightofs, styles)
-            else:
-                Q.rad_world(sc, dev, p, want_added=False)
-            lump = sc.lighting()
+            sc2 = Q.Scene(bsp)
+            t1 = time.perf_counter()
+            sc2.prepare(p)
+            t2 = time.perf_counter()
+            Q.rad_world(sc2, dev, p, want_added=False)
+            t3 = time.perf_counter()
+            if rank == 0:
+                sc2.write(bsp)
+            lump = sc2.lighting()
             barrier()
+            t4 = time.perf_counter()
+            s1 = dev.stats()
             if i:
-                e2e_times.append(time.perf_counter() - t0)
+                e2e_times.append(t4 - t0)
+                e2e_parts.append([t1 - t0, t2 - t1, t3 - t2, t4 - t3])
+                h2d, d2h = s1["h2d_bytes"] - s0["h2d_bytes"], s1["d2h_bytes"] - s0["d2h_bytes"]
+            sc2.close()
         e2e_s = float(np.mean(e2e_times))
         t = torch.tensor([e2e_s], device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-        d2h = len(lump) + counts["numfaces"] * 8
-        import hashlib
+        parts = np.mean(e2e_parts, axis=0)
         lump_md5 = hashlib.md5(bytes(lump)).hexdigest()   # the same at every GPU count: sharding changes no byte
 
-        # ---- roofline of the dominant bandwidth kernel (k_bounce) ----
+        # ---- roofline of the HBM-bound kernel (k_bounce) ----
         peak, peak_src = measured_peak()
         b = 4 if st["num_patches"] <= 65535 else 6   # transfer_t is 4 B up to 65 535 patches
-        # per GPU: a launch of k_bounce processes this rank's share of the matrix (1/world of the slices)
-        alg_bytes = (st["total_transfers"] * b + 64 * st["num_patches"]) / world
+        alg_bytes = (st["total_transfers"] * b + 64 * st["num_patches"]) / world   # per GPU: this rank's slices
         kb_ms = float(np.mean(bounce_ms))
-        achieved = alg_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else 0.0
         stored_bytes = st["transfer_bytes"]     # what this rank's launch actually streams (dense-slice format)
-        roofline = {"bound": "hbm", "kernel": "k_bounce", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": alg_bytes, "stored_bytes_per_launch": stored_bytes,
-                    "stored_gbs": stored_bytes / (kb_ms * 1e-3) / 1e9 if kb_ms > 0 else 0.0,
-                    "stored_frac": stored_bytes / (kb_ms * 1e-3) / 1e9 / peak if kb_ms > 0 else 0.0,
-                    "note": "achieved = algorithmic bytes (nnz*b + 64*N, SURVEY 8d) / CUDA-event time of k_bounce. The "
-                            "stored dense-slice layout is smaller than the algorithmic record (3.6 B against 6 B per "
-                            "transfer on C5), so frac can exceed 1; stored_frac = bytes the launch really streams / time "
-                            "/ peak is the HBM utilisation, and traffic is ncu's DRAM bytes of one launch. The step "
-                            "is dominated by k_visibility (trace_kernel_ms), which is instruction-issue bound, not "
-                            "HBM bound: see trace_rays_per_s and profiles/",
+        sec = kb_ms * 1e-3
+        roofline = {"bound": "hbm", "kernel": "k_bounce", "achieved": stored_bytes / sec / 1e9 if sec > 0 else 0.0,
+                    "peak": peak, "unit": "GB/s", "frac": stored_bytes / sec / 1e9 / peak if sec > 0 else 0.0,
+                    "traffic": None, "peak_source": peak_src,
+                    "stored_bytes_per_launch": stored_bytes, "algorithmic_bytes_per_launch": alg_bytes,
+                    "algorithmic_gbs": alg_bytes / sec / 1e9 if sec > 0 else 0.0,
+                    "algorithmic_frac": alg_bytes / sec / 1e9 / peak if sec > 0 else 0.0,
+                    "note": "achieved / frac = bytes the launch streams from HBM (the stored dense-slice matrix: u32 source "
+                            "+ 32 x u16 weights per list entry, 3.6 B per transfer on C5) / CUDA-event time of k_bounce / "
+                            "measured copy bandwidth. algorithmic_* uses SURVEY 8d's record (nnz*b + 64*N, b = 6 B): that "
+                            "count is not a lower bound for this layout, so its fraction can exceed 1. traffic: ncu "
+                            "dram__bytes of one launch is on file for N = 1 only (profiles/), null here.",
                     "ms_per_launch": kb_ms, "launches_per_step": p.numbounce, "per_gpu": world > 1}
-        prof = ROOT / "profiles" / "bounce_traffic.json"
-        if prof.exists():
-            try:
-                roofline["traffic"] = json.loads(prof.read_text()).get(args.workload)
-            except Exception:
-                pass
+        tr_ms = float(np.mean(trace_ms))
 
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "flags": " ".join(flags), "patches": st["num_patches"],
+            "config": {"workload": workload_name, "flags": " ".join(flags), "patches": st["num_patches"],
                        "faces": counts["numfaces"], "luxels": st["num_luxels"], "clusters": st["num_clusters"],
                        "transfers_nnz": st["total_transfers"], "rays_per_step": rays,
                        "l2_policy": "inputs larger than L2 / every phase recomputed each step",
-                       "lump_bytes": len(lump), "lump_md5": lump_md5,
-                       "parallelism": f"rows x{world}"},
+                       "lump_bytes": len(lump), "lump_md5": lump_md5, "parallelism": f"rows+faces x{world}"},
             "s_per_map": step_ms * 1e-3,
             "phase_ms": dict(zip(["facelights", "transfers", "bounce", "final"], [float(x) for x in np.mean(phase, axis=0)])),
-            "exchange_ms": getattr(dev, "exchange_ms", None),
-            "trace_kernel_ms": float(np.mean(trace_ms)),
+            "exchange_ms": {k: st[k] for k in ("ms_x_matrix", "ms_x_small", "ms_x_radiosity")} if world > 1 else None,
+            "trace_kernel_ms": tr_ms,
             "transfers_breakdown_ms": {k: st[k] for k in ("ms_tr_setup", "ms_transfers_trace", "ms_tr_lists", "ms_tr_rows", "ms_tr_columns")},
-            "trace_rays_per_s": st["rays_transfers"] / (float(np.mean(trace_ms)) * 1e-3) if np.mean(trace_ms) > 0 else None,
-            "bounce_gbs": achieved,
+            "trace_rays_per_s": st["rays_transfers"] / (tr_ms * 1e-3) if tr_ms > 0 else None,
             "wall_s_per_step": wall / args.steps,
             "e2e": {"value": rays / e2e_s, "unit": "rays/s", "s_per_map": e2e_s, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h)},
+                    "d2h_bytes_per_step": int(d2h),
+                    "parts_s": dict(zip(["host_load", "host_prepare", "rad_world", "host_write"], [float(x) for x in parts])),
+                    "includes": "LoadBSPFile+ParseEntities+CalcTextureReflectivity, MakePatches+SubdividePatches+"
+                                "CreateDirectLights, uploads + all device phases + lump read-back, WriteBSPFile"},
+            "host_prepare_s": float(parts[1]), "host_load_s": float(parts[0]),
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "roofline_visibility": visibility_issue_block(args.workload, tr_ms, st["rays_transfers"] / world),
             "clocks": clk.summary(),
         }
         if rank == 0 and not args.no_cpu_baseline and world == 1:
-            r = run_reference_cpu(REF_SAMPLE, 1, 0)
+            r = run_reference_cpu(args.workload, 3)
             if r is not None:
-                dt = r["times"][0]
-                rr = r["rays"]["rays_transfers"] + r["rays"]["rays_direct"]
-                line["cpu_baseline"] = {
-                    "value": rr / dt, "unit": "rays/s", "cores": 1, "kind": "reference",
-                    "sample": f"{REF_SAMPLE}: {r['desc']}; {r['info']['num_patches']} patches, {rr} rays, {dt:.2f} s "
-                              f"(reference qrad3 is single-threaded on Linux)",
-                    "s_per_map": dt,
-                    "phases_s": {k: r["info"].get(k) for k in ("facelights_s", "transfers_s", "bounce_s", "final_s")},
-                }
+                s = reference_summary(r, slice(1, None))
+                line["cpu_baseline"] = {"value": s["value"], "unit": "rays/s", "cores": 1, "kind": "reference",
+                                        "sample": s["sample"], "s_per_map_extrapolated": s["s_per_map_extrapolated"],
+                                        "phases_s": s["phases_s"], "same_map": True}
         if rank == 0:
             print(json.dumps(line))
     finally:

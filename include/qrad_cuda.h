@@ -130,6 +130,12 @@ typedef struct {
   float   ms_tr_setup, ms_tr_lists, ms_tr_rows, ms_tr_columns;
   int64_t full_walks;         /* MakeTransfers rays that needed the full TestLine walk (counted with node counting on) */
   int64_t box_pruned_rays;    /* MakeTransfers rays settled by a whole-word box proof (counted with node counting on)  */
+  int64_t h2d_bytes, d2h_bytes;   /* bytes this context's calls copied host -> device / device -> host since its creation */
+  /* multi-GPU (a context that joined a communicator): milliseconds spent in the exchanges of the last RadWorld */
+  float   ms_x_matrix;        /* all-to-all of the visibility matrix (rows of the owner -> owners of the receiver slices) */
+  float   ms_x_small;         /* row totals / counts, samplelight, totallight, lump */
+  float   ms_x_radiosity;     /* radiosity vector, all bounces */
+  int32_t world, rank;
 } qrad_cuda_stats;
 
 int  qrad_cuda_abi_version(void);
@@ -183,6 +189,11 @@ int  qrad_cuda_download_numtransfers(qrad_cuda_ctx *ctx, int32_t *out /*[N]*/);
 /* All transfer rows in the reference's order (by source patch, receivers ascending): row_ptr[N+1],
    then `patch` / `transfer` arrays of total_transfer entries (transfer_t, qrad.h:57-61; patch widened to u32). */
 int  qrad_cuda_download_transfers(qrad_cuda_ctx *ctx, int64_t *row_ptr, uint32_t *patch, uint16_t *transfer);
+/* The rows of `nrows` selected source patches only (row-sample checks on maps whose whole matrix is tens of GB):
+   row_ptr[nrows+1]; patch / transfer must hold `capacity` >= sum of their numtransfers records; rays (may be NULL)
+   receives per row the root TestLine_r calls MakeTransfers issues for it (qrad3.c:244). */
+int  qrad_cuda_download_rows(qrad_cuda_ctx *ctx, int32_t nrows, const int32_t *rows /*patch indices*/, int64_t *row_ptr,
+                             uint32_t *patch, uint16_t *transfer, int64_t capacity, int64_t *rays);
 int  qrad_cuda_download_patch_light(qrad_cuda_ctx *ctx, float *totallight /*[N][3]*/, float *samplelight /*[N][3]*/,
                                     int32_t *samples /*[N]*/, float *radiosity /*[N][3]*/);
 int  qrad_cuda_upload_patch_light(qrad_cuda_ctx *ctx, const float *totallight, const float *samplelight, const int32_t *samples);

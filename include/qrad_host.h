@@ -43,10 +43,25 @@ typedef struct {
   int32_t max_patches;    /* 0 = unlimited (the reference stops at 65000, qrad.h:63) */
 } qrad_host_params;
 
+/* what the flag loop of main() (qrad3.c:555-601) collects besides the tunables */
+typedef struct {
+  int32_t next_arg;       /* index of the first argument that is not a flag (the reference `break`s there) */
+  int32_t threads;        /* -threads n: parsed, unused (the reference's Linux build forces 1, threads.c:379-420) */
+  int32_t tmpin, tmpout;  /* -tmpin / -tmpout: "/tmp" prefix of the input / output file name (qrad3.c:595-598) */
+  int32_t dump, glview;   /* -dump / -glview: accepted; the debugging dumps are not produced */
+  int32_t device;         /* -gpu n   (extension) CUDA ordinal of the first GPU */
+  int32_t ngpus;          /* -gpus n  (extension) GPUs of this box to spread the map over, default 1 */
+  int32_t direct_given, entity_given;   /* -direct / -entity were seen (the reference echoes the resulting scale) */
+} qrad_host_cli;
+
 void qrad_host_default_params(qrad_host_params *p);
+/* The reference's flag parser applied to *params (which must hold the defaults); never fails. */
+int  qrad_host_parse_flags(int argc, char **argv, qrad_host_params *params, qrad_host_cli *cli);
 const char *qrad_host_last_error(void);
 
 int  qrad_host_load(const char *bsp_path, qrad_host_scene **out);
+/* the same with the file to read and the path that locates pics/ and textures/ given separately (-tmpin) */
+int  qrad_host_load_as(const char *file_path, const char *qdir_path, qrad_host_scene **out);
 void qrad_host_free(qrad_host_scene *s);
 /* After load: numbounce/ambient are forced like qrad3.c:627-631 when the map has no vis data. */
 int  qrad_host_prepare(qrad_host_scene *s, qrad_host_params *params);
@@ -69,6 +84,12 @@ int  qrad_host_write(qrad_host_scene *s, const char *bsp_path);
 
 /* RadWorld (qrad3.c:494-536) over an already loaded+prepared scene on one GPU context. */
 int  qrad_rad_world(qrad_host_scene *s, qrad_cuda_ctx *ctx, const qrad_host_params *params, float *added_out);
+
+/* RadWorld spread over `ngpus` GPUs of this box (devices first_device .. first_device+ngpus-1): one host thread and one
+   context per GPU, exchanges over NCCL inside the library.  stats_out (may be NULL) receives
+   the statistics of GPU 0 with the ray counts summed over the GPUs. */
+int  qrad_rad_world_multi(qrad_host_scene *s, int first_device, int ngpus, const qrad_host_params *params,
+                          float *added_out, qrad_cuda_stats *stats_out);
 
 /* Drop-in for the reference executable. */
 int  qrad3_main(int argc, char **argv);

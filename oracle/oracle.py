@@ -218,6 +218,12 @@ class Oracle:
         return np.array([self.L.oq_test_line(starts[i].ctypes.data_as(fp), stops[i].ctypes.data_as(fp))
                          for i in range(len(starts))], np.int32)
 
+    def point_in_leaf(self, pts):
+        """PointInLeafnum, qrad3.c:131-150, per point."""
+        pts = np.ascontiguousarray(pts, np.float32)
+        fp = C.POINTER(C.c_float)
+        return np.array([self.L.oq_point_in_leaf(pts[i].ctypes.data_as(fp)) for i in range(len(pts))], np.int32)
+
     def rad_world(self):
         """RadWorld, qrad3.c:494-536. Returns (lump bytes, added)."""
         self.make_patches()

@@ -13,8 +13,26 @@
  *   so that `added` and totallight can be captured after each bounce; the work
  *   itself is done by the reference's ShootLight / CollectLight).
  *
- * usage: ref_harness [qrad3 flags] [-dumpdir DIR] [-stopafter PHASE] bspfile
+ * usage: ref_harness [qrad3 flags] [-dumpdir DIR] [-stopafter PHASE] [sampling mode] bspfile
  * Dump files are flat little-endian binaries documented in tests/refdump.py.
+ *
+ * Sampling modes (for maps on which the whole O(N^2) MakeTransfers is hours of CPU; they need the
+ * limit-lifted build ref_harness_big for more than 65 000 patches, see oracle/Makefile):
+ *   -rows F:S -rowsout FILE        MakeTransfers(i) (qrad3.c:185-293) for i = F, F+S, ...; every row is
+ *                                  written out with its root TestLine_r count
+ *   -cols A:N [-part k:K] -colsout FILE
+ *                                  every source that can see one of the receivers A .. A+N-1: its
+ *                                  radiosity (BuildFacelights of its face, qrad3.c:455-459) and its
+ *                                  weights towards those receivers -- what ShootLight (qrad3.c:419-441)
+ *                                  adds to them during the first bounce; -part splits the sources
+ *                                  over K processes
+ *   -benchsteps K -rows F:S -facesample F2:S2
+ *                                  K timed steps for bench.py's reference arm: step s lights the faces
+ *                                  f = (F2+s) mod S2 (BuildFacelights) and the rows i = (F+s) mod S
+ *                                  (MakeTransfers) and prints one "REFSTEP {json}" line; S = 0 picks
+ *                                  S = S2 = ceil(num_patches / 128), i.e. about 128 rows per step
+ * Root TestLine_r calls are counted without touching the reference: the link wraps the symbol
+ * (-Wl,--wrap=TestLine_r); the recursion inside trace.c binds locally and is not counted.
  * Phase timings (clock_gettime, finding F10: the reference timer has 1 s
  * resolution) are printed as one JSON line prefixed "REFTIMING ".
  */
@@ -42,6 +60,7 @@ float CollectLight(void);
 void FreeTransfers(void);
 void CheckPatches(void);
 void WriteGlView(void);
+int PointInLeafnum(vec3_t point);
 
 /* layout of lightmap.c's file-local facelight_t (lightmap.c:681-688) */
 #define H_MAX_STYLES 32
@@ -54,6 +73,15 @@ typedef struct
   float *samples[H_MAX_STYLES];
 } h_facelight_t;
 extern h_facelight_t facelight[MAX_MAP_FACES];
+
+/* root TestLine_r calls (qrad3.c:244, lightmap.c:647,898), counted through ld --wrap */
+int __real_TestLine_r(int node, vec3_t start, vec3_t stop);
+static long long harness_rays;
+int __wrap_TestLine_r(int node, vec3_t start, vec3_t stop)
+{
+  harness_rays++;
+  return __real_TestLine_r(node, start, stop);
+}
 
 static char dumpdir[1024];
 static double now(void)
@@ -218,6 +246,7 @@ static void dump_vec3_array(const char *name, int which)
 static void dump_rays(int want)
 {
   FILE *f = dopen("rays.bin");
+  FILE *fl = dopen("rayleafs.bin"); /* i32 per ray of rays.bin */
   unsigned a, b, n = 0, step;
   unsigned long long pairs = (unsigned long long) num_patches * num_patches;
   step = (unsigned) (pairs / (want ? want : 1));
@@ -235,12 +264,178 @@ static void dump_rays(int want)
       wf(f, patches[a].origin, 3);
       wf(f, patches[b].origin, 3);
       wi(f, r);
+      /* PointInLeafnum (qrad3.c:131-150) of a point next to the ray's end: pushed onto the 16-unit grid in x, where
+         many node planes of the maps lie, so that the `dist > 0` tie is exercised */
+      {
+        vec3_t q;
+        VectorCopy(patches[b].origin, q);
+        if (n & 1)
+          q[0] = (float) (16 * (int) (q[0] / 16));
+        wi(fl, PointInLeafnum(q));
+      }
       n++;
     }
   }
   fseek(f, 0, SEEK_SET);
   wi(f, n);
   fclose(f);
+}
+
+
+/* ---- sampling modes -------------------------------------------------------------------------- */
+static int *face_of_patch(void)
+{
+  int *faceof = malloc(sizeof(int) * (num_patches + 1));
+  unsigned i;
+  int fn;
+  patch_t *q;
+  for (i = 0; i < num_patches; i++)
+    faceof[i] = -1;
+  for (fn = 0; fn < numfaces; fn++)
+    for (q = face_patches[fn]; q; q = q->next)
+      faceof[q - patches] = fn;
+  return faceof;
+}
+
+/* rows file: i32 count; per row: i32 patch, i32 numtransfers, i64 rays, u32 patch[numtransfers], u16 transfer[numtransfers] */
+static void run_rows(int first, int stride, const char *out)
+{
+  FILE *f = fopen(out, "wb");
+  unsigned i;
+  int n = 0, k;
+  double t0 = now();
+  long long rays_total = 0;
+  if (!f)
+    Error("harness: cannot open %s", out);
+  wi(f, 0);
+  for (i = first; i < num_patches; i += stride) {
+    patch_t *p = &patches[i];
+    long long r0 = harness_rays, r;
+    MakeTransfers(i);
+    r = harness_rays - r0;
+    rays_total += r;
+    wi(f, (int) i);
+    wi(f, p->numtransfers);
+    fwrite(&r, 8, 1, f);
+    for (k = 0; k < p->numtransfers; k++) {
+      unsigned pj = p->transfers[k].patch;
+      fwrite(&pj, 4, 1, f);
+    }
+    for (k = 0; k < p->numtransfers; k++) {
+      unsigned short w = p->transfers[k].transfer;
+      fwrite(&w, 2, 1, f);
+    }
+    if (p->numtransfers)
+      free(p->transfers);
+    p->transfers = NULL;
+    p->numtransfers = 0;
+    n++;
+  }
+  fseek(f, 0, SEEK_SET);
+  wi(f, n);
+  fclose(f);
+  printf("REFTIMING {\"rows\": %d, \"rows_s\": %.6f, \"rays_transfers\": %lld, \"num_patches\": %u}\n", n, now() - t0,
+         rays_total, num_patches);
+}
+
+/* cols file: i32 A, i32 N; N x {f32 area, i32 sky, f32 totallight[3], f32 reflectivity[3]};
+   then until EOF: i32 source, f32 radiosity[3], i32 n, n x {i32 receiver, i32 transfer} */
+static void run_cols(int a, int n, int part, int parts, const char *out)
+{
+  FILE *f = fopen(out, "wb");
+  byte pvs[(MAX_MAP_LEAFS + 7) / 8];
+  byte *facedone = calloc(numfaces + 1, 1);
+  int *faceof = face_of_patch();
+  unsigned i;
+  int j, k, seen = 0, mine = 0;
+  double t0 = now();
+  if (!f)
+    Error("harness: cannot open %s", out);
+  if (a < 0 || n < 1 || a + n > (int) num_patches)
+    Error("harness: bad -cols window");
+  wi(f, a);
+  wi(f, n);
+  for (j = a; j < a + n; j++) {
+    wf(f, &patches[j].area, 1);
+    wi(f, patches[j].sky);
+    wf(f, patches[j].totallight, 3);
+    wf(f, patches[j].reflectivity, 3);
+  }
+  for (i = 0; i < num_patches; i++) {
+    patch_t *p = &patches[i];
+    int want = 0, cnt = 0;
+    vec3_t rad;
+    if (!PvsForOrigin(p->origin, pvs))
+      continue; /* MakeTransfers returns at once (qrad3.c:208) */
+    for (j = a; j < a + n && !want; j++) {
+      int c = patches[j].cluster;
+      if (nopvs || (c != -1 && (pvs[c >> 3] & (1 << (c & 7)))))
+        want = 1;
+    }
+    if (!want)
+      continue;
+    if (seen++ % parts != part)
+      continue;
+    mine++;
+    if (faceof[i] >= 0 && !facedone[faceof[i]]) {
+      facedone[faceof[i]] = 1;
+      BuildFacelights(faceof[i]);
+    }
+    for (k = 0; k < 3; k++)
+      rad[k] = p->samplelight[k] * p->reflectivity[k] * p->area; /* qrad3.c:455-459 */
+    MakeTransfers(i);
+    for (k = 0; k < p->numtransfers; k++)
+      if ((int) p->transfers[k].patch >= a && (int) p->transfers[k].patch < a + n)
+        cnt++;
+    wi(f, (int) i);
+    wf(f, rad, 3);
+    wi(f, cnt);
+    for (k = 0; k < p->numtransfers; k++)
+      if ((int) p->transfers[k].patch >= a && (int) p->transfers[k].patch < a + n) {
+        wi(f, (int) p->transfers[k].patch);
+        wi(f, (int) p->transfers[k].transfer);
+      }
+    if (p->numtransfers)
+      free(p->transfers);
+    p->transfers = NULL;
+    p->numtransfers = 0;
+  }
+  fclose(f);
+  printf("REFTIMING {\"sources\": %d, \"sources_this_part\": %d, \"cols_s\": %.6f, \"num_patches\": %u}\n", seen, mine,
+         now() - t0, num_patches);
+}
+
+static void run_benchsteps(int steps, int rfirst, int rstride, int ffirst, int fstride, double setup_s)
+{
+  int s;
+  if (rstride <= 0) /* auto: about 128 rows per step, the same fraction of the faces */
+    rstride = fstride = (num_patches + 127) / 128;
+  for (s = 0; s < steps; s++) {
+    double t0 = now(), t1, t2;
+    long long r0 = harness_rays, r1, r2;
+    int fn, nf = 0, nr = 0;
+    unsigned i;
+    long long nnz = 0;
+    for (fn = (ffirst + s) % fstride; fn < numfaces; fn += fstride, nf++)
+      BuildFacelights(fn);
+    t1 = now();
+    r1 = harness_rays;
+    for (i = (rfirst + s) % rstride; i < num_patches; i += rstride, nr++) {
+      patch_t *p = &patches[i];
+      MakeTransfers(i);
+      nnz += p->numtransfers;
+      if (p->numtransfers)
+        free(p->transfers);
+      p->transfers = NULL;
+      p->numtransfers = 0;
+    }
+    t2 = now();
+    r2 = harness_rays;
+    printf("REFSTEP {\"step\": %d, \"faces\": %d, \"numfaces\": %d, \"rows\": %d, \"num_patches\": %u, \"facelights_s\": %.6f, "
+           "\"transfers_s\": %.6f, \"rays_direct\": %lld, \"rays_transfers\": %lld, \"transfers\": %lld, \"setup_s\": %.6f, "
+           "\"stride\": %d}\n",
+           s, nf, numfaces, nr, num_patches, t1 - t0, t2 - t1, r1 - r0, r2 - r1, nnz, setup_s, rstride);
+  }
 }
 
 int main(int argc, char **argv)
@@ -252,6 +447,10 @@ int main(int argc, char **argv)
   int stopafter = 99;
   float added[64];
   int nadded = 0;
+  int rows_first = -1, rows_stride = 1, cols_a = -1, cols_n = 0, part = 0, parts = 1, benchsteps = 0;
+  int fs_first = 0, fs_stride = 1;
+  const char *rowsout = NULL, *colsout = NULL;
+  long long rays_direct = 0, rays_transfers = 0;
 
   /* finding F1: keep every allocation on the brk heap (< 2 GB with -no-pie) */
   mallopt(M_MMAP_MAX, 0);
@@ -290,6 +489,20 @@ int main(int argc, char **argv)
       dump = 1;
     } else if (!strcmp(argv[i], "-stopafter"))
       stopafter = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "-rows"))
+      sscanf(argv[++i], "%d:%d", &rows_first, &rows_stride);
+    else if (!strcmp(argv[i], "-rowsout"))
+      rowsout = argv[++i];
+    else if (!strcmp(argv[i], "-cols"))
+      sscanf(argv[++i], "%d:%d", &cols_a, &cols_n);
+    else if (!strcmp(argv[i], "-part"))
+      sscanf(argv[++i], "%d:%d", &part, &parts);
+    else if (!strcmp(argv[i], "-colsout"))
+      colsout = argv[++i];
+    else if (!strcmp(argv[i], "-benchsteps"))
+      benchsteps = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "-facesample"))
+      sscanf(argv[++i], "%d:%d", &fs_first, &fs_stride);
     else
       break;
   }
@@ -339,9 +552,25 @@ int main(int argc, char **argv)
   }
   if (stopafter < 1)
     goto done;
+  if ((rows_stride < 1 && !benchsteps) || fs_stride < 1 || parts < 1)
+    Error("harness: bad sampling stride");
+  if (benchsteps > 0) {
+    run_benchsteps(benchsteps, rows_first < 0 ? 0 : rows_first, rows_stride, fs_first, fs_stride, t[0]);
+    return 0;
+  }
+  if (colsout) {
+    run_cols(cols_a, cols_n, part, parts, colsout);
+    return 0;
+  }
+  if (rowsout) {
+    run_rows(rows_first < 0 ? 0 : rows_first, rows_stride, rowsout);
+    return 0;
+  }
 
   t0 = now();
+  harness_rays = 0;
   RunThreadsOnIndividual(numfaces, false, BuildFacelights);
+  rays_direct = harness_rays;
   t[1] = now() - t0;
   if (dump) {
     dump_facelight();
@@ -355,7 +584,9 @@ int main(int argc, char **argv)
     unsigned k;
     int j, b;
     t0 = now();
+    harness_rays = 0;
     RunThreadsOnIndividual(num_patches, false, MakeTransfers);
+    rays_transfers = harness_rays;
     t[2] = now() - t0;
     if (dump)
       dump_transfers();
@@ -392,8 +623,8 @@ int main(int argc, char **argv)
 
   printf("REFTIMING {\"setup_s\": %.6f, \"facelights_s\": %.6f, \"transfers_s\": %.6f, \"bounce_s\": %.6f, "
          "\"final_s\": %.6f, \"num_patches\": %u, \"total_transfer\": %d, \"numdlights\": %d, \"lightdatasize\": %d, "
-         "\"added\": [",
-         t[0], t[1], t[2], t[3], t[4], num_patches, total_transfer, numdlights, lightdatasize);
+         "\"rays_direct\": %lld, \"rays_transfers\": %lld, \"added\": [",
+         t[0], t[1], t[2], t[3], t[4], num_patches, total_transfer, numdlights, lightdatasize, rays_direct, rays_transfers);
   for (i = 0; i < nadded; i++)
     printf("%s%.9g", i ? ", " : "", added[i]);
   printf("]}\n");

@@ -93,6 +93,7 @@ int qrad_cuda_create(int device, qrad_cuda_ctx **out) {
     if (prop.major < 10) dfail("libqrad_cuda is built for sm_100a; device %d is sm_%d%d", device, prop.major, prop.minor);
     qrad_cuda_ctx *c = new qrad_cuda_ctx;
     c->device = device;
+    c->traffic0 = traffic();
     c->sm_count = prop.multiProcessorCount;
     QCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     *out = c;
@@ -497,6 +498,10 @@ int qrad_cuda_final_light(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t 
 
 int qrad_cuda_get_stats(qrad_cuda_ctx *c, qrad_cuda_stats *out) {
   *out = c->stats;
+  out->h2d_bytes = traffic().h2d - c->traffic0.h2d;
+  out->d2h_bytes = traffic().d2h - c->traffic0.d2h;
+  out->world = c->world;
+  out->rank = c->rank;
   return 0;
 }
 
@@ -515,6 +520,15 @@ int qrad_cuda_download_transfers(qrad_cuda_ctx *c, int64_t *row_ptr, uint32_t *p
     QCUDA(cudaSetDevice(c->device));
     if (!c->transfers_done) dfail("make_transfers has not run");
     download_transfers_impl(c, row_ptr, patch, transfer);
+  });
+}
+
+int qrad_cuda_download_rows(qrad_cuda_ctx *c, int32_t nrows, const int32_t *rows, int64_t *row_ptr, uint32_t *patch,
+                            uint16_t *transfer, int64_t capacity, int64_t *rays) {
+  return guarded([&] {
+    QCUDA(cudaSetDevice(c->device));
+    if (!c->transfers_done) dfail("make_transfers has not run");
+    download_rows_impl(c, nrows, rows, row_ptr, patch, transfer, capacity, rays);
   });
 }
 

@@ -4,6 +4,7 @@
 #include <memory>
 #include <cstdio>
 #include <cstdlib>
+#include <unistd.h>
 
 #include "host_scene.hpp"
 
@@ -36,16 +37,20 @@ void qrad_host_default_params(qrad_host_params *p) {  // qrad3.c:49-74
   p->entity_scale = 1.0f;
 }
 
-int qrad_host_load(const char *bsp_path, qrad_host_scene **out) {
+// file_path is read; qdir_path (the command-line argument in the reference) decides where pics/ and textures/ are
+// looked up (SetQdirFromPath, cmdlib.c:187-217) -- the two differ only under -tmpin.
+int qrad_host_load_as(const char *file_path, const char *qdir_path, qrad_host_scene **out) {
   *out = nullptr;
   return guarded([&] {
     std::unique_ptr<qrad_host_scene> s(new qrad_host_scene);
-    set_gamedir_from_path(bsp_path, s->scene.bsp);
-    load_bsp(bsp_path, s->scene.bsp);
+    set_gamedir_from_path(qdir_path, s->scene.bsp);
+    load_bsp(file_path, s->scene.bsp);
     calc_texture_reflectivity(s->scene);
     *out = s.release();
   });
 }
+
+int qrad_host_load(const char *bsp_path, qrad_host_scene **out) { return qrad_host_load_as(bsp_path, bsp_path, out); }
 
 void qrad_host_free(qrad_host_scene *s) { delete s; }
 
@@ -258,54 +263,72 @@ int qrad_rad_world(qrad_host_scene *hs, qrad_cuda_ctx *ctx, const qrad_host_para
   });
 }
 
+// The flag loop of main(), qrad3.c:555-601: same flags, same side effects on the tunables; silent (qrad3_main prints
+// the reference's chatter).  Parsing stops at the first argument that is not a known flag (cli->next_arg), like the reference's `else break`.
+int qrad_host_parse_flags(int argc, char **argv, qrad_host_params *p, qrad_host_cli *cli) {
+  memset(cli, 0, sizeof *cli);
+  cli->ngpus = 1;
+  int i;
+  for (i = 1; i < argc; i++) {
+    const char *a = argv[i];
+    auto arg = [&]() -> const char * { return (i + 1 < argc) ? argv[++i] : "0"; };
+    if (!strcmp(a, "-dump"))
+      cli->dump = 1;
+    else if (!strcmp(a, "-bounce"))
+      p->numbounce = atoi(arg());
+    else if (!strcmp(a, "-v"))
+      p->verbose = 1;
+    else if (!strcmp(a, "-extra"))
+      p->extrasamples = 1;
+    else if (!strcmp(a, "-threads"))
+      cli->threads = atoi(arg());  // parsed; the reference's Linux build then forces 1 (threads.c:379-420)
+    else if (!strcmp(a, "-chop"))
+      p->subdiv = (float) atoi(arg());
+    else if (!strcmp(a, "-scale"))
+      p->lightscale = (float) atof(arg());
+    else if (!strcmp(a, "-direct")) {
+      p->direct_scale *= atof(arg());
+      cli->direct_given = 1;
+    } else if (!strcmp(a, "-entity")) {
+      p->entity_scale *= atof(arg());
+      cli->entity_given = 1;
+    } else if (!strcmp(a, "-glview"))
+      cli->glview = 1;
+    else if (!strcmp(a, "-nopvs"))
+      p->nopvs = 1;
+    else if (!strcmp(a, "-ambient"))
+      p->ambient = (float) (atof(arg()) * 128);
+    else if (!strcmp(a, "-maxlight"))
+      p->maxlight = (float) (atof(arg()) * 128);
+    else if (!strcmp(a, "-tmpin"))
+      cli->tmpin = 1;
+    else if (!strcmp(a, "-tmpout"))
+      cli->tmpout = 1;
+    else if (!strcmp(a, "-gpu"))   // extension: CUDA device ordinal of the (first) GPU
+      cli->device = atoi(arg());
+    else if (!strcmp(a, "-gpus"))  // extension: number of GPUs of this box to spread the map over
+      cli->ngpus = atoi(arg());
+    else
+      break;
+  }
+  if (p->maxlight > 255) p->maxlight = 255;
+  cli->next_arg = i;
+  return 0;
+}
+
 // main(), qrad3.c:545-643.  Same flags, same messages where they are part of the contract.
 int qrad3_main(int argc, char **argv) {
   printf("----- Radiosity ----\n");
   qrad_host_params p;
   qrad_host_default_params(&p);
-  int device = 0;
-  int i;
-  for (i = 1; i < argc; i++) {
-    const char *a = argv[i];
-    auto arg = [&]() -> const char * { return (i + 1 < argc) ? argv[++i] : "0"; };
-    if (!strcmp(a, "-dump")) {
-      // patch dumps (bounceN.txt) are a debugging aid of the reference; accepted and ignored
-    } else if (!strcmp(a, "-bounce"))
-      p.numbounce = atoi(arg());
-    else if (!strcmp(a, "-v"))
-      p.verbose = 1;
-    else if (!strcmp(a, "-extra")) {
-      p.extrasamples = 1;
-      printf("extrasamples = true\n");
-    } else if (!strcmp(a, "-threads"))
-      (void) arg();  // parsed and discarded, as on the reference's Linux build (threads.c:379-420)
-    else if (!strcmp(a, "-chop"))
-      p.subdiv = (float) atoi(arg());
-    else if (!strcmp(a, "-scale"))
-      p.lightscale = (float) atof(arg());
-    else if (!strcmp(a, "-direct")) {
-      p.direct_scale *= atof(arg());
-      printf("direct light scaling at %f\n", p.direct_scale);
-    } else if (!strcmp(a, "-entity")) {
-      p.entity_scale *= atof(arg());
-      printf("entity light scaling at %f\n", p.entity_scale);
-    } else if (!strcmp(a, "-glview")) {
-      printf("glview = true\n");
-    } else if (!strcmp(a, "-nopvs")) {
-      p.nopvs = 1;
-      printf("nopvs = true\n");
-    } else if (!strcmp(a, "-ambient"))
-      p.ambient = (float) (atof(arg()) * 128);
-    else if (!strcmp(a, "-maxlight"))
-      p.maxlight = (float) (atof(arg()) * 128);
-    else if (!strcmp(a, "-gpu"))  // extension: CUDA device ordinal
-      device = atoi(arg());
-    else if (!strcmp(a, "-tmpin") || !strcmp(a, "-tmpout")) {
-      fprintf(stderr, "-tmpin/-tmpout are not supported\n");
-    } else
-      break;
-  }
-  if (p.maxlight > 255) p.maxlight = 255;
+  qrad_host_cli cli;
+  qrad_host_parse_flags(argc, argv, &p, &cli);
+  if (p.extrasamples) printf("extrasamples = true\n");
+  if (cli.direct_given) printf("direct light scaling at %f\n", p.direct_scale);
+  if (cli.entity_given) printf("entity light scaling at %f\n", p.entity_scale);
+  if (cli.glview) printf("glview = true\n");
+  if (p.nopvs) printf("nopvs = true\n");
+  const int i = cli.next_arg;
   auto die = [](const std::string &msg) {  // Error(), cmdlib.c:142-155
     printf("\n************ ERROR ************\n%s\n", msg.c_str());
     return 1;
@@ -313,37 +336,51 @@ int qrad3_main(int argc, char **argv) {
   if (i != argc - 1)
     return die("usage: qrad [-v] [-chop num] [-scale num] [-ambient num] [-maxlight num] [-threads num] bspfile");
   auto t0 = std::chrono::steady_clock::now();
-  std::string name = argv[i];
-  {  // StripExtension + DefaultExtension(".bsp")
-    size_t slash = name.find_last_of('/');
-    size_t dot = name.find_last_of('.');
-    if (dot != std::string::npos && (slash == std::string::npos || dot > slash)) name.resize(dot);
-    name += ".bsp";
+  // SetQdirFromPath(argv[i]) works on the argument as given; source = ExpandArg + StripExtension + DefaultExtension
+  std::string source = argv[i];
+  if (source[0] != '/') {   // ExpandArg, cmdlib.c:219-229
+    char cwd[1024];
+    if (!getcwd(cwd, sizeof cwd - 1)) return die("Couldn't determine current directory");
+    source = std::string(cwd) + "/" + source;
   }
-  printf("reading %s\n", name.c_str());
+  {
+    size_t slash = source.find_last_of('/');
+    size_t dot = source.find_last_of('.');
+    if (dot != std::string::npos && (slash == std::string::npos || dot > slash)) source.resize(dot);
+    source += ".bsp";
+  }
+  // -tmpin / -tmpout prefix the expanded path with "/tmp" (inbase / outbase, qrad3.c:595-598, 619, 635)
+  const std::string inname = (cli.tmpin ? "/tmp" : "") + source, outname = (cli.tmpout ? "/tmp" : "") + source;
+  printf("reading %s\n", inname.c_str());
   qrad_host_scene *hs = nullptr;
-  if (qrad_host_load(name.c_str(), &hs)) return die(g_host_error);
+  if (qrad_host_load_as(inname.c_str(), argv[i], &hs)) return die(g_host_error);
   if (qrad_host_prepare(hs, &p)) {
     qrad_host_free(hs);
     return die(g_host_error);
   }
-  qrad_cuda_ctx *ctx = nullptr;
-  if (qrad_cuda_create(device, &ctx)) {
-    qrad_host_free(hs);
-    return die(qrad_cuda_last_error());
+  if (cli.dump || cli.glview)
+    printf("-dump / -glview: the debugging dumps (bounceN.txt, .glr) are not produced by this build\n");
+  int rc;
+  qrad_cuda_stats st{};
+  if (cli.ngpus > 1) {
+    rc = qrad_rad_world_multi(hs, cli.device, cli.ngpus, &p, nullptr, &st);
+  } else {
+    qrad_cuda_ctx *ctx = nullptr;
+    if (qrad_cuda_create(cli.device, &ctx)) {
+      qrad_host_free(hs);
+      return die(qrad_cuda_last_error());
+    }
+    rc = qrad_rad_world(hs, ctx, &p, nullptr);
+    if (rc == 0) qrad_cuda_get_stats(ctx, &st);
+    qrad_cuda_destroy(ctx);
   }
-  int rc = qrad_rad_world(hs, ctx, &p, nullptr);
   if (rc == 0) {
-    printf("writing %s\n", name.c_str());
-    rc = qrad_host_write(hs, name.c_str());
+    printf("writing %s\n", outname.c_str());
+    rc = qrad_host_write(hs, outname.c_str());
   }
-  if (p.verbose && rc == 0) {
-    qrad_cuda_stats st;
-    if (!qrad_cuda_get_stats(ctx, &st))
-      printf("gpu: facelights %.2f ms, transfers %.2f ms, bounce %.2f ms, final %.2f ms; %lld rays\n", st.ms_facelights,
-             st.ms_transfers, st.ms_bounce, st.ms_final, (long long) (st.rays_transfers + st.rays_direct));
-  }
-  qrad_cuda_destroy(ctx);
+  if (p.verbose && rc == 0)
+    printf("gpu: facelights %.2f ms, transfers %.2f ms, bounce %.2f ms, final %.2f ms; %lld rays\n", st.ms_facelights,
+           st.ms_transfers, st.ms_bounce, st.ms_final, (long long) (st.rays_transfers + st.rays_direct));
   qrad_host_free(hs);
   if (rc) return die(g_host_error);
   double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

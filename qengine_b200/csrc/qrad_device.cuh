@@ -33,6 +33,16 @@ struct CudaError : std::runtime_error {
     if (e__ != cudaSuccess) ::qrad::dfail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// Host <-> device traffic of this thread's contexts, counted where the copies are issued (qrad_cuda_stats.h2d_bytes /
+// d2h_bytes report the totals since the context was created).
+struct Traffic {
+  int64_t h2d = 0, d2h = 0;
+};
+inline Traffic &traffic() {
+  static thread_local Traffic t;
+  return t;
+}
+
 // Device buffer.  alloc() keeps the allocation when it is already large enough: a host that lights map after map
 // (or a benchmark that repeats a step) does not pay cudaMalloc/cudaFree of multi-GB buffers every time.
 template <class T> struct DBuf {
@@ -63,10 +73,12 @@ template <class T> struct DBuf {
   void upload(const T *h, size_t count, cudaStream_t s) {
     alloc(count);
     if (count) QCUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    traffic().h2d += (int64_t) (count * sizeof(T));
   }
   void upload(const std::vector<T> &h, cudaStream_t s) { upload(h.data(), h.size(), s); }
   void download(T *h, size_t count, cudaStream_t s) const {
     if (count) QCUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    traffic().d2h += (int64_t) (count * sizeof(T));
     QCUDA(cudaStreamSynchronize(s));
   }
 };
@@ -415,6 +427,7 @@ struct qrad_cuda_ctx {
   int rank = 0, world = 1;
   bool count_nodes = false;
   qrad_cuda_stats stats{};
+  qrad::Traffic traffic0;              // thread counters when the context was created
 
   // ---- BSP (qrad_cuda_upload_bsp) ----
   int numnodes = 0, numleafs = 0, numclusters = 0, tree_depth = 0, pvs_words = 0;
@@ -552,6 +565,8 @@ void bounce_end(qrad_cuda_ctx *c);
 void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out, int32_t cap, int32_t *size,
                       int32_t *lightofs, uint8_t *styles);
 void download_transfers_impl(qrad_cuda_ctx *c, int64_t *row_ptr, uint32_t *patch, uint16_t *transfer);
+void download_rows_impl(qrad_cuda_ctx *c, int nrows, const int32_t *rows, int64_t *row_ptr, uint32_t *patch,
+                        uint16_t *transfer, int64_t capacity, int64_t *rays);
 void test_lines_impl(qrad_cuda_ctx *c, int64_t n, const float *starts, const float *stops, uint8_t *results);
 void point_in_leaf_impl(qrad_cuda_ctx *c, int64_t n, const float *pts, int32_t *out);
 }  // namespace qrad

@@ -418,13 +418,23 @@ struct RowArgs {
   const int64_t *row_ptr;
   uint32_t *out_patch;
   uint16_t *out_transfer;
+  // download of selected rows: warp k handles source slot sel_slots[k] and writes at row_ptr[k]
+  const int32_t *sel_slots;
+  int nsel;
+  long long *sel_rays;             // [nsel] root TestLine_r calls of the row (k_row_rays)
 };
 
 template <bool EMIT>
 __global__ void __launch_bounds__(kThreads) k_row_totals(const RowArgs a) {
   const int lane = threadIdx.x & 31;
-  const int sslot = a.slot_lo + blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (sslot >= a.slot_hi) return;
+  const int widx = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  int sslot = a.slot_lo + widx;
+  if (a.sel_slots) {
+    if (widx >= a.nsel) return;
+    sslot = a.sel_slots[widx];
+    if (sslot < 0) return;
+  } else if (sslot >= a.slot_hi)
+    return;
   const int spatch = a.slot_patch[sslot];
   if (spatch < 0) return;
   const int c = a.slot_cluster[sslot];
@@ -438,7 +448,7 @@ __global__ void __launch_bounds__(kThreads) k_row_totals(const RowArgs a) {
   int64_t outp = 0;
   if (EMIT) {
     rtotal = a.row_total[sslot];
-    outp = a.row_ptr[spatch];
+    outp = a.sel_slots ? a.row_ptr[widx] : a.row_ptr[spatch];
   }
   // The list has ~40 candidates per accepted receiver.  Each 32-entry chunk has a precomputed summary of the (at
   // most two) row words it can touch, so 32 chunks are ruled out per step with one masked test per lane and only
@@ -500,6 +510,31 @@ __global__ void __launch_bounds__(kThreads) k_row_totals(const RowArgs a) {
     a.row_total[sslot] = total;
     a.row_count[sslot] = count;
   }
+}
+
+// Root TestLine_r calls of selected rows: the candidates of the row (PVS-visible receivers other than the source) that
+// pass the sign test of qrad3.c:238-241 -- the pairs the reference hands to TestLine_r at qrad3.c:244.
+__global__ void __launch_bounds__(kThreads) k_row_rays(const RowArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int widx = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (widx >= a.nsel) return;
+  const int sslot = a.sel_slots[widx];
+  long long n = 0;
+  if (sslot >= 0 && a.slot_patch[sslot] >= 0) {
+    const int c = a.slot_cluster[sslot];
+    const float4 so = a.s_origin_area[sslot];
+    const float4 sn = a.s_normal[sslot];
+    for (int64_t k = a.Lptr[c] + lane; k < a.Lptr[c + 1]; k += 32) {
+      const uint32_t rslot = a.L_slot[k];
+      if ((int) rslot == sslot) continue;
+      float dist;
+      bool wr;
+      form_factor_pre(so, sn, a.s_origin_area[rslot], a.s_normal[rslot], dist, wr);
+      n += wr ? 1 : 0;
+    }
+  }
+  for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if (lane == 0) a.sel_rays[widx] = n;
 }
 
 // pass 2, lane = row: one warp sums 32 consecutive source rows of one cluster at once.  The rows share the cluster's
@@ -1583,6 +1618,74 @@ void download_transfers_impl(qrad_cuda_ctx *c, int64_t *row_ptr, uint32_t *patch
   c->launch_check("k_row_totals<emit>");
   d_patch.download(patch, (size_t) nnz, st);
   d_tr.download(transfer, (size_t) nnz, st);
+}
+
+// the same for selected source patches only (row-sample parity checks on maps whose whole matrix is tens of GB)
+void download_rows_impl(qrad_cuda_ctx *c, int nrows, const int32_t *rows, int64_t *row_ptr, uint32_t *patch,
+                        uint16_t *transfer, int64_t capacity, int64_t *rays) {
+  if (c->world > 1) dfail("download_rows: not available on a shard");
+  if (nrows <= 0) return;
+  cudaStream_t st = c->stream;
+  std::vector<int32_t> rc((size_t) c->M);
+  c->row_count.download(rc.data(), rc.size(), st);
+  std::vector<int32_t> sel((size_t) nrows);
+  row_ptr[0] = 0;
+  for (int k = 0; k < nrows; k++) {
+    if (rows[k] < 0 || rows[k] >= c->N) dfail("download_rows: patch %d out of range", rows[k]);
+    sel[k] = c->h_patch_slot[rows[k]];
+    row_ptr[k + 1] = row_ptr[k] + (sel[k] >= 0 ? rc[sel[k]] : 0);
+  }
+  const int64_t nnz = row_ptr[nrows];
+  if (nnz > capacity) dfail("download_rows: %lld records do not fit the caller's %lld", (long long) nnz, (long long) capacity);
+  DBuf<int64_t> d_row_ptr;
+  d_row_ptr.upload(row_ptr, (size_t) nrows + 1, st);
+  DBuf<int32_t> d_sel;
+  d_sel.upload(sel, st);
+  DBuf<uint32_t> d_patch;
+  DBuf<uint16_t> d_tr;
+  DBuf<long long> d_rays;
+  d_patch.alloc((size_t) nnz + 1);
+  d_tr.alloc((size_t) nnz + 1);
+  d_rays.alloc((size_t) nrows);
+  RowArgs ra{};
+  ra.s_origin_area = c->s_origin_area.p;
+  ra.s_normal = c->s_normal.p;
+  ra.slot_patch = c->slot_patch.p;
+  ra.slot_cluster = c->slot_cluster.p;
+  ra.bits_base = c->d_bits_base.p;
+  ra.Lptr = c->d_Lptr.p;
+  ra.nwords = c->d_nwords.p;
+  ra.cl_slot_start = c->d_cl_slot_start.p;
+  ra.L_slot = c->L_slot.p;
+  ra.L_pos = c->L_pos.p;
+  ra.L_sum = c->L_sum.p;
+  ra.chunk_base = c->d_chunk_base.p;
+  ra.bits = c->bits.p;
+  ra.M = c->M;
+  ra.slot_lo = 0;
+  ra.slot_hi = c->M;
+  ra.row_total = c->row_total.p;
+  ra.row_count = c->row_count.p;
+  ra.row_ptr = d_row_ptr.p;
+  ra.out_patch = d_patch.p;
+  ra.out_transfer = d_tr.p;
+  ra.sel_slots = d_sel.p;
+  ra.nsel = nrows;
+  ra.sel_rays = d_rays.p;
+  const int blocks = (nrows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  k_row_totals<true><<<blocks, kThreads, 0, st>>>(ra);
+  c->launch_check("k_row_totals<emit, selected>");
+  if (rays) {
+    k_row_rays<<<blocks, kThreads, 0, st>>>(ra);
+    c->launch_check("k_row_rays");
+  }
+  d_patch.download(patch, (size_t) nnz, st);
+  d_tr.download(transfer, (size_t) nnz, st);
+  if (rays) {
+    std::vector<long long> hr((size_t) nrows);
+    d_rays.download(hr.data(), hr.size(), st);
+    for (int k = 0; k < nrows; k++) rays[k] = hr[k];
+  }
 }
 
 // BounceLight, qrad3.c:448-473, in three parts so that a multi-GPU host can all-gather the radiosity vector

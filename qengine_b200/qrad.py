@@ -59,6 +59,12 @@ class HostParams(C.Structure):
                 ("entity_scale", C.c_float), ("nopvs", C.c_int32), ("verbose", C.c_int32), ("max_patches", C.c_int32)]
 
 
+class HostCli(C.Structure):
+    _fields_ = [("next_arg", C.c_int32), ("threads", C.c_int32), ("tmpin", C.c_int32), ("tmpout", C.c_int32),
+                ("dump", C.c_int32), ("glview", C.c_int32), ("device", C.c_int32), ("ngpus", C.c_int32),
+                ("direct_given", C.c_int32), ("entity_given", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("rays_transfers", C.c_int64), ("rays_direct", C.c_int64), ("node_visits", C.c_int64),
                 ("candidate_pairs", C.c_int64), ("total_transfers", C.c_int64), ("transfer_bytes", C.c_int64),
@@ -69,7 +75,9 @@ class Stats(C.Structure):
                 ("ms_transfers_trace", C.c_float), ("ms_bounce", C.c_float), ("ms_bounce_kernel", C.c_float),
                 ("ms_final", C.c_float), ("kernel_launches", C.c_int32),
                 ("ms_tr_setup", C.c_float), ("ms_tr_lists", C.c_float), ("ms_tr_rows", C.c_float),
-                ("ms_tr_columns", C.c_float), ("full_walks", C.c_int64), ("box_pruned_rays", C.c_int64)]
+                ("ms_tr_columns", C.c_float), ("full_walks", C.c_int64), ("box_pruned_rays", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("ms_x_matrix", C.c_float), ("ms_x_small", C.c_float),
+                ("ms_x_radiosity", C.c_float), ("world", C.c_int32), ("rank", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -121,6 +129,18 @@ def default_params(**kw) -> HostParams:
             raise KeyError(k)
         setattr(p, k, v)
     return p
+
+
+def params_from_flags(flags, with_cli: bool = False):
+    """The reference's flag loop (qrad3.c:555-601) as implemented by the library (qrad_host_parse_flags)."""
+    p = default_params()
+    cli = HostCli()
+    args = [b"qrad3"] + [str(a).encode() for a in flags]
+    arr = (C.c_char_p * (len(args) + 1))(*args, None)
+    lib().qrad_host_parse_flags(C.c_int(len(args)), arr, C.byref(p), C.byref(cli))
+    if cli.next_arg != len(args):
+        raise ValueError(f"unknown qrad3 flag {flags[cli.next_arg - 1]!r}")
+    return (p, cli) if with_cli else p
 
 
 def _np_from(ptr, shape, dtype):
@@ -323,6 +343,21 @@ class Device:
                                                 patch.ctypes.data_as(C.POINTER(C.c_uint32)),
                                                 transfer.ctypes.data_as(C.POINTER(C.c_uint16))))
         return row_ptr, patch, transfer
+
+    def rows(self, patches):
+        """Transfer rows of the selected source patches: (row_ptr[n+1], patch u32[], transfer u16[], rays i64[n])."""
+        sel = np.ascontiguousarray(patches, np.int32)
+        cnt = self.numtransfers()[sel]
+        nnz = int(cnt.astype(np.int64).sum())
+        row_ptr = np.zeros(sel.size + 1, np.int64)
+        patch = np.zeros(max(nnz, 1), np.uint32)
+        transfer = np.zeros(max(nnz, 1), np.uint16)
+        rays = np.zeros(sel.size, np.int64)
+        _dck(lib().qrad_cuda_download_rows(self._h, C.c_int32(sel.size), _ip(sel), row_ptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                           patch.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                           transfer.ctypes.data_as(C.POINTER(C.c_uint16)), C.c_int64(nnz),
+                                           rays.ctypes.data_as(C.POINTER(C.c_int64))))
+        return row_ptr, patch[:nnz], transfer[:nnz], rays
 
     def patch_light(self):
         n = self._n

@@ -160,10 +160,15 @@ def main():
         cnt.astype("<i4").tofile(HERE / (name + ".numtransfers"))
         rays = R.read_rays(dump / "rays.bin")
         rays[:: max(1, len(rays) // 3000)].tofile(HERE / (name + ".rays"))
+        leafs = np.fromfile(dump / "rayleafs.bin", "<i4")
+        assert len(leafs) == len(rays)
+        leafs[:: max(1, len(rays) // 3000)].tofile(HERE / (name + ".rayleafs"))
         meta = dict(
             bsp=kind + ".bsp", flags=flags, num_patches=int(info["num_patches"]),
             total_transfer=int(info.get("total_transfer", 0)), numdlights=int(info.get("numdlights", 0)),
             lightdatasize=len(lump), added=[float(np.float32(a)) for a in info.get("added", [])],
+            rays_stride=max(1, len(rays) // 3000), rays_direct=int(info.get("rays_direct", 0)),
+            rays_transfers=int(info.get("rays_transfers", 0)),
             lump_md5=hashlib.md5(lump).hexdigest(), faces_md5=hashlib.md5(R.faces_lump(staged)).hexdigest(),
             file_md5=hashlib.md5(staged.read_bytes()).hexdigest(),
             totallight_md5=hashlib.md5(R.read_vec3(dump / "totallight.bin").tobytes()).hexdigest()

@@ -34,40 +34,26 @@ def stage_case(name, tmp: Path) -> Path:
 
 
 def params_from_flags(flags):
-    """The reference's flag parser (qrad3.c:555-601) applied to a HostParams."""
+    """The reference's flag parser (qrad3.c:555-601) as the library implements it."""
     from qengine_b200 import qrad as Q
-    p = Q.default_params()
-    it = iter(flags)
-    for f in it:
-        if f == "-bounce":
-            p.numbounce = int(next(it))
-        elif f == "-extra":
-            p.extrasamples = 1
-        elif f == "-chop":
-            p.subdiv = float(int(next(it)))
-        elif f == "-scale":
-            p.lightscale = float(next(it))
-        elif f == "-direct":
-            p.direct_scale = p.direct_scale * float(next(it))
-        elif f == "-entity":
-            p.entity_scale = p.entity_scale * float(next(it))
-        elif f == "-nopvs":
-            p.nopvs = 1
-        elif f == "-ambient":
-            p.ambient = float(next(it)) * 128
-        elif f == "-maxlight":
-            p.maxlight = min(float(next(it)) * 128, 255.0)
-        elif f == "-threads":
-            next(it)
-        elif f == "-v":
-            p.verbose = 1
-        else:
-            raise ValueError(f)
-    return p
+    return Q.params_from_flags(flags)
 
 
 def golden_rays(name):
     return np.fromfile(GOLDEN / (name + ".rays"), dtype=RAY_DTYPE)
+
+
+def golden_rayleafs(name):
+    """(points, PointInLeafnum of the reference) -- the point is the ray's end, snapped to the 16-grid in x for odd rays
+    of the harness's own numbering (oracle/ref_harness.c dump_rays); the committed sample keeps every k-th ray."""
+    rays = golden_rays(name)
+    leafs = np.fromfile(GOLDEN / (name + ".rayleafs"), dtype="<i4")
+    meta = json.loads((GOLDEN / (name + ".json")).read_text())
+    stride = meta["rays_stride"]
+    pts = rays["stop"].copy()
+    odd = (np.arange(len(rays)) * stride) & 1 == 1
+    pts[odd, 0] = (16 * (pts[odd, 0] / np.float32(16)).astype(np.int32)).astype(np.float32)
+    return pts, leafs
 
 
 def golden_numtransfers(name):

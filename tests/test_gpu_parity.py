@@ -78,11 +78,41 @@ def test_testline_decisions(Q, case, tmp_path):
     rays = G.golden_rays(case)
     got = dev.test_lines(rays["start"], rays["stop"])
     assert np.array_equal(got != 0, rays["result"] != 0)
-    # direction matters in the reference (epsilon handling): the reverse ray is a separate known answer,
-    # but a ray from a point to itself never hits anything new
-    same = dev.test_lines(rays["start"][:64], rays["start"][:64])
-    leaf = dev.point_in_leaf(rays["start"][:64])
-    assert same.shape == (64,) and leaf.min() >= 0
+    # reversed rays are separate known answers (the epsilon handling is not symmetric): checker = the C oracle
+    import sys
+    sys.path.insert(0, str(G.ROOT / "oracle"))
+    import oracle as O
+    o = O.Oracle(bsp)
+    k = slice(0, 2000)
+    assert np.array_equal(dev.test_lines(rays["stop"][k], rays["start"][k]) != 0,
+                          o.test_lines(rays["stop"][k], rays["start"][k]) != 0)
+
+
+@pytest.mark.parametrize("case", ["samplec", "grid3_chop16", "angled"])
+def test_point_in_leaf_matches_oracle(Q, case, tmp_path):
+    """PointInLeafnum (qrad3.c:131-150): patch origins, ray ends, and points on / next to node planes."""
+    import sys
+    sys.path.insert(0, str(G.ROOT / "oracle"))
+    import oracle as O
+    meta, flags = G.load_case(case)
+    bsp = G.stage_case(case, tmp_path)
+    sc = Q.Scene(bsp).prepare(G.params_from_flags(flags))
+    dev = Q.Device(0).upload(sc)
+    o = O.Oracle(bsp)
+    rays = G.golden_rays(case)
+    rng = np.random.default_rng(7)
+    pts = [sc.patches()["origin"], rays["start"][:1500], rays["stop"][:1500],
+           rng.uniform(-600, 600, (3000, 3)).astype(np.float32)]
+    # points exactly on node planes and one ulp to either side (`dist > 0` picks child 0, everything else child 1)
+    on = rays["stop"][:600].copy()
+    on[:, 0] = np.round(on[:, 0] / 16) * 16
+    on[:, 1] = np.round(on[:, 1] / 16) * 16
+    pts += [on, np.nextafter(on, np.float32(1e9)), np.nextafter(on, np.float32(-1e9))]
+    pts = np.concatenate(pts).astype(np.float32)
+    assert np.array_equal(dev.point_in_leaf(pts), o.point_in_leaf(pts))
+    # and against the reference's own PointInLeafnum answers (golden)
+    gp, gl = G.golden_rayleafs(case)
+    assert np.array_equal(dev.point_in_leaf(gp), gl)
 
 
 @pytest.mark.parametrize("case", ["samplec", "samplec_extra", "grid2", "grid3_chop16", "hall", "styles"])
@@ -149,7 +179,7 @@ def test_rerun_is_identical(Q, tmp_path):
 
 
 def test_nopvs_superset(Q, tmp_path):
-    """-nopvs only adds candidates: every PVS-mode transfer is still there and counts never shrink."""
+    """-nopvs only adds candidates: counts never shrink; the PVS-mode counts are the reference's (golden)."""
     meta, flags = G.load_case("samplec")
     bsp = G.stage_case("samplec", tmp_path)
     p = G.params_from_flags(flags)
@@ -157,6 +187,7 @@ def test_nopvs_superset(Q, tmp_path):
     dev = Q.Device(0).upload(sc)
     dev.make_transfers(0)
     a = dev.numtransfers()
+    assert np.array_equal(a, G.golden_numtransfers("samplec"))
     dev.make_transfers(1)
     b = dev.numtransfers()
     assert (b >= a).all()

@@ -66,3 +66,43 @@ def test_oracle_testline_golden(case, tmp_path):
     meta, o = make(case, tmp_path)
     rays = G.golden_rays(case)
     assert np.array_equal(o.test_lines(rays["start"], rays["stop"]) != 0, rays["result"] != 0)
+
+
+@pytest.mark.parametrize("case", ["samplec", "grid2", "grid3_chop16", "hall", "angled"])
+def test_oracle_point_in_leaf_golden(case, tmp_path):
+    """PointInLeafnum (qrad3.c:131-150) of the reference for points next to / on node planes."""
+    meta, o = make(case, tmp_path)
+    pts, leafs = G.golden_rayleafs(case)
+    assert np.array_equal(o.point_in_leaf(pts), leafs)
+
+
+@pytest.mark.parametrize("case", ["samplec", "samplec_extra", "grid2", "styles", "angled"])
+def test_oracle_ray_counts_match_reference(case, tmp_path):
+    """Unit of the rays/s metric: one root TestLine_r call.  The reference's own count (ld --wrap in oracle/ref_harness.c)
+    is in the golden metadata."""
+    meta, o = make(case, tmp_path)
+    o.rad_world()
+    assert o.ray_counts() == (meta["rays_direct"], meta["rays_transfers"])
+
+
+def test_limit_lifted_harness_is_byte_identical_to_the_unmodified_reference(tmp_path):
+    """oracle/_ref/ref_harness_big (MAX_PATCHES / u16 patch index lifted by sed on a scratch copy, oracle/Makefile)
+    writes the same file and counts the same rays as the unmodified reference on every golden case."""
+    import hashlib
+    import json
+    import subprocess
+    import refdump as R
+    if not (R.REF_DIR / "ref_harness_big").exists():
+        pytest.skip("oracle/_ref (reference-built harnesses) not present")
+    for case in G.CASES:
+        meta, flags = G.load_case(case)
+        got = {}
+        for exe in ("ref_harness", "ref_harness_big"):
+            bsp = G.stage_case(case, tmp_path / exe)
+            r = subprocess.run([str(R.REF_DIR / exe), *flags, str(bsp)], capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+            info = json.loads([l for l in r.stdout.splitlines() if l.startswith("REFTIMING ")][0][10:])
+            got[exe] = (hashlib.md5(bsp.read_bytes()).hexdigest(), info["rays_direct"], info["rays_transfers"],
+                        info["total_transfer"], info["added"])
+        assert got["ref_harness"] == got["ref_harness_big"], case
+        assert got["ref_harness"][0] == meta["file_md5"], case
