@@ -41,6 +41,8 @@ typedef struct {
   int32_t nopvs;          /* -nopvs               */
   int32_t verbose;        /* -v                   */
   int32_t max_patches;    /* 0 = unlimited (the reference stops at 65000, qrad.h:63) */
+  int32_t threads;        /* -threads n: host threads of the set-up (patch dicing); 0 = all cores.  The reference parses
+                             the flag and then runs single-threaded on Linux (threads.c:379-420); results do not depend on it */
 } qrad_host_params;
 
 /* what the flag loop of main() (qrad3.c:555-601) collects besides the tunables */

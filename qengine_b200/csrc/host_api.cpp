@@ -66,22 +66,9 @@ int qrad_host_prepare(qrad_host_scene *hs, qrad_host_params *params) {
     if (s.bsp.numnodes() == 0 || s.bsp.numfaces() == 0) fail("Empty map");
     s.winding.clear(); s.origin.clear(); s.normal.clear(); s.reflectivity.clear(); s.baselight.clear();
     s.totallight.clear(); s.planedist.clear(); s.area.clear(); s.cluster.clear(); s.face.clear();
-    s.next.clear(); s.sky.clear();
+    s.next.clear(); s.sky.clear(); s.wpts.clear(); s.wfirst.clear(); s.wcount.clear(); s.bounds.clear();
     make_patches(s);
     subdivide_patches(s);
-    if (s.bounds.size() != (size_t) s.num_patches() * 6) {  // subdiv < 1: no dicing, bounds still needed
-      s.bounds.resize((size_t) s.num_patches() * 6);
-      for (int i = 0; i < s.num_patches(); i++) {
-        float *mn = &s.bounds[i * 6], *mx = mn + 3;
-        mn[0] = mn[1] = mn[2] = 99999;
-        mx[0] = mx[1] = mx[2] = -99999;
-        for (auto &p : s.winding[i].p)
-          for (int k = 0; k < 3; k++) {
-            if (p[k] < mn[k]) mn[k] = p[k];
-            if (p[k] > mx[k]) mx[k] = p[k];
-          }
-      }
-    }
     create_direct_lights(s);
     build_face_frames(s);
     s.prepared = true;
@@ -181,9 +168,10 @@ int qrad_host_windings(qrad_host_scene *hs, int32_t *numpoints, float *pts) {
   Scene &s = hs->scene;
   size_t o = 0;
   for (int i = 0; i < s.num_patches(); i++) {
-    numpoints[i] = (int32_t) s.winding[i].p.size();
+    numpoints[i] = s.wcount[i];
     if (pts)
-      for (auto &p : s.winding[i].p) {
+      for (int k = 0; k < s.wcount[i]; k++) {
+        const Vec3 &p = s.wpts[(size_t) s.wfirst[i] + k];
         pts[o++] = p[0];
         pts[o++] = p[1];
         pts[o++] = p[2];
@@ -281,7 +269,7 @@ int qrad_host_parse_flags(int argc, char **argv, qrad_host_params *p, qrad_host_
     else if (!strcmp(a, "-extra"))
       p->extrasamples = 1;
     else if (!strcmp(a, "-threads"))
-      cli->threads = atoi(arg());  // parsed; the reference's Linux build then forces 1 (threads.c:379-420)
+      cli->threads = p->threads = atoi(arg());  // the reference's Linux build then forces 1 (threads.c:379-420); here: host set-up threads
     else if (!strcmp(a, "-chop"))
       p->subdiv = (float) atoi(arg());
     else if (!strcmp(a, "-scale"))

@@ -83,7 +83,10 @@ struct Scene {
   std::vector<Vec3> texture_reflectivity;
 
   // patches (SoA)
-  std::vector<Winding> winding;
+  std::vector<Winding> winding;         // the face patches while MakePatches runs; emptied by subdivide_patches
+  std::vector<Vec3> wpts;               // winding points of all patches, pooled ...
+  std::vector<int64_t> wfirst;          // ... first point and
+  std::vector<int32_t> wcount;          // ... number of points of patch i
   std::vector<Vec3> origin, normal, reflectivity, baselight, totallight;
   std::vector<float> planedist, area, bounds;  // bounds: 6 per patch
   std::vector<int32_t> cluster, face, next;

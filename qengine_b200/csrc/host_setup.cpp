@@ -5,9 +5,12 @@
 // (SURVEY.md section 8a, row a12).  The float/double mix of each expression follows
 // the reference's C promotion rules (vec_t = float, FLT_EVAL_METHOD 0, no FMA):
 // see the comments citing common/mathlib.c and common/polylib.c below.
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 
 #include "host_scene.hpp"
 
@@ -281,43 +284,145 @@ int new_patch(Scene &s) {
   return s.num_patches() - 1;
 }
 
-// DicePatch, patches.c:425-470 (recursion order: first the front half, then the back half)
-void dice_patch(Scene &s, int p) {
-  float mins[3], maxs[3];
-  winding_bounds(s.winding[p], mins, maxs);
-  const float subdiv = s.params.subdiv;
-  int i;
-  for (i = 0; i < 3; i++)
-    if (floor((double) ((mins[i] + 1) / subdiv)) < floor((double) ((maxs[i] - 1) / subdiv))) break;
-  if (i == 3) return;
-  float split[3] = {0, 0, 0};
-  split[i] = 1;
-  float dist = (float) ((double) subdiv * (1 + floor((double) ((mins[i] + 1) / subdiv))));
-  Winding o1, o2;
-  bool hf, hb;
-  clip_winding(s.winding[p], split, dist, 0.1f, o1, o2, hf, hb);
-  if (!hf || !hb) fail("DicePatch: split produced an empty side");
-  int np = new_patch(s);
-  s.next[np] = s.next[p];
-  s.next[p] = np;
-  s.winding[p] = std::move(o1);
-  s.winding[np] = std::move(o2);
-  // FinishSplit
-  s.baselight[np] = s.baselight[p];
-  s.totallight[np] = s.totallight[p];
-  s.reflectivity[np] = s.reflectivity[p];
-  s.normal[np] = s.normal[p];
-  s.planedist[np] = s.planedist[p];
-  s.sky[np] = s.sky[p];
-  s.face[np] = s.face[p];
-  s.area[p] = winding_area(s.winding[p]);
-  s.area[np] = winding_area(s.winding[np]);
-  if (s.area[p] <= 1) s.area[p] = 1;
-  if (s.area[np] <= 1) s.area[np] = 1;
-  place_patch(s, p);
-  place_patch(s, np);
-  dice_patch(s, p);
-  dice_patch(s, np);
+// ---- DicePatch, patches.c:425-470 -------------------------------------------------------------------------
+// The dicing of one face patch touches nothing but that patch and its own descendants, so the faces are diced in
+// parallel, each into thread-local arrays, and the results are stitched together afterwards with the indices the
+// reference's serial loop would have produced: the original keeps its index i, and the k-th patch created while
+// dicing it (creation order = the order of the `num_patches++` in DicePatch: split, recurse into the front half,
+// then into the back half) gets  numoriginals + (patches created by the originals before i) + k.
+constexpr int kMaxWindingPoints = 64;   // MAX_POINTS_ON_WINDING, polylib.h
+
+struct LocalPatches {          // everything one thread has produced so far
+  std::vector<Vec3> pts;       // winding points, pooled
+  std::vector<int64_t> wfirst;
+  std::vector<int32_t> wcount, next, cluster;   // next: local index within the same original, -1 = the original's next
+  std::vector<Vec3> origin;
+  std::vector<float> area;
+  int add() {
+    wfirst.push_back(0); wcount.push_back(0); next.push_back(-1); cluster.push_back(-1);
+    origin.push_back(Vec3{{0, 0, 0}}); area.push_back(0);
+    return (int) wcount.size() - 1;
+  }
+};
+
+struct Dicer {
+  const Scene &s;
+  LocalPatches &L;
+  const float *normal;        // of the face being diced
+  int base = 0;               // index in L of the original being diced
+  const qrad_dleaf_t *leafs;
+
+  void set_winding(int p, const Vec3 *w, int n) {
+    L.wfirst[p] = (int64_t) L.pts.size();
+    L.wcount[p] = n;
+    L.pts.insert(L.pts.end(), w, w + n);
+  }
+  // the tail shared by MakePatchForFace (:222-236) and FinishSplit (:326-352)
+  void finish(int p) {
+    const Vec3 *w = &L.pts[(size_t) L.wfirst[p]];
+    const int n = L.wcount[p];
+    float total = 0;   // WindingArea, polylib.c:137-151
+    for (int i = 2; i < n; i++) {
+      float d1[3], d2[3], c[3];
+      for (int k = 0; k < 3; k++) {
+        d1[k] = w[i - 1][k] - w[0][k];
+        d2[k] = w[i][k] - w[0][k];
+      }
+      cross(d1, d2, c);
+      total = (float) ((double) total + 0.5 * length_d(c));
+    }
+    L.area[p] = total <= 1 ? 1 : total;
+    float c[3] = {0, 0, 0};   // WindingCenter, polylib.c:177-188
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < 3; j++) c[j] = w[i][j] + c[j];
+    const float scale = (float) (1.0 / (double) n);
+    for (int j = 0; j < 3; j++) L.origin[p][j] = scale * c[j] + normal[j];
+    L.cluster[p] = leafs[s.bsp.point_in_leaf(L.origin[p].v)].cluster;
+  }
+  void dice(int p) {
+    const Vec3 *w = &L.pts[(size_t) L.wfirst[p]];
+    const int n = L.wcount[p];
+    float mins[3] = {99999, 99999, 99999}, maxs[3] = {-99999, -99999, -99999};
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < 3; j++) {
+        if (w[i][j] < mins[j]) mins[j] = w[i][j];
+        if (w[i][j] > maxs[j]) maxs[j] = w[i][j];
+      }
+    const float subdiv = s.params.subdiv;
+    int ax;
+    for (ax = 0; ax < 3; ax++)
+      if (floor((double) ((mins[ax] + 1) / subdiv)) < floor((double) ((maxs[ax] - 1) / subdiv))) break;
+    if (ax == 3) return;
+    const float dist = (float) ((double) subdiv * (1 + floor((double) ((mins[ax] + 1) / subdiv))));
+    // ClipWindingEpsilon (polylib.c:297-392) against the axial plane x[ax] = dist, epsilon 0.1f
+    Vec3 in[kMaxWindingPoints + 4], front[kMaxWindingPoints + 4], back[kMaxWindingPoints + 4];
+    float dists[kMaxWindingPoints + 5];
+    int sides[kMaxWindingPoints + 5], counts[3] = {0, 0, 0};
+    if (n > kMaxWindingPoints) fail("ClipWinding: MAX_POINTS_ON_WINDING");
+    for (int i = 0; i < n; i++) {
+      in[i] = w[i];
+      float d = in[i][ax];   // DotProduct with the axial normal: x*0 + y*0 + z*1 adds exact zeros
+      d -= dist;
+      dists[i] = d;
+      sides[i] = d > 0.1f ? 0 : (d < -0.1f ? 1 : 2);
+      counts[sides[i]]++;
+    }
+    sides[n] = sides[0];
+    dists[n] = dists[0];
+    if (!counts[0] || !counts[1]) fail("DicePatch: split produced an empty side");
+    int nf = 0, nb = 0;
+    for (int i = 0; i < n; i++) {
+      const Vec3 &p1 = in[i];
+      if (sides[i] == 2) {
+        front[nf++] = p1;
+        back[nb++] = p1;
+        continue;
+      }
+      if (sides[i] == 0) front[nf++] = p1;
+      if (sides[i] == 1) back[nb++] = p1;
+      if (sides[i + 1] == 2 || sides[i + 1] == sides[i]) continue;
+      const Vec3 &p2 = in[(i + 1) % n];
+      const float d = dists[i] / (dists[i] - dists[i + 1]);
+      Vec3 mid;
+      for (int j = 0; j < 3; j++) mid[j] = j == ax ? dist : p1[j] + d * (p2[j] - p1[j]);
+      front[nf++] = mid;
+      back[nb++] = mid;
+      if (nf > kMaxWindingPoints || nb > kMaxWindingPoints) fail("ClipWinding: MAX_POINTS_ON_WINDING");
+    }
+    const int np = L.add();
+    L.next[np] = L.next[p];
+    L.next[p] = np - base;
+    set_winding(p, front, nf);
+    set_winding(np, back, nb);
+    finish(p);
+    finish(np);
+    dice(p);
+    dice(np);
+  }
+};
+
+int host_threads(const Scene &s, int work_items) {
+  int n = s.params.threads > 0 ? s.params.threads : (int) std::thread::hardware_concurrency();
+  if (n < 1) n = 1;
+  if (n > 64) n = 64;
+  if (n > work_items) n = work_items > 0 ? work_items : 1;
+  return n;
+}
+
+template <class F> void parallel_for(int nthreads, F &&f) {   // f(thread index); exceptions are carried over
+  std::vector<std::thread> th;
+  std::vector<std::string> err((size_t) nthreads);
+  for (int t = 0; t < nthreads; t++)
+    th.emplace_back([&, t] {
+      try {
+        f(t);
+      } catch (const std::exception &e) {
+        err[t] = e.what()[0] ? e.what() : "error";
+      }
+    });
+  for (auto &t : th) t.join();
+  for (auto &e : err)
+    if (!e.empty()) fail("%s", e.c_str());
 }
 
 }  // namespace
@@ -405,12 +510,97 @@ void make_patches(Scene &s) {
 }
 
 void subdivide_patches(Scene &s) {  // patches.c:477-492
-  if (s.params.subdiv < 1) return;
-  int num = s.num_patches();
-  for (int i = 0; i < num; i++) dice_patch(s, i);
-  if (s.params.verbose) printf("%i patches after subdivision\n", s.num_patches());
-  s.bounds.resize((size_t) s.num_patches() * 6);
-  for (int i = 0; i < s.num_patches(); i++) winding_bounds(s.winding[i], &s.bounds[i * 6], &s.bounds[i * 6 + 3]);
+  const int num = s.num_patches();   // the originals: one per face
+  const qrad_dleaf_t *leafs = s.bsp.as<qrad_dleaf_t>(kLumpLeafs);
+  const bool dice = !(s.params.subdiv < 1);
+  const int nth = host_threads(s, num / 16);
+  std::vector<LocalPatches> locals((size_t) nth);
+  struct Where { int32_t thread, first, count; };
+  std::vector<Where> where((size_t) num);
+  std::atomic<int> cursor{0};
+  parallel_for(nth, [&](int t) {
+    LocalPatches &L = locals[t];
+    for (;;) {
+      const int i0 = cursor.fetch_add(16);
+      if (i0 >= num) break;
+      for (int i = i0; i < std::min(num, i0 + 16); i++) {
+        Dicer d{s, L, s.normal[i].v, 0, leafs};
+        d.base = L.add();
+        d.set_winding(d.base, s.winding[i].p.data(), (int) s.winding[i].p.size());
+        L.origin[d.base] = s.origin[i];
+        L.area[d.base] = s.area[i];
+        L.cluster[d.base] = s.cluster[i];
+        if (dice) d.dice(d.base);
+        where[i] = Where{t, d.base, (int32_t) L.wcount.size() - d.base};
+      }
+    }
+  });
+  // global indices: original i stays i, its created patches follow the originals in creation order
+  std::vector<int64_t> created_before((size_t) num + 1, 0), pts_before((size_t) num + 1, 0);
+  for (int i = 0; i < num; i++) {
+    const Where &w = where[i];
+    created_before[i + 1] = created_before[i] + (w.count - 1);
+    int64_t np = 0;
+    const LocalPatches &L = locals[w.thread];
+    for (int k = 0; k < w.count; k++) np += L.wcount[w.first + k];
+    pts_before[i + 1] = pts_before[i] + np;
+  }
+  const int64_t total = num + created_before[num];
+  if (s.params.max_patches && total > s.params.max_patches) fail("MAX_PATCHES");
+  if (total > 0x7fffffff) fail("MAX_PATCHES");
+  const size_t N = (size_t) total;
+  s.origin.resize(N); s.normal.resize(N); s.reflectivity.resize(N); s.baselight.resize(N); s.totallight.resize(N);
+  s.planedist.resize(N); s.area.resize(N); s.cluster.resize(N); s.face.resize(N); s.next.resize(N); s.sky.resize(N);
+  s.wfirst.resize(N); s.wcount.resize(N); s.bounds.resize(N * 6);
+  s.wpts.resize((size_t) pts_before[num]);
+  std::atomic<int> cursor2{0};
+  parallel_for(nth, [&](int) {
+    for (;;) {
+      const int i0 = cursor2.fetch_add(64);
+      if (i0 >= num) break;
+      for (int i = i0; i < std::min(num, i0 + 64); i++) {
+        const Where &w = where[i];
+        const LocalPatches &L = locals[w.thread];
+        const int64_t gbase = num + created_before[i];
+        auto gidx = [&](int k) -> int64_t { return k == 0 ? i : gbase + k - 1; };
+        const int32_t orig_next = s.next[i];
+        int64_t po = pts_before[i];
+        for (int k = 0; k < w.count; k++) {
+          const int l = w.first + k;
+          const size_t g = (size_t) gidx(k);
+          s.origin[g] = L.origin[l];
+          s.area[g] = L.area[l];
+          s.cluster[g] = L.cluster[l];
+          s.next[g] = L.next[l] < 0 ? orig_next : (int32_t) gidx(L.next[l]);
+          if (k) {   // FinishSplit copies the parent's face-constant fields, patches.c:326-336
+            s.normal[g] = s.normal[i]; s.reflectivity[g] = s.reflectivity[i]; s.baselight[g] = s.baselight[i];
+            s.totallight[g] = s.totallight[i]; s.planedist[g] = s.planedist[i]; s.sky[g] = s.sky[i]; s.face[g] = s.face[i];
+          }
+          s.wfirst[g] = po;
+          s.wcount[g] = L.wcount[l];
+          const Vec3 *src = &L.pts[(size_t) L.wfirst[l]];
+          float *mn = &s.bounds[g * 6], *mx = mn + 3;   // WindingBounds, polylib.c:153-170
+          mn[0] = mn[1] = mn[2] = 99999;
+          mx[0] = mx[1] = mx[2] = -99999;
+          for (int q = 0; q < L.wcount[l]; q++) {
+            s.wpts[(size_t) po + q] = src[q];
+            for (int j = 0; j < 3; j++) {
+              if (src[q][j] < mn[j]) mn[j] = src[q][j];
+              if (src[q][j] > mx[j]) mx[j] = src[q][j];
+            }
+          }
+          po += L.wcount[l];
+        }
+      }
+    }
+  });
+  if (s.params.verbose) {
+    for (size_t g = 0; g < N; g++)
+      if (s.cluster[g] == -1 && (int) g >= num) printf("patch->cluster == -1\n");
+    if (dice) printf("%i patches after subdivision\n", s.num_patches());
+  }
+  s.winding.clear();
+  s.winding.shrink_to_fit();
 }
 
 // ---------------------------------------------------------------------------

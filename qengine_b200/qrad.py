@@ -56,7 +56,8 @@ class FinalParams(C.Structure):
 class HostParams(C.Structure):
     _fields_ = [("numbounce", C.c_int32), ("extrasamples", C.c_int32), ("subdiv", C.c_float), ("ambient", C.c_float),
                 ("maxlight", C.c_float), ("lightscale", C.c_float), ("direct_scale", C.c_float),
-                ("entity_scale", C.c_float), ("nopvs", C.c_int32), ("verbose", C.c_int32), ("max_patches", C.c_int32)]
+                ("entity_scale", C.c_float), ("nopvs", C.c_int32), ("verbose", C.c_int32), ("max_patches", C.c_int32),
+                ("threads", C.c_int32)]
 
 
 class HostCli(C.Structure):
