@@ -67,10 +67,22 @@ int qrad_host_prepare(qrad_host_scene *hs, qrad_host_params *params) {
     s.winding.clear(); s.origin.clear(); s.normal.clear(); s.reflectivity.clear(); s.baselight.clear();
     s.totallight.clear(); s.planedist.clear(); s.area.clear(); s.cluster.clear(); s.face.clear();
     s.next.clear(); s.sky.clear(); s.wpts.clear(); s.wfirst.clear(); s.wcount.clear(); s.bounds.clear();
+    const bool timing = getenv("QRAD_DEBUG_TIMING") != nullptr;
+    auto tp = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+      if (!timing) return;
+      auto now = std::chrono::steady_clock::now();
+      fprintf(stderr, "prepare: %-22s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(now - tp).count());
+      tp = now;
+    };
     make_patches(s);
+    lap("MakePatches");
     subdivide_patches(s);
+    lap("SubdividePatches");
     create_direct_lights(s);
+    lap("CreateDirectLights");
     build_face_frames(s);
+    lap("face frames");
     s.prepared = true;
   });
 }

@@ -5,6 +5,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -71,6 +72,16 @@ void load_bsp(const std::string &path, Bsp &bsp);        // LoadBSPFile + ParseE
 void write_bsp(const Bsp &bsp, const std::string &path);  // WriteBSPFile
 void set_gamedir_from_path(const std::string &path, Bsp &bsp);
 
+// std::vector whose resize() leaves new elements uninitialised: the per-patch arrays of a 1M-patch map are hundreds of
+// MB that are completely overwritten (in parallel) right after they are sized.
+template <class T> struct DefaultInitAlloc : std::allocator<T> {
+  template <class U> struct rebind { using other = DefaultInitAlloc<U>; };
+  using std::allocator<T>::allocator;
+  template <class U> void construct(U *p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void *>(p)) U; }
+  template <class U, class... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+template <class T> using RawVec = std::vector<T, DefaultInitAlloc<T>>;
+
 struct Winding {
   std::vector<Vec3> p;
 };
@@ -84,13 +95,13 @@ struct Scene {
 
   // patches (SoA)
   std::vector<Winding> winding;         // the face patches while MakePatches runs; emptied by subdivide_patches
-  std::vector<Vec3> wpts;               // winding points of all patches, pooled ...
-  std::vector<int64_t> wfirst;          // ... first point and
-  std::vector<int32_t> wcount;          // ... number of points of patch i
-  std::vector<Vec3> origin, normal, reflectivity, baselight, totallight;
-  std::vector<float> planedist, area, bounds;  // bounds: 6 per patch
-  std::vector<int32_t> cluster, face, next;
-  std::vector<uint8_t> sky;
+  RawVec<Vec3> wpts;                    // winding points of all patches, pooled ...
+  RawVec<int64_t> wfirst;               // ... first point and
+  RawVec<int32_t> wcount;               // ... number of points of patch i
+  RawVec<Vec3> origin, normal, reflectivity, baselight, totallight;
+  RawVec<float> planedist, area, bounds;  // bounds: 6 per patch
+  RawVec<int32_t> cluster, face, next;
+  RawVec<uint8_t> sky;
   std::vector<int32_t> face_head;
   std::vector<Vec3> face_offset;
   std::vector<int32_t> face_entity;

@@ -7,6 +7,7 @@
 // see the comments citing common/mathlib.c and common/polylib.c below.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -339,7 +340,10 @@ struct Dicer {
     for (int j = 0; j < 3; j++) L.origin[p][j] = scale * c[j] + normal[j];
     L.cluster[p] = leafs[s.bsp.point_in_leaf(L.origin[p].v)].cluster;
   }
-  void dice(int p) {
+  // `dirty`: the winding of p has changed since its area / origin / cluster were computed.  The reference recomputes
+  // them after every split (FinishSplit); only the values of the final patches are ever read, so they are computed once,
+  // when a patch turns out not to be split any further.
+  void dice(int p, bool dirty) {
     const Vec3 *w = &L.pts[(size_t) L.wfirst[p]];
     const int n = L.wcount[p];
     float mins[3] = {99999, 99999, 99999}, maxs[3] = {-99999, -99999, -99999};
@@ -352,7 +356,10 @@ struct Dicer {
     int ax;
     for (ax = 0; ax < 3; ax++)
       if (floor((double) ((mins[ax] + 1) / subdiv)) < floor((double) ((maxs[ax] - 1) / subdiv))) break;
-    if (ax == 3) return;
+    if (ax == 3) {
+      if (dirty) finish(p);
+      return;
+    }
     const float dist = (float) ((double) subdiv * (1 + floor((double) ((mins[ax] + 1) / subdiv))));
     // ClipWindingEpsilon (polylib.c:297-392) against the axial plane x[ax] = dist, epsilon 0.1f
     Vec3 in[kMaxWindingPoints + 4], front[kMaxWindingPoints + 4], back[kMaxWindingPoints + 4];
@@ -394,10 +401,8 @@ struct Dicer {
     L.next[p] = np - base;
     set_winding(p, front, nf);
     set_winding(np, back, nb);
-    finish(p);
-    finish(np);
-    dice(p);
-    dice(np);
+    dice(p, true);
+    dice(np, true);
   }
 };
 
@@ -514,6 +519,14 @@ void subdivide_patches(Scene &s) {  // patches.c:477-492
   const qrad_dleaf_t *leafs = s.bsp.as<qrad_dleaf_t>(kLumpLeafs);
   const bool dice = !(s.params.subdiv < 1);
   const int nth = host_threads(s, num / 16);
+  const bool timing = getenv("QRAD_DEBUG_TIMING") != nullptr;
+  auto tp = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "  subdivide: %-18s %7.1f ms (%d threads)\n", what, std::chrono::duration<double, std::milli>(now - tp).count(), nth);
+    tp = now;
+  };
   std::vector<LocalPatches> locals((size_t) nth);
   struct Where { int32_t thread, first, count; };
   std::vector<Where> where((size_t) num);
@@ -530,11 +543,12 @@ void subdivide_patches(Scene &s) {  // patches.c:477-492
         L.origin[d.base] = s.origin[i];
         L.area[d.base] = s.area[i];
         L.cluster[d.base] = s.cluster[i];
-        if (dice) d.dice(d.base);
+        if (dice) d.dice(d.base, false);
         where[i] = Where{t, d.base, (int32_t) L.wcount.size() - d.base};
       }
     }
   });
+  lap("dice");
   // global indices: original i stays i, its created patches follow the originals in creation order
   std::vector<int64_t> created_before((size_t) num + 1, 0), pts_before((size_t) num + 1, 0);
   for (int i = 0; i < num; i++) {
@@ -553,6 +567,7 @@ void subdivide_patches(Scene &s) {  // patches.c:477-492
   s.planedist.resize(N); s.area.resize(N); s.cluster.resize(N); s.face.resize(N); s.next.resize(N); s.sky.resize(N);
   s.wfirst.resize(N); s.wcount.resize(N); s.bounds.resize(N * 6);
   s.wpts.resize((size_t) pts_before[num]);
+  lap("prefix + resize");
   std::atomic<int> cursor2{0};
   parallel_for(nth, [&](int) {
     for (;;) {
@@ -594,6 +609,7 @@ void subdivide_patches(Scene &s) {  // patches.c:477-492
       }
     }
   });
+  lap("merge");
   if (s.params.verbose) {
     for (size_t g = 0; g < N; g++)
       if (s.cluster[g] == -1 && (int) g >= num) printf("patch->cluster == -1\n");
