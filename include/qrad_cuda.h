@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define QRAD_CUDA_ABI_VERSION 1
+#define QRAD_CUDA_ABI_VERSION 2
 
 typedef struct qrad_cuda_ctx qrad_cuda_ctx;
 
@@ -143,9 +143,16 @@ const char *qrad_cuda_last_error(void);
 
 int  qrad_cuda_create(int device, qrad_cuda_ctx **out);
 void qrad_cuda_destroy(qrad_cuda_ctx *ctx);
-/* Restrict this context to a shard of the work (multi-GPU, one process per GPU):
-   source rows of the transfer matrix and faces are split into `world` contiguous shards. */
-int  qrad_cuda_set_shard(qrad_cuda_ctx *ctx, int rank, int world);
+/* ---- several GPUs of one box: one context per GPU (one process or one host thread each) ----
+   The reference has no multi-process mode; this is the sharding of SURVEY.md section 8e behind the same seams.  Rank 0
+   obtains an id, the host hands it to every rank by any means (a file, MPI, torch.distributed, shared memory of its own
+   threads), and every rank calls qrad_cuda_comm_init.  From then on the SAME entry points (upload_*, build_facelights,
+   make_transfers, bounce, final_light), called on every rank in the same order, each do their share of the faces / source
+   rows / receiver slices and exchange inside the library with NCCL over NVLink (loaded at run time: libnccl.so.2): an
+   all-to-all of the visibility rows before the transposition, one broadcast round of the radiosity vector per bounce,
+   sums of the per-patch light.  Every rank ends with the complete lighting lump.  world = 1 leaves the communicator. */
+int  qrad_cuda_comm_unique_id(uint8_t *id128 /*[128]*/);
+int  qrad_cuda_comm_init(qrad_cuda_ctx *ctx, int rank, int world, const uint8_t *id128);
 int  qrad_cuda_set_count_nodes(qrad_cuda_ctx *ctx, int enable);
 
 int  qrad_cuda_upload_bsp(qrad_cuda_ctx *ctx, const qrad_bsp_view *bsp);
@@ -167,20 +174,27 @@ int  qrad_cuda_final_light(qrad_cuda_ctx *ctx, const qrad_final_params *params,
                            uint8_t *dlightdata_out, int32_t lightdata_capacity, int32_t *lightdatasize,
                            int32_t *lightofs_out /*[F]*/, uint8_t *styles_out /*[F][4]*/);
 
-/* ---- multi-GPU (one process per GPU): the phases of make_transfers / bounce with the exchange points exposed.
-   After qrad_cuda_set_shard(rank, world) the host runs, on every rank:
-     make_transfers_phase(0)  ->  all-reduce(sum, u32) of QRAD_XBUF_BITS         (each word is written by one rank)
-     make_transfers_phase(1)  ->  all-gather of QRAD_XBUF_ROW_TOTAL and QRAD_XBUF_ROW_COUNT
-     make_transfers_phase(2)
-     bounce_phase(0); numbounce x { bounce_phase(1) -> all-gather of QRAD_XBUF_RADIOSITY };
-     all-gather of QRAD_XBUF_TOTALLIGHT; bounce_phase(2)
-   (the reference has no multi-process mode; this is the sharding of SURVEY.md section 8e). ---- */
-enum { QRAD_XBUF_BITS = 0, QRAD_XBUF_ROW_TOTAL = 1, QRAD_XBUF_ROW_COUNT = 2, QRAD_XBUF_RADIOSITY = 3, QRAD_XBUF_TOTALLIGHT = 4 };
-int  qrad_cuda_make_transfers_phase(qrad_cuda_ctx *ctx, int nopvs, int phase);
-int  qrad_cuda_bounce_phase(qrad_cuda_ctx *ctx, int phase);
-/* Device pointer and geometry of an exchange buffer: total_bytes of the whole buffer; for the all-gather buffers
-   every rank owns shard_bytes at offset rank * shard_bytes. */
-int  qrad_cuda_exchange_buffer(qrad_cuda_ctx *ctx, int which, void **devptr, int64_t *total_bytes, int64_t *shard_bytes);
+/* ---- planning (host only, no GPU needed): the geometry of the transfer matrix and of its distribution over `world`
+   ranks, exactly as make_transfers uses it (qengine_b200/csrc/plan.hpp).  Lets a host size its memory per GPU, and lets
+   the CPU tests drive the exchange protocol over any transport with the product's own addressing. ---- */
+typedef struct qrad_plan qrad_plan;
+const char *qrad_plan_last_error(void);
+int  qrad_plan_create(int32_t num_patches, const int32_t *cluster /*[N] patch->cluster*/, const uint8_t *visdata,
+                      int32_t visdatasize, int nopvs, int world, int rank, qrad_plan **out);
+void qrad_plan_destroy(qrad_plan *plan);
+/* out[0] slots, [1] slices (32 receivers each), [2] words of this rank's row buffer, [3] row groups, [4] own row groups,
+   [5] pass-1 runs of this rank, [6] clusters, [7] words of the whole matrix */
+int  qrad_plan_info(const qrad_plan *plan, int64_t *out8);
+int  qrad_plan_slices(const qrad_plan *plan, int32_t *lo /*[world]*/, int32_t *hi /*[world]*/);
+int  qrad_plan_slots(const qrad_plan *plan, int32_t *slot_owner /*[slots] or NULL*/, int32_t *patch_slot /*[N] or NULL*/);
+/* the contiguous piece of rank q's row buffer that rank r needs for its slices (what q sends r before pass 3) */
+int  qrad_plan_piece(const qrad_plan *plan, int q, int r, int64_t *first_word, int64_t *num_words);
+/* address of the word (source slot -> slice) in the row buffer of the source's owner; -1 = the pair has no word */
+int64_t qrad_plan_word_address(const qrad_plan *plan, int32_t source_slot, int32_t slice);
+/* pass 3's walk of a slice: its candidate sources in ascending patch index, who owns each, and where its word lies inside
+   the piece the owner sends to the slice's owner */
+int  qrad_plan_column_list(const qrad_plan *plan, int32_t slice, int32_t *slots, int32_t *owner, int64_t *addr_in_piece,
+                           int64_t capacity, int64_t *count);
 
 /* ---- inspection (parity tests, multi-GPU exchange); not needed by a production host ---- */
 int  qrad_cuda_get_stats(qrad_cuda_ctx *ctx, qrad_cuda_stats *out);

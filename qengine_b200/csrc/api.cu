@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstring>
 
+#include "comm.hpp"
 #include "qrad_device.cuh"
 
 using namespace qrad;
@@ -96,6 +97,8 @@ int qrad_cuda_create(int device, qrad_cuda_ctx **out) {
     c->traffic0 = traffic();
     c->sm_count = prop.multiProcessorCount;
     QCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    QCUDA(cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) QCUDA(cudaEventCreate(&e));
     *out = c;
   });
 }
@@ -103,17 +106,55 @@ int qrad_cuda_create(int device, qrad_cuda_ctx **out) {
 void qrad_cuda_destroy(qrad_cuda_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStream_t s = c->stream;
+  cudaStream_t s = c->stream, x = c->xstream;
   if (s) cudaStreamSynchronize(s);
+  if (x) cudaStreamSynchronize(x);
+  if (c->comm) {
+    try {
+      nccl().CommDestroy(c->comm);
+    } catch (...) {
+    }
+  }
+  for (auto e : c->bounce_ev) cudaEventDestroy(e);
+  for (auto e : c->ev)
+    if (e) cudaEventDestroy(e);
   delete c;
   if (s) cudaStreamDestroy(s);
+  if (x) cudaStreamDestroy(x);
 }
 
-int qrad_cuda_set_shard(qrad_cuda_ctx *c, int rank, int world) {
+// ---- several GPUs: the context joins an NCCL communicator; from then on the same entry points do their share of the work
+// and exchange inside the library (transfers.cu, direct.cu, final.cu) ----
+int qrad_cuda_comm_unique_id(uint8_t *id128) {
   return guarded([&] {
-    if (world < 1 || rank < 0 || rank >= world) dfail("bad shard %d/%d", rank, world);
-    c->rank = rank;
-    c->world = world;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId");
+    ncclUniqueId id;
+    ncclResult_t r = nccl().GetUniqueId(&id);
+    if (r != ncclSuccess) dfail("ncclGetUniqueId failed: %s", nccl().GetErrorString(r));
+    memcpy(id128, &id, 128);
+  });
+}
+
+int qrad_cuda_comm_init(qrad_cuda_ctx *c, int rank, int world, const uint8_t *id128) {
+  return guarded([&] {
+    if (world < 1 || rank < 0 || rank >= world) dfail("bad rank %d of %d", rank, world);
+    if (world > 16) dfail("at most 16 ranks");
+    QCUDA(cudaSetDevice(c->device));
+    if (c->comm) {
+      nccl().CommDestroy(c->comm);
+      c->comm = nullptr;
+    }
+    c->rank = 0;
+    c->world = 1;
+    if (world > 1) {
+      ncclUniqueId id;
+      memcpy(&id, id128, 128);
+      ncclResult_t r = nccl().CommInitRank(&c->comm, world, id, rank);
+      if (r != ncclSuccess) dfail("ncclCommInitRank failed: %s", nccl().GetErrorString(r));
+      c->rank = rank;
+      c->world = world;
+    }
+    c->transfers_done = c->facelights_done = false;
   });
 }
 
@@ -226,38 +267,10 @@ int qrad_cuda_upload_bsp(qrad_cuda_ctx *c, const qrad_bsp_view *b) {
     c->numclusters = 0;
     c->h_pvs.clear();
     if (c->have_vis) {
-      if (b->visdatasize < 4) dfail("visibility lump too small");
-      int32_t nc;
-      memcpy(&nc, b->visdata, 4);
-      if (nc < 0 || nc > 65536 || (int64_t) 4 + (int64_t) nc * 8 > b->visdatasize) dfail("bad visibility header");
-      c->numclusters = nc;
-      int rowbytes = (nc + 7) >> 3;
-      c->pvs_words = (nc + 31) >> 5;
-      c->h_pvs.assign((size_t) nc * c->pvs_words, 0);
-      std::vector<uint8_t> row((size_t) c->pvs_words * 4 + 8);
-      for (int cl = 0; cl < nc; cl++) {
-        int32_t ofs;
-        memcpy(&ofs, b->visdata + 4 + (size_t) cl * 8, 4);  // bitofs[cl][DVIS_PVS]
-        if (ofs < 0 || ofs >= b->visdatasize) dfail("PVS offset of cluster %d out of range", cl);
-        const uint8_t *in = b->visdata + ofs, *end = b->visdata + b->visdatasize;
-        std::fill(row.begin(), row.end(), 0);
-        int o = 0;
-        do {
-          if (in >= end) dfail("PVS row of cluster %d runs past the lump", cl);
-          if (*in) {
-            row[o++] = *in++;
-            continue;
-          }
-          if (in + 1 >= end) dfail("PVS row of cluster %d runs past the lump", cl);
-          int rep = in[1];
-          if (!rep) dfail("DecompressVis: 0 repeat");
-          in += 2;
-          while (rep && o < rowbytes) {
-            row[o++] = 0;
-            rep--;
-          }
-        } while (o < rowbytes);
-        memcpy(&c->h_pvs[(size_t) cl * c->pvs_words], row.data(), (size_t) c->pvs_words * 4);
+      try {
+        expand_pvs(b->visdata, b->visdatasize, c->numclusters, c->pvs_words, c->h_pvs);
+      } catch (const std::exception &e) {
+        dfail("%s", e.what());
       }
       c->pvs.upload(c->h_pvs, c->stream);
     }
@@ -424,63 +437,6 @@ int qrad_cuda_make_transfers(qrad_cuda_ctx *c, int nopvs, int64_t *total_transfe
   });
 }
 
-int qrad_cuda_make_transfers_phase(qrad_cuda_ctx *c, int nopvs, int phase) {
-  return guarded([&] {
-    QCUDA(cudaSetDevice(c->device));
-    if (phase == 0) transfers_trace(c, nopvs);
-    else if (phase == 1) transfers_rows(c);
-    else if (phase == 2) transfers_columns(c);
-    else dfail("make_transfers_phase: bad phase %d", phase);
-  });
-}
-
-int qrad_cuda_bounce_phase(qrad_cuda_ctx *c, int phase) {
-  return guarded([&] {
-    QCUDA(cudaSetDevice(c->device));
-    if (phase == 0) bounce_begin(c, false);
-    else if (phase == 1) {
-      bounce_step(c);
-      c->sync("bounce_step");
-    } else if (phase == 2) bounce_end(c);
-    else dfail("bounce_phase: bad phase %d", phase);
-  });
-}
-
-int qrad_cuda_exchange_buffer(qrad_cuda_ctx *c, int which, void **devptr, int64_t *total_bytes, int64_t *shard_bytes) {
-  return guarded([&] {
-    if (!c->M) dfail("exchange_buffer: make_transfers_phase(0) has not run");
-    switch (which) {
-      case QRAD_XBUF_BITS:
-        *devptr = c->bits.p;
-        *total_bytes = (int64_t) c->bits_words * 4;
-        *shard_bytes = 0;
-        break;
-      case QRAD_XBUF_ROW_TOTAL:
-        *devptr = c->row_total.p;
-        *total_bytes = (int64_t) c->Mpad * 4;
-        *shard_bytes = (int64_t) c->shard_slots * 4;
-        break;
-      case QRAD_XBUF_ROW_COUNT:
-        *devptr = c->row_count.p;
-        *total_bytes = (int64_t) c->Mpad * 4;
-        *shard_bytes = (int64_t) c->shard_slots * 4;
-        break;
-      case QRAD_XBUF_RADIOSITY:
-        *devptr = c->rad_cur;
-        *total_bytes = (int64_t) c->Mpad * 16;
-        *shard_bytes = (int64_t) c->shard_slots * 16;
-        break;
-      case QRAD_XBUF_TOTALLIGHT:
-        *devptr = c->s_total.p;
-        *total_bytes = (int64_t) c->Mpad * 16;
-        *shard_bytes = (int64_t) c->shard_slots * 16;
-        break;
-      default: dfail("exchange_buffer: bad id %d", which);
-    }
-    if (!*devptr) dfail("exchange_buffer %d is not allocated yet", which);
-  });
-}
-
 int qrad_cuda_bounce(qrad_cuda_ctx *c, int numbounce, float *added_out) {
   return guarded([&] {
     QCUDA(cudaSetDevice(c->device));
@@ -511,7 +467,7 @@ int qrad_cuda_download_numtransfers(qrad_cuda_ctx *c, int32_t *out) {
     if (!c->transfers_done) dfail("make_transfers has not run");
     std::vector<int32_t> rc((size_t) c->M);
     c->row_count.download(rc.data(), rc.size(), c->stream);
-    for (int i = 0; i < c->N; i++) out[i] = c->h_patch_slot[i] >= 0 ? rc[c->h_patch_slot[i]] : 0;
+    for (int i = 0; i < c->N; i++) out[i] = c->plan.patch_slot[i] >= 0 ? rc[c->plan.patch_slot[i]] : 0;
   });
 }
 

@@ -1,0 +1,24 @@
+// NCCL, loaded at run time (dlopen "libnccl.so.2"): a single-GPU host needs no NCCL at all, and inside a process that
+// already carries a copy (torch) the same library instance is used.  Only the multi-GPU entry points call in here.
+#pragma once
+#include <nccl.h>
+
+namespace qrad {
+
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  const char *(*GetErrorString)(ncclResult_t);
+  int version = 0;
+};
+
+const NcclApi &nccl();   // throws CudaError when no NCCL library can be loaded
+
+}  // namespace qrad

@@ -1,0 +1,375 @@
+// Host-side geometry of the transfer matrix and of its distribution over GPUs (see plan.hpp).  No CUDA in this file.
+#include "plan.hpp"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/qrad_cuda.h"
+
+namespace qrad {
+
+namespace {
+[[noreturn]] void pfail(const std::string &m) { throw std::runtime_error(m); }
+}  // namespace
+
+// DecompressVis (bspfile.c:129-154) for every cluster at once: row c, bit d = cluster d is in the PVS of cluster c.
+void expand_pvs(const uint8_t *visdata, int visdatasize, int &nc, int &pvs_words, std::vector<uint32_t> &out) {
+  if (visdatasize < 4) pfail("visibility lump too small");
+  int32_t n;
+  memcpy(&n, visdata, 4);
+  if (n < 0 || n > 65536 || (int64_t) 4 + (int64_t) n * 8 > visdatasize) pfail("bad visibility header");
+  nc = n;
+  const int rowbytes = (nc + 7) >> 3;
+  pvs_words = (nc + 31) >> 5;
+  out.assign((size_t) nc * pvs_words, 0);
+  std::vector<uint8_t> row((size_t) pvs_words * 4 + 8);
+  for (int cl = 0; cl < nc; cl++) {
+    int32_t ofs;
+    memcpy(&ofs, visdata + 4 + (size_t) cl * 8, 4);  // bitofs[cl][DVIS_PVS]
+    if (ofs < 0 || ofs >= visdatasize) pfail("PVS offset of cluster " + std::to_string(cl) + " out of range");
+    const uint8_t *in = visdata + ofs, *end = visdata + visdatasize;
+    std::fill(row.begin(), row.end(), 0);
+    int o = 0;
+    do {
+      if (in >= end) pfail("PVS row of cluster " + std::to_string(cl) + " runs past the lump");
+      if (*in) {
+        row[o++] = *in++;
+        continue;
+      }
+      if (in + 1 >= end) pfail("PVS row of cluster " + std::to_string(cl) + " runs past the lump");
+      int rep = in[1];
+      if (!rep) pfail("DecompressVis: 0 repeat");
+      in += 2;
+      while (rep && o < rowbytes) {
+        row[o++] = 0;
+        rep--;
+      }
+    } while (o < rowbytes);
+    memcpy(&out[(size_t) cl * pvs_words], row.data(), (size_t) pvs_words * 4);
+  }
+}
+
+int64_t TransferPlan::column_offset(int q, int d, int slot) const {
+  const int c = slot_cluster[slot];
+  const int32_t *b = &seer_cluster[seer_ptr[d]], *e = &seer_cluster[seer_ptr[d + 1]];
+  const int32_t *it = std::lower_bound(b, e, c);
+  if (it == e || *it != c) return -1;
+  const int g = group_of_slot(slot);
+  if (grp_owner[g] != q) return -1;
+  const size_t entry = (size_t) (it - seer_cluster.data());
+  return (int64_t) coff[(size_t) q * seer_cluster.size() + entry] + grp_ownbase[g] + (slot - grp_slot0[g]);
+}
+
+void build_plan(TransferPlan &p, int N, const int32_t *eff, int nc, const uint32_t *pvs, int pvs_words, int world, int rank,
+                int owner_chunks) {
+  if (world < 1 || rank < 0 || rank >= world) pfail("bad rank / world");
+  if (nc <= 0) pfail("make_transfers: no clusters");
+  p = TransferPlan();
+  p.N = N;
+  p.nc = nc;
+  p.world = world;
+  p.rank = rank;
+  // ---- slots ----
+  p.cl_count.assign(nc, 0);
+  for (int i = 0; i < N; i++) {
+    if (eff[i] >= nc) pfail("patch " + std::to_string(i) + " has cluster " + std::to_string(eff[i]) + " >= numclusters");
+    if (eff[i] >= 0) p.cl_count[eff[i]]++;
+  }
+  p.cl_slot_start.assign(nc + 1, 0);
+  for (int k = 0; k < nc; k++) p.cl_slot_start[k + 1] = p.cl_slot_start[k] + ((p.cl_count[k] + 31) & ~31);
+  const int M = p.cl_slot_start[nc];
+  p.M = M;
+  p.nslices = M / 32;
+  if (M == 0) pfail("make_transfers: no patch lies in a valid cluster");
+  p.slot_patch.assign(M, -1);
+  p.patch_slot.assign(N, -1);
+  p.slot_cluster.assign(M, 0);
+  {
+    std::vector<int32_t> fill(p.cl_slot_start.begin(), p.cl_slot_start.end() - 1);
+    for (int i = 0; i < N; i++)
+      if (eff[i] >= 0) {
+        const int s = fill[eff[i]]++;
+        p.slot_patch[s] = i;
+        p.patch_slot[i] = s;
+      }
+    for (int k = 0; k < nc; k++)
+      for (int s = p.cl_slot_start[k]; s < p.cl_slot_start[k + 1]; s++) p.slot_cluster[s] = k;
+  }
+  p.slice_count.assign(p.nslices, 0);
+  for (int s = 0; s < p.nslices; s++) {
+    const int c = p.slot_cluster[(size_t) s * 32];
+    p.slice_count[s] = std::min(32, p.cl_count[c] - (s * 32 - p.cl_slot_start[c]));
+  }
+  // ---- who sees whom ----
+  p.vis_ptr.assign(nc + 1, 0);
+  p.nwords.assign(nc, 0);
+  p.wb_first.assign(nc + 1, 0);
+  p.Lptr.assign(nc + 1, 0);
+  p.Rptr.assign(nc + 1, 0);
+  std::vector<int32_t> seer_n(nc + 1, 0);
+  for (int a = 0; a < nc; a++) {
+    int w = 0;
+    int64_t cand = 0;
+    if (p.cl_count[a] > 0)
+      for (int d = 0; d < nc; d++) {
+        const bool vis = pvs ? ((pvs[(size_t) a * pvs_words + (d >> 5)] >> (d & 31)) & 1u) != 0 : true;
+        if (!vis || p.cl_count[d] == 0) continue;
+        p.vis_cluster.push_back(d);
+        p.vis_woff.push_back(w);
+        w += (p.cl_slot_start[d + 1] - p.cl_slot_start[d]) >> 5;
+        cand += p.cl_count[d];
+        p.Rptr[d + 1] += p.cl_count[a];
+        seer_n[d + 1]++;
+      }
+    p.vis_ptr[a + 1] = (int32_t) p.vis_cluster.size();
+    p.nwords[a] = w;
+    p.wb_first[a + 1] = p.wb_first[a] + w;
+    p.Lptr[a + 1] = p.Lptr[a] + cand;
+  }
+  for (int d = 0; d < nc; d++) p.Rptr[d + 1] += p.Rptr[d];
+  if (p.Lptr[nc] >= ((int64_t) 1 << 40)) pfail("make_transfers: candidate lists too large");
+  p.seer_ptr.assign(nc + 1, 0);
+  for (int d = 0; d < nc; d++) p.seer_ptr[d + 1] = p.seer_ptr[d] + seer_n[d + 1];
+  p.seer_cluster.assign(p.vis_cluster.size(), 0);
+  p.vis_seer.assign(p.vis_cluster.size(), 0);
+  {
+    std::vector<int32_t> fill(p.seer_ptr.begin(), p.seer_ptr.end() - 1);
+    for (int a = 0; a < nc; a++)   // a ascending: every seer list comes out sorted
+      for (int v = p.vis_ptr[a]; v < p.vis_ptr[a + 1]; v++) {
+        const int e = fill[p.vis_cluster[v]]++;
+        p.seer_cluster[e] = a;
+        p.vis_seer[v] = e;
+      }
+  }
+  const size_t E = p.seer_cluster.size();
+  // ---- row groups and their owners ----
+  p.grp_first.assign(nc + 1, 0);
+  for (int c = 0; c < nc; c++) {
+    const int padded = p.cl_slot_start[c + 1] - p.cl_slot_start[c];
+    const int ng = (padded + kGroupRows - 1) / kGroupRows;
+    p.grp_first[c + 1] = p.grp_first[c] + ng;
+    for (int g = 0; g < ng; g++) {
+      p.grp_cluster.push_back(c);
+      p.grp_slot0.push_back(p.cl_slot_start[c] + g * kGroupRows);
+      p.grp_rows.push_back(std::min(kGroupRows, padded - g * kGroupRows));
+    }
+  }
+  const int G = (int) p.grp_cluster.size();
+  p.grp_owner.assign(G, 0);
+  if (world > 1) {
+    // dealt in `chunks` contiguous chunks per rank of (nearly) equal candidate words, chunk j -> rank j mod world: every
+    // rank samples the whole map (the cost of a candidate word varies over the map) and still only touches about
+    // 1 / world of the clusters, so its lists and pass 2 shrink with the rank count
+    int chunks = owner_chunks > 0 ? owner_chunks : 8;
+    if (const char *e = getenv("QRAD_OWNER_CHUNKS")) chunks = std::max(1, atoi(e));
+    double total = 0;
+    for (int g = 0; g < G; g++) total += (double) p.grp_rows[g] * p.nwords[p.grp_cluster[g]];
+    const int nchunks = world * chunks;
+    const double per = total > 0 ? total / nchunks : 1;
+    double cum = 0;
+    for (int g = 0; g < G; g++) {
+      const double w = (double) p.grp_rows[g] * p.nwords[p.grp_cluster[g]];
+      int ch = (int) ((cum + 0.5 * w) / per);
+      ch = std::max(0, std::min(nchunks - 1, ch));
+      p.grp_owner[g] = ch % world;
+      cum += w;
+    }
+  }
+  p.nown.assign((size_t) world * nc, 0);
+  p.grp_ownbase.assign(G, 0);
+  for (int g = 0; g < G; g++) {
+    int32_t &n = p.nown[(size_t) p.grp_owner[g] * nc + p.grp_cluster[g]];
+    p.grp_ownbase[g] = n;
+    n += p.grp_rows[g];
+  }
+  p.coff.assign((size_t) world * E, 0);
+  p.colh.assign((size_t) world * nc, 0);
+  for (int q = 0; q < world; q++)
+    for (int d = 0; d < nc; d++) {
+      int64_t acc = 0;
+      for (int e = p.seer_ptr[d]; e < p.seer_ptr[d + 1]; e++) {
+        p.coff[(size_t) q * E + e] = (int32_t) acc;
+        acc += p.nown[(size_t) q * nc + p.seer_cluster[e]];
+      }
+      if (acc > 0x7fffffff) pfail("make_transfers: a slice column exceeds 2^31 words");
+      p.colh[(size_t) q * nc + d] = (int32_t) acc;
+    }
+  // ---- receiver slices: contiguous runs of (nearly) equal candidate sources ----
+  p.slice_lo.assign(world, 0);
+  p.slice_hi.assign(world, 0);
+  {
+    double total = 0;
+    for (int s = 0; s < p.nslices; s++) {
+      const int d = p.slot_cluster[(size_t) s * 32];
+      total += (double) (p.Rptr[d + 1] - p.Rptr[d]);
+    }
+    double cum = 0;
+    int r = 0;
+    for (int s = 0; s < p.nslices; s++) {
+      const int d = p.slot_cluster[(size_t) s * 32];
+      const double w = (double) (p.Rptr[d + 1] - p.Rptr[d]);
+      while (r < world - 1 && cum + 0.5 * w >= total * (r + 1) / world) {
+        p.slice_hi[r] = s;
+        p.slice_lo[++r] = s;
+      }
+      cum += w;
+    }
+    while (r < world - 1) {
+      p.slice_hi[r] = p.nslices;
+      p.slice_lo[++r] = p.nslices;
+    }
+    p.slice_hi[world - 1] = p.nslices;
+  }
+  p.sbase.assign((size_t) world * (p.nslices + 1), 0);
+  for (int q = 0; q < world; q++) {
+    int64_t *sb = &p.sbase[(size_t) q * (p.nslices + 1)];
+    for (int s = 0; s < p.nslices; s++) sb[s + 1] = sb[s] + p.colh[(size_t) q * nc + p.slot_cluster[(size_t) s * 32]];
+  }
+  // ---- this rank ----
+  p.own_runbase.assign(1, 0);
+  for (int g = 0; g < G; g++) {
+    if (p.grp_owner[g] != rank) continue;
+    const int c = p.grp_cluster[g];
+    p.own_groups.push_back(g);
+    p.own_runbase.push_back(p.own_runbase.back() + (p.nwords[c] + kChunkWords - 1) / kChunkWords);
+    for (int r = 0; r < p.grp_rows[g]; r += 32) {
+      p.own_rowslice_slot0.push_back(p.grp_slot0[g] + r);
+      p.own_rowslice_row0.push_back(p.grp_ownbase[g] + r);
+    }
+  }
+  p.Lown_ptr.assign(nc + 1, 0);
+  p.Rown_ptr.assign(nc + 1, 0);
+  for (int c = 0; c < nc; c++) {
+    const bool rows_here = p.nown[(size_t) rank * nc + c] > 0;
+    p.Lown_ptr[c + 1] = p.Lown_ptr[c] + (rows_here ? p.Lptr[c + 1] - p.Lptr[c] : 0);
+    const int s0 = p.cl_slot_start[c] >> 5, s1 = p.cl_slot_start[c + 1] >> 5;
+    const bool slices_here = std::max(s0, p.slice_lo[rank]) < std::min(s1, p.slice_hi[rank]);
+    p.Rown_ptr[c + 1] = p.Rown_ptr[c] + (slices_here ? p.Rptr[c + 1] - p.Rptr[c] : 0);
+  }
+}
+
+}  // namespace qrad
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C entry points (include/qrad_cuda.h, "planning"): the same plan the CUDA half builds, without a GPU.
+struct qrad_plan {
+  qrad::TransferPlan p;
+};
+
+static thread_local std::string g_plan_error;
+extern "C" {
+
+const char *qrad_plan_last_error(void) { return g_plan_error.c_str(); }
+
+int qrad_plan_create(int32_t num_patches, const int32_t *cluster, const uint8_t *visdata, int32_t visdatasize, int nopvs,
+                     int world, int rank, qrad_plan **out) {
+  *out = nullptr;
+  try {
+    int nc = 0, pw = 0;
+    std::vector<uint32_t> pvs;
+    qrad::expand_pvs(visdata, visdatasize, nc, pw, pvs);
+    std::vector<int32_t> eff(cluster, cluster + num_patches);
+    if (nopvs) std::fill(eff.begin(), eff.end(), 0);
+    qrad_plan *h = new qrad_plan;
+    try {
+      qrad::build_plan(h->p, num_patches, eff.data(), nopvs ? 1 : nc, nopvs ? nullptr : pvs.data(), pw, world, rank, 0);
+    } catch (...) {
+      delete h;
+      throw;
+    }
+    *out = h;
+    return 0;
+  } catch (const std::exception &e) {
+    g_plan_error = e.what();
+    return 1;
+  }
+}
+
+void qrad_plan_destroy(qrad_plan *h) { delete h; }
+
+// out[0] slots, [1] slices, [2] words of this rank's row buffer, [3] row groups, [4] own groups, [5] pass-1 runs of this
+// rank, [6] clusters, [7] words of the whole matrix (sum over ranks)
+int qrad_plan_info(const qrad_plan *h, int64_t *out) {
+  const qrad::TransferPlan &p = h->p;
+  out[0] = p.M;
+  out[1] = p.nslices;
+  out[2] = p.rowbuf_words();
+  out[3] = (int64_t) p.grp_cluster.size();
+  out[4] = (int64_t) p.own_groups.size();
+  out[5] = p.own_runbase.back();
+  out[6] = p.nc;
+  int64_t all = 0;
+  for (int q = 0; q < p.world; q++) all += p.sbase[(size_t) q * (p.nslices + 1) + p.nslices];
+  out[7] = all;
+  return 0;
+}
+
+int qrad_plan_slices(const qrad_plan *h, int32_t *lo, int32_t *hi) {
+  for (int r = 0; r < h->p.world; r++) {
+    lo[r] = h->p.slice_lo[r];
+    hi[r] = h->p.slice_hi[r];
+  }
+  return 0;
+}
+
+// per slot: owner rank of its row group; per patch: its slot (-1 = no valid cluster)
+int qrad_plan_slots(const qrad_plan *h, int32_t *slot_owner /*[M]*/, int32_t *patch_slot /*[N]*/) {
+  const qrad::TransferPlan &p = h->p;
+  if (slot_owner)
+    for (int s = 0; s < p.M; s++) slot_owner[s] = p.grp_owner[p.group_of_slot(s)];
+  if (patch_slot) memcpy(patch_slot, p.patch_slot.data(), sizeof(int32_t) * (size_t) p.N);
+  return 0;
+}
+
+// first word and number of words of the contiguous piece of rank q's row buffer that describes the receiver slices of rank r
+int qrad_plan_piece(const qrad_plan *h, int q, int r, int64_t *first, int64_t *count) {
+  const qrad::TransferPlan &p = h->p;
+  if (q < 0 || q >= p.world || r < 0 || r >= p.world) return 1;
+  *first = p.sbase[(size_t) q * (p.nslices + 1) + p.slice_lo[r]];
+  *count = p.words_for(q, r);
+  return 0;
+}
+
+// address, in the row buffer of the rank that owns source slot `source_slot`, of its word towards `slice`; -1 when the
+// source's cluster cannot see the slice's cluster (no such word exists)
+int64_t qrad_plan_word_address(const qrad_plan *h, int32_t source_slot, int32_t slice) {
+  const qrad::TransferPlan &p = h->p;
+  if (source_slot < 0 || source_slot >= p.M || slice < 0 || slice >= p.nslices) return -1;
+  const int q = p.grp_owner[p.group_of_slot(source_slot)];
+  const int64_t off = p.column_offset(q, p.slot_cluster[(size_t) slice * 32], source_slot);
+  if (off < 0) return -1;
+  return p.sbase[(size_t) q * (p.nslices + 1) + slice] + off;
+}
+
+// The column list of `slice` as pass 3 walks it: candidate sources in ascending patch index, each with the rank that
+// owns its row and the address of its word for this slice inside THE PIECE that rank sends to the slice's owner.
+int qrad_plan_column_list(const qrad_plan *h, int32_t slice, int32_t *slots, int32_t *owner, int64_t *addr_in_piece,
+                          int64_t capacity, int64_t *count) {
+  const qrad::TransferPlan &p = h->p;
+  if (slice < 0 || slice >= p.nslices) return 1;
+  const int d = p.slot_cluster[(size_t) slice * 32];
+  int r = 0;
+  while (r < p.world - 1 && slice >= p.slice_hi[r]) r++;
+  int64_t n = 0;
+  for (int i = 0; i < p.N; i++) {
+    const int s = p.patch_slot[i];
+    if (s < 0) continue;
+    const int q = p.grp_owner[p.group_of_slot(s)];
+    const int64_t off = p.column_offset(q, d, s);
+    if (off < 0) continue;
+    if (n < capacity) {
+      slots[n] = s;
+      owner[n] = q;
+      const int64_t *sb = &p.sbase[(size_t) q * (p.nslices + 1)];
+      addr_in_piece[n] = sb[slice] - sb[p.slice_lo[r]] + off;
+    }
+    n++;
+  }
+  *count = n;
+  return 0;
+}
+
+}  // extern "C"

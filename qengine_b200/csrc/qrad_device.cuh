@@ -12,7 +12,10 @@
 #include <string>
 #include <vector>
 
+#include <nccl.h>
+
 #include "../../include/qrad_cuda.h"
+#include "plan.hpp"
 
 namespace qrad {
 
@@ -477,53 +480,47 @@ struct qrad_cuda_ctx {
   std::vector<int32_t> h_fl_numstyles, h_fl_stylenums;  // [F], [F][32] (slot indices into h_style_ids)
   bool facelights_done = false;
 
-  // ---- transfer matrix (qrad_cuda_make_transfers) ----
-  // "slot" order: patches grouped by PVS cluster, each cluster padded to a multiple of 32.
-  int M = 0;                            // number of slots
-  int nc_eff = 0;
-  std::vector<int32_t> h_slot_patch;    // [M] patch or -1
-  std::vector<int32_t> h_patch_slot;    // [N] slot or -1
-  std::vector<int32_t> h_cl_slot_start, h_cl_count, h_slot_cluster;
-  qrad::DBuf<int32_t> slot_patch, patch_slot, slot_cluster;
+  // ---- transfer matrix (qrad_cuda_make_transfers): geometry in plan.hpp ----
+  qrad::TransferPlan plan;
+  int M = 0;                            // number of slots (= plan.M)
+  qrad::DBuf<int32_t> slot_patch, patch_slot, slot_cluster, slice_count, d_cl_slot_start, d_cl_count, d_nwords;
+  qrad::DBuf<uint8_t> slot_flags;
+  qrad::DBuf<int64_t> d_wb_first, d_sbase, d_own_runbase, wbase;
+  qrad::DBuf<int32_t> wslice, d_vis_ptr, d_vis_cluster, d_vis_woff, d_vis_seer, d_vis_src, d_coff;
+  qrad::DBuf<int32_t> d_grp_first, d_grp_cluster, d_grp_slot0, d_grp_rows, d_grp_owner, d_grp_ownbase, d_own_groups;
+  qrad::DBuf<int32_t> d_rowslice_slot0, d_rowslice_row0;
   qrad::DBuf<float4> s_origin_area, s_normal, wbox_min, wbox_max;
-  uint64_t bits_words = 0;
-  qrad::DBuf<uint32_t> bits;            // visibility*formfactor>0 bit matrix, rows of source slots
+  qrad::DBuf<uint32_t> bits;            // this rank's rows of the visibility*formfactor>0 bit matrix, slice-major
+  qrad::DBuf<uint32_t> colbuf;          // several GPUs: the other ranks' words about this rank's slices
+  std::vector<int64_t> piece_first;     // [world] where rank q's piece starts in colbuf
+  qrad::DBuf<int2> d_runs;              // the patch order as runs of consecutive slots
+  qrad::DBuf<int64_t> d_vl_ptr, d_vr_ptr;
+  qrad::DBuf<int4> vl, vr;              // row / column run lists (transfers.cu)
   qrad::DBuf<float> row_total;          // [M]
   qrad::DBuf<int32_t> row_count;        // [M] numtransfers of the source in slot s
   // gather-form matrix, "dense slices": see k_columns / k_bounce in transfers.cu
-  int64_t sell_entries = 0;             // list entries over all slices (each slice padded to a multiple of 8)
+  int64_t sell_entries = 0;             // list entries over all slices (each slice padded to a multiple of 32)
   qrad::DBuf<int32_t> slice_len;        // [M/32] list entries of a slice
   qrad::DBuf<int64_t> slice_base;       // [M/32 + 1] first entry of a slice
   qrad::DBuf<uint32_t> g_src;           // [entries] source slot
   qrad::DBuf<uint4> g_w;                // [entries/8][32] 8 u16 weights per lane
-  qrad::DBuf<int32_t> col_blk_slice0, col_blk_n;   // k_columns block table
   qrad::DBuf<int32_t> slice_order;      // this rank's slices, longest list first (k_bounce work order)
   qrad::DBuf<int32_t> bounce_next;      // [2] k_bounce work counters
+  qrad::DBuf<int32_t> negative_light;   // CheckPatches flag
   int bounce_blocks_per_sm = 0, bounce_regs_blocks_per_sm = 0;
-  // row-major helper lists kept for inspection / download
-  std::vector<int64_t> h_Lptr, h_bits_base;
-  std::vector<int32_t> h_nwords;
-  qrad::DBuf<int64_t> d_Lptr, d_bits_base;
-  qrad::DBuf<int32_t> d_nwords, d_cl_slot_start, d_cl_count;
-  qrad::DBuf<uint32_t> L_slot, L_pos;
-  qrad::DBuf<uint4> L_sum;              // per 32-entry chunk of a row list: row words / masks it can touch
-  qrad::DBuf<int64_t> d_chunk_base;
   bool transfers_done = false;
   int64_t total_transfers = 0;
-  // state kept between the phases of make_transfers / bounce (multi-GPU hosts exchange in between)
-  int slice_lo = 0, slice_hi = 0;       // this rank's slices (32 slots each)
-  int shard_slots = 0, Mpad = 0;        // slots per shard, world * shard_slots
-  std::vector<int64_t> h_Rptr;
-  qrad::DBuf<int32_t> d_vis_ptr, d_vis_cluster, d_vis_woff, d_woff_table;
-  qrad::DBuf<int64_t> d_Rptr, d_task_base;
-  qrad::DBuf<uint32_t> R_slot;
-  qrad::DBuf<int64_t> R_addr;
   qrad::DBuf<unsigned long long> counters;
   qrad::DBuf<float> rad_sum;
   qrad::Timer t_transfers, t_bounce;
   float4 *rad_cur = nullptr, *rad_nxt = nullptr;
-  float bounce_kernel_ms = 0;
   int bounce_steps = 0;
+  std::vector<cudaEvent_t> bounce_ev;   // two per bounce: around the kernel launch
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // pass 1 begin / end, matrix exchange begin / end
+  // ---- several GPUs ----
+  ncclComm_t comm = nullptr;
+  cudaStream_t xstream = nullptr;       // the matrix exchange runs beside the lists and pass 2
+  int face_lo = 0, face_hi = 0;         // faces this rank lights (all of them on one GPU)
 
   // ---- FinalLightFace scratch (per resident warp) ----
   qrad::DBuf<uint16_t> fin_matrix, fin_ep0, fin_ep1, fin_tedges, fin_stack;
@@ -565,6 +562,7 @@ void bounce_end(qrad_cuda_ctx *c);
 void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out, int32_t cap, int32_t *size,
                       int32_t *lightofs, uint8_t *styles);
 void download_transfers_impl(qrad_cuda_ctx *c, int64_t *row_ptr, uint32_t *patch, uint16_t *transfer);
+void expand_pvs(const uint8_t *visdata, int visdatasize, int &nc, int &pvs_words, std::vector<uint32_t> &out);
 void download_rows_impl(qrad_cuda_ctx *c, int nrows, const int32_t *rows, int64_t *row_ptr, uint32_t *patch,
                         uint16_t *transfer, int64_t capacity, int64_t *rays);
 void test_lines_impl(qrad_cuda_ctx *c, int64_t n, const float *starts, const float *stops, uint8_t *results);

@@ -1,36 +1,41 @@
 // MakeTransfers (qrad3.c:185-293) and BounceLight (qrad3.c:383-473) on the GPU.
 //
-// Layout ("slot order"): patches are grouped by the PVS cluster of their origin, every
-// cluster padded to a multiple of 32 slots, so one 32-bit word of the visibility matrix
-// = one source patch x 32 consecutive receivers of one cluster.
+// Layout ("slot order", plan.hpp): patches are grouped by the PVS cluster of their origin, every cluster padded to a
+// multiple of 32 slots, so one 32-bit word of the visibility matrix = one source patch x the 32 receivers of one slice.
+// The matrix is stored slice-major: word(source row, slice s) = bits[wbase(cluster of the row, word) + own row], i.e.
+// the words of 32 consecutive source rows towards one slice are 32 consecutive words.  PVS pruning is structural:
+// invisible pairs have no word.
 //
-//   pass 1  k_visibility   one warp per task (1 source x <= 1024 receivers, PVS pruning is structural):
-//                          whole-word interval proofs, form factor sign tests, blocker-guess walks, full
-//                          TestLine for the rest; writes the accept bit  trans > 0  (qrad3.c:216-257).
-//   pass 2  k_row_totals32 one warp per 32 source rows of a cluster, lane = row: walks the shared candidate list in
-//                          ascending receiver index (the reference's j order); every lane forms the SERIAL float
-//                          sum `total` (qrad3.c:254) and numtransfers of its own row.
+//   pass 1  k_visibility   one warp per run = (row group of <= 128 sources, chunk of <= 32 words = 1024 receivers): the
+//                          same receivers seen from neighbouring sources.  Whole-word interval proofs, form factor
+//                          sign tests, blocker-guess walks, full TestLine for the rest; writes the accept bit
+//                          trans > 0  (qrad3.c:216-257).
+//   pass 2  k_row_totals32 one warp per 32 source rows, lane = row: walks the receivers in ascending patch index (the
+//                          reference's j order) run by run, reading its words coalesced; every lane forms the SERIAL
+//                          float sum `total` (qrad3.c:254) and numtransfers of its own row.
 //   pass 3  k_column_counts / k_columns
-//                          one warp per 32 receivers (slice): walks the potential sources in ascending
-//                          patch index, reads ONE word per source, and emits the quantised weights
-//                          (int)(trans * 0x10000 / total)  (qrad3.c:283) as "dense slice" lists -- the
-//                          transposed (gather) form ShootLight's scatter needs (finding F7), already in
-//                          the source order the reference adds them.
+//                          one warp per slice (32 receivers): walks the sources that can see it in ascending patch
+//                          index, streaming ONE word per source from the slice's column, and emits the quantised
+//                          weights (int)(trans * 0x10000 / total) (qrad3.c:283) as "dense slice" lists -- the
+//                          transposed (gather) form ShootLight's scatter needs (finding F7), already in the source
+//                          order the reference adds them.
 //   bounce  k_bounce       persistent warps, one slice at a time, lane = receiver, 128-bit loads of 8 weights per
 //                          lane, radiosity vectors broadcast from shared memory, packed multiplies, serial
 //                          accumulation in source order, CollectLight fused.
 //
-// Multi-GPU: every phase takes this rank's share (task granules / slices); the host exchanges in between
-// (qrad_cuda_make_transfers_phase, qrad_cuda_bounce_phase, qrad_cuda_exchange_buffer).
+// Several GPUs (a context that joined a communicator, qrad_cuda_comm_init): source rows are owned in row groups, receiver
+// slices in contiguous runs (plan.hpp).  Pass 1 and pass 2 are local; before pass 3 every rank sends each peer the
+// contiguous piece of its row buffer that describes the peer's slices (grouped ncclSend / ncclRecv), row totals are
+// summed over ranks, and every bounce ends with the owners broadcasting their part of the radiosity vector.
 //
-// Everything is float arithmetic in the reference's operation order; this TU is compiled
-// with -fmad=false.
+// Everything is float arithmetic in the reference's operation order; this TU is compiled with -fmad=false.
 #include <algorithm>
 #include <chrono>
 #include <climits>
 #include <cstdlib>
 #include <cstring>
 
+#include "comm.hpp"
 #include "qrad_device.cuh"
 
 namespace qrad {
@@ -57,45 +62,48 @@ __device__ __forceinline__ float form_factor_pre(const float4 so, const float4 s
   return trans;
 }
 
-constexpr int kChunkWords = 32;   // one task = one source patch x up to 32 words (1024 receivers)
-constexpr int kTaskRun = 128;       // consecutive tasks (same receivers, neighbouring sources) handled by one warp
-constexpr int kTaskGranule = 512;   // multi-GPU: granule g of tasks belongs to rank g % world
+// What every kernel needs to find a word of the matrix (device copies of the plan, plan.hpp).
+struct Geo {
+  const int32_t *cl_slot_start, *cl_count;   // [nc + 1], [nc]
+  const int32_t *slot_patch, *slot_cluster;  // [M]
+  const uint8_t *slot_flags;                 // [M] bit 0: holds a patch, bit 1: may shoot (its origin lies in a valid cluster)
+  const int32_t *slice_count;                // [M / 32] valid receivers of a slice
+  const int64_t *wb_first;                   // [nc + 1] first entry of a source cluster in the word tables
+  const int32_t *wslice;                     // receiver slice of word w of a row of the cluster
+  const int64_t *wbase;                      // address of that word for own row 0 of the cluster in this rank's buffer
+  const int32_t *nwords;                     // [nc]
+  int nc;
+};
 
 struct VisArgs {
   Tree tree;
   const int4 *leaf_path;          // root -> leaf ancestor records (reaches_leaf)
   const int32_t *leaf_path_first;
-  const float4 *wbox_min, *wbox_max;  // [M/32] bounding box of the patch origins of each 32-slot word
+  const float4 *wbox_min, *wbox_max;  // [M/32] bounding box of the patch origins of each slice
   const float4 *s_origin_area, *s_normal;
-  const int64_t *bits_base;      // [nc+1] word offset of the first row of each source cluster
-  const int64_t *task_base;      // [nc+1] task offset of each source cluster (rows x chunks per row)
-  const int32_t *nwords;         // [nc]   words per row
-  const int32_t *cl_slot_start;  // [nc]
-  const int32_t *cl_count;       // [nc]
-  const int32_t *vis_ptr;        // [nc+1] CSR of visible receiver clusters per source cluster
-  const int32_t *vis_cluster;    // receiver cluster
-  const int32_t *vis_woff;       // word offset of that cluster inside a row
-  int nc;
-  uint64_t num_tasks;             // all tasks
-  uint64_t my_tasks;              // upper bound of this rank's local task index
-  int rank, world;                // tasks are dealt to ranks in granules of kTaskGranule
+  Geo g;
+  const int32_t *own_groups;      // this rank's row groups ...
+  const int64_t *own_runbase;     // ... and the prefix of their chunk counts: run r = (group, chunk)
+  int n_own_groups;
+  const int32_t *grp_cluster, *grp_slot0, *grp_rows, *grp_ownbase;
+  uint64_t num_runs;
   uint32_t *bits;
   unsigned long long *counters;   // [0] rays, [1] node visits, [2] candidate pairs
 };
 
-// One warp lights one task = one source patch x one chunk of <= 32 words (1024 receivers).  Tasks are numbered
-// chunk-major inside a source cluster, so the consecutive tasks a warp takes are the SAME receivers seen from
-// neighbouring source patches; what blocked a receiver last time is an excellent guess for this time
-// (measured with the CPU oracle on C5: 95 % of the rays are blocked, 94-99 % of those by the leaf that blocked the
-// same receiver from the previous source, and a single leaf blocks a whole word for about half of the words).
-//   (1) lane w looks up word w of the chunk and runs the interval walk box_reaches_leaf() for the bounding box of its
-//       32 receivers with the word's last blocker: a proven word needs no ray at all;
+// One warp lights one run = the rows of one row group (<= 128 consecutive source patches of one cluster) against one
+// chunk of <= 32 words (1024 receivers), row after row: the SAME receivers seen from neighbouring source patches, so
+// what blocked a receiver last time is an excellent guess for this time (measured with the CPU oracle on C5: 95 % of
+// the rays are blocked, 94-99 % of those by the leaf that blocked the same receiver from the previous source, and a
+// single leaf blocks a whole word for about half of the words).  Per row ("task"):
+//   (1) lane w runs the interval walk box_reaches_leaf() for the bounding box of the 32 receivers of word w with the
+//       word's last blocker: a proven word needs no ray at all;
 //   (2) form-factor sign tests for all receivers (they define which pairs the reference would hand to TestLine_r,
 //       qrad3.c:244, and are counted as rays either way); pairs of unproven words are compacted into a queue;
 //   (3) the queue is consumed 32 rays at a time: reaches_leaf() with the receiver's last blocker (one root -> leaf
 //       path, no stack); rays that are not settled collect in a second queue and take the full TestLine walk in full
 //       batches, which refreshes the guesses;
-//   (4) accept bits are OR-ed into 32 result words in shared memory and stored with one coalesced write.
+//   (4) accept bits are OR-ed into 32 result words in shared memory and stored into the 32 slice columns.
 // Measured alternatives (profiles/README.md): one word per warp without compaction leaves 46 % of the lanes idle;
 // refilling finished lanes from the queue decorrelates the lanes and is slower.
 template <int STACK, bool COUNT>
@@ -106,6 +114,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
   __shared__ uint32_t s_res[kWarpsPerBlock][kChunkWords];
   __shared__ int32_t s_wbase[kWarpsPerBlock][kChunkWords];         // first receiver slot of the word
   __shared__ int32_t s_wcnt[kWarpsPerBlock][kChunkWords];          // valid receivers in the word
+  __shared__ int64_t s_waddr[kWarpsPerBlock][kChunkWords];         // where the word of own row 0 of the cluster is stored
   __shared__ uint16_t s_fb[kWarpsPerBlock][64];                    // rays whose guess failed (receiver index)
   // what the word's box walk learned when it did not prove the word (see box_reaches_leaf): the leaf it was run for,
   // the first ancestor not passed by all rays (0x80 | .. = all rays leave the path there) and the splits before it
@@ -117,63 +126,60 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
   const uint64_t warp0 = (uint64_t) blockIdx.x * kWarpsPerBlock + wid;
   const uint64_t nwarps = (uint64_t) gridDim.x * kWarpsPerBlock;
   unsigned long long rays = 0, pairs = 0, visits_total = 0, fallbacks = 0, boxed = 0;
-  int guess_c = -1, guess_w0 = -1;   // which (source cluster, chunk) the guesses belong to
   long long tk0 = 0, tk_box = 0, tk_pairs = 0, tk_guess = 0, tk_full = 0, tk_misc = 0;   // COUNT: warp cycles per phase
-  for (uint64_t lrun = warp0 * kTaskRun; lrun < a.my_tasks; lrun += nwarps * kTaskRun)
-  for (uint64_t ltask = lrun; ltask < lrun + kTaskRun && ltask < a.my_tasks; ltask++) {
-    const uint64_t task = ((ltask / kTaskGranule) * a.world + a.rank) * kTaskGranule + ltask % kTaskGranule;
-    if (task >= a.num_tasks) continue;
-    // ---- decode: source cluster, chunk, row (chunk-major) ----
-    int lo = 0, hi = a.nc;
+  for (uint64_t run = warp0; run < a.num_runs; run += nwarps) {
+    // ---- decode the run: row group, chunk ----
+    int lo = 0, hi = a.n_own_groups;
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
-      if ((uint64_t) a.task_base[mid] <= task) lo = mid; else hi = mid;
+      if ((uint64_t) a.own_runbase[mid] <= run) lo = mid; else hi = mid;
     }
-    const int c = lo;
-    const int nw = a.nwords[c];
-    const int rows = a.cl_count[c];
-    const uint64_t rel = task - (uint64_t) a.task_base[c];
-    const int chunk = (int) (rel / (uint64_t) rows);
-    const int row = (int) (rel - (uint64_t) chunk * rows);
+    const int grp = a.own_groups[lo];
+    const int chunk = (int) (run - (uint64_t) a.own_runbase[lo]);
+    const int c = a.grp_cluster[grp];
+    const int nw = a.g.nwords[c];
     const int w0 = chunk * kChunkWords;
     const int nwc = min(kChunkWords, nw - w0);
-    const int sslot = a.cl_slot_start[c] + row;
+    const int slot0 = a.grp_slot0[grp], nrows = a.grp_rows[grp], ownbase = a.grp_ownbase[grp];
+    __syncwarp();
+    if (lane < nwc) {
+      const int64_t e = a.g.wb_first[c] + w0 + lane;
+      const int sl = a.g.wslice[e];
+      s_wbase[wid][lane] = sl * 32;
+      s_wcnt[wid][lane] = a.g.slice_count[sl];
+      s_waddr[wid][lane] = a.g.wbase[e];
+    }
+    for (int k = lane; k < kChunkWords * 32; k += 32) s_rguess[wid][k] = 0xffffu;   // new receivers: forget the guesses
+    s_wguess[wid][lane] = 0xffffu;
+    __syncwarp();
+  for (int r = 0; r < nrows; r++) {
+    const int sslot = slot0 + r;
+    const unsigned flags = a.g.slot_flags[sslot];
+    if (!(flags & 1u)) continue;                        // padding slot at the end of the cluster: nobody reads its words
+    if (!(flags & 2u)) {                                // a source in solid never shoots (qrad3.c:208); only under -nopvs
+      if (lane < nwc) a.bits[s_waddr[wid][lane] + ownbase + r] = 0u;
+      continue;
+    }
     const float4 so = __ldg(a.s_origin_area + sslot);
     const float4 sn = __ldg(a.s_normal + sslot);
-    if (c != guess_c || w0 != guess_w0) {   // new receivers: forget the guesses
-      guess_c = c;
-      guess_w0 = w0;
-      for (int k = lane; k < kChunkWords * 32; k += 32) s_rguess[wid][k] = 0xffffu;
-      s_wguess[wid][lane] = 0xffffu;
-    }
     s_res[wid][lane] = 0;
     if (COUNT) { const long long t = clock64(); if (tk0) tk_misc += t - tk0; tk0 = t; }
-    // ---- (1) per word: receiver slots, box test ----
+    // ---- (1) per word: box test ----
     bool proven = false;
     if (lane < nwc) {
-      const int w = w0 + lane;
-      int v = a.vis_ptr[c], vhi = a.vis_ptr[c + 1];
-      while (vhi - v > 1) {  // last entry of c's visible list with woff <= w
-        const int mid = (v + vhi) >> 1;
-        if (a.vis_woff[mid] <= w) v = mid; else vhi = mid;
-      }
-      const int d = a.vis_cluster[v];
-      const int off = (w - a.vis_woff[v]) * 32;
-      const int base = a.cl_slot_start[d] + off;
-      s_wbase[wid][lane] = base;
-      s_wcnt[wid][lane] = min(32, a.cl_count[d] - off);
+      const int base = s_wbase[wid][lane];
       const int g = s_wguess[wid][lane];
       s_bleaf[wid][lane] = 0xffffu;
       if (g != 0xffff) {
         const int p0 = __ldg(a.leaf_path_first + g), p1 = __ldg(a.leaf_path_first + g + 1);
         int first;
         unsigned long long splits;
-        const int r = box_reaches_leaf(a.leaf_path + p0, p1 - p0, so, __ldg(a.wbox_min + (base >> 5)),
-                                       __ldg(a.wbox_max + (base >> 5)), first, splits);
-        proven = r == kBoxProven;
+        const int rr = box_reaches_leaf(a.leaf_path + p0, p1 - p0, so, __ldg(a.wbox_min + (base >> 5)),
+                                        __ldg(a.wbox_max + (base >> 5)), first, splits);
+        proven = rr == kBoxProven;
         if (!proven) {
           s_bleaf[wid][lane] = (uint16_t) g;
-          s_bfirst[wid][lane] = (uint8_t) (first | (r == kBoxElsewhere ? 0x80 : 0));
+          s_bfirst[wid][lane] = (uint8_t) (first | (rr == kBoxElsewhere ? 0x80 : 0));
           s_bsplits[wid][lane] = splits;
         }
       }
@@ -277,8 +283,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
     if (fbn > 0) full_batch(fbn);
     __syncwarp();
     if (COUNT) { const long long t = clock64(); tk_guess += t - tk0; tk0 = t; }
-    if (lane < nwc) a.bits[a.bits_base[c] + (int64_t) row * nw + w0 + lane] = s_res[wid][lane];
+    // consecutive rows of the run fill consecutive words of each column: L2 merges them into whole sectors
+    if (lane < nwc) a.bits[s_waddr[wid][lane] + ownbase + r] = s_res[wid][lane];
     __syncwarp();
+  }
   }
   for (int o = 16; o; o >>= 1) {
     rays += __shfl_xor_sync(0xffffffffu, rays, o);
@@ -303,212 +311,221 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
   }
 }
 
-// Ordered list builder: for each cluster c (one block), all slots j (walking PATCH index ascending)
-// whose cluster is related to c by table[c][cluster(j)] >= 0 (row lists) or table[cluster(j)][c] >= 0
-// (column lists).  out_a = slot of j, out_b = bit position / word address material.
-struct ListArgs {
-  int N, nc;
-  const int32_t *patch_slot;     // [N]
-  const int32_t *slot_cluster;   // [M]
-  const int32_t *woff_table;     // [nc][nc] word offset of receiver cluster d in a row of source cluster c, -1 = not visible
-  const int32_t *cl_slot_start;
-  const int64_t *list_ptr;       // [nc+1]
-  uint32_t *out_slot;
-  uint32_t *out_aux;
-  int c_first;                   // first cluster handled by this launch (blockIdx.x is relative to it)
-  int transpose;                 // 0: row lists (aux = bit position in the row); 1: column lists (addr = word address)
-  const int64_t *bits_base;      // column lists: geometry of the bit matrix
-  const int32_t *nwords;
-  int64_t *out_addr;             // column lists: word of (source row, first slice of the receiver cluster)
+// ---- word tables ---------------------------------------------------------------------------------------------------
+// For every source cluster a and every word w of its rows: the receiver slice the word is about and the address of the
+// word of own row 0 (plan.hpp).  One warp per visible pair (a, d).
+__global__ void __launch_bounds__(kThreads) k_word_tables(int nvis, const int32_t *__restrict__ vis_src,
+                                                          const int32_t *__restrict__ vis_cluster,
+                                                          const int32_t *__restrict__ vis_woff, const int32_t *__restrict__ vis_seer,
+                                                          const int32_t *__restrict__ cl_slot_start, const int64_t *__restrict__ wb_first,
+                                                          const int64_t *__restrict__ sbase, const int32_t *__restrict__ coff,
+                                                          int32_t *__restrict__ wslice, int64_t *__restrict__ wbase) {
+  const int v = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (v >= nvis) return;
+  const int a = vis_src[v], d = vis_cluster[v];
+  const int s0 = cl_slot_start[d] >> 5, ns = (cl_slot_start[d + 1] >> 5) - s0;
+  const int64_t e0 = wb_first[a] + vis_woff[v];
+  const int co = coff[vis_seer[v]];
+  for (int j = threadIdx.x & 31; j < ns; j += 32) {
+    wslice[e0 + j] = s0 + j;
+    wbase[e0 + j] = sbase[s0 + j] + co;
+  }
+}
+
+// ---- ordered run lists ---------------------------------------------------------------------------------------------
+// The receivers of a row must be visited in ascending PATCH index (the reference's j loop), the sources of a column
+// likewise (the order ShootLight adds them).  Slots are cluster-major, but consecutive patches mostly share a cluster and
+// then have consecutive slots, so the patch order is kept as a list of RUNS = (first slot, length <= 32) of consecutive
+// patches inside one slice.  Per source cluster c the runs whose cluster c can see form its row list; per receiver
+// cluster d the runs whose cluster can see d form its column list.  Both are an ordered compaction of the one global
+// run list: one block per cluster.
+struct RunListArgs {
+  int nruns;
+  const int2 *runs;                 // {first slot, length}
+  const int32_t *slot_cluster, *cl_slot_start;
+  const int32_t *vis_ptr, *vis_cluster, *vis_woff, *vis_seer;
+  const int32_t *clusters;          // clusters handled by this launch (blockIdx.x indexes it)
+  const int64_t *list_ptr;          // [nc + 1] where the list of a cluster starts (fill mode)
+  int32_t *count;                   // [nc] count mode output
+  // row lists
+  const int64_t *wb_first, *wbase;
+  const int32_t *wslice;
+  int4 *vl;                         // {addr lo, addr hi, mask, slice}
+  // column lists
+  const int32_t *grp_first, *grp_owner, *grp_ownbase, *grp_slot0;
+  const int32_t *coff;              // [world][E]
+  int64_t E;
+  int4 *vr;                         // {first slot, offset in the owner's column, length, owner}
 };
 
-__global__ void __launch_bounds__(1024) k_build_lists(const ListArgs a) {
-  const int c = a.c_first + blockIdx.x;
+__device__ __forceinline__ int find_visible(const RunListArgs &a, const int src_cluster, const int dst_cluster) {
+  int lo = a.vis_ptr[src_cluster], hi = a.vis_ptr[src_cluster + 1];
+  while (lo < hi) {   // lower bound of dst_cluster in the (ascending) visible list of src_cluster
+    const int mid = (lo + hi) >> 1;
+    if (a.vis_cluster[mid] < dst_cluster) lo = mid + 1; else hi = mid;
+  }
+  return (lo < a.vis_ptr[src_cluster + 1] && a.vis_cluster[lo] == dst_cluster) ? lo : -1;
+}
+
+template <bool COLUMNS, bool FILL>
+__global__ void __launch_bounds__(1024) k_run_lists(const RunListArgs a) {
+  const int c = a.clusters[blockIdx.x];
   __shared__ int warp_sums[32];
   __shared__ int64_t base_s;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) base_s = a.list_ptr[c];
+  if (threadIdx.x == 0) base_s = FILL ? a.list_ptr[c] : 0;
   __syncthreads();
-  for (int j0 = 0; j0 < a.N; j0 += blockDim.x) {
-    const int j = j0 + threadIdx.x;
-    bool flag = false;
-    int slot = -1, woff = -1, d = -1;
-    if (j < a.N) {
-      slot = a.patch_slot[j];
-      if (slot >= 0) {
-        d = a.slot_cluster[slot];
-        woff = a.transpose ? a.woff_table[(size_t) d * a.nc + c] : a.woff_table[(size_t) c * a.nc + d];
-        flag = woff >= 0;
-      }
+  for (int k0 = 0; k0 < a.nruns; k0 += blockDim.x) {
+    const int k = k0 + threadIdx.x;
+    int v = -1;
+    int2 run = make_int2(0, 0);
+    int rc = 0;
+    if (k < a.nruns) {
+      run = a.runs[k];
+      rc = a.slot_cluster[run.x];
+      v = COLUMNS ? find_visible(a, rc, c) : find_visible(a, c, rc);
     }
+    const bool flag = v >= 0;
     const unsigned m = __ballot_sync(0xffffffffu, flag);
     if (lane == 0) warp_sums[wid] = __popc(m);
     __syncthreads();
     int before = 0, total = 0;
-    for (int k = 0; k < (int) (blockDim.x >> 5); k++) {
-      const int v = warp_sums[k];
-      if (k < wid) before += v;
-      total += v;
+    for (int j = 0; j < (int) (blockDim.x >> 5); j++) {
+      const int n = warp_sums[j];
+      if (j < wid) before += n;
+      total += n;
     }
-    if (flag) {
+    if (FILL && flag) {
       const int64_t o = base_s + before + __popc(m & ((1u << lane) - 1));
-      a.out_slot[o] = (uint32_t) slot;
-      if (!a.transpose) a.out_aux[o] = (uint32_t) woff * 32u + (uint32_t) (slot - a.cl_slot_start[d]);
-      else a.out_addr[o] = a.bits_base[d] + (int64_t) (slot - a.cl_slot_start[d]) * a.nwords[d] + woff;
+      const int rel = run.x - a.cl_slot_start[rc];
+      if (!COLUMNS) {
+        const int64_t e = a.wb_first[c] + a.vis_woff[v] + (rel >> 5);
+        const int64_t addr = a.wbase[e];
+        const unsigned mask = (run.y >= 32 ? 0xffffffffu : ((1u << run.y) - 1u)) << (rel & 31);
+        a.vl[o] = make_int4((int) (uint32_t) (addr & 0xffffffffll), (int) (addr >> 32), (int) mask, a.wslice[e]);
+      } else {
+        const int grp = a.grp_first[rc] + rel / kGroupRows;
+        const int q = a.grp_owner[grp];
+        const int off = a.coff[(int64_t) q * a.E + a.vis_seer[v]] + a.grp_ownbase[grp] + (run.x - a.grp_slot0[grp]);
+        a.vr[o] = make_int4(run.x, off, run.y, q);
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) base_s += total;
     __syncthreads();
   }
+  if (!FILL && threadIdx.x == 0) a.count[c] = (int) base_s;
 }
 
-// Summaries of the row lists: which row words a 32-entry chunk can touch, as up to four {word, mask} pairs in two
-// uint4 (entries that are neighbours in patch order are neighbours in slot order as long as they lie in one cluster, so
-// a chunk usually lies inside one or two words, three or four where the list moves on to another cluster).
-// out[2 * chunk].x == 0xffffffff marks a chunk with more than four words; an unused pair has word 0xffffffff.
-__global__ void __launch_bounds__(kThreads) k_list_summaries(int nc, const int64_t *__restrict__ Lptr,
-                                                             const int64_t *__restrict__ chunk_base,
-                                                             const uint32_t *__restrict__ L_pos, uint4 *__restrict__ out,
-                                                             const int64_t chunk_lo, const int64_t chunk_hi) {
-  const int lane = threadIdx.x & 31;
-  const int64_t chunk = chunk_lo + (int64_t) blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (chunk >= chunk_hi) return;
-  int lo = 0, hi = nc;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (chunk_base[mid] <= chunk) lo = mid; else hi = mid;
-  }
-  const int64_t k = Lptr[lo] + ((chunk - chunk_base[lo]) << 5) + lane;
-  const bool have = k < Lptr[lo + 1];
-  const uint32_t pos = have ? L_pos[k] : 0;
-  const uint32_t word = pos >> 5, bit = have ? 1u << (pos & 31) : 0u;
-  uint32_t w[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}, m[4] = {0, 0, 0, 0};
-  bool left = have;   // lane 0 always has an entry
-#pragma unroll
-  for (int t = 0; t < 4; t++) {
-    const unsigned rest = __ballot_sync(0xffffffffu, left);
-    if (rest) {
-      w[t] = __shfl_sync(0xffffffffu, word, __ffs(rest) - 1);
-      m[t] = __reduce_or_sync(0xffffffffu, (left && word == w[t]) ? bit : 0u);
-      left = left && word != w[t];
-    }
-  }
-  const bool complex_chunk = __ballot_sync(0xffffffffu, left) != 0;
-  if (lane == 0) {
-    out[2 * chunk] = complex_chunk ? make_uint4(0xffffffffu, 0, 0, 0) : make_uint4(w[0], m[0], w[1], m[1]);
-    out[2 * chunk + 1] = make_uint4(w[2], m[2], w[3], m[3]);
-  }
-}
+__device__ __forceinline__ int64_t vl_addr(const int4 e) { return ((int64_t) e.y << 32) | (uint32_t) e.x; }
 
-// pass 2: serial row sums in ascending receiver order.
+// ---- pass 2: serial row sums in ascending receiver order ----------------------------------------------------------
 struct RowArgs {
   const float4 *s_origin_area, *s_normal;
-  const int32_t *slot_patch, *slot_cluster;
-  const int64_t *bits_base, *Lptr;
-  const int32_t *nwords, *cl_slot_start;
-  const uint32_t *L_slot, *L_pos;
-  const uint4 *L_sum;            // per 32-entry chunk of a list: {word0, mask0, word1, mask1} it can touch
-  const int64_t *chunk_base;     // [nc+1] first chunk of each cluster's list
+  Geo g;
+  const int64_t *vl_ptr;           // [nc + 1]
+  const int4 *vl;
   const uint32_t *bits;
-  int M;
-  int slot_lo, slot_hi;          // this rank's rows
-  float *row_total;
-  int32_t *row_count;
-  // download mode (reference row format): when out_patch != nullptr, rows are written at row_ptr[patch]
-  const int64_t *row_ptr;
+  const int32_t *rowslice_slot0, *rowslice_row0;   // the 32-row slices this launch handles: first slot, first own row
+  int n_rowslices;
+  float *row_total;                // [M]
+  int32_t *row_count;              // [M] numtransfers of the source in slot s
+  // download of selected rows (reference row format): warp k handles source slot sel_slots[k] / own row sel_rows[k]
+  const int32_t *sel_slots, *sel_rows;
+  int nsel;
+  const int64_t *row_ptr;          // [nsel + 1]
   uint32_t *out_patch;
   uint16_t *out_transfer;
-  // download of selected rows: warp k handles source slot sel_slots[k] and writes at row_ptr[k]
-  const int32_t *sel_slots;
-  int nsel;
   long long *sel_rays;             // [nsel] root TestLine_r calls of the row (k_row_rays)
 };
 
-template <bool EMIT>
-__global__ void __launch_bounds__(kThreads) k_row_totals(const RowArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int widx = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  int sslot = a.slot_lo + widx;
-  if (a.sel_slots) {
-    if (widx >= a.nsel) return;
-    sslot = a.sel_slots[widx];
-    if (sslot < 0) return;
-  } else if (sslot >= a.slot_hi)
-    return;
-  const int spatch = a.slot_patch[sslot];
-  if (spatch < 0) return;
-  const int c = a.slot_cluster[sslot];
-  const uint32_t *row = a.bits + a.bits_base[c] + (int64_t) (sslot - a.cl_slot_start[c]) * a.nwords[c];
+// lane = row: one warp sums 32 consecutive source rows of one cluster at once.  The rows share the cluster's row list,
+// and neighbouring sources accept nearly the same receivers, so the warp walks the list once; per run (<= 32 receivers of
+// one slice) every lane reads its own word of that slice -- 32 consecutive words -- and a run no row accepts is skipped.
+// Otherwise the receivers some row accepts are staged in shared memory and every accepting lane adds its own form factor
+// to its own SERIAL sum (qrad3.c:254): `total` stays bit-identical while 32 sums advance together.
+__global__ void __launch_bounds__(kThreads) k_row_totals32(const RowArgs a) {
+  __shared__ float4 s_po[kWarpsPerBlock][32], s_pn[kWarpsPerBlock][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rs = blockIdx.x * kWarpsPerBlock + wid;
+  if (rs >= a.n_rowslices) return;
+  const int sslot0 = a.rowslice_slot0[rs];
+  const int sslot = sslot0 + lane;
+  const int64_t row = (int64_t) a.rowslice_row0[rs] + lane;
+  const int c = a.g.slot_cluster[sslot0];              // a 32-slot slice lies in one cluster
+  const bool live_row = (a.g.slot_flags[sslot] & 2u) != 0;
   const float4 so = a.s_origin_area[sslot];
   const float4 sn = a.s_normal[sslot];
-  const int64_t l0 = a.Lptr[c], l1 = a.Lptr[c + 1];
+  const int64_t e0 = a.vl_ptr[c], e1 = a.vl_ptr[c + 1];
   float total = 0.f;
   int count = 0;
-  float rtotal = 0.f;
-  int64_t outp = 0;
-  if (EMIT) {
-    rtotal = a.row_total[sslot];
-    outp = a.sel_slots ? a.row_ptr[widx] : a.row_ptr[spatch];
+  int4 ent_n = make_int4(0, 0, 0, 0);
+  uint32_t word_n = 0;
+  if (e0 < e1) {
+    ent_n = __ldg(a.vl + e0);
+    word_n = __ldcs(a.bits + vl_addr(ent_n) + row);
   }
-  // The list has ~40 candidates per accepted receiver.  Each 32-entry chunk has a precomputed summary of the (at
-  // most two) row words it can touch, so 32 chunks are ruled out per step with one masked test per lane and only
-  // chunks holding an accept bit take the ordered walk below (the order of the float sum is untouched).
-  const int64_t nchunks = (l1 - l0 + 31) >> 5;
-  const uint4 *sum = a.L_sum + 2 * a.chunk_base[c];
-  for (int64_t g0 = 0; g0 < nchunks; g0 += 32) {
-    bool live = false;
-    if (g0 + lane < nchunks) {
-      const uint4 sm = __ldg(sum + 2 * (g0 + lane));
-      if (sm.x == 0xffffffffu) live = true;  // touches more than four words: always walk it
-      else {
-        live = (row[sm.x] & sm.y) != 0;
-        if (!live && sm.z != 0xffffffffu) {
-          live = (row[sm.z] & sm.w) != 0;
-          const uint4 sn2 = __ldg(sum + 2 * (g0 + lane) + 1);
-          if (!live && sn2.x != 0xffffffffu) live = (row[sn2.x] & sn2.y) != 0;
-          if (!live && sn2.z != 0xffffffffu) live = (row[sn2.z] & sn2.w) != 0;
-        }
-      }
+  for (int64_t e = e0; e < e1; e++) {
+    const int4 ent = ent_n;
+    const uint32_t acc = live_row ? (word_n & (uint32_t) ent.z) : 0u;
+    if (e + 1 < e1) {
+      ent_n = __ldg(a.vl + e + 1);
+      word_n = __ldcs(a.bits + vl_addr(ent_n) + row);
     }
-    unsigned lm = __ballot_sync(0xffffffffu, live);
-    while (lm) {
-      const int ci = __ffs(lm) - 1;
-      lm &= lm - 1;
-      const int64_t k = l0 + ((g0 + ci) << 5) + lane;
-      bool set = false;
-      float trans = 0.f;
-      uint32_t rslot = 0;
-      if (k < l1) {
-        rslot = a.L_slot[k];
-        const uint32_t pos = a.L_pos[k];
-        set = (row[pos >> 5] >> (pos & 31)) & 1u;
-        if (set) {
-          float dist;
-          bool wr;
-          trans = form_factor_pre(so, sn, a.s_origin_area[rslot], a.s_normal[rslot], dist, wr);
-        }
-      }
-      unsigned m = __ballot_sync(0xffffffffu, set);
-      if (EMIT) {
-        if (set) {
-          const int64_t o = outp + __popc(m & ((1u << lane) - 1));
-          a.out_patch[o] = (uint32_t) a.slot_patch[rslot];
-          a.out_transfer[o] = (uint16_t) (int) (trans * 65536.0f / rtotal);
-        }
-        outp += __popc(m);
-      } else {
-        count += __popc(m);
-        while (m) {  // serial float sum in receiver order (qrad3.c:254); uniform across the warp
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          total += __shfl_sync(0xffffffffu, trans, src);
-        }
+    unsigned hot = __reduce_or_sync(0xffffffffu, acc);
+    if (!hot) continue;
+    __syncwarp();
+    if ((hot >> lane) & 1u) {
+      s_po[wid][lane] = a.s_origin_area[ent.w * 32 + lane];
+      s_pn[wid][lane] = a.s_normal[ent.w * 32 + lane];
+    }
+    __syncwarp();
+    while (hot) {
+      const int kk = __ffs(hot) - 1;
+      hot &= hot - 1;
+      if ((acc >> kk) & 1u) {
+        float dist;
+        bool wr;
+        const float trans = form_factor_pre(so, sn, s_po[wid][kk], s_pn[wid][kk], dist, wr);
+        total += trans;
+        count++;
       }
     }
   }
-  if (!EMIT && lane == 0) {
+  if (a.g.slot_flags[sslot] & 1u) {
     a.row_total[sslot] = total;
     a.row_count[sslot] = count;
+  }
+}
+
+// Reference row format of selected rows (parity tests): one warp per row; the receivers of a run are tested by 32 lanes
+// and written in ascending patch index: {patch, (int)(trans * 0x10000 / total)} (qrad3.c:283-289).
+__global__ void __launch_bounds__(kThreads) k_rows_emit(const RowArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int widx = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (widx >= a.nsel) return;
+  const int sslot = a.sel_slots[widx];
+  if (sslot < 0 || !(a.g.slot_flags[sslot] & 1u)) return;
+  const int64_t row = a.sel_rows[widx];
+  const int c = a.g.slot_cluster[sslot];
+  const float4 so = a.s_origin_area[sslot];
+  const float4 sn = a.s_normal[sslot];
+  const float rtotal = a.row_total[sslot];
+  int64_t outp = a.row_ptr[widx];
+  for (int64_t e = a.vl_ptr[c]; e < a.vl_ptr[c + 1]; e++) {
+    const int4 ent = __ldg(a.vl + e);
+    const uint32_t word = a.bits[vl_addr(ent) + row] & (uint32_t) ent.z;   // the same word for every lane
+    if (!word) continue;
+    if ((word >> lane) & 1u) {
+      const int rslot = ent.w * 32 + lane;
+      float dist;
+      bool wr;
+      const float trans = form_factor_pre(so, sn, a.s_origin_area[rslot], a.s_normal[rslot], dist, wr);
+      const int64_t o = outp + __popc(word & ((1u << lane) - 1));
+      a.out_patch[o] = (uint32_t) a.g.slot_patch[rslot];
+      a.out_transfer[o] = (uint16_t) (int) (trans * 65536.0f / rtotal);
+    }
+    outp += __popc(word);
   }
 }
 
@@ -520,13 +537,14 @@ __global__ void __launch_bounds__(kThreads) k_row_rays(const RowArgs a) {
   if (widx >= a.nsel) return;
   const int sslot = a.sel_slots[widx];
   long long n = 0;
-  if (sslot >= 0 && a.slot_patch[sslot] >= 0) {
-    const int c = a.slot_cluster[sslot];
+  if (sslot >= 0 && (a.g.slot_flags[sslot] & 2u)) {
+    const int c = a.g.slot_cluster[sslot];
     const float4 so = a.s_origin_area[sslot];
     const float4 sn = a.s_normal[sslot];
-    for (int64_t k = a.Lptr[c] + lane; k < a.Lptr[c + 1]; k += 32) {
-      const uint32_t rslot = a.L_slot[k];
-      if ((int) rslot == sslot) continue;
+    for (int64_t e = a.vl_ptr[c]; e < a.vl_ptr[c + 1]; e++) {
+      const int4 ent = __ldg(a.vl + e);
+      const int rslot = ent.w * 32 + lane;
+      if (!(((uint32_t) ent.z >> lane) & 1u) || rslot == sslot) continue;
       float dist;
       bool wr;
       form_factor_pre(so, sn, a.s_origin_area[rslot], a.s_normal[rslot], dist, wr);
@@ -537,98 +555,7 @@ __global__ void __launch_bounds__(kThreads) k_row_rays(const RowArgs a) {
   if (lane == 0) a.sel_rays[widx] = n;
 }
 
-// pass 2, lane = row: one warp sums 32 consecutive source rows of one cluster at once.  The rows share the cluster's
-// candidate list, and neighbouring sources accept nearly the same receivers, so the warp walks the list once, skips a
-// 32-candidate chunk when none of its 32 rows has an accept bit in it, and otherwise visits only the candidates some
-// row accepts: their receiver is staged in shared memory and every lane that accepts it adds its own form factor to
-// its own serial sum (qrad3.c:254) -- the sums of 32 rows advance together instead of one shuffle + add per transfer
-// with 31 lanes looking on (k_row_totals, kept for the download path: 206 ms on C5 against ~40 ms here).
-__global__ void __launch_bounds__(kThreads) k_row_totals32(const RowArgs a) {
-  __shared__ float4 s_po[kWarpsPerBlock][32], s_pn[kWarpsPerBlock][32];
-  __shared__ uint32_t s_pos[kWarpsPerBlock][32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int sslot0 = a.slot_lo + (blockIdx.x * kWarpsPerBlock + wid) * 32;
-  if (sslot0 >= a.slot_hi) return;
-  const int sslot = sslot0 + lane;
-  const int c = a.slot_cluster[sslot0];              // a 32-slot slice lies in one cluster
-  const bool live_row = a.slot_patch[sslot] >= 0;
-  const uint32_t *row = a.bits + a.bits_base[c] + (int64_t) (sslot - a.cl_slot_start[c]) * a.nwords[c];
-  const float4 so = a.s_origin_area[sslot];
-  const float4 sn = a.s_normal[sslot];
-  const int64_t l0 = a.Lptr[c], l1 = a.Lptr[c + 1];
-  const int64_t nchunks = (l1 - l0 + 31) >> 5;
-  const uint4 *sum = a.L_sum + 2 * a.chunk_base[c];
-  float total = 0.f;
-  int count = 0;
-  uint4 sa_n = make_uint4(0, 0, 0, 0), sb_n = sa_n;
-  if (nchunks > 0) {
-    sa_n = __ldg(sum);
-    sb_n = __ldg(sum + 1);
-  }
-  for (int64_t g = 0; g < nchunks; g++) {
-    const uint4 sa = sa_n, sb = sb_n;
-    if (g + 1 < nchunks) {
-      sa_n = __ldg(sum + 2 * (g + 1));
-      sb_n = __ldg(sum + 2 * (g + 1) + 1);
-    }
-    const bool cx = sa.x == 0xffffffffu;             // chunk touches more than four row words
-    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;         // this row's accept bits in the chunk's words
-    if (!cx) {
-      if (live_row) {
-        a0 = row[sa.x] & sa.y;
-        if (sa.z != 0xffffffffu) a1 = row[sa.z] & sa.w;
-        if (sb.x != 0xffffffffu) a2 = row[sb.x] & sb.y;
-        if (sb.z != 0xffffffffu) a3 = row[sb.z] & sb.w;
-      }
-      if (!__any_sync(0xffffffffu, (a0 | a1 | a2 | a3) != 0)) continue;
-    }
-    // stage the chunk's candidates: lane k holds candidate k; s_pos = which of the four words << 5 | bit
-    const int64_t k = l0 + (g << 5) + lane;
-    const bool have = k < l1;
-    const uint32_t rslot = have ? a.L_slot[k] : 0u;
-    const uint32_t pos = have ? a.L_pos[k] : 0u;
-    const uint32_t w = pos >> 5;
-    const uint32_t t = w == sa.x ? 0u : (w == sa.z ? 1u : (w == sb.x ? 2u : 3u));
-    __syncwarp();
-    s_pos[wid][lane] = cx ? pos : (t << 5 | (pos & 31));
-    s_po[wid][lane] = a.s_origin_area[rslot];
-    s_pn[wid][lane] = a.s_normal[rslot];
-    __syncwarp();
-    // candidates accepted by at least one of the 32 rows
-    unsigned hot;
-    if (!cx) {
-      const uint32_t u0 = __reduce_or_sync(0xffffffffu, a0), u1 = __reduce_or_sync(0xffffffffu, a1);
-      const uint32_t u2 = __reduce_or_sync(0xffffffffu, a2), u3 = __reduce_or_sync(0xffffffffu, a3);
-      const uint32_t u = t == 0 ? u0 : (t == 1 ? u1 : (t == 2 ? u2 : u3));
-      hot = __ballot_sync(0xffffffffu, have && ((u >> (pos & 31)) & 1u));
-    } else
-      hot = __ballot_sync(0xffffffffu, have);
-    while (hot) {
-      const int kk = __ffs(hot) - 1;
-      hot &= hot - 1;
-      const uint32_t pk = s_pos[wid][kk];   // the same for every lane
-      uint32_t word;
-      if (!cx) {
-        const uint32_t tk = pk >> 5;
-        word = tk == 0 ? a0 : (tk == 1 ? a1 : (tk == 2 ? a2 : a3));
-      } else
-        word = live_row ? row[pk >> 5] : 0u;
-      if ((word >> (pk & 31)) & 1u) {
-        float dist;
-        bool wr;
-        const float trans = form_factor_pre(so, sn, s_po[wid][kk], s_pn[wid][kk], dist, wr);
-        total += trans;
-        count++;
-      }
-    }
-  }
-  if (live_row) {
-    a.row_total[sslot] = total;
-    a.row_count[sslot] = count;
-  }
-}
-
-// pass 3: columns.  One warp = 32 receivers (a slice), lane = receiver.
+// ---- pass 3: columns -----------------------------------------------------------------------------------------------
 // pass 3 + bounce share the gather-form layout ("dense slices"): for every slice of 32 receivers the list of
 // sources that reach at least one of them (ascending patch index = the order ShootLight adds them), one u32 source
 // slot per list entry and 32 u16 weights per entry (0 = no transfer to that receiver; adding send * 0 leaves the
@@ -637,108 +564,90 @@ __global__ void __launch_bounds__(kThreads) k_row_totals32(const RowArgs a) {
 // 32 receivers of a listed source are hit on average, so this stores 3.6 B per transfer instead of 6 and turns
 // the per-transfer gather of the radiosity vector into one broadcast load per 18.8 transfers (the per-column ELL
 // of the first version was bound by L1 sector lookups at 43 % of HBM peak, profiles/r01c_full_c5_k_bounce.txt).
+constexpr int kMaxWorld = 16;
 struct ColArgs {
   const float4 *s_origin_area, *s_normal;
-  const int32_t *slot_patch, *slot_cluster;
-  const int64_t *bits_base, *Rptr;
-  const int32_t *nwords, *cl_slot_start;
-  const int32_t *woff_table;
-  int nc;
-  const uint32_t *R_slot;
-  const int64_t *R_addr;         // word address of (source row, first slice of this receiver cluster)
-  const uint32_t *bits;
+  Geo g;
+  const int64_t *vr_ptr;           // [nc + 1]
+  const int4 *vr;                  // {first source slot, offset in the owner's column, sources (<= 32), owner rank}
+  const uint32_t *col[kMaxWorld];  // per owner rank: its words about this rank's slices, biased so that the index is
+                                   //   sbase[owner][slice] + offset  (the own rank points into the row buffer itself)
+  const int64_t *sbase;            // [world][nslices + 1]
+  int nslices;
   const float *row_total;
-  int M;
-  const int32_t *blk_slice0;     // k_columns, per block: first slice (up to 8 consecutive slices of ONE cluster)
-  const int32_t *blk_n;          // per block: slices (1..8)
-  int32_t *slice_len;            // count mode output: list entries of the slice
-  const int64_t *slice_base;     // fill mode: first entry of the slice (multiple of 32)
-  uint32_t *g_src;               // [entries]      source slot
-  uint4 *g_w;                    // [entries / 8][32] 8 x u16 weights per lane
+  int slice_lo, slice_hi;          // this rank's slices
+  int32_t *slice_len;              // count mode output: list entries of the slice
+  const int64_t *slice_base;       // fill mode: first entry of the slice (multiple of 32)
+  uint32_t *g_src;                 // [entries]      source slot
+  uint4 *g_w;                      // [entries / 8][32] 8 x u16 weights per lane
 };
 
-// pass 3a: list lengths.  One block per receiver cluster, lane = SOURCE: per batch of 32 sources a lane reads the
-// words of its source row for up to 32 slices of the cluster back to back (consecutive sectors of one row, used
-// completely) and the warp counts the non-zero words per slice with one ballot each; lane j keeps the count of slice
-// j; the 8 warps of the block take every 8th batch.  Measured on C5 (profiles/r01k_full_c5_columns.txt): counting with
-// one word per lane and slice reads the 26.7 GB matrix ten times over from HBM.
-__global__ void __launch_bounds__(kThreads) k_column_counts(const ColArgs a, const int c_first, const int slice_lo,
-                                                            const int slice_hi) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int d = c_first + blockIdx.x;
-  const int cs0 = a.cl_slot_start[d] >> 5, cs1 = a.cl_slot_start[d + 1] >> 5;   // the cluster's slices
-  const int s_lo = max(cs0, slice_lo), s_hi = min(cs1, slice_hi);               // ... that belong to this rank
-  const int64_t r0 = a.Rptr[d], r1 = a.Rptr[d + 1];
-  constexpr int64_t kStep = 32 * kWarpsPerBlock;
-  for (int p0 = s_lo; p0 < s_hi; p0 += 32) {             // passes of 32 slices (one for all but huge clusters)
-    const int np = min(32, s_hi - p0);
-    const int woff = p0 - cs0;
-    int mycnt = 0;
-    const int64_t first = r0 + wid * 32 + lane;
-    int64_t addr_n = first < r1 ? a.R_addr[first] : -1;
-    for (int64_t k = first; k - lane < r1; k += kStep) {   // k - lane is warp-uniform
-      const int64_t addr = addr_n;
-      addr_n = k + kStep < r1 ? a.R_addr[k + kStep] : -1;
-      for (int j0 = 0; j0 < np; j0 += 8) {
-        uint32_t w[8];
+// pass 3a: list lengths = non-zero words of the slice's column, streamed once.  One warp per slice.
+__global__ void __launch_bounds__(kThreads) k_column_counts(const ColArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int slice = a.slice_lo + blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (slice >= a.slice_hi) return;
+  const int d = a.g.slot_cluster[slice * 32];
+  const int64_t e0 = a.vr_ptr[d], e1 = a.vr_ptr[d + 1];
+  int cnt = 0;
+  for (int64_t e = e0; e < e1; e += 4) {   // four runs in flight
+    uint32_t w[4];
 #pragma unroll
-        for (int j = 0; j < 8; j++) w[j] = (addr >= 0 && j0 + j < np) ? __ldcs(a.bits + addr + woff + j0 + j) : 0u;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int cnt = __popc(__ballot_sync(0xffffffffu, w[j] != 0));
-          if (lane == j0 + j) mycnt += cnt;
-        }
+    for (int j = 0; j < 4; j++) {
+      w[j] = 0;
+      if (e + j < e1) {
+        const int4 ent = __ldg(a.vr + e + j);
+        if (lane < ent.z) w[j] = __ldcs(a.col[ent.w] + a.sbase[(int64_t) ent.w * (a.nslices + 1) + slice] + ent.y + lane);
       }
     }
-    if (lane < np && mycnt) atomicAdd(a.slice_len + p0 + lane, mycnt);
+#pragma unroll
+    for (int j = 0; j < 4; j++) cnt += __popc(__ballot_sync(0xffffffffu, w[j] != 0));
   }
+  if (lane == 0) a.slice_len[slice] = cnt;
 }
 
-// pass 3b: the lists.  One warp per slice, lane = receiver; the 8 warps of a block own 8 neighbouring slices of one
-// cluster and walk the cluster's source list together, re-aligned by a barrier every 16 batches of 32 sources, so
-// that the words they fetch for one source (one 32-byte sector) come from HBM once and are then served by L1 -- a
-// warp per slice on its own reads the matrix 25 times over (profiles/r01k_full_c5_columns.txt: 661 GB, HBM-bound),
-// and a barrier per batch makes every warp wait for the one with the most entries.
-// Sources are taken 32 at a time: lane k fetches the word of source k (addresses and words are requested two / one
-// batch ahead); when some word is non-zero the sources that own one are staged in shared memory (origin, normal, row
-// total: one gather per batch instead of a dependent L2 round trip per list entry), and the warp then emits the
-// entries in source order.
+// pass 3b: the lists.  One warp per slice, lane = receiver.  The sources come in runs of <= 32 consecutive slots whose
+// words are consecutive in the slice's column: lane k fetches the word of source k of the run (the next run's words are
+// requested one run ahead); when some word is non-zero the sources that own one are staged in shared memory (origin,
+// normal, row total: one gather per run instead of a dependent L2 round trip per list entry), and the warp then emits
+// the entries in source order.
 __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
   __shared__ float4 s_so[kWarpsPerBlock][32], s_sn[kWarpsPerBlock][32];
   __shared__ float s_rt[kWarpsPerBlock][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int slice0 = a.blk_slice0[blockIdx.x];
-  const bool active = wid < a.blk_n[blockIdx.x];
-  const int slice = slice0 + (active ? wid : 0);
+  const int slice = a.slice_lo + blockIdx.x * kWarpsPerBlock + wid;
+  if (slice >= a.slice_hi) return;
   const int rslot = slice * 32 + lane;
-  const int d = a.slot_cluster[slice0 * 32];           // all slots of the block share the cluster
-  const int wslice = (slice * 32 - a.cl_slot_start[d]) >> 5;
-  const bool valid = active && a.slot_patch[rslot] >= 0;
+  const int d = a.g.slot_cluster[slice * 32];
+  const bool valid = (a.g.slot_flags[rslot] & 1u) != 0;
   float4 po = make_float4(0, 0, 0, 0), pn = po;
   if (valid) {
     po = a.s_origin_area[rslot];
     pn = a.s_normal[rslot];
   }
-  const int64_t r0 = a.Rptr[d], r1 = a.Rptr[d + 1];
+  const int64_t e0 = a.vr_ptr[d], e1 = a.vr_ptr[d + 1];
   int n = 0;                                           // list entries so far (uniform)
   const int64_t base = a.slice_base[slice];
   uint32_t wq[4] = {0, 0, 0, 0};                       // this lane's weights of the current group of 8 entries
-  // pipeline: addresses two batches ahead, words one batch ahead
-  int64_t addr_n = (active && r0 + lane < r1) ? a.R_addr[r0 + lane] : -1;
-  uint32_t word_n = addr_n >= 0 ? a.bits[addr_n + wslice] : 0u;
-  addr_n = (active && r0 + 32 + lane < r1) ? a.R_addr[r0 + 32 + lane] : -1;
-  int batch = 0;
-  for (int64_t k0 = r0; k0 < r1; k0 += 32, batch++) {
-    if ((batch & 15) == 0) __syncthreads();
+  int4 ent_n = make_int4(0, 0, 0, 0);
+  uint32_t word_n = 0;
+  if (e0 < e1) {
+    ent_n = __ldg(a.vr + e0);
+    if (lane < ent_n.z) word_n = __ldcs(a.col[ent_n.w] + a.sbase[(int64_t) ent_n.w * (a.nslices + 1) + slice] + ent_n.y + lane);
+  }
+  for (int64_t e = e0; e < e1; e++) {
+    const int4 ent = ent_n;
     const uint32_t word = word_n;
-    word_n = addr_n >= 0 ? a.bits[addr_n + wslice] : 0u;
-    addr_n = (active && k0 + 64 + lane < r1) ? a.R_addr[k0 + 64 + lane] : -1;
+    word_n = 0;
+    if (e + 1 < e1) {
+      ent_n = __ldg(a.vr + e + 1);
+      if (lane < ent_n.z) word_n = __ldcs(a.col[ent_n.w] + a.sbase[(int64_t) ent_n.w * (a.nslices + 1) + slice] + ent_n.y + lane);
+    }
     unsigned nz = __ballot_sync(0xffffffffu, word != 0);
     if (nz == 0) continue;
-    uint32_t sslot = 0;
+    const uint32_t sslot = (uint32_t) ent.x + lane;
     __syncwarp();
     if (word != 0) {
-      sslot = a.R_slot[k0 + lane];
       s_so[wid][lane] = a.s_origin_area[sslot];
       s_sn[wid][lane] = a.s_normal[sslot];
       s_rt[wid][lane] = a.row_total[sslot];
@@ -748,7 +657,6 @@ __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
       const int src = __ffs(nz) - 1;
       nz &= nz - 1;
       const uint32_t w = __shfl_sync(0xffffffffu, word, src);
-      const uint32_t ss = __shfl_sync(0xffffffffu, sslot, src);
       uint32_t itrans = 0;
       if ((w >> lane) & 1u) {
         float dist;
@@ -758,7 +666,7 @@ __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
       }
       const int q = n & 7;
       wq[q >> 1] |= itrans << ((q & 1) * 16);
-      if (lane == 0) a.g_src[base + n] = ss;
+      if (lane == 0) a.g_src[base + n] = (uint32_t) ent.x + src;
       n++;
       if ((n & 7) == 0) {
         a.g_w[((base + n) / 8 - 1) * 32 + lane] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
@@ -766,7 +674,7 @@ __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
       }
     }
   }
-  if (active && (n & 7)) {
+  if (n & 7) {
     // last, partial group; the rest of the 32-entry batch stays zero (source slot 0, zero weights: buffers are cleared)
     a.g_w[((base + n) / 8) * 32 + lane] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
   }
@@ -1156,12 +1064,13 @@ __global__ void k_init_bounce(int M, const int32_t *__restrict__ slot_patch, con
 
 __global__ void k_finish_bounce(int N, const int32_t *__restrict__ patch_slot, const float4 *__restrict__ total,
                                 const float4 *__restrict__ send, float *__restrict__ totallight,
-                                float *__restrict__ radiosity) {
+                                float *__restrict__ radiosity, int32_t *__restrict__ negative) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= N) return;
   const int s = patch_slot[p];
   if (s < 0) return;
   const float4 t = total[s];
+  if (t.x < 0 || t.y < 0 || t.z < 0) *negative = 1;   // CheckPatches, qrad3.c:476-486
   totallight[p * 3] = t.x;
   totallight[p * 3 + 1] = t.y;
   totallight[p * 3 + 2] = t.z;
@@ -1171,10 +1080,91 @@ __global__ void k_finish_bounce(int N, const int32_t *__restrict__ patch_slot, c
   radiosity[p * 3 + 2] = r.z * 65536.0f;
 }
 
+
+// slot-order copies of the patch geometry, and the bounding box of every slice's patch origins (box_reaches_leaf)
+__global__ void k_slot_geometry(int M, const int32_t *__restrict__ slot_patch, const float4 *__restrict__ p_origin_area,
+                                const float4 *__restrict__ p_normal, float4 *__restrict__ s_origin_area,
+                                float4 *__restrict__ s_normal, float4 *__restrict__ box_min, float4 *__restrict__ box_max) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;   // blockDim.x is a multiple of 32 and so is M
+  if (s >= M) return;
+  const int p = slot_patch[s];
+  float4 o = make_float4(0, 0, 0, 0), n = o;
+  if (p >= 0) {
+    o = p_origin_area[p];
+    n = p_normal[p];
+  }
+  s_origin_area[s] = o;
+  s_normal[s] = n;
+  float lo[3] = {p >= 0 ? o.x : 3e38f, p >= 0 ? o.y : 3e38f, p >= 0 ? o.z : 3e38f};
+  float hi[3] = {p >= 0 ? o.x : -3e38f, p >= 0 ? o.y : -3e38f, p >= 0 ? o.z : -3e38f};
+  for (int d = 16; d; d >>= 1)
+    for (int k = 0; k < 3; k++) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], d));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], d));
+    }
+  if ((threadIdx.x & 31) == 0) {
+    box_min[s >> 5] = make_float4(lo[0], lo[1], lo[2], 0);
+    box_max[s >> 5] = make_float4(hi[0], hi[1], hi[2], 0);
+  }
+}
+
+void nccl_ok(ncclResult_t r, const char *what) {
+  if (r != ncclSuccess) dfail("%s failed: %s", what, nccl().GetErrorString(r));
+}
+
+Geo geo_of(qrad_cuda_ctx *c) {
+  Geo g{};
+  g.cl_slot_start = c->d_cl_slot_start.p;
+  g.cl_count = c->d_cl_count.p;
+  g.slot_patch = c->slot_patch.p;
+  g.slot_cluster = c->slot_cluster.p;
+  g.slot_flags = c->slot_flags.p;
+  g.slice_count = c->slice_count.p;
+  g.wb_first = c->d_wb_first.p;
+  g.wslice = c->wslice.p;
+  g.wbase = c->wbase.p;
+  g.nwords = c->d_nwords.p;
+  g.nc = c->plan.nc;
+  return g;
+}
+
+RowArgs row_args(qrad_cuda_ctx *c) {
+  RowArgs ra{};
+  ra.s_origin_area = c->s_origin_area.p;
+  ra.s_normal = c->s_normal.p;
+  ra.g = geo_of(c);
+  ra.vl_ptr = c->d_vl_ptr.p;
+  ra.vl = c->vl.p;
+  ra.bits = c->bits.p;
+  ra.row_total = c->row_total.p;
+  ra.row_count = c->row_count.p;
+  return ra;
+}
+
+// Every owner sends its part of a per-slot array to everybody (in place): one broadcast per rank, grouped.
+void share_slices(qrad_cuda_ctx *c, void *buf, size_t bytes_per_slot, cudaStream_t st) {
+  const TransferPlan &P = c->plan;
+  const NcclApi &n = nccl();
+  nccl_ok(n.GroupStart(), "ncclGroupStart");
+  for (int q = 0; q < P.world; q++) {
+    const size_t first = (size_t) P.slice_lo[q] * 32 * bytes_per_slot, count = (size_t) (P.slice_hi[q] - P.slice_lo[q]) * 32 * bytes_per_slot;
+    if (!count) continue;
+    char *p = (char *) buf + first;
+    nccl_ok(n.Broadcast(p, p, count, ncclChar, q, c->comm, st), "ncclBroadcast");
+  }
+  nccl_ok(n.GroupEnd(), "ncclGroupEnd");
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0;
+  QCUDA(cudaEventElapsedTime(&ms, a, b));
+  return ms;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
-// phase 0: slot order, row geometry, pass 1 (this rank's granules of tasks)
+// phase 0: the plan, slot order, word tables, pass 1 (this rank's row groups)
 void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   if (!c->numnodes || !c->N) dfail("make_transfers: BSP and patches must be uploaded first");
   if (!c->have_vis) dfail("make_transfers: map has no visibility data (the reference forces numbounce = 0)");
@@ -1182,136 +1172,96 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   const auto wall0 = std::chrono::steady_clock::now();
   c->transfers_done = false;
   const int N = c->N;
-  // ---- host: slot order ----
+  cudaStream_t st = c->stream;
   // With -nopvs every patch receives (even those in solid); sources still need a valid cluster
   // (PvsForOrigin fails for them, qrad3.c:208-209).  That case is one pseudo cluster holding everybody.
   const int nc = nopvs ? 1 : c->numclusters;
-  if (nc <= 0) dfail("make_transfers: no clusters");
-  if ((int64_t) nc * nc > (int64_t) 1 << 28) dfail("make_transfers: %d clusters exceed the dense PVS table limit", nc);
-  std::vector<int32_t> eff(N);
-  for (int i = 0; i < N; i++) {
-    int cl = c->h_cluster[i];
-    if (cl >= c->numclusters) dfail("patch %d has cluster %d >= numclusters %d", i, cl, c->numclusters);
-    eff[i] = nopvs ? 0 : cl;
+  {
+    std::vector<int32_t> eff((size_t) N);
+    for (int i = 0; i < N; i++) {
+      const int cl = c->h_cluster[i];
+      if (cl >= c->numclusters) dfail("patch %d has cluster %d >= numclusters %d", i, cl, c->numclusters);
+      eff[i] = nopvs ? 0 : cl;
+    }
+    try {
+      build_plan(c->plan, N, eff.data(), nc, nopvs ? nullptr : c->h_pvs.data(), c->pvs_words, c->world, c->rank, 0);
+    } catch (const std::exception &e) {
+      dfail("%s", e.what());
+    }
   }
-  c->nc_eff = nc;
-  c->h_cl_count.assign(nc, 0);
-  for (int i = 0; i < N; i++)
-    if (eff[i] >= 0) c->h_cl_count[eff[i]]++;
-  c->h_cl_slot_start.assign(nc + 1, 0);
-  for (int k = 0; k < nc; k++) c->h_cl_slot_start[k + 1] = c->h_cl_slot_start[k] + ((c->h_cl_count[k] + 31) & ~31);
-  const int M = c->h_cl_slot_start[nc];
+  const TransferPlan &P = c->plan;
+  if (P.world > kMaxWorld) dfail("make_transfers: at most %d ranks", kMaxWorld);
+  const int M = P.M;
   c->M = M;
-  {  // shards of slots for passes 2, 3 and the bounces: equal runs of whole slices
-    const int nsl = M / 32, per = (nsl + c->world - 1) / c->world;
-    c->slice_lo = std::min(nsl, per * c->rank);
-    c->slice_hi = std::min(nsl, per * (c->rank + 1));
-    c->shard_slots = per * 32;
-    c->Mpad = c->shard_slots * c->world;
-  }
-  if (M == 0) dfail("make_transfers: no patch lies in a valid cluster");
-  c->h_slot_patch.assign(M, -1);
-  c->h_patch_slot.assign(N, -1);
-  c->h_slot_cluster.assign(M, 0);
   {
-    std::vector<int32_t> fill(c->h_cl_slot_start.begin(), c->h_cl_slot_start.end() - 1);
-    for (int i = 0; i < N; i++)
-      if (eff[i] >= 0) {
-        int s = fill[eff[i]]++;
-        c->h_slot_patch[s] = i;
-        c->h_patch_slot[i] = s;
-      }
-    for (int k = 0; k < nc; k++)
-      for (int s = c->h_cl_slot_start[k]; s < c->h_cl_slot_start[k + 1]; s++) c->h_slot_cluster[s] = k;
-  }
-  // sources in solid never shoot under -nopvs: remember them so their rows are skipped
-  std::vector<uint8_t> source_ok(M, 0);
-  for (int s = 0; s < M; s++) {
-    int p = c->h_slot_patch[s];
-    source_ok[s] = p >= 0 && c->h_cluster[p] >= 0;
-  }
-  // ---- host: visible cluster lists and row geometry ----
-  std::vector<int32_t> vis_ptr(nc + 1, 0), vis_cluster, vis_woff, woff_table((size_t) nc * nc, -1);
-  c->h_nwords.assign(nc, 0);
-  c->h_bits_base.assign(nc + 1, 0);
-  c->h_Lptr.assign(nc + 1, 0);
-  std::vector<int64_t> task_base(nc + 1, 0);
-  std::vector<int64_t> Rptr(nc + 1, 0);
-  for (int a = 0; a < nc; a++) {
-    int w = 0;
-    int64_t cand = 0;
-    for (int d = 0; d < nc; d++) {
-      bool vis = nopvs ? true : ((c->h_pvs[(size_t) a * c->pvs_words + (d >> 5)] >> (d & 31)) & 1u);
-      if (!vis || c->h_cl_count[d] == 0) continue;
-      vis_cluster.push_back(d);
-      vis_woff.push_back(w);
-      woff_table[(size_t) a * nc + d] = w;
-      w += (c->h_cl_slot_start[d + 1] - c->h_cl_slot_start[d]) >> 5;
-      cand += c->h_cl_count[d];
-      Rptr[d + 1] += c->h_cl_count[a];
+    std::vector<uint8_t> flags((size_t) M, 0);
+    for (int s = 0; s < M; s++) {
+      const int p = P.slot_patch[s];
+      if (p >= 0) flags[s] = (uint8_t) (1 | (c->h_cluster[p] >= 0 ? 2 : 0));
     }
-    vis_ptr[a + 1] = (int32_t) vis_cluster.size();
-    c->h_nwords[a] = w;
-    c->h_bits_base[a + 1] = c->h_bits_base[a] + (int64_t) c->h_cl_count[a] * w;
-    task_base[a + 1] = task_base[a] + (int64_t) c->h_cl_count[a] * ((w + kChunkWords - 1) / kChunkWords);
-    c->h_Lptr[a + 1] = c->h_Lptr[a] + cand;
+    c->slot_flags.upload(flags, st);
   }
-  for (int d = 0; d < nc; d++) Rptr[d + 1] += Rptr[d];
-  // a cluster that sees nothing would leave a row of zero words; bits_base must stay strictly usable
-  const uint64_t W = (uint64_t) c->h_bits_base[nc];
-  c->bits_words = W;
-  if (c->h_Lptr[nc] >= ((int64_t) 1 << 40)) dfail("make_transfers: candidate lists too large");
-
-  cudaStream_t st = c->stream;
-  c->slot_patch.upload(c->h_slot_patch, st);
-  c->patch_slot.upload(c->h_patch_slot, st);
-  c->slot_cluster.upload(c->h_slot_cluster, st);
+  c->slot_patch.upload(P.slot_patch, st);
+  c->patch_slot.upload(P.patch_slot, st);
+  c->slot_cluster.upload(P.slot_cluster, st);
+  c->slice_count.upload(P.slice_count, st);
+  c->d_cl_slot_start.upload(P.cl_slot_start, st);
+  c->d_cl_count.upload(P.cl_count, st);
+  c->d_nwords.upload(P.nwords, st);
+  c->d_wb_first.upload(P.wb_first, st);
+  c->d_vis_ptr.upload(P.vis_ptr, st);
+  c->d_vis_cluster.upload(P.vis_cluster, st);
+  c->d_vis_woff.upload(P.vis_woff, st);
+  c->d_vis_seer.upload(P.vis_seer, st);
+  c->d_coff.upload(P.coff, st);
+  c->d_sbase.upload(P.sbase, st);
+  c->d_grp_first.upload(P.grp_first, st);
+  c->d_grp_cluster.upload(P.grp_cluster, st);
+  c->d_grp_slot0.upload(P.grp_slot0, st);
+  c->d_grp_rows.upload(P.grp_rows, st);
+  c->d_grp_owner.upload(P.grp_owner, st);
+  c->d_grp_ownbase.upload(P.grp_ownbase, st);
   {
-    std::vector<float4> so(M, make_float4(0, 0, 0, 0)), sn(M, make_float4(0, 0, 0, 0));
-    const std::vector<float4> &po = c->h_origin_area, &pn = c->h_normal;   // host copies kept by upload_patches
-    for (int s = 0; s < M; s++) {
-      int p = c->h_slot_patch[s];
-      if (p >= 0) {
-        so[s] = po[p];
-        sn[s] = pn[p];
-      }
-    }
-    c->s_origin_area.upload(so, st);
-    c->s_normal.upload(sn, st);
-    std::vector<float4> bmn((size_t) M / 32, make_float4(3e38f, 3e38f, 3e38f, 0)), bmx((size_t) M / 32, make_float4(-3e38f, -3e38f, -3e38f, 0));
-    for (int s = 0; s < M; s++) {
-      if (c->h_slot_patch[s] < 0) continue;
-      float4 &lo4 = bmn[s >> 5], &hi4 = bmx[s >> 5];
-      lo4.x = std::min(lo4.x, so[s].x); lo4.y = std::min(lo4.y, so[s].y); lo4.z = std::min(lo4.z, so[s].z);
-      hi4.x = std::max(hi4.x, so[s].x); hi4.y = std::max(hi4.y, so[s].y); hi4.z = std::max(hi4.z, so[s].z);
-    }
-    c->wbox_min.upload(bmn, st);
-    c->wbox_max.upload(bmx, st);
+    std::vector<int32_t> og(P.own_groups);
+    if (og.empty()) og.push_back(0);
+    c->d_own_groups.upload(og, st);
+    c->d_own_runbase.upload(P.own_runbase, st);
   }
-  c->d_vis_ptr.upload(vis_ptr, st);
-  c->d_vis_cluster.upload(vis_cluster, st);
-  c->d_vis_woff.upload(vis_woff, st);
-  c->d_woff_table.upload(woff_table, st);
-  c->d_bits_base.upload(c->h_bits_base, st);
-  c->d_Lptr.upload(c->h_Lptr, st);
-  c->d_nwords.upload(c->h_nwords, st);
-  c->d_cl_slot_start.upload(c->h_cl_slot_start, st);
-  c->d_cl_count.upload(c->h_cl_count, st);
-  c->h_Rptr = Rptr;
-  c->d_Rptr.upload(Rptr, st);
-  c->d_task_base.upload(task_base, st);
+  const int nvis = (int) P.vis_cluster.size();
+  {
+    std::vector<int32_t> vis_src((size_t) std::max(nvis, 1));
+    for (int a = 0; a < nc; a++)
+      for (int v = P.vis_ptr[a]; v < P.vis_ptr[a + 1]; v++) vis_src[v] = a;
+    c->d_vis_src.upload(vis_src, st);
+  }
+  c->s_origin_area.alloc((size_t) M);
+  c->s_normal.alloc((size_t) M);
+  c->wbox_min.alloc((size_t) M / 32);
+  c->wbox_max.alloc((size_t) M / 32);
+  k_slot_geometry<<<(M + 255) / 256, 256, 0, st>>>(M, c->slot_patch.p, c->p_origin_area.p, c->p_normal.p, c->s_origin_area.p,
+                                                   c->s_normal.p, c->wbox_min.p, c->wbox_max.p);
+  c->launch_check("k_slot_geometry");
+  const int64_t nwords_all = P.wb_first[nc];
+  c->wslice.alloc((size_t) nwords_all + 1);
+  c->wbase.alloc((size_t) nwords_all + 1);
+  const size_t E = P.seer_cluster.size();
+  if (nvis > 0) {
+    k_word_tables<<<(nvis + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(
+        nvis, c->d_vis_src.p, c->d_vis_cluster.p, c->d_vis_woff.p, c->d_vis_seer.p, c->d_cl_slot_start.p, c->d_wb_first.p,
+        c->d_sbase.p + (size_t) P.rank * (P.nslices + 1), c->d_coff.p + (size_t) P.rank * E, c->wslice.p, c->wbase.p);
+    c->launch_check("k_word_tables");
+  }
+  const int64_t W = P.rowbuf_words();
   c->bits.alloc((size_t) W + 1);
   c->counters.alloc(16);
   c->counters.zero(st);
-
-  c->sync("make_transfers uploads");
+  c->sync("make_transfers set-up");
   c->stats.ms_tr_setup = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   // ---- pass 1 ----
-  Timer ttrace;
-  ttrace.start(st);
-  if (W) {
-    // rows of patches that sit in solid (only possible under -nopvs) are cleared afterwards
-    VisArgs a;
+  QCUDA(cudaEventRecord(c->ev[0], st));
+  const uint64_t runs = (uint64_t) P.own_runbase.back();
+  if (runs) {
+    VisArgs a{};
     a.tree = c->tree();
     a.leaf_path = c->leaf_path.p;
     a.leaf_path_first = c->leaf_path_first.p;
@@ -1319,29 +1269,18 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
     a.wbox_max = c->wbox_max.p;
     a.s_origin_area = c->s_origin_area.p;
     a.s_normal = c->s_normal.p;
-    a.bits_base = c->d_bits_base.p;
-    a.task_base = c->d_task_base.p;
-    a.nwords = c->d_nwords.p;
-    a.cl_slot_start = c->d_cl_slot_start.p;
-    a.cl_count = c->d_cl_count.p;
-    a.vis_ptr = c->d_vis_ptr.p;
-    a.vis_cluster = c->d_vis_cluster.p;
-    a.vis_woff = c->d_vis_woff.p;
-    a.nc = nc;
-    // multi-GPU: tasks are dealt to the ranks in granules; words of other ranks stay zero so that the exchange
-    // is one sum all-reduce of the matrix (each word is written by exactly one rank)
-    const uint64_t T = (uint64_t) task_base[nc];
-    const uint64_t granules = (T + kTaskGranule - 1) / kTaskGranule;
-    const uint64_t mine_g = granules / c->world + ((granules % c->world) > (uint64_t) c->rank ? 1 : 0);
-    a.num_tasks = T;
-    a.my_tasks = mine_g * kTaskGranule;
-    a.rank = c->rank;
-    a.world = c->world;
-    if (c->world > 1) c->bits.zero(st);
+    a.g = geo_of(c);
+    a.own_groups = c->d_own_groups.p;
+    a.own_runbase = c->d_own_runbase.p;
+    a.n_own_groups = (int) P.own_groups.size();
+    a.grp_cluster = c->d_grp_cluster.p;
+    a.grp_slot0 = c->d_grp_slot0.p;
+    a.grp_rows = c->d_grp_rows.p;
+    a.grp_ownbase = c->d_grp_ownbase.p;
+    a.num_runs = runs;
     a.bits = c->bits.p;
     a.counters = c->counters.p;
-    const uint64_t mine = a.my_tasks;
-    const uint64_t want_blocks = (mine / kTaskRun + kWarpsPerBlock) / kWarpsPerBlock;
+    const uint64_t want_blocks = (runs + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>(want_blocks, (uint64_t) c->sm_count * 8));
     const bool big = c->tree_depth > kTraceStack;
     if (c->count_nodes) {
@@ -1353,157 +1292,187 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
     }
     c->launch_check("k_visibility");
   }
-  c->stats.ms_transfers_trace = ttrace.stop();
-  if (nopvs) {
-    // clear rows of sources in solid: they never shoot (qrad3.c:208)
-    for (int s = 0; s < M; s++)
-      if (c->h_slot_patch[s] >= 0 && !source_ok[s])
-        QCUDA(cudaMemsetAsync(c->bits.p + c->h_bits_base[0] + (int64_t) s * c->h_nwords[0], 0, (size_t) c->h_nwords[0] * 4, st));
+  QCUDA(cudaEventRecord(c->ev[1], st));
+  // several GPUs: while this rank goes on with its lists and pass 2, every peer receives the contiguous piece of the
+  // row buffer that describes its receiver slices (second stream; pass 3 waits for it)
+  c->stats.ms_x_matrix = 0;
+  if (P.world > 1) {
+    const NcclApi &n = nccl();
+    int64_t recv_total = 0;
+    c->piece_first.assign(P.world, 0);
+    for (int q = 0; q < P.world; q++) {
+      c->piece_first[q] = recv_total;
+      if (q != P.rank) recv_total += P.words_for(q, P.rank);
+    }
+    c->colbuf.alloc((size_t) recv_total + 1);
+    QCUDA(cudaStreamWaitEvent(c->xstream, c->ev[1], 0));
+    QCUDA(cudaEventRecord(c->ev[2], c->xstream));
+    nccl_ok(n.GroupStart(), "ncclGroupStart");
+    for (int q = 0; q < P.world; q++) {
+      if (q == P.rank) continue;
+      const int64_t sfirst = P.sbase[(size_t) P.rank * (P.nslices + 1) + P.slice_lo[q]], scount = P.words_for(P.rank, q);
+      if (scount) nccl_ok(n.Send(c->bits.p + sfirst, (size_t) scount, ncclUint32, q, c->comm, c->xstream), "ncclSend");
+      const int64_t rcount = P.words_for(q, P.rank);
+      if (rcount) nccl_ok(n.Recv(c->colbuf.p + c->piece_first[q], (size_t) rcount, ncclUint32, q, c->comm, c->xstream), "ncclRecv");
+    }
+    nccl_ok(n.GroupEnd(), "ncclGroupEnd");
+    QCUDA(cudaEventRecord(c->ev[3], c->xstream));
   }
-
   c->sync("make_transfers pass 1");
+  c->stats.ms_transfers_trace = elapsed(c->ev[0], c->ev[1]);
 }
 
-// phase 1: ordered lists + pass 2 (row totals of this rank's slots).  Needs the complete bit matrix.
+// phase 1: ordered run lists + pass 2 (row totals of this rank's rows)
 void transfers_rows(qrad_cuda_ctx *c) {
   cudaStream_t st = c->stream;
   auto wall0 = std::chrono::steady_clock::now();
-  const int N = c->N, M = c->M, nc = c->nc_eff;
-  // ---- ordered lists ----
-  c->L_slot.alloc((size_t) c->h_Lptr[nc] + 1);
-  c->L_pos.alloc((size_t) c->h_Lptr[nc] + 1);
-  c->R_slot.alloc((size_t) c->h_Rptr[nc] + 1);
-  {
-    ListArgs la;
-    la.N = N;
-    la.nc = nc;
-    la.patch_slot = c->patch_slot.p;
-    la.slot_cluster = c->slot_cluster.p;
-    la.woff_table = c->d_woff_table.p;
-    la.cl_slot_start = c->d_cl_slot_start.p;
-    la.list_ptr = c->d_Lptr.p;
-    la.out_slot = c->L_slot.p;
-    la.out_aux = c->L_pos.p;
-    la.transpose = 0;
-    la.bits_base = nullptr;
-    la.nwords = nullptr;
-    la.out_addr = nullptr;
-    // only the clusters this rank's slots belong to (all of them on one GPU)
-    const int c_lo = c->slice_hi > c->slice_lo ? c->h_slot_cluster[(size_t) c->slice_lo * 32] : 0;
-    const int c_hi = c->slice_hi > c->slice_lo ? c->h_slot_cluster[(size_t) c->slice_hi * 32 - 1] : -1;
-    const int c_n = c_hi - c_lo + 1;
-    la.c_first = c_lo;
-    if (c_n > 0) k_build_lists<<<c_n, 1024, 0, st>>>(la);
-    c->launch_check("k_build_lists(rows)");
-    la.list_ptr = c->d_Rptr.p;
-    la.out_slot = c->R_slot.p;
-    la.out_aux = nullptr;
-    la.transpose = 1;
-    la.bits_base = c->d_bits_base.p;
-    la.nwords = c->d_nwords.p;
-    c->R_addr.alloc((size_t) c->h_Rptr[nc] + 1);
-    la.out_addr = c->R_addr.p;
-    if (c_n > 0) k_build_lists<<<c_n, 1024, 0, st>>>(la);
-    c->launch_check("k_build_lists(cols)");
-  }
-
-  {
-    std::vector<int64_t> chunk_base((size_t) nc + 1, 0);
-    for (int k = 0; k < nc; k++) chunk_base[k + 1] = chunk_base[k] + ((c->h_Lptr[k + 1] - c->h_Lptr[k] + 31) >> 5);
-    c->d_chunk_base.upload(chunk_base, st);
-    c->L_sum.alloc((size_t) 2 * chunk_base[nc] + 2);
-    const int c_lo = c->slice_hi > c->slice_lo ? c->h_slot_cluster[(size_t) c->slice_lo * 32] : 0;
-    const int c_hi = c->slice_hi > c->slice_lo ? c->h_slot_cluster[(size_t) c->slice_hi * 32 - 1] : -1;
-    const int64_t ch_lo = chunk_base[c_lo], ch_hi = c_hi >= c_lo ? chunk_base[c_hi + 1] : chunk_base[c_lo];
-    if (ch_hi > ch_lo) {
-      k_list_summaries<<<(unsigned) ((ch_hi - ch_lo + kWarpsPerBlock - 1) / kWarpsPerBlock), kThreads, 0, st>>>(
-          nc, c->d_Lptr.p, c->d_chunk_base.p, c->L_pos.p, c->L_sum.p, ch_lo, ch_hi);
-      c->launch_check("k_list_summaries");
+  const TransferPlan &P = c->plan;
+  const int N = c->N, M = P.M, nc = P.nc;
+  // ---- the patch order as runs of consecutive slots inside one slice ----
+  std::vector<int2> runs;
+  runs.reserve((size_t) M / 8);
+  for (int i = 0; i < N; i++) {
+    const int s = P.patch_slot[i];
+    if (s < 0) continue;
+    if (!runs.empty()) {
+      int2 &r = runs.back();
+      if (s == r.x + r.y && (s >> 5) == (r.x >> 5)) {   // the next slot of the same slice: the run goes on
+        r.y++;
+        continue;
+      }
     }
+    runs.push_back(make_int2(s, 1));
+  }
+  c->d_runs.upload(runs, st);
+  std::vector<int32_t> row_clusters, col_clusters;
+  for (int k = 0; k < nc; k++) {
+    if (P.Lown_ptr[k + 1] > P.Lown_ptr[k]) row_clusters.push_back(k);
+    if (P.Rown_ptr[k + 1] > P.Rown_ptr[k]) col_clusters.push_back(k);
+  }
+  RunListArgs la{};
+  la.nruns = (int) runs.size();
+  la.runs = c->d_runs.p;
+  la.slot_cluster = c->slot_cluster.p;
+  la.cl_slot_start = c->d_cl_slot_start.p;
+  la.vis_ptr = c->d_vis_ptr.p;
+  la.vis_cluster = c->d_vis_cluster.p;
+  la.vis_woff = c->d_vis_woff.p;
+  la.vis_seer = c->d_vis_seer.p;
+  la.wb_first = c->d_wb_first.p;
+  la.wbase = c->wbase.p;
+  la.wslice = c->wslice.p;
+  la.grp_first = c->d_grp_first.p;
+  la.grp_owner = c->d_grp_owner.p;
+  la.grp_ownbase = c->d_grp_ownbase.p;
+  la.grp_slot0 = c->d_grp_slot0.p;
+  la.coff = c->d_coff.p;
+  la.E = (int64_t) P.seer_cluster.size();
+  DBuf<int32_t> d_rowcl, d_colcl, d_cnt_row, d_cnt_col;
+  d_rowcl.upload(row_clusters, st);
+  d_colcl.upload(col_clusters, st);
+  d_cnt_row.alloc((size_t) nc);
+  d_cnt_col.alloc((size_t) nc);
+  d_cnt_row.zero(st);
+  d_cnt_col.zero(st);
+  if (!row_clusters.empty()) {
+    la.clusters = d_rowcl.p;
+    la.count = d_cnt_row.p;
+    k_run_lists<false, false><<<(int) row_clusters.size(), 1024, 0, st>>>(la);
+    c->launch_check("k_run_lists(rows, count)");
+  }
+  if (!col_clusters.empty()) {
+    la.clusters = d_colcl.p;
+    la.count = d_cnt_col.p;
+    k_run_lists<true, false><<<(int) col_clusters.size(), 1024, 0, st>>>(la);
+    c->launch_check("k_run_lists(columns, count)");
+  }
+  std::vector<int32_t> cnt_row((size_t) nc), cnt_col((size_t) nc);
+  d_cnt_row.download(cnt_row.data(), (size_t) nc, st);
+  d_cnt_col.download(cnt_col.data(), (size_t) nc, st);
+  std::vector<int64_t> vl_ptr((size_t) nc + 1, 0), vr_ptr((size_t) nc + 1, 0);
+  for (int k = 0; k < nc; k++) {
+    vl_ptr[k + 1] = vl_ptr[k] + cnt_row[k];
+    vr_ptr[k + 1] = vr_ptr[k] + cnt_col[k];
+  }
+  c->d_vl_ptr.upload(vl_ptr, st);
+  c->d_vr_ptr.upload(vr_ptr, st);
+  c->vl.alloc((size_t) vl_ptr[nc] + 1);
+  c->vr.alloc((size_t) vr_ptr[nc] + 1);
+  la.vl = c->vl.p;
+  la.vr = c->vr.p;
+  if (!row_clusters.empty()) {
+    la.clusters = d_rowcl.p;
+    la.list_ptr = c->d_vl_ptr.p;
+    k_run_lists<false, true><<<(int) row_clusters.size(), 1024, 0, st>>>(la);
+    c->launch_check("k_run_lists(rows)");
+  }
+  if (!col_clusters.empty()) {
+    la.clusters = d_colcl.p;
+    la.list_ptr = c->d_vr_ptr.p;
+    k_run_lists<true, true><<<(int) col_clusters.size(), 1024, 0, st>>>(la);
+    c->launch_check("k_run_lists(columns)");
   }
   c->sync("make_transfers lists");
   c->stats.ms_tr_lists = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   wall0 = std::chrono::steady_clock::now();
   // ---- pass 2 ----
-  c->row_total.alloc((size_t) c->Mpad);
-  c->row_count.alloc((size_t) c->Mpad);
+  c->row_total.alloc((size_t) M);
+  c->row_count.alloc((size_t) M);
   c->row_total.zero(st);
   c->row_count.zero(st);
-  {
-    RowArgs ra{};
-    ra.s_origin_area = c->s_origin_area.p;
-    ra.s_normal = c->s_normal.p;
-    ra.slot_patch = c->slot_patch.p;
-    ra.slot_cluster = c->slot_cluster.p;
-    ra.bits_base = c->d_bits_base.p;
-    ra.Lptr = c->d_Lptr.p;
-    ra.nwords = c->d_nwords.p;
-    ra.cl_slot_start = c->d_cl_slot_start.p;
-    ra.L_slot = c->L_slot.p;
-    ra.L_pos = c->L_pos.p;
-    ra.L_sum = c->L_sum.p;
-    ra.chunk_base = c->d_chunk_base.p;
-    ra.bits = c->bits.p;
-    ra.M = M;
-    ra.slot_lo = c->slice_lo * 32;
-    ra.slot_hi = c->slice_hi * 32;
-    ra.row_total = c->row_total.p;
-    ra.row_count = c->row_count.p;
-    const int rows = ra.slot_hi - ra.slot_lo;   // whole 32-slot slices
-    if (rows > 0) {
-      k_row_totals32<<<(rows / 32 + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(ra);
-      c->launch_check("k_row_totals32");
-    }
+  const int nrs = (int) P.own_rowslice_slot0.size();
+  if (nrs > 0) {
+    c->d_rowslice_slot0.upload(P.own_rowslice_slot0, st);
+    c->d_rowslice_row0.upload(P.own_rowslice_row0, st);
+    RowArgs ra = row_args(c);
+    ra.rowslice_slot0 = c->d_rowslice_slot0.p;
+    ra.rowslice_row0 = c->d_rowslice_row0.p;
+    ra.n_rowslices = nrs;
+    k_row_totals32<<<(nrs + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(ra);
+    c->launch_check("k_row_totals32");
+  }
+  if (P.world > 1) {   // every row was summed by exactly one rank
+    // one communicator: its collectives are kept in one order by making this stream wait for the matrix exchange
+    QCUDA(cudaStreamWaitEvent(st, c->ev[3], 0));
+    const NcclApi &n = nccl();
+    nccl_ok(n.AllReduce(c->row_total.p, c->row_total.p, (size_t) M, ncclFloat, ncclSum, c->comm, st), "ncclAllReduce");
+    nccl_ok(n.AllReduce(c->row_count.p, c->row_count.p, (size_t) M, ncclInt32, ncclSum, c->comm, st), "ncclAllReduce");
   }
   c->sync("make_transfers pass 2");
   c->stats.ms_tr_rows = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
 }
 
-// phase 2: pass 3 (gather lists of this rank's slices).  Needs the row totals of every source.
+// phase 2: pass 3 (gather lists of this rank's slices).  Needs the row totals of every source and, on several GPUs, the
+// pieces of the other ranks' row buffers.
 void transfers_columns(qrad_cuda_ctx *c) {
   cudaStream_t st = c->stream;
   const auto wall0 = std::chrono::steady_clock::now();
-  const int M = c->M, nc = c->nc_eff;
-  const int nslices = M / 32;
+  const TransferPlan &P = c->plan;
+  const int M = P.M, nslices = P.nslices;
+  const int lo = P.slice_lo[P.rank], hi = P.slice_hi[P.rank];
   c->slice_len.alloc((size_t) nslices);
   c->slice_len.zero(st);
   ColArgs ca{};
   ca.s_origin_area = c->s_origin_area.p;
   ca.s_normal = c->s_normal.p;
-  ca.slot_patch = c->slot_patch.p;
-  ca.slot_cluster = c->slot_cluster.p;
-  ca.bits_base = c->d_bits_base.p;
-  ca.Rptr = c->d_Rptr.p;
-  ca.nwords = c->d_nwords.p;
-  ca.cl_slot_start = c->d_cl_slot_start.p;
-  ca.woff_table = c->d_woff_table.p;
-  ca.nc = nc;
-  ca.R_slot = c->R_slot.p;
-  ca.R_addr = c->R_addr.p;
-  ca.bits = c->bits.p;
+  ca.g = geo_of(c);
+  ca.vr_ptr = c->d_vr_ptr.p;
+  ca.vr = c->vr.p;
+  for (int q = 0; q < P.world; q++) {
+    if (q == P.rank) ca.col[q] = c->bits.p;
+    else ca.col[q] = c->colbuf.p + c->piece_first[q] - P.sbase[(size_t) q * (nslices + 1) + lo];
+  }
+  ca.sbase = c->d_sbase.p;
+  ca.nslices = nslices;
   ca.row_total = c->row_total.p;
-  ca.M = M;
-  // blocks: runs of up to 8 consecutive slices that lie in one cluster and in this rank's range
-  std::vector<int32_t> blk_slice0, blk_n;
-  for (int s = c->slice_lo; s < c->slice_hi;) {
-    const int cl = c->h_slot_cluster[(size_t) s * 32];
-    const int cl_end = c->h_cl_slot_start[cl + 1] / 32;
-    const int e = std::min(std::min(s + kWarpsPerBlock, cl_end), c->slice_hi);
-    blk_slice0.push_back(s);
-    blk_n.push_back(e - s);
-    s = e;
-  }
-  const int cblocks = (int) blk_slice0.size();
-  c->col_blk_slice0.upload(blk_slice0, st);
-  c->col_blk_n.upload(blk_n, st);
-  ca.blk_slice0 = c->col_blk_slice0.p;
-  ca.blk_n = c->col_blk_n.p;
+  ca.slice_lo = lo;
+  ca.slice_hi = hi;
   ca.slice_len = c->slice_len.p;
-  if (c->slice_hi > c->slice_lo) {   // slice_len was cleared above
-    const int c_lo = c->h_slot_cluster[(size_t) c->slice_lo * 32], c_hi = c->h_slot_cluster[(size_t) c->slice_hi * 32 - 1];
-    k_column_counts<<<c_hi - c_lo + 1, kThreads, 0, st>>>(ca, c_lo, c->slice_lo, c->slice_hi);
+  const int cblocks = (hi - lo + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  if (cblocks > 0) {
+    k_column_counts<<<cblocks, kThreads, 0, st>>>(ca);
+    c->launch_check("k_column_counts");
   }
-  c->launch_check("k_column_counts");
   std::vector<int32_t> h_len((size_t) nslices);
   c->slice_len.download(h_len.data(), (size_t) nslices, st);
   std::vector<int64_t> h_slice_base((size_t) nslices + 1, 0);
@@ -1525,7 +1494,7 @@ void transfers_columns(qrad_cuda_ctx *c) {
   c->slice_base.upload(h_slice_base, st);
   {  // k_bounce hands this rank's slices to its warps longest list first
     std::vector<int32_t> order;
-    for (int s = c->slice_lo; s < c->slice_hi; s++) order.push_back(s);
+    for (int s = lo; s < hi; s++) order.push_back(s);
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return h_len[x] > h_len[y]; });
     if (order.empty()) order.push_back(0);
     c->slice_order.upload(order, st);
@@ -1538,13 +1507,16 @@ void transfers_columns(qrad_cuda_ctx *c) {
   ca.slice_base = c->slice_base.p;
   ca.g_src = c->g_src.p;
   ca.g_w = c->g_w.p;
-  if (cblocks > 0) k_columns<<<cblocks, kThreads, 0, st>>>(ca);
-  c->launch_check("k_columns");
+  if (cblocks > 0) {
+    k_columns<<<cblocks, kThreads, 0, st>>>(ca);
+    c->launch_check("k_columns");
+  }
   std::vector<int32_t> h_rc((size_t) M);
   c->row_count.download(h_rc.data(), (size_t) M, st);
   int64_t nnz = 0;
   for (int s = 0; s < M; s++) nnz += h_rc[s];
   c->sync("make_transfers");
+  if (P.world > 1) c->stats.ms_x_matrix = elapsed(c->ev[2], c->ev[3]);
 
   unsigned long long hc[16];
   c->counters.download(hc, 16, st);
@@ -1570,150 +1542,105 @@ void transfers_columns(qrad_cuda_ctx *c) {
 }
 
 void make_transfers_impl(qrad_cuda_ctx *c, int nopvs) {
-  if (c->world > 1) dfail("make_transfers: this context is a shard (%d/%d); use qrad_cuda_make_transfers_phase and exchange", c->rank, c->world);
   transfers_trace(c, nopvs);
   transfers_rows(c);
   transfers_columns(c);
 }
 
-// reference row format for parity tests: rows by source patch, receivers ascending
-void download_transfers_impl(qrad_cuda_ctx *c, int64_t *row_ptr, uint32_t *patch, uint16_t *transfer) {
-  if (c->world > 1) dfail("download_transfers: not available on a shard (row lists exist only for this rank's clusters)");
-  const int N = c->N, M = c->M;
-  cudaStream_t st = c->stream;
-  std::vector<int32_t> rc((size_t) M);
-  c->row_count.download(rc.data(), rc.size(), st);
-  row_ptr[0] = 0;
-  for (int i = 0; i < N; i++) row_ptr[i + 1] = row_ptr[i] + (c->h_patch_slot[i] >= 0 ? rc[c->h_patch_slot[i]] : 0);
-  const int64_t nnz = row_ptr[N];
-  DBuf<int64_t> d_row_ptr;
-  d_row_ptr.upload(row_ptr, (size_t) N + 1, st);
-  DBuf<uint32_t> d_patch;
-  DBuf<uint16_t> d_tr;
-  d_patch.alloc((size_t) nnz + 1);
-  d_tr.alloc((size_t) nnz + 1);
-  RowArgs ra{};
-  ra.s_origin_area = c->s_origin_area.p;
-  ra.s_normal = c->s_normal.p;
-  ra.slot_patch = c->slot_patch.p;
-  ra.slot_cluster = c->slot_cluster.p;
-  ra.bits_base = c->d_bits_base.p;
-  ra.Lptr = c->d_Lptr.p;
-  ra.nwords = c->d_nwords.p;
-  ra.cl_slot_start = c->d_cl_slot_start.p;
-  ra.L_slot = c->L_slot.p;
-  ra.L_pos = c->L_pos.p;
-  ra.L_sum = c->L_sum.p;
-  ra.chunk_base = c->d_chunk_base.p;
-  ra.bits = c->bits.p;
-  ra.M = M;
-  ra.slot_lo = 0;
-  ra.slot_hi = M;
-  ra.row_total = c->row_total.p;
-  ra.row_count = c->row_count.p;
-  ra.row_ptr = d_row_ptr.p;
-  ra.out_patch = d_patch.p;
-  ra.out_transfer = d_tr.p;
-  k_row_totals<true><<<(M + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(ra);
-  c->launch_check("k_row_totals<emit>");
-  d_patch.download(patch, (size_t) nnz, st);
-  d_tr.download(transfer, (size_t) nnz, st);
-}
-
-// the same for selected source patches only (row-sample parity checks on maps whose whole matrix is tens of GB)
+// reference row format for parity tests: the rows of selected source patches, receivers ascending, and the root
+// TestLine_r calls of each row
 void download_rows_impl(qrad_cuda_ctx *c, int nrows, const int32_t *rows, int64_t *row_ptr, uint32_t *patch,
                         uint16_t *transfer, int64_t capacity, int64_t *rays) {
-  if (c->world > 1) dfail("download_rows: not available on a shard");
-  if (nrows <= 0) return;
+  if (c->world > 1) dfail("download of transfer rows: not available on a context that is part of a communicator");
+  if (nrows <= 0) {
+    row_ptr[0] = 0;
+    return;
+  }
+  const TransferPlan &P = c->plan;
   cudaStream_t st = c->stream;
-  std::vector<int32_t> rc((size_t) c->M);
+  std::vector<int32_t> rc((size_t) P.M);
   c->row_count.download(rc.data(), rc.size(), st);
-  std::vector<int32_t> sel((size_t) nrows);
+  std::vector<int32_t> sel((size_t) nrows), selrow((size_t) nrows, 0);
   row_ptr[0] = 0;
   for (int k = 0; k < nrows; k++) {
     if (rows[k] < 0 || rows[k] >= c->N) dfail("download_rows: patch %d out of range", rows[k]);
-    sel[k] = c->h_patch_slot[rows[k]];
+    sel[k] = P.patch_slot[rows[k]];
+    if (sel[k] >= 0) {
+      const int g = P.group_of_slot(sel[k]);
+      selrow[k] = P.grp_ownbase[g] + (sel[k] - P.grp_slot0[g]);
+    }
     row_ptr[k + 1] = row_ptr[k] + (sel[k] >= 0 ? rc[sel[k]] : 0);
   }
   const int64_t nnz = row_ptr[nrows];
   if (nnz > capacity) dfail("download_rows: %lld records do not fit the caller's %lld", (long long) nnz, (long long) capacity);
   DBuf<int64_t> d_row_ptr;
   d_row_ptr.upload(row_ptr, (size_t) nrows + 1, st);
-  DBuf<int32_t> d_sel;
+  DBuf<int32_t> d_sel, d_selrow;
   d_sel.upload(sel, st);
+  d_selrow.upload(selrow, st);
   DBuf<uint32_t> d_patch;
   DBuf<uint16_t> d_tr;
   DBuf<long long> d_rays;
   d_patch.alloc((size_t) nnz + 1);
   d_tr.alloc((size_t) nnz + 1);
   d_rays.alloc((size_t) nrows);
-  RowArgs ra{};
-  ra.s_origin_area = c->s_origin_area.p;
-  ra.s_normal = c->s_normal.p;
-  ra.slot_patch = c->slot_patch.p;
-  ra.slot_cluster = c->slot_cluster.p;
-  ra.bits_base = c->d_bits_base.p;
-  ra.Lptr = c->d_Lptr.p;
-  ra.nwords = c->d_nwords.p;
-  ra.cl_slot_start = c->d_cl_slot_start.p;
-  ra.L_slot = c->L_slot.p;
-  ra.L_pos = c->L_pos.p;
-  ra.L_sum = c->L_sum.p;
-  ra.chunk_base = c->d_chunk_base.p;
-  ra.bits = c->bits.p;
-  ra.M = c->M;
-  ra.slot_lo = 0;
-  ra.slot_hi = c->M;
-  ra.row_total = c->row_total.p;
-  ra.row_count = c->row_count.p;
+  RowArgs ra = row_args(c);
   ra.row_ptr = d_row_ptr.p;
   ra.out_patch = d_patch.p;
   ra.out_transfer = d_tr.p;
   ra.sel_slots = d_sel.p;
+  ra.sel_rows = d_selrow.p;
   ra.nsel = nrows;
   ra.sel_rays = d_rays.p;
   const int blocks = (nrows + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  k_row_totals<true><<<blocks, kThreads, 0, st>>>(ra);
-  c->launch_check("k_row_totals<emit, selected>");
+  if (patch && transfer) {
+    k_rows_emit<<<blocks, kThreads, 0, st>>>(ra);
+    c->launch_check("k_rows_emit");
+    d_patch.download(patch, (size_t) nnz, st);
+    d_tr.download(transfer, (size_t) nnz, st);
+  }
   if (rays) {
     k_row_rays<<<blocks, kThreads, 0, st>>>(ra);
     c->launch_check("k_row_rays");
-  }
-  d_patch.download(patch, (size_t) nnz, st);
-  d_tr.download(transfer, (size_t) nnz, st);
-  if (rays) {
     std::vector<long long> hr((size_t) nrows);
     d_rays.download(hr.data(), hr.size(), st);
     for (int k = 0; k < nrows; k++) rays[k] = hr[k];
   }
 }
 
-// BounceLight, qrad3.c:448-473, in three parts so that a multi-GPU host can all-gather the radiosity vector
-// between bounces: begin (radiosity = samplelight * reflectivity * area), step (one ShootLight + CollectLight
-// over this rank's slices), end (totallight back to patch order).
+void download_transfers_impl(qrad_cuda_ctx *c, int64_t *row_ptr, uint32_t *patch, uint16_t *transfer) {
+  std::vector<int32_t> all((size_t) c->N);
+  for (int i = 0; i < c->N; i++) all[i] = i;
+  download_rows_impl(c, c->N, all.data(), row_ptr, patch, transfer, INT64_MAX, nullptr);
+}
+
+// BounceLight, qrad3.c:448-473: begin (radiosity = samplelight * reflectivity * area), step (one ShootLight +
+// CollectLight over this rank's slices; on several GPUs the owners then broadcast their part of the new radiosity), end
+// (totallight back to patch order).
 void bounce_begin(qrad_cuda_ctx *c, bool want_sum) {
   if (!c->transfers_done) dfail("bounce: make_transfers has not run");
   c->t_bounce.start(c->stream);
   cudaStream_t st = c->stream;
   const int M = c->M;
-  c->rad_a.alloc((size_t) c->Mpad);
-  c->rad_b.alloc((size_t) c->Mpad);
-  c->s_total.alloc((size_t) c->Mpad);
-  c->s_refl_area.alloc((size_t) c->Mpad);
+  c->rad_a.alloc((size_t) M);
+  c->rad_b.alloc((size_t) M);
+  c->s_total.alloc((size_t) M);
+  c->s_refl_area.alloc((size_t) M);
   c->rad_a.zero(st);
   c->rad_b.zero(st);
   c->s_total.zero(st);
   k_init_bounce<<<(M + 255) / 256, 256, 0, st>>>(M, c->slot_patch.p, c->p_samplelight.p, c->p_totallight.p, c->p_refl.p,
                                                  c->p_origin_area.p, c->rad_a.p, c->s_total.p, c->s_refl_area.p);
   c->launch_check("k_init_bounce");
-  if (want_sum) c->rad_sum.alloc((size_t) c->Mpad);
+  if (want_sum) c->rad_sum.alloc((size_t) M);
   else c->rad_sum.release();
   c->rad_cur = c->rad_a.p;
   c->rad_nxt = c->rad_b.p;
-  c->bounce_kernel_ms = 0;
   c->bounce_steps = 0;
   c->bounce_next.alloc(2);
   c->bounce_next.zero(st);
+  c->negative_light.alloc(1);
+  c->negative_light.zero(st);
   if (c->bounce_blocks_per_sm == 0) {
     int per_sm = 0;
     QCUDA(cudaFuncSetAttribute(k_bounce, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarpsPerBlock * kBounceWarpBytes));
@@ -1722,11 +1649,11 @@ void bounce_begin(qrad_cuda_ctx *c, bool want_sum) {
     QCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce_regs, kThreads, 0));
     c->bounce_regs_blocks_per_sm = std::max(1, per_sm);
   }
-  c->sync("bounce_begin");
 }
 
 void bounce_step(qrad_cuda_ctx *c) {
   cudaStream_t st = c->stream;
+  const TransferPlan &P = c->plan;
   BounceArgs a{};
   a.slice_len = c->slice_len.p;
   a.slice_base = c->slice_base.p;
@@ -1736,46 +1663,58 @@ void bounce_step(qrad_cuda_ctx *c) {
   a.refl_area = c->s_refl_area.p;
   a.rad_sum = c->rad_sum.p;
   a.M = c->M;
-  a.slice_lo = c->slice_lo;
-  a.slice_hi = c->slice_hi;
+  a.slice_lo = P.slice_lo[P.rank];
+  a.slice_hi = P.slice_hi[P.rank];
   a.send = c->rad_cur;
   a.send_next = c->rad_nxt;
   a.order = c->slice_order.p;
   a.next = c->bounce_next.p;
   a.parity = c->bounce_steps & 1;
   a.slice_cut = INT_MAX;
-  int nsl = c->slice_hi - c->slice_lo;
+  int nsl = a.slice_hi - a.slice_lo;
   if (const char *f = getenv("QRAD_DEBUG_BOUNCE_SHARD")) {   // time the launch an n-GPU shard would see, on one GPU
     nsl = std::max(1, (int) (nsl * atof(f)));
-    a.slice_cut = c->slice_lo + nsl;
+    a.slice_cut = a.slice_lo + nsl;
   }
   // persistent warps: as many blocks as fit on the chip, slices are drawn from the work counter
-  const int want = std::max(1, (c->slice_hi - c->slice_lo + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  Timer tk;
-  tk.start(st);
+  const int want = std::max(1, (a.slice_hi - a.slice_lo + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  // CUDA events around every launch, read once at the end: no host synchronisation between bounces
+  while ((int) c->bounce_ev.size() < 2 * (c->bounce_steps + 1)) {
+    cudaEvent_t e;
+    QCUDA(cudaEventCreate(&e));
+    c->bounce_ev.push_back(e);
+  }
+  QCUDA(cudaEventRecord(c->bounce_ev[2 * c->bounce_steps], st));
   // few slices per resident warp: the launch lasts as long as ONE warp needs for the longest list -> bulk-copy ring
   bool ring = (int64_t) nsl < (int64_t) 4 * c->sm_count * 40;
   if (const char *force = getenv("QRAD_BOUNCE_KERNEL")) ring = strcmp(force, "regs") != 0;   // tests cover both
   if (ring) k_bounce<<<std::min(want, c->sm_count * c->bounce_blocks_per_sm), kThreads, kWarpsPerBlock * kBounceWarpBytes, st>>>(a);
   else k_bounce_regs<<<std::min(want, c->sm_count * c->bounce_regs_blocks_per_sm), kThreads, 0, st>>>(a);
   c->launch_check("k_bounce");
-  c->bounce_kernel_ms += tk.stop();
+  QCUDA(cudaEventRecord(c->bounce_ev[2 * c->bounce_steps + 1], st));
   c->bounce_steps++;
   std::swap(c->rad_cur, c->rad_nxt);   // rad_cur now holds the new radiosity (this rank's slots)
+  if (P.world > 1) {
+    share_slices(c, c->rad_cur, sizeof(float4), st);
+    if (c->rad_sum.p) share_slices(c, c->rad_sum.p, sizeof(float), st);
+  }
 }
 
 void bounce_end(qrad_cuda_ctx *c) {
   cudaStream_t st = c->stream;
+  if (c->plan.world > 1) share_slices(c, c->s_total.p, sizeof(float4), st);
   k_finish_bounce<<<(c->N + 255) / 256, 256, 0, st>>>(c->N, c->patch_slot.p, c->s_total.p, c->rad_cur, c->p_totallight.p,
-                                                      c->d_radiosity.p);
+                                                      c->d_radiosity.p, c->negative_light.p);
   c->launch_check("k_finish_bounce");
   c->sync("bounce");
-  c->stats.ms_bounce_kernel = c->bounce_steps > 0 ? c->bounce_kernel_ms / c->bounce_steps : 0;
+  float kernel_ms = 0;
+  for (int b = 0; b < c->bounce_steps; b++) kernel_ms += elapsed(c->bounce_ev[2 * b], c->bounce_ev[2 * b + 1]);
+  c->stats.ms_bounce_kernel = c->bounce_steps > 0 ? kernel_ms / c->bounce_steps : 0;
   c->stats.ms_bounce = c->t_bounce.stop();
+  c->stats.ms_x_radiosity = c->plan.world > 1 ? std::max(0.f, c->stats.ms_bounce - kernel_ms) : 0;
 }
 
 void bounce_impl(qrad_cuda_ctx *c, int numbounce, float *added_out) {
-  if (c->world > 1) dfail("bounce: this context is a shard (%d/%d); use qrad_cuda_bounce_phase and exchange", c->rank, c->world);
   bounce_begin(c, added_out != nullptr);
   DBuf<float> d_added;
   if (added_out) d_added.alloc((size_t) std::max(numbounce, 1));
@@ -1788,6 +1727,12 @@ void bounce_impl(qrad_cuda_ctx *c, int numbounce, float *added_out) {
   }
   if (added_out && numbounce > 0) d_added.download(added_out, (size_t) numbounce, c->stream);
   bounce_end(c);
+  // CheckPatches, qrad3.c:476-486
+  if (c->negative_light.p) {
+    int neg = 0;
+    c->negative_light.download(&neg, 1, c->stream);
+    if (neg) dfail("negative patch totallight\n");
+  }
 }
 
 }  // namespace qrad

@@ -260,9 +260,6 @@ class Device:
         except Exception:
             pass
 
-    def set_shard(self, rank, world):
-        _dck(lib().qrad_cuda_set_shard(self._h, C.c_int(rank), C.c_int(world)))
-
     def set_count_nodes(self, on=True):
         _dck(lib().qrad_cuda_set_count_nodes(self._h, C.c_int(1 if on else 0)))
 
@@ -407,68 +404,29 @@ def rad_world(scene: Scene, dev: Device, params: HostParams, want_added: bool = 
     return added[:max(params.numbounce, 0)]
 
 
-XBUF_BITS, XBUF_ROW_TOTAL, XBUF_ROW_COUNT, XBUF_RADIOSITY, XBUF_TOTALLIGHT = range(5)
-
-
-class _DevArray:
-    """Zero-copy view of a library-owned device buffer for torch (CUDA array interface v2)."""
-
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
-def exchange_tensor(dev: Device, which: int, dtype_str: str):
-    """torch tensor over one of the exchange buffers (include/qrad_cuda.h, QRAD_XBUF_*) + elements per shard."""
-    import torch
-    ptr = C.c_void_p()
-    total = C.c_int64()
-    shard = C.c_int64()
-    _dck(lib().qrad_cuda_exchange_buffer(dev._h, C.c_int(which), C.byref(ptr), C.byref(total), C.byref(shard)))
-    t = torch.as_tensor(_DevArray(ptr.value, total.value // 4, dtype_str), device="cuda")
-    return t, shard.value // 4
-
-
-def rad_world_sharded(scene: Scene, dev: Device, params: HostParams, rank: int, world: int, upload: bool = True):
-    """RadWorld (qrad3.c:494-536) with the source rows / receiver slices sharded over `world` ranks, one process
-    per GPU, exchanges over torch.distributed (NCCL over NVLink): one sum all-reduce of the visibility bit matrix,
-    all-gathers of the row totals, one all-gather of the radiosity vector per bounce.
-    Direct lighting and FinalLightFace are replicated (together ~1 % of the work).  Returns (lump, lightofs, styles)."""
-    import time
+def join_communicator(dev: Device, rank: int, world: int):
+    """Make `dev` rank `rank` of a `world`-GPU communicator (one process per GPU, launched by torchrun): rank 0 creates the
+    NCCL id inside the library and torch.distributed only carries its 128 bytes to the other ranks.  Afterwards the same
+    calls (Device.upload / build_facelights / make_transfers / bounce / final_light, or rad_world) on every rank light the
+    map together; every exchange of patch, matrix or radiosity data happens inside libqrad_cuda."""
     import torch
     import torch.distributed as dist
-    L = lib()
-    xt = {"bits_allreduce_ms": 0.0, "allgather_ms": 0.0}
-    dev.set_shard(rank, world)
-    if upload:
-        dev.upload(scene)
-    dev.build_facelights(params.extrasamples, params.numbounce)
+    ident = np.zeros(128, np.uint8)
+    if rank == 0:
+        _dck(lib().qrad_cuda_comm_unique_id(ident.ctypes.data_as(c_u8)))
+    t = torch.from_numpy(ident).cuda()
+    dist.broadcast(t, 0)
+    ident = t.cpu().numpy()
+    _dck(lib().qrad_cuda_comm_init(dev._h, C.c_int(rank), C.c_int(world), ident.ctypes.data_as(c_u8)))
 
-    def gather_in_place(which, typestr):
-        t0 = time.perf_counter()
-        t, shard = exchange_tensor(dev, which, typestr)
-        dist.all_gather_into_tensor(t, t[rank * shard:(rank + 1) * shard])
-        torch.cuda.synchronize()
-        xt["allgather_ms"] += (time.perf_counter() - t0) * 1e3
 
-    if params.numbounce > 0:
-        _dck(L.qrad_cuda_make_transfers_phase(dev._h, C.c_int(params.nopvs), C.c_int(0)))
-        t0 = time.perf_counter()
-        bits, _ = exchange_tensor(dev, XBUF_BITS, "<i4")
-        dist.all_reduce(bits)          # every word is written by exactly one rank, the others hold 0
-        torch.cuda.synchronize()
-        xt["bits_allreduce_ms"] = (time.perf_counter() - t0) * 1e3
-        _dck(L.qrad_cuda_make_transfers_phase(dev._h, C.c_int(params.nopvs), C.c_int(1)))
-        gather_in_place(XBUF_ROW_TOTAL, "<f4")
-        gather_in_place(XBUF_ROW_COUNT, "<i4")
-        _dck(L.qrad_cuda_make_transfers_phase(dev._h, C.c_int(params.nopvs), C.c_int(2)))
-        _dck(L.qrad_cuda_bounce_phase(dev._h, C.c_int(0)))
-        for _ in range(params.numbounce):
-            _dck(L.qrad_cuda_bounce_phase(dev._h, C.c_int(1)))
-            gather_in_place(XBUF_RADIOSITY, "<f4")
-        gather_in_place(XBUF_TOTALLIGHT, "<f4")
-        _dck(L.qrad_cuda_bounce_phase(dev._h, C.c_int(2)))
-    dev.exchange_ms = xt
-    return dev.final_light(params.ambient, params.maxlight, params.lightscale, params.subdiv, params.numbounce)
+def rad_world_multi(scene: Scene, params: HostParams, ngpus: int, first_device: int = 0, want_added: bool = True):
+    """RadWorld on `ngpus` GPUs of this box from ONE process (one host thread per GPU inside the library)."""
+    added = np.zeros(max(params.numbounce, 1), np.float32)
+    st = Stats()
+    _hck(lib().qrad_rad_world_multi(scene._h, C.c_int(first_device), C.c_int(ngpus), C.byref(params),
+                                    _fp(added) if want_added else None, C.byref(st)))
+    return added[:max(params.numbounce, 0)], st.as_dict()
 
 
 def qrad3(argv) -> int:

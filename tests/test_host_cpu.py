@@ -32,7 +32,7 @@ def declared_symbols():
     names = set()
     for h in (ROOT / "include").glob("*.h"):
         txt = re.sub(r"/\*.*?\*/", "", h.read_text(), flags=re.S)
-        for m in re.finditer(r"^\s*(?:const\s+)?(?:int|void|char)\s*\*?\s*(qrad\w+)\s*\(", txt, flags=re.M):
+        for m in re.finditer(r"^\s*(?:const\s+)?(?:int|void|char|int64_t)\s*\*?\s*(qrad\w+)\s*\(", txt, flags=re.M):
             names.add(m.group(1))
     return sorted(names)
 
@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol(Q):
     assert len(names) >= 30
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/ but not exported by libqrad_cuda.so"
-    assert lib.qrad_cuda_abi_version() == 1
+    assert lib.qrad_cuda_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu(Q):

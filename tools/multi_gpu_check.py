@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Multi-GPU parity check (run under torchrun, one rank per GPU): the sharded RadWorld must write the same
-lighting lump as the reference on every rank.  usage:
+"""Multi-GPU parity check (run under torchrun, one rank per GPU): RadWorld spread over the ranks (exchanges inside
+libqrad_cuda, NCCL) must write the same lighting lump and `added` energies as the reference on every rank.  usage:
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py
 """
 import os
@@ -29,9 +29,12 @@ for case in sys.argv[1:] or ["samplec", "grid2", "grid3_chop16", "hall", "styles
         p = G.params_from_flags(flags)
         sc = Q.Scene(bsp).prepare(p)
         dev = Q.Device(local)
-        data, lightofs, styles = Q.rad_world_sharded(sc, dev, p, rank, world)
+        Q.join_communicator(dev, rank, world)
+        added = Q.rad_world(sc, dev, p)
+        data = np.frombuffer(sc.lighting(), np.uint8)
         want = np.frombuffer((G.GOLDEN / (case + ".lump")).read_bytes(), np.uint8)
-        same = data.size == want.size and bool((data == want).all())
+        same = data.size == want.size and bool((data == want).all()) and \
+            bool(np.array_equal(added, np.array(meta["added"], np.float32)))
         nt = dev.numtransfers()
         same_nt = bool(np.array_equal(nt, G.golden_numtransfers(case)))
         print(f"rank {rank}/{world} {case}: lump identical={same} numtransfers identical={same_nt}", flush=True)
