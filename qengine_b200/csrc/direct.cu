@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "comm.hpp"
 #include "qrad_device.cuh"
 
 namespace qrad {
@@ -22,6 +23,7 @@ struct FaceArgs {
   const float *f_normal, *f_texorg, *f_textoworld, *f_exactmins, *f_exactmaxs;
   const int32_t *f_texmins, *f_texsize;
   int L, numsamples;
+  int lux_lo, lux_n;             // the luxels this launch lights (several GPUs: the luxels of this rank's faces)
   float *surfpt;                 // [numsamples][L][3]
   // lights
   const int32_t *light_first, *l_type, *l_styleslot, *l_cluster;
@@ -38,9 +40,9 @@ template <int STACK, bool COUNT>
 __global__ void __launch_bounds__(128) k_calc_points(const FaceArgs a) {
   const int64_t gid = blockIdx.x * (int64_t) blockDim.x + threadIdx.x;
   unsigned long long rays = 0, visits_total = 0;
-  if (gid < (int64_t) a.L * a.numsamples) {
-    const int smp = (int) (gid / a.L);
-    const int lux = (int) (gid - (int64_t) smp * a.L);
+  if (gid < (int64_t) a.lux_n * a.numsamples) {
+    const int smp = (int) (gid / a.lux_n);
+    const int lux = a.lux_lo + (int) (gid - (int64_t) smp * a.lux_n);
     const int f = a.luxel_face[lux];
     const int idx = lux - a.luxel_first[f];
     const int w = a.f_texsize[f * 2] + 1;
@@ -104,9 +106,9 @@ __global__ void __launch_bounds__(128) k_calc_points(const FaceArgs a) {
 // the accumulation into a style table is a serial chain of rounded double multiply-adds.
 template <int STACK, bool COUNT>
 __global__ void __launch_bounds__(128) k_gather(const FaceArgs a) {
-  const int lux = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lux = a.lux_lo + blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long rays = 0, visits_total = 0;
-  if (lux < a.L) {
+  if (lux < a.lux_lo + a.lux_n) {
     const int f = a.luxel_face[lux];
     const float nx = a.f_normal[f * 3], ny = a.f_normal[f * 3 + 1], nz = a.f_normal[f * 3 + 2];
     const float lightscale = a.numsamples == 5 ? (float) (1.0 / 5) : 1.0f;
@@ -199,9 +201,9 @@ __global__ void __launch_bounds__(128) k_gather_warp(const FaceArgs a) {
   __shared__ int32_t s_q[4][64];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1;
-  const int lux = blockIdx.x * 4 + wid;
+  const int lux = a.lux_lo + blockIdx.x * 4 + wid;
   unsigned long long rays = 0, visits_total = 0;
-  if (lux < a.L) {
+  if (lux < a.lux_lo + a.lux_n) {
     const int f = a.luxel_face[lux];
     const float nx = a.f_normal[f * 3], ny = a.f_normal[f * 3 + 1], nz = a.f_normal[f * 3 + 2];
     const float lightscale = a.numsamples == 5 ? (float) (1.0 / 5) : 1.0f;
@@ -320,13 +322,14 @@ __global__ void __launch_bounds__(128) k_gather_warp(const FaceArgs a) {
 __global__ void k_add_samples(int N, const int32_t *__restrict__ p_face, const float *__restrict__ p_bounds,
                               const uint8_t *__restrict__ f_lit, const int32_t *__restrict__ luxel_first,
                               const float *__restrict__ surfpt0, const float *__restrict__ samples0,
-                              float *__restrict__ samplelight, int32_t *__restrict__ nsamples) {
+                              float *__restrict__ samplelight, int32_t *__restrict__ nsamples, const int face_lo,
+                              const int face_hi) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= N) return;
   const int f = p_face[p];
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
   int n = 0;
-  if (f_lit[f]) {
+  if (f_lit[f] && f >= face_lo && f < face_hi) {   // several GPUs: the other faces' patches stay 0 here and are summed in
     const float *mn = p_bounds + (size_t) p * 6, *mx = mn + 3;
     const float mn0 = mn[0], mn1 = mn[1], mn2 = mn[2], mx0 = mx[0], mx1 = mx[1], mx2 = mx[2];
     for (int l = luxel_first[f]; l < luxel_first[f + 1]; l++) {
@@ -371,6 +374,24 @@ __global__ void k_add_baselight(int L, const int32_t *__restrict__ luxel_face, c
 
 }  // namespace
 
+// Several GPUs: faces are lit (BuildFacelights) and finished (FinalLightFace) by contiguous runs of faces with (nearly)
+// equal luxel counts; one GPU owns them all.
+void face_range(qrad_cuda_ctx *c) {
+  const int F = c->F;
+  c->face_lo = 0;
+  c->face_hi = F;
+  if (c->world <= 1) return;
+  const int64_t L = c->h_luxel_first[F];
+  auto bound = [&](int r) {   // first face whose luxels start at or after r / world of all luxels
+    if (r <= 0) return 0;
+    if (r >= c->world) return F;
+    const int64_t want = L * r / c->world;
+    return (int) (std::lower_bound(c->h_luxel_first.begin(), c->h_luxel_first.begin() + F, (int32_t) want) - c->h_luxel_first.begin());
+  };
+  c->face_lo = bound(c->rank);
+  c->face_hi = bound(c->rank + 1);
+}
+
 void build_facelights_impl(qrad_cuda_ctx *c, int extrasamples, int numbounce) {
   if (!c->numnodes || !c->N || !c->F) dfail("build_facelights: BSP, patches, lights and faces must be uploaded first");
   Timer t;
@@ -405,6 +426,10 @@ void build_facelights_impl(qrad_cuda_ctx *c, int extrasamples, int numbounce) {
   a.f_texsize = c->f_texsize.p;
   a.L = L;
   a.numsamples = ns;
+  face_range(c);
+  const int lux_lo = c->h_luxel_first[c->face_lo], lux_n = c->h_luxel_first[c->face_hi] - lux_lo;
+  a.lux_lo = lux_lo;
+  a.lux_n = lux_n;
   a.surfpt = c->fl_surfpt.p;
   a.light_first = c->light_first.p;
   a.l_type = c->l_type.p;
@@ -419,9 +444,9 @@ void build_facelights_impl(qrad_cuda_ctx *c, int extrasamples, int numbounce) {
   a.touched = c->fl_touched.p;
   a.counters = counters.p;
   const bool big = c->tree_depth > kTraceStack;
-  if (L > 0) {
-    const int64_t npts = (int64_t) L * ns;
-    const int pb = (int) ((npts + 127) / 128), gb = (L + 127) / 128;
+  if (lux_n > 0) {
+    const int64_t npts = (int64_t) lux_n * ns;
+    const int pb = (int) ((npts + 127) / 128), gb = (lux_n + 127) / 128;
 #define QRAD_LAUNCH2(K, G)                                                                  \
   do {                                                                                      \
     if (c->count_nodes) {                                                                   \
@@ -439,7 +464,7 @@ void build_facelights_impl(qrad_cuda_ctx *c, int extrasamples, int numbounce) {
       // many lights per luxel: one warp per luxel (coherent shadow rays); few: one thread per luxel
       const bool warp_mode = getenv("QRAD_GATHER_THREAD") == nullptr && c->numlights >= 64;
       if (warp_mode) {
-        QRAD_LAUNCH2(k_gather_warp, (L + 3) / 4);
+        QRAD_LAUNCH2(k_gather_warp, (lux_n + 3) / 4);
         c->launch_check("k_gather_warp");
       } else {
         QRAD_LAUNCH2(k_gather, gb);
@@ -447,13 +472,29 @@ void build_facelights_impl(qrad_cuda_ctx *c, int extrasamples, int numbounce) {
       }
     }
 #undef QRAD_LAUNCH2
-    if (numbounce > 0) {
-      k_add_samples<<<(c->N + 127) / 128, 128, 0, st>>>(c->N, c->p_face.p, c->p_bounds.p, c->f_lit.p, c->f_luxel_first.p,
-                                                        c->fl_surfpt.p, c->fl_samples.p, c->p_samplelight.p, c->p_samples.p);
-      c->launch_check("k_add_samples");
+  }
+  if (numbounce > 0) {
+    // AddSampleToPatch sees the luxel colours BEFORE the emissive baselight is added (lightmap.c:1024 vs 1046-1055).
+    // Several GPUs: patches of faces lit elsewhere get 0 here and the sum over ranks below fills them in.
+    k_add_samples<<<(c->N + 127) / 128, 128, 0, st>>>(c->N, c->p_face.p, c->p_bounds.p, c->f_lit.p, c->f_luxel_first.p,
+                                                      c->fl_surfpt.p, c->fl_samples.p, c->p_samplelight.p, c->p_samples.p,
+                                                      c->face_lo, c->face_hi);
+    c->launch_check("k_add_samples");
+    if (c->world > 1) {
+      const NcclApi &n = nccl();
+      ncclResult_t r = n.AllReduce(c->p_samplelight.p, c->p_samplelight.p, (size_t) c->N * 3, ncclFloat, ncclSum, c->comm, st);
+      if (r == ncclSuccess) r = n.AllReduce(c->p_samples.p, c->p_samples.p, (size_t) c->N, ncclInt32, ncclSum, c->comm, st);
+      if (r != ncclSuccess) dfail("ncclAllReduce(samplelight) failed: %s", n.GetErrorString(r));
     }
+  }
+  if (L > 0) {
     k_add_baselight<<<(L + 255) / 256, 256, 0, st>>>(L, c->luxel_face.p, c->face_head.p, c->p_baselight.p, c->fl_samples.p);
     c->launch_check("k_add_baselight");
+  }
+  if (c->world > 1) {   // which style tables exist per face (any rank may have lit the face: exactly one did)
+    const NcclApi &n = nccl();
+    ncclResult_t r = n.AllReduce(c->fl_touched.p, c->fl_touched.p, (size_t) c->F * c->numstyles_map, ncclUint32, ncclMax, c->comm, st);
+    if (r != ncclSuccess) dfail("ncclAllReduce(styles) failed: %s", n.GetErrorString(r));
   }
   // style bookkeeping of facelight_t (lightmap.c:1036-1044): style 0 always, others when touched; ascending ids
   std::vector<uint32_t> touched((size_t) c->F * c->numstyles_map + 1);

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <map>
 
+#include "comm.hpp"
 #include "qrad_device.cuh"
 
 namespace qrad {
@@ -23,6 +24,7 @@ enum { kErrNone = 0, kErrEdges = 1, kErrTris = 2, kErrStack = 3 };
 // ---- gather the triangulation points of each face (lightmap.c:1119-1135) ---------------------
 struct PointArgs {
   int F;
+  int face_lo, face_hi;           // faces this rank finishes (the others report 0 points)
   const uint8_t *f_lit;
   const int32_t *group_of_face;   // [F] plane group or -1
   const int32_t *group_first;     // [G+1] into group_patch
@@ -41,7 +43,7 @@ __global__ void __launch_bounds__(256) k_tri_points(const PointArgs a) {
   const int f = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (f >= a.F) return;
   int total = 0;
-  const int g = a.f_lit[f] ? a.group_of_face[f] : -1;
+  const int g = (a.f_lit[f] && f >= a.face_lo && f < a.face_hi) ? a.group_of_face[f] : -1;
   if (g >= 0) {
     const float *mn = a.f_bounds + (size_t) f * 6, *mx = mn + 3;
     const int k0 = a.group_first[g], k1 = a.group_first[g + 1];
@@ -76,6 +78,7 @@ struct Scratch {
 
 struct FinalArgs {
   int F, pmax;
+  int face_hi;                   // faces are drawn from a counter that starts at this rank's first face
   const uint8_t *f_lit;
   const int32_t *luxel_first;
   const int32_t *tri_count;
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_final(const FinalArgs a) {
     int f = 0;
     if (lane == 0) f = atomicAdd(a.face_counter, 1);
     f = __shfl_sync(0xffffffffu, f, 0);
-    if (f >= a.F) break;
+    if (f >= a.face_hi) break;   // the counter starts at this rank's first face
     if (!a.f_lit[f]) continue;
     const int P = a.numbounce > 0 ? a.tri_count[f] : 0;
     const int32_t *pidx = a.tri_points + (a.numbounce > 0 ? a.tri_first[f] : 0);
@@ -416,6 +419,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_final(const FinalArgs a) {
 void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out, int32_t cap, int32_t *size,
                       int32_t *lightofs_out, uint8_t *styles_out) {
   if (!c->facelights_done) dfail("final_light: build_facelights has not run");
+  face_range(c);
   Timer t;
   t.start(c->stream);
   cudaStream_t st = c->stream;
@@ -483,6 +487,8 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
     tri_count.alloc((size_t) F);
     PointArgs pa{};
     pa.F = F;
+    pa.face_lo = c->face_lo;
+    pa.face_hi = c->face_hi;
     pa.f_lit = c->f_lit.p;
     pa.group_of_face = d_group_of_face.p;
     pa.group_first = d_group_first.p;
@@ -521,14 +527,16 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
   d_out.alloc((size_t) total + 4);
   d_out.zero(st);
   DBuf<float> &lb_out = c->fin_lb;
-  if (any_minlight) lb_out.alloc((size_t) 4 * L * 3 + 1);
+  if (any_minlight) {
+    lb_out.alloc((size_t) 4 * L * 3 + 1);
+    if (c->world > 1) lb_out.zero(st);
+  }
   DBuf<int32_t> &d_err = c->fin_i32[8], &d_counter = c->fin_i32[9];
   d_err.alloc(1);
   d_err.zero(st);
-  d_counter.alloc(1);
-  d_counter.zero(st);
+  d_counter.upload(&c->face_lo, 1, st);   // k_final draws faces from here
 
-  const int blocks = std::max(1, std::min((F + kWarps - 1) / kWarps, c->sm_count * 2));
+  const int blocks = std::max(1, std::min((c->face_hi - c->face_lo + kWarps - 1) / kWarps, c->sm_count * 2));
   const size_t nw = (size_t) blocks * kWarps;
   // scratch pools live in the context so that repeated calls reuse the allocations
   DBuf<uint16_t> &matrix_pool = c->fin_matrix, &ep0 = c->fin_ep0, &ep1 = c->fin_ep1, &tedges = c->fin_tedges, &stack = c->fin_stack;
@@ -545,6 +553,7 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
 
   FinalArgs fa{};
   fa.F = F;
+  fa.face_hi = c->face_hi;
   fa.pmax = pmax;
   fa.f_lit = c->f_lit.p;
   fa.luxel_first = c->f_luxel_first.p;
@@ -579,11 +588,22 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
   fa.face_counter = d_counter.p;
   k_final<<<blocks, kWarps * 32, 0, st>>>(fa);
   c->launch_check("k_final");
+  if (c->world > 1) {   // all ranks must agree on failure before anybody enters the sums below
+    ncclResult_t r = nccl().AllReduce(d_err.p, d_err.p, 1, ncclInt32, ncclMax, c->comm, st);
+    if (r != ncclSuccess) dfail("ncclAllReduce(error flag) failed: %s", nccl().GetErrorString(r));
+  }
   int err = 0;
   d_err.download(&err, 1, st);
   if (err == kErrEdges) dfail("trian->numedges > MAX_TRI_EDGES-2");
   if (err == kErrTris) dfail("trian->numtris >= MAX_TRI_TRIS");
   if (err) dfail("triangulation stack overflow");
+  if (c->world > 1 && total) {   // every face was finished by one rank; the others hold zeros there
+    const NcclApi &n = nccl();
+    ncclResult_t r = n.AllReduce(d_out.p, d_out.p, (size_t) total, ncclUint8, ncclSum, c->comm, st);
+    if (r == ncclSuccess && any_minlight)
+      r = n.AllReduce(lb_out.p, lb_out.p, (size_t) 4 * L * 3, ncclFloat, ncclSum, c->comm, st);
+    if (r != ncclSuccess) dfail("ncclAllReduce(lightmap) failed: %s", n.GetErrorString(r));
+  }
   if (total) d_out.download(out, (size_t) total, st);
 
   if (any_minlight) {

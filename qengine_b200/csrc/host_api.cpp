@@ -11,6 +11,9 @@
 using namespace qrad;
 
 static thread_local std::string g_host_error;
+namespace qrad {
+void set_host_error(const std::string &m) { g_host_error = m; }
+}
 
 template <class F> static int guarded(F &&f) {
   try {
@@ -218,50 +221,60 @@ int qrad_host_write(qrad_host_scene *hs, const char *path) {
   return guarded([&] { write_bsp(hs->scene.bsp, path); });
 }
 
-// RadWorld, qrad3.c:494-536, with the five dispatch sites replaced by libqrad_cuda calls.
+// RadWorld, qrad3.c:494-536, with the five dispatch sites replaced by libqrad_cuda calls.  `store`: keep the result in
+// the scene (on several GPUs every rank ends with the same lump; one of them stores it).
 int qrad_rad_world(qrad_host_scene *hs, qrad_cuda_ctx *ctx, const qrad_host_params *p, float *added_out) {
-  return guarded([&] {
-    Scene &s = hs->scene;
-    auto ck = [&](int rc) {
-      if (rc) fail("%s", qrad_cuda_last_error());
-    };
-    qrad_bsp_view bv;
-    qrad_patches_view pv;
-    qrad_lights_view lv;
-    qrad_faces_view fv;
-    qrad_host_bsp_view(hs, &bv);
-    if (qrad_host_patches_view(hs, &pv) || qrad_host_lights_view(hs, &lv) || qrad_host_faces_view(hs, &fv))
-      fail("%s", g_host_error.c_str());
-    ck(qrad_cuda_upload_bsp(ctx, &bv));
-    ck(qrad_cuda_upload_patches(ctx, &pv));
-    ck(qrad_cuda_upload_lights(ctx, &lv));
-    ck(qrad_cuda_upload_faces(ctx, &fv));
-    ck(qrad_cuda_build_facelights(ctx, p->extrasamples, p->numbounce));
-    if (p->numbounce > 0) {
-      int64_t total = 0;
-      ck(qrad_cuda_make_transfers(ctx, p->nopvs, &total));
-      if (p->verbose) printf("transfer lists: %5.1f megs\n", (float) total * 4 / (1024 * 1024));
-      std::vector<float> added(p->numbounce);
-      ck(qrad_cuda_bounce(ctx, p->numbounce, (p->verbose || added_out) ? added.data() : nullptr));
-      for (int i = 0; i < p->numbounce; i++) {
-        if (p->verbose) printf("bounce:%i added:%f\n", i, added[i]);
-        if (added_out) added_out[i] = added[i];
-      }
-    }
-    qrad_final_params fp;
-    fp.ambient = p->ambient;
-    fp.maxlight = p->maxlight;
-    fp.lightscale = p->lightscale;
-    fp.subdiv = p->subdiv;
-    fp.numbounce = p->numbounce;
-    std::vector<uint8_t> light(kMaxMapLighting);
-    std::vector<int32_t> lightofs(s.bsp.numfaces());
-    std::vector<uint8_t> styles((size_t) s.bsp.numfaces() * 4);
-    int32_t size = 0;
-    ck(qrad_cuda_final_light(ctx, &fp, light.data(), kMaxMapLighting, &size, lightofs.data(), styles.data()));
-    if (qrad_host_store_lighting(hs, light.data(), size, lightofs.data(), styles.data())) fail("%s", g_host_error.c_str());
-  });
+  return guarded([&] { rad_world_impl(hs, ctx, p, added_out, true); });
 }
+
+}  // extern "C"
+
+namespace qrad {
+void rad_world_impl(qrad_host_scene *hs, qrad_cuda_ctx *ctx, const qrad_host_params *p, float *added_out, bool store) {
+  Scene &s = hs->scene;
+  auto ck = [&](int rc) {
+    if (rc) fail("%s", qrad_cuda_last_error());
+  };
+  qrad_bsp_view bv;
+  qrad_patches_view pv;
+  qrad_lights_view lv;
+  qrad_faces_view fv;
+  qrad_host_bsp_view(hs, &bv);
+  if (qrad_host_patches_view(hs, &pv) || qrad_host_lights_view(hs, &lv) || qrad_host_faces_view(hs, &fv))
+    fail("%s", qrad_host_last_error());
+  ck(qrad_cuda_upload_bsp(ctx, &bv));
+  ck(qrad_cuda_upload_patches(ctx, &pv));
+  ck(qrad_cuda_upload_lights(ctx, &lv));
+  ck(qrad_cuda_upload_faces(ctx, &fv));
+  ck(qrad_cuda_build_facelights(ctx, p->extrasamples, p->numbounce));
+  if (p->numbounce > 0) {
+    int64_t total = 0;
+    ck(qrad_cuda_make_transfers(ctx, p->nopvs, &total));
+    if (p->verbose && store) printf("transfer lists: %5.1f megs\n", (float) total * 4 / (1024 * 1024));
+    std::vector<float> added(p->numbounce);
+    ck(qrad_cuda_bounce(ctx, p->numbounce, (p->verbose || added_out) ? added.data() : nullptr));
+    for (int i = 0; i < p->numbounce; i++) {
+      if (p->verbose && store) printf("bounce:%i added:%f\n", i, added[i]);
+      if (added_out) added_out[i] = added[i];
+    }
+  }
+  qrad_final_params fp;
+  fp.ambient = p->ambient;
+  fp.maxlight = p->maxlight;
+  fp.lightscale = p->lightscale;
+  fp.subdiv = p->subdiv;
+  fp.numbounce = p->numbounce;
+  std::vector<uint8_t> light(kMaxMapLighting);
+  std::vector<int32_t> lightofs(s.bsp.numfaces());
+  std::vector<uint8_t> styles((size_t) s.bsp.numfaces() * 4);
+  int32_t size = 0;
+  ck(qrad_cuda_final_light(ctx, &fp, light.data(), kMaxMapLighting, &size, lightofs.data(), styles.data()));
+  if (store && qrad_host_store_lighting(hs, light.data(), size, lightofs.data(), styles.data()))
+    fail("%s", qrad_host_last_error());
+}
+}  // namespace qrad
+
+extern "C" {
 
 // The flag loop of main(), qrad3.c:555-601: same flags, same side effects on the tunables; silent (qrad3_main prints
 // the reference's chatter).  Parsing stops at the first argument that is not a known flag (cli->next_arg), like the reference's `else break`.

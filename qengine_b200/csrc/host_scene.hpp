@@ -133,3 +133,9 @@ void build_face_frames(Scene &s);          // lightmap.c:480-603, 42-52, 1109-11
 struct qrad_host_scene {
   qrad::Scene scene;
 };
+
+namespace qrad {
+// RadWorld on one context (host_api.cpp); the scene is only read unless `store`
+void rad_world_impl(qrad_host_scene *hs, qrad_cuda_ctx *ctx, const qrad_host_params *p, float *added_out, bool store);
+void set_host_error(const std::string &m);   // what qrad_host_last_error() returns on this thread
+}

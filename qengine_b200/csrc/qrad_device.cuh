@@ -550,6 +550,7 @@ struct qrad_cuda_ctx {
 
 namespace qrad {
 // implemented in the phase translation units
+void face_range(qrad_cuda_ctx *c);
 void build_facelights_impl(qrad_cuda_ctx *c, int extrasamples, int numbounce);
 void make_transfers_impl(qrad_cuda_ctx *c, int nopvs);
 void bounce_impl(qrad_cuda_ctx *c, int numbounce, float *added_out);

@@ -285,13 +285,32 @@ def test_unvised_map_is_direct_only(Q, tmp_path):
     assert lump.size == 8928 and (lump == 1).all()
 
 
-def test_two_gpu_sharded_parity(Q):
-    """Sharded RadWorld (one process per GPU, NCCL) writes the reference's bytes on every rank."""
-    import sys
+def _two_gpus():
     import torch
-    if torch.cuda.device_count() < 2:
+    return torch.cuda.device_count() >= 2
+
+
+def test_two_gpu_sharded_parity(Q):
+    """RadWorld over 2 ranks (one process per GPU, exchanges inside the library over NCCL) writes the reference's
+    bytes on every rank; includes C3 (149 021 patches, the > 65 535-patch path)."""
+    import sys
+    if not _two_gpus():
         pytest.skip("needs 2 GPUs")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(G.ROOT / "tools" / "multi_gpu_check.py"),
-                        "samplec", "grid2", "styles"], capture_output=True, text=True, timeout=600)
+                        "samplec", "grid2", "styles", "manystyles", "hall", "c3_grid13", "c4_hall2000_b2"],
+                       capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "MULTI_GPU_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_cli_two_gpus(Q, tmp_path):
+    """`qrad3 -gpus 2`: one process, one host thread per GPU (qrad_rad_world_multi); same bytes out."""
+    from qengine_b200 import build
+    if not _two_gpus():
+        pytest.skip("needs 2 GPUs")
+    for case in ("samplec_extra", "grid3_chop16"):
+        meta, flags = G.load_case(case)
+        bsp = G.stage_case(case, tmp_path / case)
+        r = subprocess.run([str(build.EXE), *flags, "-gpus", "2", str(bsp)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert hashlib.md5(bsp.read_bytes()).hexdigest() == meta["file_md5"]
