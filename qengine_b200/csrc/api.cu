@@ -1,6 +1,7 @@
 // extern "C" surface of the CUDA half (include/qrad_cuda.h): context, uploads,
 // batched ray / point queries, inspection downloads.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "comm.hpp"
@@ -253,6 +254,34 @@ int qrad_cuda_upload_bsp(qrad_cuda_ctx *c, const qrad_bsp_view *b) {
       for (int k = 0; k < 4; k++) recs.push_back(make_int4(0, 0, 0, 0));   // the walkers fetch records four at a time
       c->leaf_path.upload(recs, c->stream);
       c->leaf_path_first.upload(first, c->stream);
+      // cells of the leaves: a leaf whose ancestors are all axial planes is the box between the tightest of them
+      // (shaft_blocked() in qrad_device.cuh); lo.w = 1 marks a SOLID leaf with such a cell
+      std::vector<float4> cell_lo((size_t) b->numleafs), cell_hi((size_t) b->numleafs);
+      float extent = 0;
+      for (int l = 0; l < b->numleafs; l++) {
+        float lo[3] = {-1e30f, -1e30f, -1e30f}, hi[3] = {1e30f, 1e30f, 1e30f};
+        bool axial = true;
+        int node = lparent[l], sd = lside[l];
+        while (node >= 0) {
+          const int type = flat[node].y;
+          float dist;
+          memcpy(&dist, &flat[node].x, 4);
+          if (type < 3) {
+            if (sd == 0) lo[type] = std::max(lo[type], dist);   // child 0 = in front of the plane
+            else hi[type] = std::min(hi[type], dist);
+            extent = std::max(extent, fabsf(dist));
+          } else
+            axial = false;
+          sd = pside[node];
+          node = parent[node];
+        }
+        const bool solid = (contents[l] & 1) != 0;
+        cell_lo[l] = make_float4(lo[0], lo[1], lo[2], (axial && solid) ? 1.f : 0.f);
+        cell_hi[l] = make_float4(hi[0], hi[1], hi[2], 0.f);
+      }
+      c->leaf_cell_lo.upload(cell_lo, c->stream);
+      c->leaf_cell_hi.upload(cell_hi, c->stream);
+      c->bsp_extent = extent;
     }
     if (maxdepth > kTraceStackBig) dfail("BSP depth %d exceeds the supported trace stack (%d)", maxdepth, kTraceStackBig);
     c->numnodes = next_new;
@@ -303,6 +332,20 @@ int qrad_cuda_upload_patches(qrad_cuda_ctx *c, const qrad_patches_view *p) {
     }
     c->h_origin_area = pack4(p->origin, p->area, n);
     c->h_normal = pack4(p->normal, nullptr, n);
+    // w of the normal: +-(axis + 1) for an exactly axial normal, 0 otherwise (the sign test of MakeTransfers then
+    // needs one coordinate difference instead of a normalised dot product, form_factor_sign() in transfers.cu)
+    float extent = 0;
+    for (int i = 0; i < n; i++) {
+      float4 &nn = c->h_normal[i];
+      const float v[3] = {nn.x, nn.y, nn.z};
+      int code = 0;
+      for (int k = 0; k < 3; k++)
+        if (fabsf(v[k]) == 1.f && v[(k + 1) % 3] == 0.f && v[(k + 2) % 3] == 0.f) code = v[k] > 0 ? k + 1 : -(k + 1);
+      nn.w = (float) code;
+      const float4 &o = c->h_origin_area[i];
+      extent = std::max(extent, std::max(fabsf(o.x), std::max(fabsf(o.y), fabsf(o.z))));
+    }
+    c->patch_extent = extent;
     c->p_origin_area.upload(c->h_origin_area, c->stream);
     c->p_normal.upload(c->h_normal, c->stream);
     std::vector<float> skyf(n);

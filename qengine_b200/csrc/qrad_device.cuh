@@ -368,6 +368,59 @@ __device__ __forceinline__ int box_reaches_leaf(const int4 *__restrict__ path, c
   return kBoxProven;
 }
 
+// Shaft proof: does EVERY segment from a point of box A = [amn, amx] to a point of box B = [bmn, bmx] make TestLine_r
+// return 1 because of solid leaf X?  X must be a leaf whose ancestors are all axial planes, so that its cell is the box
+// [clo, chi] (clo.w = 1 marks such a solid leaf).  Sufficient condition used here: the segment contains a point q that
+// lies inside the cell by more than `margin` > ON_EPSILON on every side.  Then TestLine_r(0, s, e) reaches X:
+//  * at an ancestor where both ends pass the first test (front, back >= -0.1) the plane distance of q, a convex
+//    combination of front and back, is >= -0.1 too, so X cannot lie behind that plane by more than 0.1: the walk turns
+//    towards X; the same for the second test (< 0.1);
+//  * at a split, mid lies on the plane (up to float rounding) and q, more than `margin` away from it, stays on the half
+//    that is handed to the child on X's side; the recursion visits both halves unless the first already returned 1.
+// By induction the sub-segment handed down always contains q (up to the accumulated rounding of the clip points,
+// ~1e-3 per split at |x| <= 8192; `margin` = 0.1 + slack covers hundreds of splits) until leaf X itself is reached.
+// The box version: A and B lie on opposite sides of the (shrunken) cell along some axis k; every segment then crosses
+// the plane x_k = c through the middle of the cell at parameter t in [tmin, tmax] (t is monotone in a_k and b_k), and the
+// other two coordinates of the crossing point, convex combinations of a_j and b_j, are bounded by their values at the
+// interval ends; if that rectangle lies inside the shrunken cell, every segment passes through it.  No tree walk.
+__device__ __forceinline__ bool shaft_blocked(const float4 clo, const float4 chi, const float margin, const float4 amn,
+                                              const float4 amx, const float4 bmn, const float4 bmx) {
+  if (clo.w == 0.f) return false;
+  const float lo[3] = {clo.x + margin, clo.y + margin, clo.z + margin};
+  const float hi[3] = {chi.x - margin, chi.y - margin, chi.z - margin};
+  const float an[3] = {amn.x, amn.y, amn.z}, ax[3] = {amx.x, amx.y, amx.z};
+  const float bn[3] = {bmn.x, bmn.y, bmn.z}, bx[3] = {bmx.x, bmx.y, bmx.z};
+  bool ok = false;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const bool below = ax[k] < lo[k] && bn[k] > hi[k];   // A below the cell, B above it
+    const bool above = bx[k] < lo[k] && an[k] > hi[k];
+    if (!(below || above) || !(hi[k] > lo[k])) continue;
+    const float cc = 0.5f * (lo[k] + hi[k]);
+    // t = (c - a_k) / (b_k - a_k): smallest / largest over the boxes
+    float tmin, tmax;
+    if (below) {
+      tmin = (cc - ax[k]) / (bx[k] - ax[k]);
+      tmax = (cc - an[k]) / (bn[k] - an[k]);
+    } else {
+      tmin = (cc - an[k]) / (bn[k] - an[k]);
+      tmax = (cc - ax[k]) / (bx[k] - ax[k]);
+    }
+    tmin = fmaxf(tmin - 1e-5f, 0.f);
+    tmax = fminf(tmax + 1e-5f, 1.f);
+    bool inside = true;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      if (j == k) continue;
+      const float q0 = fminf(an[j] + (bn[j] - an[j]) * tmin, an[j] + (bn[j] - an[j]) * tmax) - 0.01f;
+      const float q1 = fmaxf(ax[j] + (bx[j] - ax[j]) * tmin, ax[j] + (bx[j] - ax[j]) * tmax) + 0.01f;
+      inside = inside && q0 >= lo[j] && q1 <= hi[j];
+    }
+    ok = ok || inside;
+  }
+  return ok;
+}
+
 // PointInLeafnum, qrad3.c:131-150: full dot product on every node, `dist > 0` picks child 0.
 __device__ __forceinline__ int point_in_leaf(const Tree tree, float x, float y, float z) {
   int node = 0;
@@ -439,6 +492,8 @@ struct qrad_cuda_ctx {
   qrad::DBuf<float4> node_normals;
   qrad::DBuf<int4> leaf_path;           // root -> leaf ancestor records of every leaf, see reaches_leaf()
   qrad::DBuf<int32_t> leaf_path_first;  // [numleafs + 1]
+  qrad::DBuf<float4> leaf_cell_lo, leaf_cell_hi;   // [numleafs] box cells of the leaves, see shaft_blocked()
+  float bsp_extent = 0, patch_extent = 0;           // largest |coordinate| of the axial planes / patch origins
   qrad::Tree tree() const { return qrad::Tree{nodes.p, node_normals.p}; }
   qrad::DBuf<int32_t> leaf_contents, leaf_cluster;
   qrad::DBuf<uint32_t> pvs;            // [numclusters][pvs_words], bit d of row c = cluster d visible from c

@@ -62,6 +62,31 @@ __device__ __forceinline__ float form_factor_pre(const float4 so, const float4 s
   return trans;
 }
 
+// The part of the pair test that decides whether the reference calls TestLine_r (qrad3.c:232-244), and whether the pair
+// can carry a transfer at all (trans > 0).  sn.w / pn.w hold +-(axis + 1) for exactly axial plane normals: the normalised
+// dot product then is ONE coordinate of delta times 1 / dist -- a positive factor that cannot underflow for world
+// coordinates -- so the sign of scale = (delta . n_i) * -(delta . n_j) follows from two coordinate differences, without
+// the square root and the division.  For such pairs trans = scale * area / dist^2 > 0 exactly when scale > 0 (area >= 1,
+// scale >= 1e-17: nothing underflows).  Other normals take the reference's arithmetic.
+__device__ __forceinline__ bool pair_wants_ray(const float4 so, const float4 sn, const float4 po, const float4 pn,
+                                               bool &positive) {
+  const float dx = po.x - so.x, dy = po.y - so.y, dz = po.z - so.z;
+  const int cs = (int) sn.w, cr = (int) pn.w;
+  if (cs != 0 && cr != 0) {
+    const float a = axis_pick(abs(cs) - 1, dx, dy, dz), b = axis_pick(abs(cr) - 1, dx, dy, dz);
+    // a' = +-a / dist, b' = +-b / dist;  scale = a' * -b' > 0
+    const bool apos = cs > 0 ? a > 0 : a < 0, aneg = cs > 0 ? a < 0 : a > 0;
+    const bool bpos = cr > 0 ? b > 0 : b < 0, bneg = cr > 0 ? b < 0 : b > 0;
+    positive = (apos && bneg) || (aneg && bpos);
+    return positive;
+  }
+  float dist;
+  bool wants;
+  const float trans = form_factor_pre(so, sn, po, pn, dist, wants);
+  positive = trans > 0;
+  return wants;
+}
+
 // What every kernel needs to find a word of the matrix (device copies of the plan, plan.hpp).
 struct Geo {
   const int32_t *cl_slot_start, *cl_count;   // [nc + 1], [nc]
@@ -89,6 +114,10 @@ struct VisArgs {
   uint64_t num_runs;
   uint32_t *bits;
   unsigned long long *counters;   // [0] rays, [1] node visits, [2] candidate pairs
+  const float4 *cell_lo, *cell_hi;   // [numleafs] leaf cells (shaft_blocked)
+  float margin;                   // how deep inside a solid cell a segment must pass to count as proven blocked
+  int mode;                       // bit 0: slice x word shaft proofs, 1: source x word shaft proofs, 2: per-ray shaft
+                                  // proofs, 3: interval walks for words the shaft leaves open, 4: guess walks
 };
 
 // One warp lights one run = the rows of one row group (<= 128 consecutive source patches of one cluster) against one
@@ -125,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
   const unsigned lt = (1u << lane) - 1;
   const uint64_t warp0 = (uint64_t) blockIdx.x * kWarpsPerBlock + wid;
   const uint64_t nwarps = (uint64_t) gridDim.x * kWarpsPerBlock;
-  unsigned long long rays = 0, pairs = 0, visits_total = 0, fallbacks = 0, boxed = 0;
+  unsigned long long rays = 0, pairs = 0, visits_total = 0, fallbacks = 0, boxed = 0, shafted = 0;
   long long tk0 = 0, tk_box = 0, tk_pairs = 0, tk_guess = 0, tk_full = 0, tk_misc = 0;   // COUNT: warp cycles per phase
   for (uint64_t run = warp0; run < a.num_runs; run += nwarps) {
     // ---- decode the run: row group, chunk ----
@@ -151,6 +180,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
     }
     for (int k = lane; k < kChunkWords * 32; k += 32) s_rguess[wid][k] = 0xffffu;   // new receivers: forget the guesses
     s_wguess[wid][lane] = 0xffffu;
+    s_bleaf[wid][lane] = 0xffffu;
+    unsigned slice_proven = 0;      // words proven blocked for ALL sources of the current source slice
     __syncwarp();
   for (int r = 0; r < nrows; r++) {
     const int sslot = slot0 + r;
@@ -164,57 +195,93 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
     const float4 sn = __ldg(a.s_normal + sslot);
     s_res[wid][lane] = 0;
     if (COUNT) { const long long t = clock64(); if (tk0) tk_misc += t - tk0; tk0 = t; }
-    // ---- (1) per word: box test ----
-    bool proven = false;
-    if (lane < nwc) {
+    // ---- (1) per word: proofs that settle all 32 receivers at once ----
+    // every 32 rows the sources move on to the next slice: its two-sided proofs start afresh
+    if ((r & 31) == 0) slice_proven = 0;
+    bool proven = (slice_proven >> lane) & 1u;
+    bool proven_now2 = false;
+    if (lane < nwc && !proven) {
       const int base = s_wbase[wid][lane];
       const int g = s_wguess[wid][lane];
       s_bleaf[wid][lane] = 0xffffu;
       if (g != 0xffff) {
-        const int p0 = __ldg(a.leaf_path_first + g), p1 = __ldg(a.leaf_path_first + g + 1);
-        int first;
-        unsigned long long splits;
-        const int rr = box_reaches_leaf(a.leaf_path + p0, p1 - p0, so, __ldg(a.wbox_min + (base >> 5)),
-                                        __ldg(a.wbox_max + (base >> 5)), first, splits);
-        proven = rr == kBoxProven;
-        if (!proven) {
-          s_bleaf[wid][lane] = (uint16_t) g;
-          s_bfirst[wid][lane] = (uint8_t) (first | (rr == kBoxElsewhere ? 0x80 : 0));
-          s_bsplits[wid][lane] = splits;
+        const float4 clo = __ldg(a.cell_lo + g), chi = __ldg(a.cell_hi + g);
+        const float4 bmn = __ldg(a.wbox_min + (base >> 5)), bmx = __ldg(a.wbox_max + (base >> 5));
+        // (a) all 32 sources of the slice x all 32 receivers of the word
+        if ((a.mode & 1) && shaft_blocked(clo, chi, a.margin, __ldg(a.wbox_min + (sslot >> 5)), __ldg(a.wbox_max + (sslot >> 5)), bmn, bmx))
+          proven = proven_now2 = true;
+        // (b) this source x all 32 receivers
+        else if ((a.mode & 2) && shaft_blocked(clo, chi, a.margin, so, so, bmn, bmx))
+          proven = true;
+        else if (a.mode & 8) {
+          const int p0 = __ldg(a.leaf_path_first + g), p1 = __ldg(a.leaf_path_first + g + 1);
+          int first;
+          unsigned long long splits;
+          const int rr = box_reaches_leaf(a.leaf_path + p0, p1 - p0, so, bmn, bmx, first, splits);
+          proven = rr == kBoxProven;
+          if (!proven) {
+            s_bleaf[wid][lane] = (uint16_t) g;
+            s_bfirst[wid][lane] = (uint8_t) (first | (rr == kBoxElsewhere ? 0x80 : 0));
+            s_bsplits[wid][lane] = splits;
+          }
         }
       }
     }
+    slice_proven |= __ballot_sync(0xffffffffu, proven_now2);
     const unsigned proven_mask = __ballot_sync(0xffffffffu, proven);
     __syncwarp();
     if (COUNT) { const long long t = clock64(); tk_box += t - tk0; tk0 = t; }
-    // ---- (2) cheap tests, compaction ----
-    int n = 0;
-    // receivers stream through (32 KB per task and warp): they bypass L1, which holds the tree and the paths, and the
-    // next word's 32 receivers are requested before this word's are tested (an L2 round trip per word otherwise)
-    float4 po_n = make_float4(0, 0, 0, 0), pn_n = po_n;
-    if (nwc > 0) {
-      po_n = __ldcg(a.s_origin_area + s_wbase[wid][0] + lane);
-      pn_n = __ldcg(a.s_normal + s_wbase[wid][0] + lane);
-    }
-    for (int wi = 0; wi < nwc; wi++) {
-      const int rslot = s_wbase[wid][wi] + lane;
-      const float4 po = po_n, pn = pn_n;
-      if (wi + 1 < nwc) {   // slots are padded to whole words: every lane has a valid address
-        po_n = __ldcg(a.s_origin_area + s_wbase[wid][wi + 1] + lane);
-        pn_n = __ldcg(a.s_normal + s_wbase[wid][wi + 1] + lane);
-      }
-      bool want = false;
-      if (lane < s_wcnt[wid][wi] && rslot != sslot) {
-        float dist;
-        bool wants_ray;
-        const float trans = form_factor_pre(so, sn, po, pn, dist, wants_ray);
-        pairs++;
-        if (wants_ray) {
-          rays++;
-          want = trans > 0 && !((proven_mask >> wi) & 1u);
-          if (COUNT && trans > 0 && !want) boxed++;
+    // ---- (2) which pairs would the reference trace (qrad3.c:232-244)?  compaction of the unproven ones ----
+    // Word level first: when source and receivers have axial normals and the word's bounding box lies strictly on one
+    // side of the source along both normals' axes, the sign test has the same outcome for all 32 receivers (the
+    // coordinate differences are monotone in the receiver's coordinate): such a word costs one test, not 32 loads.
+    int wclass = 0;   // 0: no receiver passes, 1: all do, 2: receiver by receiver
+    if (lane < nwc) {
+      wclass = 2;
+      const float4 bmn = __ldg(a.wbox_min + (s_wbase[wid][lane] >> 5)), bmx = __ldg(a.wbox_max + (s_wbase[wid][lane] >> 5));
+      const int cs = (int) sn.w, cr = (int) bmn.w;
+      if (cs != 0 && cr != 0) {
+        const int ks = abs(cs) - 1, kr = abs(cr) - 1;
+        const float os = axis_pick(ks, so.x, so.y, so.z), orr = axis_pick(kr, so.x, so.y, so.z);
+        const float alo = axis_pick(ks, bmn.x, bmn.y, bmn.z) - os, ahi = axis_pick(ks, bmx.x, bmx.y, bmx.z) - os;
+        const float blo = axis_pick(kr, bmn.x, bmn.y, bmn.z) - orr, bhi = axis_pick(kr, bmx.x, bmx.y, bmx.z) - orr;
+        const int sa = alo > 0 ? 1 : (ahi < 0 ? -1 : 0), sb = blo > 0 ? 1 : (bhi < 0 ? -1 : 0);
+        if (sa != 0 && sb != 0) {
+          const bool apos = (cs > 0) == (sa > 0), bpos = (cr > 0) == (sb > 0);
+          wclass = (apos != bpos) ? 1 : 0;
+          const int cnt = s_wcnt[wid][lane];
+          pairs += cnt;
+          if (wclass == 1) {
+            rays += cnt;
+            if (COUNT && proven) boxed += cnt;
+          }
         }
       }
+    }
+    const unsigned all_mask = __ballot_sync(0xffffffffu, wclass == 1) & ~proven_mask;
+    const unsigned each_mask = __ballot_sync(0xffffffffu, wclass == 2);
+    int n = 0;
+    for (unsigned todo = all_mask | each_mask; todo;) {
+      const int wi = __ffs(todo) - 1;
+      todo &= todo - 1;
+      bool want;
+      if ((each_mask >> wi) & 1u) {
+        const int rslot = s_wbase[wid][wi] + lane;
+        want = false;
+        if (lane < s_wcnt[wid][wi] && rslot != sslot) {
+          // receivers stream past L1, which holds the tree and the cells
+          const float4 po = __ldcg(a.s_origin_area + rslot), pn = __ldcg(a.s_normal + rslot);
+          bool positive;
+          const bool wants_ray = pair_wants_ray(so, sn, po, pn, positive);
+          pairs++;
+          if (wants_ray) {
+            rays++;
+            want = positive && !((proven_mask >> wi) & 1u);
+            if (COUNT && positive && !want) boxed++;
+          }
+        }
+      } else
+        want = lane < s_wcnt[wid][wi];
       const unsigned m = __ballot_sync(0xffffffffu, want);
       if (want) s_queue[wid][n + __popc(m & lt)] = (uint16_t) (wi * 32 + lane);
       n += __popc(m);
@@ -258,11 +325,21 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
         }
         if (g != 0xffff && !(first & 0x80)) {   // 0x80: no ray into this word reaches g; straight to the full walk
           const float4 po = __ldcg(a.s_origin_area + s_wbase[wid][cand >> 5] + (cand & 31));
-          const int p0 = __ldg(a.leaf_path_first + g), p1 = __ldg(a.leaf_path_first + g + 1);
-          unsigned visits = 0;
-          miss = !reaches_leaf<COUNT>(a.tree, a.leaf_path + p0, p1 - p0, so.x, so.y, so.z, po.x, po.y, po.z, visits,
-                                      first, splits);
-          if (COUNT) visits_total += visits;
+          // (c) this ray alone: does it pass deep through the cell of the leaf that blocked this receiver last time,
+          // or of the leaf that blocked a neighbour of it most recently?
+          const int g2 = s_wguess[wid][cand >> 5];
+          if ((a.mode & 4) && (shaft_blocked(__ldg(a.cell_lo + g), __ldg(a.cell_hi + g), a.margin, so, so, po, po) ||
+                               (g2 != g && g2 != 0xffff &&
+                                shaft_blocked(__ldg(a.cell_lo + g2), __ldg(a.cell_hi + g2), a.margin, so, so, po, po)))) {
+            miss = false;
+            if (COUNT) shafted++;
+          } else if (a.mode & 16) {
+            const int p0 = __ldg(a.leaf_path_first + g), p1 = __ldg(a.leaf_path_first + g + 1);
+            unsigned visits = 0;
+            miss = !reaches_leaf<COUNT>(a.tree, a.leaf_path + p0, p1 - p0, so.x, so.y, so.z, po.x, po.y, po.z, visits,
+                                        first, splits);
+            if (COUNT) visits_total += visits;
+          }
         }
       }
       const unsigned m = __ballot_sync(0xffffffffu, miss);
@@ -294,6 +371,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
     if (COUNT) visits_total += __shfl_xor_sync(0xffffffffu, visits_total, o);
     if (COUNT) fallbacks += __shfl_xor_sync(0xffffffffu, fallbacks, o);
     if (COUNT) boxed += __shfl_xor_sync(0xffffffffu, boxed, o);
+    if (COUNT) shafted += __shfl_xor_sync(0xffffffffu, shafted, o);
   }
   if (lane == 0) {
     atomicAdd(a.counters + 0, rays);
@@ -301,6 +379,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
     if (COUNT) atomicAdd(a.counters + 1, visits_total);
     if (COUNT) atomicAdd(a.counters + 3, fallbacks);
     if (COUNT) atomicAdd(a.counters + 4, boxed);
+    if (COUNT) atomicAdd(a.counters + 5, shafted);
     if (COUNT) {
       atomicAdd(a.counters + 8, (unsigned long long) tk_box);
       atomicAdd(a.counters + 9, (unsigned long long) tk_pairs);
@@ -1102,8 +1181,14 @@ __global__ void k_slot_geometry(int M, const int32_t *__restrict__ slot_patch, c
       lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], d));
       hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], d));
     }
+  // the axis code all patches of the slice share (0: none, mixed, or a normal that is not axial), for the word-level
+  // sign test of k_visibility
+  const int code = p >= 0 ? (int) n.w : 0;
+  const unsigned have = __ballot_sync(0xffffffffu, p >= 0);
+  const int first = __shfl_sync(0xffffffffu, code, have ? __ffs(have) - 1 : 0);
+  const bool same = __all_sync(0xffffffffu, p < 0 || code == first);
   if ((threadIdx.x & 31) == 0) {
-    box_min[s >> 5] = make_float4(lo[0], lo[1], lo[2], 0);
+    box_min[s >> 5] = make_float4(lo[0], lo[1], lo[2], (have && same) ? (float) first : 0.f);
     box_max[s >> 5] = make_float4(hi[0], hi[1], hi[2], 0);
   }
 }
@@ -1280,6 +1365,16 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
     a.num_runs = runs;
     a.bits = c->bits.p;
     a.counters = c->counters.p;
+    a.cell_lo = c->leaf_cell_lo.p;
+    a.cell_hi = c->leaf_cell_hi.p;
+    {
+      // ON_EPSILON + slack for the rounding of the clip points (<= ~2 ulp of the largest coordinate per split)
+      const float extent = std::max(c->bsp_extent, c->patch_extent);
+      const float ulp = std::max(extent, 1.f) * 1.2e-7f;
+      a.margin = 0.1f + std::max(0.15f, 300.f * ulp);
+    }
+    a.mode = 2 | 4;
+    if (const char *e = getenv("QRAD_VIS_MODE")) a.mode = atoi(e);
     const uint64_t want_blocks = (runs + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>(want_blocks, (uint64_t) c->sm_count * 8));
     const bool big = c->tree_depth > kTraceStack;
