@@ -421,6 +421,37 @@ __device__ __forceinline__ bool shaft_blocked(const float4 clo, const float4 chi
   return ok;
 }
 
+// The same proof for ONE segment s -> e, complete for a box cell: the segment is clipped against the shrunken cell (slab
+// method) and the middle of the clipped piece is taken as the witness q; q is then CHECKED to lie inside the shrunken
+// cell, so inaccuracies of the clipping can only lose a proof, never invent one (q, evaluated in float, is within ~1e-3 of
+// the exact segment; `margin` has 0.15 of slack).
+__device__ __forceinline__ bool segment_through_cell(const float4 clo, const float4 chi, const float margin, const float4 s,
+                                                     const float4 e) {
+  if (clo.w == 0.f) return false;
+  const float lo[3] = {clo.x + margin, clo.y + margin, clo.z + margin};
+  const float hi[3] = {chi.x - margin, chi.y - margin, chi.z - margin};
+  const float p[3] = {s.x, s.y, s.z}, d[3] = {e.x - s.x, e.y - s.y, e.z - s.z};
+  float t0 = 0.f, t1 = 1.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    if (d[k] != 0.f) {
+      const float inv = 1.0f / d[k];
+      const float ta = (lo[k] - p[k]) * inv, tb = (hi[k] - p[k]) * inv;
+      t0 = fmaxf(t0, fminf(ta, tb));
+      t1 = fminf(t1, fmaxf(ta, tb));
+    }
+  }
+  if (!(t0 <= t1)) return false;
+  const float t = 0.5f * (t0 + t1);
+  bool inside = true;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float q = p[k] + d[k] * t;
+    inside = inside && q >= lo[k] && q <= hi[k];
+  }
+  return inside;
+}
+
 // PointInLeafnum, qrad3.c:131-150: full dot product on every node, `dist > 0` picks child 0.
 __device__ __forceinline__ int point_in_leaf(const Tree tree, float x, float y, float z) {
   int node = 0;

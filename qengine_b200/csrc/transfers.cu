@@ -328,9 +328,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
           // (c) this ray alone: does it pass deep through the cell of the leaf that blocked this receiver last time,
           // or of the leaf that blocked a neighbour of it most recently?
           const int g2 = s_wguess[wid][cand >> 5];
-          if ((a.mode & 4) && (shaft_blocked(__ldg(a.cell_lo + g), __ldg(a.cell_hi + g), a.margin, so, so, po, po) ||
+          if ((a.mode & 4) && (segment_through_cell(__ldg(a.cell_lo + g), __ldg(a.cell_hi + g), a.margin, so, po) ||
                                (g2 != g && g2 != 0xffff &&
-                                shaft_blocked(__ldg(a.cell_lo + g2), __ldg(a.cell_hi + g2), a.margin, so, so, po, po)))) {
+                                segment_through_cell(__ldg(a.cell_lo + g2), __ldg(a.cell_hi + g2), a.margin, so, po)))) {
             miss = false;
             if (COUNT) shafted++;
           } else if (a.mode & 16) {
