@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
   const uint64_t warp0 = (uint64_t) blockIdx.x * kWarpsPerBlock + wid;
   const uint64_t nwarps = (uint64_t) gridDim.x * kWarpsPerBlock;
   unsigned long long rays = 0, pairs = 0, visits_total = 0, fallbacks = 0, boxed = 0, shafted = 0;
+  unsigned long long grazed = 0, uncelled = 0, wrong_guess = 0, grazed_other = 0, retested = 0, walked = 0;
   long long tk0 = 0, tk_box = 0, tk_pairs = 0, tk_guess = 0, tk_full = 0, tk_misc = 0;   // COUNT: warp cycles per phase
   for (uint64_t run = warp0; run < a.num_runs; run += nwarps) {
     // ---- decode the run: row group, chunk ----
@@ -186,8 +187,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
   for (int r = 0; r < nrows; r++) {
     const int sslot = slot0 + r;
     const unsigned flags = a.g.slot_flags[sslot];
-    if (!(flags & 1u)) continue;                        // padding slot at the end of the cluster: nobody reads its words
-    if (!(flags & 2u)) {                                // a source in solid never shoots (qrad3.c:208); only under -nopvs
+    if (!(flags & 2u)) {   // padding slot at the end of a cluster, or (only under -nopvs) a source in solid, which never
+                           // shoots (qrad3.c:208): zero words, so that every word of the row buffer is defined
       if (lane < nwc) a.bits[s_waddr[wid][lane] + ownbase + r] = 0u;
       continue;
     }
@@ -298,10 +299,28 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
         const float4 po = __ldcg(a.s_origin_area + s_wbase[wid][cand >> 5] + (cand & 31));
         unsigned visits = 0;
         int leaf = -1;
-        const int blocked = test_line<STACK, COUNT>(a.tree, so.x, so.y, so.z, po.x, po.y, po.z, visits, &leaf);
+        int blocked;
+        // the word's guess may have been refreshed by an earlier batch of this very row (a group of neighbouring
+        // receivers usually changes its blocker together): one more cell test before the walk
+        const int gw = s_wguess[wid][cand >> 5];
+        if ((a.mode & 4) && gw != 0xffff && gw != s_rguess[wid][cand] &&
+            segment_through_cell(__ldg(a.cell_lo + gw), __ldg(a.cell_hi + gw), a.margin, so, po)) {
+          blocked = 1;
+          leaf = gw;
+          if (COUNT) retested++;
+        } else {
+          blocked = test_line<STACK, COUNT>(a.tree, so.x, so.y, so.z, po.x, po.y, po.z, visits, &leaf);
+          if (COUNT) walked++;
+        }
         if (COUNT) visits_total += visits;
         if (!blocked) atomicOr(&s_res[wid][cand >> 5], 1u << (cand & 31));
         else if (leaf < 0xffff) {
+          if (COUNT) {   // why did the proofs miss this blocked ray: the guess was right but the ray only grazes the cell ...
+            if (leaf == s_rguess[wid][cand] || leaf == s_wguess[wid][cand >> 5]) grazed++;
+            else if (__ldg(a.cell_lo + leaf).w == 0.f) uncelled++;   // ... or the blocker has no box cell ...
+            else if (segment_through_cell(__ldg(a.cell_lo + leaf), __ldg(a.cell_hi + leaf), a.margin, so, po)) wrong_guess++;
+            else grazed_other++;                                     // ... or it was another leaf (provable / not)
+          }
           s_rguess[wid][cand] = (uint16_t) leaf;
           s_wguess[wid][cand >> 5] = (uint16_t) leaf;
         }
@@ -372,14 +391,29 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
     if (COUNT) fallbacks += __shfl_xor_sync(0xffffffffu, fallbacks, o);
     if (COUNT) boxed += __shfl_xor_sync(0xffffffffu, boxed, o);
     if (COUNT) shafted += __shfl_xor_sync(0xffffffffu, shafted, o);
+    if (COUNT) {
+      grazed += __shfl_xor_sync(0xffffffffu, grazed, o);
+      uncelled += __shfl_xor_sync(0xffffffffu, uncelled, o);
+      wrong_guess += __shfl_xor_sync(0xffffffffu, wrong_guess, o);
+      grazed_other += __shfl_xor_sync(0xffffffffu, grazed_other, o);
+      retested += __shfl_xor_sync(0xffffffffu, retested, o);
+      walked += __shfl_xor_sync(0xffffffffu, walked, o);
+    }
   }
   if (lane == 0) {
     atomicAdd(a.counters + 0, rays);
     atomicAdd(a.counters + 2, pairs);
     if (COUNT) atomicAdd(a.counters + 1, visits_total);
-    if (COUNT) atomicAdd(a.counters + 3, fallbacks);
+    if (COUNT) atomicAdd(a.counters + 3, walked);   // rays that took the full TestLine walk
     if (COUNT) atomicAdd(a.counters + 4, boxed);
     if (COUNT) atomicAdd(a.counters + 5, shafted);
+    if (COUNT) {
+      atomicAdd(a.counters + 6, grazed);
+      atomicAdd(a.counters + 7, uncelled);
+      atomicAdd(a.counters + 13, wrong_guess);
+      atomicAdd(a.counters + 14, grazed_other);
+      atomicAdd(a.counters + 15, retested);
+    }
     if (COUNT) {
       atomicAdd(a.counters + 8, (unsigned long long) tk_box);
       atomicAdd(a.counters + 9, (unsigned long long) tk_pairs);
@@ -538,37 +572,52 @@ __global__ void __launch_bounds__(kThreads) k_row_totals32(const RowArgs a) {
   const int64_t e0 = a.vl_ptr[c], e1 = a.vl_ptr[c + 1];
   float total = 0.f;
   int count = 0;
-  int4 ent_n = make_int4(0, 0, 0, 0);
-  uint32_t word_n = 0;
-  if (e0 < e1) {
-    ent_n = __ldg(a.vl + e0);
-    word_n = __ldcs(a.bits + vl_addr(ent_n) + row);
-  }
-  for (int64_t e = e0; e < e1; e++) {
-    const int4 ent = ent_n;
-    const uint32_t acc = live_row ? (word_n & (uint32_t) ent.z) : 0u;
-    if (e + 1 < e1) {
-      ent_n = __ldg(a.vl + e + 1);
-      word_n = __ldcs(a.bits + vl_addr(ent_n) + row);
-    }
-    unsigned hot = __reduce_or_sync(0xffffffffu, acc);
-    if (!hot) continue;
-    __syncwarp();
-    if ((hot >> lane) & 1u) {
-      s_po[wid][lane] = a.s_origin_area[ent.w * 32 + lane];
-      s_pn[wid][lane] = a.s_normal[ent.w * 32 + lane];
-    }
-    __syncwarp();
-    while (hot) {
-      const int kk = __ffs(hot) - 1;
-      hot &= hot - 1;
-      if ((acc >> kk) & 1u) {
-        float dist;
-        bool wr;
-        const float trans = form_factor_pre(so, sn, s_po[wid][kk], s_pn[wid][kk], dist, wr);
-        total += trans;
-        count++;
+  // The list is taken 32 runs at a time (lane j holds run j: one coalesced load), and the words of four runs are in
+  // flight while the previous four are summed: the walk is bound by the latency of the word loads otherwise (one
+  // dependent HBM round trip per run, profiles/r02b_launches_c5.txt: 68 ms).
+  for (int64_t eb = e0; eb < e1; eb += 32) {
+    const int nb = (int) min((int64_t) 32, e1 - eb);
+    const int4 mine = lane < nb ? __ldg(a.vl + eb + lane) : make_int4(0, 0, 0, 0);
+    const int64_t myaddr = vl_addr(mine);
+    auto fetch = [&](const int j) -> uint32_t {   // this lane's word of run j (0 past the end of the batch)
+      const int64_t ad = __shfl_sync(0xffffffffu, myaddr, j & 31);
+      return j < nb ? __ldcs(a.bits + ad + row) : 0u;
+    };
+    uint32_t cur[4], nxt[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) cur[k] = fetch(k);
+    for (int j0 = 0; j0 < nb; j0 += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) nxt[k] = fetch(j0 + 4 + k);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int j = j0 + k;
+        if (j >= nb) break;
+        const uint32_t mask = (uint32_t) __shfl_sync(0xffffffffu, mine.z, j);
+        const int slice = __shfl_sync(0xffffffffu, mine.w, j);
+        const uint32_t acc = live_row ? (cur[k] & mask) : 0u;
+        unsigned hot = __reduce_or_sync(0xffffffffu, acc);
+        if (!hot) continue;
+        __syncwarp();
+        if ((hot >> lane) & 1u) {
+          s_po[wid][lane] = a.s_origin_area[slice * 32 + lane];
+          s_pn[wid][lane] = a.s_normal[slice * 32 + lane];
+        }
+        __syncwarp();
+        while (hot) {
+          const int kk = __ffs(hot) - 1;
+          hot &= hot - 1;
+          if ((acc >> kk) & 1u) {
+            float dist;
+            bool wr;
+            const float trans = form_factor_pre(so, sn, s_po[wid][kk], s_pn[wid][kk], dist, wr);
+            total += trans;
+            count++;
+          }
+        }
       }
+#pragma unroll
+      for (int k = 0; k < 4; k++) cur[k] = nxt[k];
     }
   }
   if (a.g.slot_flags[sslot] & 1u) {
@@ -661,27 +710,27 @@ struct ColArgs {
   uint4 *g_w;                      // [entries / 8][32] 8 x u16 weights per lane
 };
 
-// pass 3a: list lengths = non-zero words of the slice's column, streamed once.  One warp per slice.
-__global__ void __launch_bounds__(kThreads) k_column_counts(const ColArgs a) {
+// pass 3a: list lengths = non-zero words of the slice's columns (one per owner rank), each a contiguous piece of memory
+// streamed once with 128-bit loads.  One warp per slice.  (Words of padding rows are zero: k_visibility writes them.)
+__global__ void __launch_bounds__(kThreads) k_column_counts(const ColArgs a, const int world) {
   const int lane = threadIdx.x & 31;
   const int slice = a.slice_lo + blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (slice >= a.slice_hi) return;
-  const int d = a.g.slot_cluster[slice * 32];
-  const int64_t e0 = a.vr_ptr[d], e1 = a.vr_ptr[d + 1];
   int cnt = 0;
-  for (int64_t e = e0; e < e1; e += 4) {   // four runs in flight
-    uint32_t w[4];
+  for (int q = 0; q < world; q++) {
+    const int64_t *sb = a.sbase + (int64_t) q * (a.nslices + 1);
+    const int64_t first = sb[slice], n = sb[slice + 1] - first;   // multiples of 32 words
+    const uint4 *p = reinterpret_cast<const uint4 *>(a.col[q] + first);
+    const int64_t n4 = n >> 2;
+    for (int64_t i = lane; i < n4; i += 128) {   // four loads in flight per lane
+      uint4 w[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      w[j] = 0;
-      if (e + j < e1) {
-        const int4 ent = __ldg(a.vr + e + j);
-        if (lane < ent.z) w[j] = __ldcs(a.col[ent.w] + a.sbase[(int64_t) ent.w * (a.nslices + 1) + slice] + ent.y + lane);
-      }
+      for (int k = 0; k < 4; k++) w[k] = i + 32 * k < n4 ? __ldcs(p + i + 32 * k) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 4; k++) cnt += (w[k].x != 0) + (w[k].y != 0) + (w[k].z != 0) + (w[k].w != 0);
     }
-#pragma unroll
-    for (int j = 0; j < 4; j++) cnt += __popc(__ballot_sync(0xffffffffu, w[j] != 0));
   }
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if (lane == 0) a.slice_len[slice] = cnt;
 }
 
@@ -708,49 +757,61 @@ __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
   int n = 0;                                           // list entries so far (uniform)
   const int64_t base = a.slice_base[slice];
   uint32_t wq[4] = {0, 0, 0, 0};                       // this lane's weights of the current group of 8 entries
-  int4 ent_n = make_int4(0, 0, 0, 0);
-  uint32_t word_n = 0;
-  if (e0 < e1) {
-    ent_n = __ldg(a.vr + e0);
-    if (lane < ent_n.z) word_n = __ldcs(a.col[ent_n.w] + a.sbase[(int64_t) ent_n.w * (a.nslices + 1) + slice] + ent_n.y + lane);
-  }
-  for (int64_t e = e0; e < e1; e++) {
-    const int4 ent = ent_n;
-    const uint32_t word = word_n;
-    word_n = 0;
-    if (e + 1 < e1) {
-      ent_n = __ldg(a.vr + e + 1);
-      if (lane < ent_n.z) word_n = __ldcs(a.col[ent_n.w] + a.sbase[(int64_t) ent_n.w * (a.nslices + 1) + slice] + ent_n.y + lane);
-    }
-    unsigned nz = __ballot_sync(0xffffffffu, word != 0);
-    if (nz == 0) continue;
-    const uint32_t sslot = (uint32_t) ent.x + lane;
-    __syncwarp();
-    if (word != 0) {
-      s_so[wid][lane] = a.s_origin_area[sslot];
-      s_sn[wid][lane] = a.s_normal[sslot];
-      s_rt[wid][lane] = a.row_total[sslot];
-    }
-    __syncwarp();
-    while (nz) {
-      const int src = __ffs(nz) - 1;
-      nz &= nz - 1;
-      const uint32_t w = __shfl_sync(0xffffffffu, word, src);
-      uint32_t itrans = 0;
-      if ((w >> lane) & 1u) {
-        float dist;
-        bool wr;
-        const float trans = form_factor_pre(s_so[wid][src], s_sn[wid][src], po, pn, dist, wr);
-        itrans = (uint32_t) (int) (trans * 65536.0f / s_rt[wid][src]) & 0xffffu;   // u16 store wraps (qrad3.c:283-285)
+  // 32 runs at a time (lane j holds run j), the words of four runs in flight while the previous four are emitted
+  for (int64_t eb = e0; eb < e1; eb += 32) {
+    const int nb = (int) min((int64_t) 32, e1 - eb);
+    const int4 mine = lane < nb ? __ldg(a.vr + eb + lane) : make_int4(0, 0, 0, 0);
+    const uint32_t *myptr = a.col[mine.w & (kMaxWorld - 1)] + a.sbase[(int64_t) mine.w * (a.nslices + 1) + slice] + mine.y;
+    auto fetch = [&](const int j) -> uint32_t {   // the word of source `lane` of run j (0 past the run / the batch)
+      const unsigned long long pj = __shfl_sync(0xffffffffu, (unsigned long long) myptr, j & 31);
+      const int len = __shfl_sync(0xffffffffu, mine.z, j & 31);
+      return (j < nb && lane < len) ? __ldcs(reinterpret_cast<const uint32_t *>(pj) + lane) : 0u;
+    };
+    uint32_t cur[4], nxt[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) cur[k] = fetch(k);
+    for (int j0 = 0; j0 < nb; j0 += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) nxt[k] = fetch(j0 + 4 + k);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int j = j0 + k;
+        if (j >= nb) break;
+        const uint32_t word = cur[k];
+        unsigned nz = __ballot_sync(0xffffffffu, word != 0);
+        if (nz == 0) continue;
+        const uint32_t slot0 = (uint32_t) __shfl_sync(0xffffffffu, mine.x, j);
+        const uint32_t sslot = slot0 + lane;
+        __syncwarp();
+        if (word != 0) {
+          s_so[wid][lane] = a.s_origin_area[sslot];
+          s_sn[wid][lane] = a.s_normal[sslot];
+          s_rt[wid][lane] = a.row_total[sslot];
+        }
+        __syncwarp();
+        while (nz) {
+          const int src = __ffs(nz) - 1;
+          nz &= nz - 1;
+          const uint32_t w = __shfl_sync(0xffffffffu, word, src);
+          uint32_t itrans = 0;
+          if ((w >> lane) & 1u) {
+            float dist;
+            bool wr;
+            const float trans = form_factor_pre(s_so[wid][src], s_sn[wid][src], po, pn, dist, wr);
+            itrans = (uint32_t) (int) (trans * 65536.0f / s_rt[wid][src]) & 0xffffu;   // u16 store wraps (qrad3.c:283-285)
+          }
+          const int q = n & 7;
+          wq[q >> 1] |= itrans << ((q & 1) * 16);
+          if (lane == 0) a.g_src[base + n] = slot0 + src;
+          n++;
+          if ((n & 7) == 0) {
+            a.g_w[((base + n) / 8 - 1) * 32 + lane] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+            wq[0] = wq[1] = wq[2] = wq[3] = 0;
+          }
+        }
       }
-      const int q = n & 7;
-      wq[q >> 1] |= itrans << ((q & 1) * 16);
-      if (lane == 0) a.g_src[base + n] = (uint32_t) ent.x + src;
-      n++;
-      if ((n & 7) == 0) {
-        a.g_w[((base + n) / 8 - 1) * 32 + lane] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
-        wq[0] = wq[1] = wq[2] = wq[3] = 0;
-      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) cur[k] = nxt[k];
     }
   }
   if (n & 7) {
@@ -1565,7 +1626,7 @@ void transfers_columns(qrad_cuda_ctx *c) {
   ca.slice_len = c->slice_len.p;
   const int cblocks = (hi - lo + kWarpsPerBlock - 1) / kWarpsPerBlock;
   if (cblocks > 0) {
-    k_column_counts<<<cblocks, kThreads, 0, st>>>(ca);
+    k_column_counts<<<cblocks, kThreads, 0, st>>>(ca, P.world);
     c->launch_check("k_column_counts");
   }
   std::vector<int32_t> h_len((size_t) nslices);
@@ -1616,6 +1677,10 @@ void transfers_columns(qrad_cuda_ctx *c) {
   unsigned long long hc[16];
   c->counters.download(hc, 16, st);
   if (c->count_nodes) {   // warp cycles per phase of k_visibility (tools/gpu_raycounts.py)
+    fprintf(stderr, "k_visibility: %llu rays settled by per-ray cell proofs; blocked full walks: %llu grazed the guessed cell, "
+            "%llu hit another leaf that a proof would have caught, %llu another leaf only grazed, %llu a leaf without a box cell; "
+            "%llu fallback rays settled by a refreshed guess\n",
+            hc[5], hc[6], hc[13], hc[14], hc[7], hc[15]);
     const double tot = (double) (hc[8] + hc[9] + hc[10] + hc[11] + hc[12]);
     if (tot > 0)
       fprintf(stderr, "k_visibility warp cycles: box walks %.1f %%, pair tests %.1f %%, guess walks %.1f %%, full walks %.1f %%, "
