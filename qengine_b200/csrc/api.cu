@@ -164,8 +164,8 @@ int qrad_cuda_set_count_nodes(qrad_cuda_ctx *c, int enable) {
   return 0;
 }
 
-// Flatten dnodes/dplanes/dleafs into the trace tree (MakeTnodes, trace.c:47-88; breadth-first here), record the
-// root -> leaf ancestor paths, and expand the RLE PVS rows (DecompressVis, bspfile.c:129-154) once, so kernels
+// Flatten dnodes/dplanes/dleafs into the trace tree (MakeTnodes, trace.c:47-88; breadth-first here), compute the box
+// cells of the leaves (shaft_blocked, qrad_device.cuh), and expand the RLE PVS rows (DecompressVis, bspfile.c:129-154) once, so kernels
 // test a cluster bit with one load.
 int qrad_cuda_upload_bsp(qrad_cuda_ctx *c, const qrad_bsp_view *b) {
   return guarded([&] {
@@ -221,7 +221,7 @@ int qrad_cuda_upload_bsp(qrad_cuda_ctx *c, const qrad_bsp_view *b) {
       flat[me] = make_int4(distbits, pl.type, child[0], child[1]);
       normals[me] = make_float4(pl.normal[0], pl.normal[1], pl.normal[2], pl.dist);
     }
-    // root -> leaf paths (for reaches_leaf): parent links in the new numbering, then one record list per leaf
+    // parent links in the new numbering, for the cells of the leaves
     {
       std::vector<int> parent((size_t) next_new, -1), pside((size_t) next_new, 0);
       std::vector<int> lparent((size_t) b->numleafs, -1), lside((size_t) b->numleafs, 0);
@@ -237,23 +237,6 @@ int qrad_cuda_upload_bsp(qrad_cuda_ctx *c, const qrad_bsp_view *b) {
           }
         }
       }
-      std::vector<int32_t> first((size_t) b->numleafs + 1, 0);
-      std::vector<int4> recs;
-      std::vector<int4> tmp;
-      for (int l = 0; l < b->numleafs; l++) {
-        tmp.clear();
-        int node = lparent[l], sd = lside[l];
-        while (node >= 0) {
-          tmp.push_back(make_int4(flat[node].x, flat[node].y | (sd << 8), node, 0));
-          sd = pside[node];
-          node = parent[node];
-        }
-        recs.insert(recs.end(), tmp.rbegin(), tmp.rend());
-        first[l + 1] = (int32_t) recs.size();
-      }
-      for (int k = 0; k < 4; k++) recs.push_back(make_int4(0, 0, 0, 0));   // the walkers fetch records four at a time
-      c->leaf_path.upload(recs, c->stream);
-      c->leaf_path_first.upload(first, c->stream);
       // cells of the leaves: a leaf whose ancestors are all axial planes is the box between the tightest of them
       // (shaft_blocked() in qrad_device.cuh); lo.w = 1 marks a SOLID leaf with such a cell
       std::vector<float4> cell_lo((size_t) b->numleafs), cell_hi((size_t) b->numleafs);

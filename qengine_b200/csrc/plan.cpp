@@ -2,10 +2,13 @@
 #include "plan.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
 
 #include "../../include/qrad_cuda.h"
 
@@ -67,6 +70,14 @@ void build_plan(TransferPlan &p, int N, const int32_t *eff, int nc, const uint32
                 int owner_chunks) {
   if (world < 1 || rank < 0 || rank >= world) pfail("bad rank / world");
   if (nc <= 0) pfail("make_transfers: no clusters");
+  const bool timing = getenv("QRAD_DEBUG_TIMING") != nullptr;
+  auto tp = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "  plan: %-22s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tp).count());
+    tp = now;
+  };
   p = TransferPlan();
   p.N = N;
   p.nc = nc;
@@ -103,6 +114,7 @@ void build_plan(TransferPlan &p, int N, const int32_t *eff, int nc, const uint32
     const int c = p.slot_cluster[(size_t) s * 32];
     p.slice_count[s] = std::min(32, p.cl_count[c] - (s * 32 - p.cl_slot_start[c]));
   }
+  lap("slots");
   // ---- who sees whom ----
   p.vis_ptr.assign(nc + 1, 0);
   p.nwords.assign(nc, 0);
@@ -110,24 +122,41 @@ void build_plan(TransferPlan &p, int N, const int32_t *eff, int nc, const uint32
   p.Lptr.assign(nc + 1, 0);
   p.Rptr.assign(nc + 1, 0);
   std::vector<int32_t> seer_n(nc + 1, 0);
-  for (int a = 0; a < nc; a++) {
-    int w = 0;
-    int64_t cand = 0;
-    if (p.cl_count[a] > 0)
-      for (int d = 0; d < nc; d++) {
-        const bool vis = pvs ? ((pvs[(size_t) a * pvs_words + (d >> 5)] >> (d & 31)) & 1u) != 0 : true;
-        if (!vis || p.cl_count[d] == 0) continue;
-        p.vis_cluster.push_back(d);
-        p.vis_woff.push_back(w);
-        w += (p.cl_slot_start[d + 1] - p.cl_slot_start[d]) >> 5;
-        cand += p.cl_count[d];
-        p.Rptr[d + 1] += p.cl_count[a];
-        seer_n[d + 1]++;
-      }
-    p.vis_ptr[a + 1] = (int32_t) p.vis_cluster.size();
-    p.nwords[a] = w;
-    p.wb_first[a + 1] = p.wb_first[a] + w;
-    p.Lptr[a + 1] = p.Lptr[a] + cand;
+  {
+    // clusters that hold patches, as a bit row: a visible list is (PVS row & this) scanned word by word
+    std::vector<uint32_t> populated((size_t) ((nc + 31) >> 5), 0);
+    size_t visible = 0;
+    for (int d = 0; d < nc; d++)
+      if (p.cl_count[d] > 0) populated[d >> 5] |= 1u << (d & 31);
+    const int nw32 = (nc + 31) >> 5;
+    if (pvs)
+      for (int a = 0; a < nc; a++)
+        if (p.cl_count[a] > 0)
+          for (int k = 0; k < nw32; k++) visible += (size_t) __builtin_popcount(pvs[(size_t) a * pvs_words + k] & populated[k]);
+    p.vis_cluster.reserve(visible + 16);
+    p.vis_woff.reserve(visible + 16);
+    for (int a = 0; a < nc; a++) {
+      int w = 0;
+      int64_t cand = 0;
+      if (p.cl_count[a] > 0)
+        for (int k = 0; k < nw32; k++) {
+          uint32_t bits = (pvs ? pvs[(size_t) a * pvs_words + k] : 0xffffffffu) & populated[k];
+          while (bits) {
+            const int d = k * 32 + __builtin_ctz(bits);
+            bits &= bits - 1;
+            p.vis_cluster.push_back(d);
+            p.vis_woff.push_back(w);
+            w += (p.cl_slot_start[d + 1] - p.cl_slot_start[d]) >> 5;
+            cand += p.cl_count[d];
+            p.Rptr[d + 1] += p.cl_count[a];
+            seer_n[d + 1]++;
+          }
+        }
+      p.vis_ptr[a + 1] = (int32_t) p.vis_cluster.size();
+      p.nwords[a] = w;
+      p.wb_first[a + 1] = p.wb_first[a] + w;
+      p.Lptr[a + 1] = p.Lptr[a] + cand;
+    }
   }
   for (int d = 0; d < nc; d++) p.Rptr[d + 1] += p.Rptr[d];
   if (p.Lptr[nc] >= ((int64_t) 1 << 40)) pfail("make_transfers: candidate lists too large");
@@ -145,6 +174,7 @@ void build_plan(TransferPlan &p, int N, const int32_t *eff, int nc, const uint32
       }
   }
   const size_t E = p.seer_cluster.size();
+  lap("visibility lists");
   // ---- row groups and their owners ----
   p.grp_first.assign(nc + 1, 0);
   for (int c = 0; c < nc; c++) {
@@ -185,18 +215,33 @@ void build_plan(TransferPlan &p, int N, const int32_t *eff, int nc, const uint32
     p.grp_ownbase[g] = n;
     n += p.grp_rows[g];
   }
-  p.coff.assign((size_t) world * E, 0);
+  p.coff.resize((size_t) world * E);
+  p.sbase.resize((size_t) world * (p.nslices + 1));
   p.colh.assign((size_t) world * nc, 0);
-  for (int q = 0; q < world; q++)
-    for (int d = 0; d < nc; d++) {
-      int64_t acc = 0;
-      for (int e = p.seer_ptr[d]; e < p.seer_ptr[d + 1]; e++) {
-        p.coff[(size_t) q * E + e] = (int32_t) acc;
-        acc += p.nown[(size_t) q * nc + p.seer_cluster[e]];
+  {
+    std::vector<std::thread> th;
+    std::vector<int> bad((size_t) world, 0);
+    auto one = [&](int q) {   // the columns of rank q
+      for (int d = 0; d < nc; d++) {
+        int64_t acc = 0;
+        for (int e = p.seer_ptr[d]; e < p.seer_ptr[d + 1]; e++) {
+          p.coff[(size_t) q * E + e] = (int32_t) acc;
+          acc += p.nown[(size_t) q * nc + p.seer_cluster[e]];
+        }
+        if (acc > 0x7fffffff) bad[q] = 1;
+        p.colh[(size_t) q * nc + d] = (int32_t) acc;
       }
-      if (acc > 0x7fffffff) pfail("make_transfers: a slice column exceeds 2^31 words");
-      p.colh[(size_t) q * nc + d] = (int32_t) acc;
-    }
+      int64_t *sb = &p.sbase[(size_t) q * (p.nslices + 1)];
+      sb[0] = 0;
+      for (int s = 0; s < p.nslices; s++) sb[s + 1] = sb[s] + p.colh[(size_t) q * nc + p.slot_cluster[(size_t) s * 32]];
+    };
+    for (int q = 1; q < world; q++) th.emplace_back(one, q);
+    one(0);
+    for (auto &t : th) t.join();
+    for (int q = 0; q < world; q++)
+      if (bad[q]) pfail("make_transfers: a slice column exceeds 2^31 words");
+  }
+  lap("groups, column offsets");
   // ---- receiver slices: contiguous runs of (nearly) equal candidate sources ----
   p.slice_lo.assign(world, 0);
   p.slice_hi.assign(world, 0);
@@ -223,11 +268,7 @@ void build_plan(TransferPlan &p, int N, const int32_t *eff, int nc, const uint32
     }
     p.slice_hi[world - 1] = p.nslices;
   }
-  p.sbase.assign((size_t) world * (p.nslices + 1), 0);
-  for (int q = 0; q < world; q++) {
-    int64_t *sb = &p.sbase[(size_t) q * (p.nslices + 1)];
-    for (int s = 0; s < p.nslices; s++) sb[s + 1] = sb[s] + p.colh[(size_t) q * nc + p.slot_cluster[(size_t) s * 32]];
-  }
+  lap("slices");
   // ---- this rank ----
   p.own_runbase.assign(1, 0);
   for (int g = 0; g < G; g++) {

@@ -18,9 +18,20 @@
 // are dealt to the ranks in several contiguous chunks each, balanced by candidate words.
 #pragma once
 #include <cstdint>
+#include <memory>
+#include <utility>
 #include <vector>
 
 namespace qrad {
+
+// std::vector whose resize() leaves new elements uninitialised (they are written, in parallel, right afterwards)
+template <class T> struct UninitAlloc : std::allocator<T> {
+  template <class U> struct rebind { using other = UninitAlloc<U>; };
+  using std::allocator<T>::allocator;
+  template <class U> void construct(U *p) noexcept { ::new (static_cast<void *>(p)) U; }
+  template <class U, class... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+template <class T> using UninitVec = std::vector<T, UninitAlloc<T>>;
 
 constexpr int kGroupRows = 128;   // rows of a row group (= consecutive tasks of one warp run in k_visibility)
 constexpr int kChunkWords = 32;   // one task = one source patch x up to 32 words (1024 receivers)
@@ -41,9 +52,9 @@ struct TransferPlan {
   std::vector<int32_t> grp_first;                        // [nc + 1] first group of a cluster
   std::vector<int32_t> grp_cluster, grp_slot0, grp_rows, grp_owner, grp_ownbase;
   std::vector<int32_t> nown;                             // [world][nc] own rows (multiple of 32)
-  std::vector<int32_t> coff;                             // [world][seer entries] offset of c's own rows in a column of d
+  UninitVec<int32_t> coff;                               // [world][seer entries] offset of c's own rows in a column of d
   std::vector<int32_t> colh;                             // [world][nc] words of one slice column of cluster d
-  std::vector<int64_t> sbase;                            // [world][nslices + 1] first word of slice s in rank q's buffer
+  UninitVec<int64_t> sbase;                              // [world][nslices + 1] first word of slice s in rank q's buffer
   // ---- receiver slices ----
   std::vector<int32_t> slice_lo, slice_hi;               // [world]
   // ---- candidate counts ----

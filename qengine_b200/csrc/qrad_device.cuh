@@ -90,8 +90,9 @@ template <class T> struct DBuf {
 // One 16-byte record per BSP node {dist, plane type, child0, child1} so that a node visit is ONE 128-bit
 // load; the plane normal (needed only by non-axial planes in TestLine_r and by PointInLeaf) sits in a
 // separate float4 array.  Nodes are numbered breadth-first: the two children of a node are adjacent
-// (same 32-byte sector) and the top levels occupy the first entries, which k_visibility stages in shared
-// memory.  Layout is free, only results matter (MakeTnode, trace.c:47-71, uses preorder).
+// (same 32-byte sector) and the top levels, which every ray visits, share a few cache lines (the whole tree is
+// <= 2 MB and lives in L1/L2; staging its top in shared memory was measured and rejected).  Layout is
+// free, only results matter (MakeTnode, trace.c:47-71, uses preorder).
 // child >= 0: node index.  child < 0: leaf, encoded kLeafFlag | solid << 30 | leaf number.
 struct Tree {
   const int4 *nodes;      // x = float bits of dist, y = plane type, z = child 0, w = child 1
@@ -179,7 +180,8 @@ __device__ __forceinline__ int test_line(const Tree tree, float sx, float sy, fl
     }
     if (sp == 0) return 0;
     sp--;
-    const float4 t = stack[sp < STACK ? sp : STACK - 1];
+    if (sp >= STACK) __trap();   // deeper than the uploaded tree allows (upload_bsp checks the depth): never a wrong answer
+    const float4 t = stack[sp];
     sx = ex;
     sy = ey;
     sz = ez;
@@ -188,184 +190,6 @@ __device__ __forceinline__ int test_line(const Tree tree, float sx, float sy, fl
     ey = t.z;
     ez = t.w;
   }
-}
-
-// Does TestLine_r(0, start, stop) reach leaf X?  The segment TestLine_r hands to a child depends only on the
-// ancestors of that child (trace.c:124-141), so walking the root -> X path with the same three-way test and the same
-// clipping arithmetic decides it exactly, without a stack and without visiting any sibling subtree.  `path` holds,
-// root first, one record per ancestor: x = float bits of dist, y = plane type | (side of X's subtree) << 8,
-// z = node index (for the normal of a non-axial plane).  Since TestLine_r's result is the OR over all reachable
-// leaves, "a SOLID leaf is reachable" proves the ray blocked; callers use the leaf that blocked a neighbouring ray
-// as the guess and fall back to the full walk when the guess is not reached.
-// The records of a path are fetched four at a time (the array is padded by four records): the loads do not depend
-// on the walk, so one L1 round trip is paid per four ancestors instead of per ancestor -- k_visibility is bound by
-// exactly this dependent-latency chain (profiles/r01g_full_c5chop16.txt: 10.5 cycles per issued instruction per warp).
-// `first` / `splits` (optional) come from a failed box_reaches_leaf() of the same leaf for a box that holds this end
-// point: the interval walk proved that the ray passes the ancestors [0, first) towards X, unclipped except at the
-// ancestors in `splits`, where it is split with the near/far half leading on.  Those splits are replayed with the
-// exact arithmetic (no three-way test needed), the other ancestors of the prefix are skipped, and the normal walk
-// starts at ancestor `first`.
-template <bool COUNT>
-__device__ __forceinline__ bool reaches_leaf(const Tree tree, const int4 *__restrict__ path, const int len, float sx,
-                                             float sy, float sz, float ex, float ey, float ez, unsigned &visits,
-                                             const int first = 0, unsigned long long splits = 0) {
-  while (splits) {
-    const int i = __ffsll((long long) splits) - 1;
-    splits &= splits - 1;
-    const int4 nd = __ldg(path + i);
-    const float dist = __int_as_float(nd.x);
-    const int type = nd.y & 0xff, want = nd.y >> 8;   // box walks stop at non-axial planes: type < 3 here
-    if (COUNT) visits++;
-    const float front = axis_pick(type, sx, sy, sz) - dist;
-    const float back = axis_pick(type, ex, ey, ez) - dist;
-    const int side = front < 0 ? 1 : 0;
-    const float frac = front / (front - back);
-    const float mx = sx + (ex - sx) * frac;
-    const float my = sy + (ey - sy) * frac;
-    const float mz = sz + (ez - sz) * frac;
-    if (want == side) {
-      ex = mx; ey = my; ez = mz;
-    } else {
-      sx = mx; sy = my; sz = mz;
-    }
-  }
-#define QRAD_PATH_STEP(ND)                                                                               \
-  do {                                                                                                   \
-    const int4 nd = ND;                                                                                  \
-    const float dist = __int_as_float(nd.x);                                                             \
-    const int type = nd.y & 0xff, want = nd.y >> 8;                                                      \
-    if (COUNT) visits++;                                                                                 \
-    float front, back;                                                                                   \
-    if (type < 3) {                                                                                      \
-      front = axis_pick(type, sx, sy, sz) - dist;                                                        \
-      back = axis_pick(type, ex, ey, ez) - dist;                                                         \
-    } else {                                                                                             \
-      const float2 fb = nonaxial_dists(tree.normals, nd.z, dist, sx, sy, sz, ex, ey, ez);                \
-      front = fb.x;                                                                                      \
-      back = fb.y;                                                                                       \
-    }                                                                                                    \
-    if (front > -0.1f && back > -0.1f) {                                                                 \
-      if (want != 0) return false;                                                                       \
-    } else if (front < 0.1f && back < 0.1f) {                                                            \
-      if (want != 1) return false;                                                                       \
-    } else {                                                                                             \
-      const int side = front < 0 ? 1 : 0;                                                                \
-      const float frac = front / (front - back);                                                         \
-      const float mx = sx + (ex - sx) * frac;                                                            \
-      const float my = sy + (ey - sy) * frac;                                                            \
-      const float mz = sz + (ez - sz) * frac;                                                            \
-      if (want == side) { /* near half: (start, mid) */                                                  \
-        ex = mx; ey = my; ez = mz;                                                                       \
-      } else {            /* far half: (mid, stop) */                                                    \
-        sx = mx; sy = my; sz = mz;                                                                       \
-      }                                                                                                  \
-    }                                                                                                    \
-  } while (0)
-  for (int i = first; i < len; i += 4) {
-    const int4 r0 = __ldg(path + i), r1 = __ldg(path + i + 1), r2 = __ldg(path + i + 2), r3 = __ldg(path + i + 3);
-    QRAD_PATH_STEP(r0);
-    if (i + 1 >= len) break;
-    QRAD_PATH_STEP(r1);
-    if (i + 2 >= len) break;
-    QRAD_PATH_STEP(r2);
-    if (i + 3 >= len) break;
-    QRAD_PATH_STEP(r3);
-  }
-#undef QRAD_PATH_STEP
-  return true;
-}
-
-// reaches_leaf for a whole BOX of end points at once: returns true only if, for EVERY end point e inside
-// [mn, mx], TestLine_r(0, s, e) provably reaches leaf X.  Interval version of the walk above:
-//  * the start / end of the clipped segment are kept as axis-aligned intervals that contain the reference's float
-//    values for every e in the box.  `coordinate - dist` is one correctly rounded subtraction, monotone in the
-//    coordinate, so evaluating it at the interval ends bounds front / back exactly;
-//  * a node is passed only when the interval ends show that every e takes the same branch of trace.c:124-141
-//    (first test, second test, or split with the same `side`) and that branch leads towards X;
-//  * at a split, frac = front / (front - back) is monotone in front and in back on the sign pattern at hand, and
-//    mid = start + (stop - start) * frac is a convex combination, monotone in start and stop, so its range follows
-//    from the interval ends; frac is widened by 1e-5 and mid by 0.02 units, an order of magnitude more than the float
-//    rounding of those three operations at world coordinates (|x| <= 8192, ulp <= 0.001);
-//  * non-axial planes are not handled (returns false = "do not know").
-// A `true` answer for a SOLID leaf X therefore proves every ray into the box blocked; `false` proves nothing and the
-// rays are tested one by one.
-//
-// Result: kBoxProven; kBoxElsewhere = every ray of the box provably leaves the path to X at ancestor `first` (so X is
-// reached by none of them); kBoxUnknown = the rays part ways (or meet a non-axial plane) at ancestor `first`.  In the
-// last two cases `splits` has bit i set for every ancestor i < first at which all rays are split; reaches_leaf() uses
-// (first, splits) to skip the proven prefix ray by ray.  Paths deeper than 64 report first = 0.
-enum { kBoxUnknown = 0, kBoxProven = 1, kBoxElsewhere = 2 };
-__device__ __forceinline__ int box_reaches_leaf(const int4 *__restrict__ path, const int len, const float4 s,
-                                                const float4 mn, const float4 mx, int &first, unsigned long long &splits) {
-  first = 0;
-  splits = 0;
-  const bool track = len <= 64;
-  float slo[3] = {s.x, s.y, s.z}, shi[3] = {s.x, s.y, s.z};
-  float elo[3] = {mn.x, mn.y, mn.z}, ehi[3] = {mx.x, mx.y, mx.z};
-  for (int i = 0; i < len; i++) {
-    const int4 nd = __ldg(path + i);
-    const float dist = __int_as_float(nd.x);
-    const int type = nd.y & 0xff, want = nd.y >> 8;
-    if (type >= 3) {
-      if (track) first = i; else splits = 0;
-      return kBoxUnknown;
-    }
-    const float f_lo = axis_pick(type, slo[0], slo[1], slo[2]) - dist;
-    const float f_hi = axis_pick(type, shi[0], shi[1], shi[2]) - dist;
-    const float b_lo = axis_pick(type, elo[0], elo[1], elo[2]) - dist;
-    const float b_hi = axis_pick(type, ehi[0], ehi[1], ehi[2]) - dist;
-    if (f_lo > -0.1f && b_lo > -0.1f) {  // every e: first test true -> child 0
-      if (want != 0) {
-        if (track) first = i; else splits = 0;
-        return kBoxElsewhere;
-      }
-      continue;
-    }
-    if ((!(f_hi > -0.1f) || !(b_hi > -0.1f)) && f_hi < 0.1f && b_hi < 0.1f) {  // every e: first false, second true
-      if (want != 1) {
-        if (track) first = i; else splits = 0;
-        return kBoxElsewhere;
-      }
-      continue;
-    }
-    int side;
-    if (!(f_lo < 0.1f) && !(b_hi > -0.1f)) side = 0;        // every e: front >= 0.1, back <= -0.1: split, side 0
-    else if (!(f_hi > -0.1f) && !(b_lo < 0.1f)) side = 1;   // every e: front <= -0.1, back >= 0.1: split, side 1
-    else {
-      if (track) first = i; else splits = 0;
-      return kBoxUnknown;
-    }
-    splits |= 1ull << (i & 63);
-    float fr_lo, fr_hi;
-    if (side == 0) {
-      fr_lo = f_lo / (f_lo - b_lo);
-      fr_hi = f_hi / (f_hi - b_hi);
-    } else {
-      fr_lo = f_hi / (f_hi - b_hi);
-      fr_hi = f_lo / (f_lo - b_lo);
-    }
-    fr_lo = fmaxf(fr_lo - 1e-5f, 0.f);
-    fr_hi = fminf(fr_hi + 1e-5f, 1.f);
-    float mlo[3], mhi[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const float c1 = slo[k] + (elo[k] - slo[k]) * fr_lo, c2 = slo[k] + (elo[k] - slo[k]) * fr_hi;
-      const float d1 = shi[k] + (ehi[k] - shi[k]) * fr_lo, d2 = shi[k] + (ehi[k] - shi[k]) * fr_hi;
-      mlo[k] = fminf(c1, c2) - 0.02f;
-      mhi[k] = fmaxf(d1, d2) + 0.02f;
-    }
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      if (want == side) {  // near half: (start, mid)
-        elo[k] = mlo[k];
-        ehi[k] = mhi[k];
-      } else {             // far half: (mid, stop)
-        slo[k] = mlo[k];
-        shi[k] = mhi[k];
-      }
-    }
-  }
-  return kBoxProven;
 }
 
 // Shaft proof: does EVERY segment from a point of box A = [amn, amx] to a point of box B = [bmn, bmx] make TestLine_r
@@ -521,8 +345,6 @@ struct qrad_cuda_ctx {
   bool have_vis = false;
   qrad::DBuf<int4> nodes;
   qrad::DBuf<float4> node_normals;
-  qrad::DBuf<int4> leaf_path;           // root -> leaf ancestor records of every leaf, see reaches_leaf()
-  qrad::DBuf<int32_t> leaf_path_first;  // [numleafs + 1]
   qrad::DBuf<float4> leaf_cell_lo, leaf_cell_hi;   // [numleafs] box cells of the leaves, see shaft_blocked()
   float bsp_extent = 0, patch_extent = 0;           // largest |coordinate| of the axial planes / patch origins
   qrad::Tree tree() const { return qrad::Tree{nodes.p, node_normals.p}; }

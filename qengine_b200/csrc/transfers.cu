@@ -102,8 +102,6 @@ struct Geo {
 
 struct VisArgs {
   Tree tree;
-  const int4 *leaf_path;          // root -> leaf ancestor records (reaches_leaf)
-  const int32_t *leaf_path_first;
   const float4 *wbox_min, *wbox_max;  // [M/32] bounding box of the patch origins of each slice
   const float4 *s_origin_area, *s_normal;
   Geo g;
@@ -116,45 +114,45 @@ struct VisArgs {
   unsigned long long *counters;   // [0] rays, [1] node visits, [2] candidate pairs
   const float4 *cell_lo, *cell_hi;   // [numleafs] leaf cells (shaft_blocked)
   float margin;                   // how deep inside a solid cell a segment must pass to count as proven blocked
-  int mode;                       // bit 0: slice x word shaft proofs, 1: source x word shaft proofs, 2: per-ray shaft
-                                  // proofs, 3: interval walks for words the shaft leaves open, 4: guess walks
+  int mode;                       // bit 0: slice x word cell proofs, 1: source x word cell proofs, 2: per-ray cell proofs
 };
 
 // One warp lights one run = the rows of one row group (<= 128 consecutive source patches of one cluster) against one
 // chunk of <= 32 words (1024 receivers), row after row: the SAME receivers seen from neighbouring source patches, so
 // what blocked a receiver last time is an excellent guess for this time (measured with the CPU oracle on C5: 95 % of
-// the rays are blocked, 94-99 % of those by the leaf that blocked the same receiver from the previous source, and a
-// single leaf blocks a whole word for about half of the words).  Per row ("task"):
-//   (1) lane w runs the interval walk box_reaches_leaf() for the bounding box of the 32 receivers of word w with the
-//       word's last blocker: a proven word needs no ray at all;
-//   (2) form-factor sign tests for all receivers (they define which pairs the reference would hand to TestLine_r,
-//       qrad3.c:244, and are counted as rays either way); pairs of unproven words are compacted into a queue;
-//   (3) the queue is consumed 32 rays at a time: reaches_leaf() with the receiver's last blocker (one root -> leaf
-//       path, no stack); rays that are not settled collect in a second queue and take the full TestLine walk in full
-//       batches, which refreshes the guesses;
+// the rays are blocked, 94-99 % of those by the leaf that blocked the same receiver from the previous source).
+// No ray is traced that a cheap exact argument settles.  Per row ("task"):
+//   (1) lane w, for word w: shaft_blocked() with the leaf that blocked somebody in the word last -- if every segment from
+//       the source (or from all 32 sources of its slice: kept for the following rows) to the word's bounding box passes
+//       deep through that leaf's solid cell, all 32 receivers are blocked (73 % of the rays on C5, no tree walk);
+//   (2) which pairs would the reference hand to TestLine_r (qrad3.c:232-244)?  They are counted as rays either way.
+//       Word level first: with axial normals and the word's box on one side of the source the sign test has one
+//       outcome for all 32 receivers; only the other words are tested receiver by receiver.  Pairs of unproven words
+//       are compacted into a queue;
+//   (3) the queue is drained 32 rays at a time: segment_through_cell() with the receiver's last blocker and with the
+//       word's (another 19 %); the rest collects in a second queue and takes the full TestLine walk in full batches
+//       (9 % of the rays: the 4.6 % that are clear, and blocked ones whose guess was wrong or only grazed), which
+//       refreshes the guesses;
 //   (4) accept bits are OR-ed into 32 result words in shared memory and stored into the 32 slice columns.
-// Measured alternatives (profiles/README.md): one word per warp without compaction leaves 46 % of the lanes idle;
-// refilling finished lanes from the queue decorrelates the lanes and is slower.
+// Measured alternatives (profiles/README.md): interval walks along the root -> leaf path of the guess
+// (round 1: 37 % of the rays per word, and a walk per remaining ray) cost 2.5 x the time of the cell proofs; one word per
+// warp without compaction leaves 46 % of the lanes idle; refilling finished lanes from the queue decorrelates the lanes.
+constexpr int kQueue = 256;   // pairs waiting for stage (3); drained whenever another word might not fit
 template <int STACK, bool COUNT>
 __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
-  __shared__ uint16_t s_queue[kWarpsPerBlock][kChunkWords * 32];
+  __shared__ uint16_t s_queue[kWarpsPerBlock][kQueue];
   __shared__ uint16_t s_rguess[kWarpsPerBlock][kChunkWords * 32];  // per receiver of the chunk: last blocker leaf
   __shared__ uint16_t s_wguess[kWarpsPerBlock][kChunkWords];       // per word: last blocker leaf seen in it
   __shared__ uint32_t s_res[kWarpsPerBlock][kChunkWords];
   __shared__ int32_t s_wbase[kWarpsPerBlock][kChunkWords];         // first receiver slot of the word
   __shared__ int32_t s_wcnt[kWarpsPerBlock][kChunkWords];          // valid receivers in the word
   __shared__ int64_t s_waddr[kWarpsPerBlock][kChunkWords];         // where the word of own row 0 of the cluster is stored
-  __shared__ uint16_t s_fb[kWarpsPerBlock][64];                    // rays whose guess failed (receiver index)
-  // what the word's box walk learned when it did not prove the word (see box_reaches_leaf): the leaf it was run for,
-  // the first ancestor not passed by all rays (0x80 | .. = all rays leave the path there) and the splits before it
-  __shared__ uint16_t s_bleaf[kWarpsPerBlock][kChunkWords];
-  __shared__ uint8_t s_bfirst[kWarpsPerBlock][kChunkWords];
-  __shared__ unsigned long long s_bsplits[kWarpsPerBlock][kChunkWords];
+  __shared__ uint16_t s_fb[kWarpsPerBlock][64];                    // rays the cell proofs left open (receiver index)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1;
   const uint64_t warp0 = (uint64_t) blockIdx.x * kWarpsPerBlock + wid;
   const uint64_t nwarps = (uint64_t) gridDim.x * kWarpsPerBlock;
-  unsigned long long rays = 0, pairs = 0, visits_total = 0, fallbacks = 0, boxed = 0, shafted = 0;
+  unsigned long long rays = 0, pairs = 0, visits_total = 0, boxed = 0, shafted = 0;
   unsigned long long grazed = 0, uncelled = 0, wrong_guess = 0, grazed_other = 0, retested = 0, walked = 0;
   long long tk0 = 0, tk_box = 0, tk_pairs = 0, tk_guess = 0, tk_full = 0, tk_misc = 0;   // COUNT: warp cycles per phase
   for (uint64_t run = warp0; run < a.num_runs; run += nwarps) {
@@ -181,7 +179,6 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
     }
     for (int k = lane; k < kChunkWords * 32; k += 32) s_rguess[wid][k] = 0xffffu;   // new receivers: forget the guesses
     s_wguess[wid][lane] = 0xffffu;
-    s_bleaf[wid][lane] = 0xffffu;
     unsigned slice_proven = 0;      // words proven blocked for ALL sources of the current source slice
     __syncwarp();
   for (int r = 0; r < nrows; r++) {
@@ -196,50 +193,29 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
     const float4 sn = __ldg(a.s_normal + sslot);
     s_res[wid][lane] = 0;
     if (COUNT) { const long long t = clock64(); if (tk0) tk_misc += t - tk0; tk0 = t; }
-    // ---- (1) per word: proofs that settle all 32 receivers at once ----
+    // ---- (1) per word: proofs that settle all 32 receivers at once; (2a) the word-level sign test ----
     // every 32 rows the sources move on to the next slice: its two-sided proofs start afresh
     if ((r & 31) == 0) slice_proven = 0;
     bool proven = (slice_proven >> lane) & 1u;
     bool proven_now2 = false;
-    if (lane < nwc && !proven) {
+    int wclass = 0;   // 0: no receiver passes the sign test, 1: all do, 2: receiver by receiver
+    if (lane < nwc) {
       const int base = s_wbase[wid][lane];
+      const float4 bmn = __ldg(a.wbox_min + (base >> 5)), bmx = __ldg(a.wbox_max + (base >> 5));
       const int g = s_wguess[wid][lane];
-      s_bleaf[wid][lane] = 0xffffu;
-      if (g != 0xffff) {
+      if (!proven && g != 0xffff) {
         const float4 clo = __ldg(a.cell_lo + g), chi = __ldg(a.cell_hi + g);
-        const float4 bmn = __ldg(a.wbox_min + (base >> 5)), bmx = __ldg(a.wbox_max + (base >> 5));
         // (a) all 32 sources of the slice x all 32 receivers of the word
         if ((a.mode & 1) && shaft_blocked(clo, chi, a.margin, __ldg(a.wbox_min + (sslot >> 5)), __ldg(a.wbox_max + (sslot >> 5)), bmn, bmx))
           proven = proven_now2 = true;
         // (b) this source x all 32 receivers
         else if ((a.mode & 2) && shaft_blocked(clo, chi, a.margin, so, so, bmn, bmx))
           proven = true;
-        else if (a.mode & 8) {
-          const int p0 = __ldg(a.leaf_path_first + g), p1 = __ldg(a.leaf_path_first + g + 1);
-          int first;
-          unsigned long long splits;
-          const int rr = box_reaches_leaf(a.leaf_path + p0, p1 - p0, so, bmn, bmx, first, splits);
-          proven = rr == kBoxProven;
-          if (!proven) {
-            s_bleaf[wid][lane] = (uint16_t) g;
-            s_bfirst[wid][lane] = (uint8_t) (first | (rr == kBoxElsewhere ? 0x80 : 0));
-            s_bsplits[wid][lane] = splits;
-          }
-        }
       }
-    }
-    slice_proven |= __ballot_sync(0xffffffffu, proven_now2);
-    const unsigned proven_mask = __ballot_sync(0xffffffffu, proven);
-    __syncwarp();
-    if (COUNT) { const long long t = clock64(); tk_box += t - tk0; tk0 = t; }
-    // ---- (2) which pairs would the reference trace (qrad3.c:232-244)?  compaction of the unproven ones ----
-    // Word level first: when source and receivers have axial normals and the word's bounding box lies strictly on one
-    // side of the source along both normals' axes, the sign test has the same outcome for all 32 receivers (the
-    // coordinate differences are monotone in the receiver's coordinate): such a word costs one test, not 32 loads.
-    int wclass = 0;   // 0: no receiver passes, 1: all do, 2: receiver by receiver
-    if (lane < nwc) {
+      // When source and receivers have axial normals and the word's bounding box lies strictly on one side of the
+      // source along both normals' axes, the sign test has the same outcome for all 32 receivers (the coordinate
+      // differences are monotone in the receiver's coordinate): such a word costs one test, not 32 loads.
       wclass = 2;
-      const float4 bmn = __ldg(a.wbox_min + (s_wbase[wid][lane] >> 5)), bmx = __ldg(a.wbox_max + (s_wbase[wid][lane] >> 5));
       const int cs = (int) sn.w, cr = (int) bmn.w;
       if (cs != 0 && cr != 0) {
         const int ks = abs(cs) - 1, kr = abs(cr) - 1;
@@ -259,39 +235,15 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
         }
       }
     }
+    slice_proven |= __ballot_sync(0xffffffffu, proven_now2);
+    const unsigned proven_mask = __ballot_sync(0xffffffffu, proven);
     const unsigned all_mask = __ballot_sync(0xffffffffu, wclass == 1) & ~proven_mask;
     const unsigned each_mask = __ballot_sync(0xffffffffu, wclass == 2);
-    int n = 0;
-    for (unsigned todo = all_mask | each_mask; todo;) {
-      const int wi = __ffs(todo) - 1;
-      todo &= todo - 1;
-      bool want;
-      if ((each_mask >> wi) & 1u) {
-        const int rslot = s_wbase[wid][wi] + lane;
-        want = false;
-        if (lane < s_wcnt[wid][wi] && rslot != sslot) {
-          // receivers stream past L1, which holds the tree and the cells
-          const float4 po = __ldcg(a.s_origin_area + rslot), pn = __ldcg(a.s_normal + rslot);
-          bool positive;
-          const bool wants_ray = pair_wants_ray(so, sn, po, pn, positive);
-          pairs++;
-          if (wants_ray) {
-            rays++;
-            want = positive && !((proven_mask >> wi) & 1u);
-            if (COUNT && positive && !want) boxed++;
-          }
-        }
-      } else
-        want = lane < s_wcnt[wid][wi];
-      const unsigned m = __ballot_sync(0xffffffffu, want);
-      if (want) s_queue[wid][n + __popc(m & lt)] = (uint16_t) (wi * 32 + lane);
-      n += __popc(m);
-    }
     __syncwarp();
-    if (COUNT) { const long long t = clock64(); tk_pairs += t - tk0; tk0 = t; }
-    // ---- (3) guess walks, full walks for the rest ----
-    int fbn = 0;
-    auto full_batch = [&](const int cnt) {  // full TestLine for the first `cnt` entries of the fallback queue
+    if (COUNT) { const long long t = clock64(); tk_box += t - tk0; tk0 = t; }
+    // ---- (3) cell proofs per ray, full walks for the rest ----
+    int n = 0, fbn = 0;
+    auto full_batch = [&](const int cnt) {  // the first `cnt` entries of the fallback queue
       long long tf0 = 0;
       if (COUNT) tf0 = clock64();
       if (lane < cnt) {
@@ -328,57 +280,79 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
       __syncwarp();
       if (COUNT) tk_full += clock64() - tf0;
     };
-    for (int base = 0; base < n; base += 32) {
-      const int k = base + lane;
-      bool miss = false;
-      int cand = 0;
-      if (k < n) {
-        cand = s_queue[wid][k];
-        const int g = s_rguess[wid][cand];
-        miss = true;
-        int first = 0;
-        unsigned long long splits = 0;
-        if (g != 0xffff && g == s_bleaf[wid][cand >> 5]) {   // the word's box walk was about this very leaf
-          first = s_bfirst[wid][cand >> 5];
-          splits = s_bsplits[wid][cand >> 5];
-        }
-        if (g != 0xffff && !(first & 0x80)) {   // 0x80: no ray into this word reaches g; straight to the full walk
-          const float4 po = __ldcg(a.s_origin_area + s_wbase[wid][cand >> 5] + (cand & 31));
-          // (c) this ray alone: does it pass deep through the cell of the leaf that blocked this receiver last time,
-          // or of the leaf that blocked a neighbour of it most recently?
-          const int g2 = s_wguess[wid][cand >> 5];
-          if ((a.mode & 4) && (segment_through_cell(__ldg(a.cell_lo + g), __ldg(a.cell_hi + g), a.margin, so, po) ||
-                               (g2 != g && g2 != 0xffff &&
-                                segment_through_cell(__ldg(a.cell_lo + g2), __ldg(a.cell_hi + g2), a.margin, so, po)))) {
-            miss = false;
-            if (COUNT) shafted++;
-          } else if (a.mode & 16) {
-            const int p0 = __ldg(a.leaf_path_first + g), p1 = __ldg(a.leaf_path_first + g + 1);
-            unsigned visits = 0;
-            miss = !reaches_leaf<COUNT>(a.tree, a.leaf_path + p0, p1 - p0, so.x, so.y, so.z, po.x, po.y, po.z, visits,
-                                        first, splits);
-            if (COUNT) visits_total += visits;
+    auto drain = [&]() {   // stage (3) for the n pairs in the queue
+      long long td0 = 0;
+      if (COUNT) td0 = clock64();
+      for (int base = 0; base < n; base += 32) {
+        const int k = base + lane;
+        bool miss = false;
+        int cand = 0;
+        if (k < n) {
+          cand = s_queue[wid][k];
+          const int g = s_rguess[wid][cand], g2 = s_wguess[wid][cand >> 5];
+          miss = true;
+          if ((a.mode & 4) && (g != 0xffff || g2 != 0xffff)) {
+            const float4 po = __ldcg(a.s_origin_area + s_wbase[wid][cand >> 5] + (cand & 31));
+            // (c) this ray alone: does it pass deep through the cell of the leaf that blocked this receiver last time,
+            // or of the leaf that blocked a neighbour of it most recently?
+            if ((g != 0xffff && segment_through_cell(__ldg(a.cell_lo + g), __ldg(a.cell_hi + g), a.margin, so, po)) ||
+                (g2 != g && g2 != 0xffff &&
+                 segment_through_cell(__ldg(a.cell_lo + g2), __ldg(a.cell_hi + g2), a.margin, so, po))) {
+              miss = false;
+              if (COUNT) shafted++;
+            }
           }
         }
+        const unsigned m = __ballot_sync(0xffffffffu, miss);
+        if (miss) s_fb[wid][fbn + __popc(m & lt)] = (uint16_t) cand;
+        fbn += __popc(m);
+        __syncwarp();
+        if (fbn >= 32) {
+          full_batch(32);
+          uint16_t t = 0;
+          if (lane < fbn - 32) t = s_fb[wid][32 + lane];
+          __syncwarp();
+          if (lane < fbn - 32) s_fb[wid][lane] = t;
+          fbn -= 32;
+          __syncwarp();
+        }
       }
-      const unsigned m = __ballot_sync(0xffffffffu, miss);
-      if (COUNT && miss) fallbacks++;
-      if (miss) s_fb[wid][fbn + __popc(m & lt)] = (uint16_t) cand;
-      fbn += __popc(m);
+      n = 0;
+      if (COUNT) tk_guess += clock64() - td0;
+    };
+    // ---- (2b) receiver-by-receiver sign tests where needed, compaction ----
+    for (unsigned todo = all_mask | each_mask; todo;) {
+      const int wi = __ffs(todo) - 1;
+      todo &= todo - 1;
+      bool want;
+      if ((each_mask >> wi) & 1u) {
+        const int rslot = s_wbase[wid][wi] + lane;
+        want = false;
+        if (lane < s_wcnt[wid][wi] && rslot != sslot) {
+          // receivers stream past L1, which holds the tree and the cells
+          const float4 po = __ldcg(a.s_origin_area + rslot), pn = __ldcg(a.s_normal + rslot);
+          bool positive;
+          const bool wants_ray = pair_wants_ray(so, sn, po, pn, positive);
+          pairs++;
+          if (wants_ray) {
+            rays++;
+            want = positive && !((proven_mask >> wi) & 1u);
+            if (COUNT && positive && !want) boxed++;
+          }
+        }
+      } else
+        want = lane < s_wcnt[wid][wi];
+      const unsigned m = __ballot_sync(0xffffffffu, want);
+      if (want) s_queue[wid][n + __popc(m & lt)] = (uint16_t) (wi * 32 + lane);
+      n += __popc(m);
       __syncwarp();
-      if (fbn >= 32) {
-        full_batch(32);
-        uint16_t t = 0;
-        if (lane < fbn - 32) t = s_fb[wid][32 + lane];
-        __syncwarp();
-        if (lane < fbn - 32) s_fb[wid][lane] = t;
-        fbn -= 32;
-        __syncwarp();
-      }
+      if (n > kQueue - 32) drain();
     }
+    if (COUNT) { const long long t = clock64(); tk_pairs += t - tk0; tk0 = t; }
+    drain();
     if (fbn > 0) full_batch(fbn);
     __syncwarp();
-    if (COUNT) { const long long t = clock64(); tk_guess += t - tk0; tk0 = t; }
+    if (COUNT) { const long long t = clock64(); tk0 = t; }
     // consecutive rows of the run fill consecutive words of each column: L2 merges them into whole sectors
     if (lane < nwc) a.bits[s_waddr[wid][lane] + ownbase + r] = s_res[wid][lane];
     __syncwarp();
@@ -387,11 +361,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
   for (int o = 16; o; o >>= 1) {
     rays += __shfl_xor_sync(0xffffffffu, rays, o);
     pairs += __shfl_xor_sync(0xffffffffu, pairs, o);
-    if (COUNT) visits_total += __shfl_xor_sync(0xffffffffu, visits_total, o);
-    if (COUNT) fallbacks += __shfl_xor_sync(0xffffffffu, fallbacks, o);
-    if (COUNT) boxed += __shfl_xor_sync(0xffffffffu, boxed, o);
-    if (COUNT) shafted += __shfl_xor_sync(0xffffffffu, shafted, o);
     if (COUNT) {
+      visits_total += __shfl_xor_sync(0xffffffffu, visits_total, o);
+      boxed += __shfl_xor_sync(0xffffffffu, boxed, o);
+      shafted += __shfl_xor_sync(0xffffffffu, shafted, o);
       grazed += __shfl_xor_sync(0xffffffffu, grazed, o);
       uncelled += __shfl_xor_sync(0xffffffffu, uncelled, o);
       wrong_guess += __shfl_xor_sync(0xffffffffu, wrong_guess, o);
@@ -403,20 +376,18 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
   if (lane == 0) {
     atomicAdd(a.counters + 0, rays);
     atomicAdd(a.counters + 2, pairs);
-    if (COUNT) atomicAdd(a.counters + 1, visits_total);
-    if (COUNT) atomicAdd(a.counters + 3, walked);   // rays that took the full TestLine walk
-    if (COUNT) atomicAdd(a.counters + 4, boxed);
-    if (COUNT) atomicAdd(a.counters + 5, shafted);
     if (COUNT) {
+      atomicAdd(a.counters + 1, visits_total);
+      atomicAdd(a.counters + 3, walked);   // rays that took the full TestLine walk
+      atomicAdd(a.counters + 4, boxed);
+      atomicAdd(a.counters + 5, shafted);
       atomicAdd(a.counters + 6, grazed);
       atomicAdd(a.counters + 7, uncelled);
       atomicAdd(a.counters + 13, wrong_guess);
       atomicAdd(a.counters + 14, grazed_other);
       atomicAdd(a.counters + 15, retested);
-    }
-    if (COUNT) {
       atomicAdd(a.counters + 8, (unsigned long long) tk_box);
-      atomicAdd(a.counters + 9, (unsigned long long) tk_pairs);
+      atomicAdd(a.counters + 9, (unsigned long long) (tk_pairs - tk_guess));
       atomicAdd(a.counters + 10, (unsigned long long) (tk_guess - tk_full));
       atomicAdd(a.counters + 11, (unsigned long long) tk_full);
       atomicAdd(a.counters + 12, (unsigned long long) tk_misc);
@@ -1221,7 +1192,7 @@ __global__ void k_finish_bounce(int N, const int32_t *__restrict__ patch_slot, c
 }
 
 
-// slot-order copies of the patch geometry, and the bounding box of every slice's patch origins (box_reaches_leaf)
+// slot-order copies of the patch geometry, and the bounding box of every slice's patch origins (shaft_blocked)
 __global__ void k_slot_geometry(int M, const int32_t *__restrict__ slot_patch, const float4 *__restrict__ p_origin_area,
                                 const float4 *__restrict__ p_normal, float4 *__restrict__ s_origin_area,
                                 float4 *__restrict__ s_normal, float4 *__restrict__ box_min, float4 *__restrict__ box_max) {
@@ -1359,8 +1330,8 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   c->d_vis_cluster.upload(P.vis_cluster, st);
   c->d_vis_woff.upload(P.vis_woff, st);
   c->d_vis_seer.upload(P.vis_seer, st);
-  c->d_coff.upload(P.coff, st);
-  c->d_sbase.upload(P.sbase, st);
+  c->d_coff.upload(P.coff.data(), P.coff.size(), st);
+  c->d_sbase.upload(P.sbase.data(), P.sbase.size(), st);
   c->d_grp_first.upload(P.grp_first, st);
   c->d_grp_cluster.upload(P.grp_cluster, st);
   c->d_grp_slot0.upload(P.grp_slot0, st);
@@ -1409,8 +1380,6 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   if (runs) {
     VisArgs a{};
     a.tree = c->tree();
-    a.leaf_path = c->leaf_path.p;
-    a.leaf_path_first = c->leaf_path_first.p;
     a.wbox_min = c->wbox_min.p;
     a.wbox_max = c->wbox_max.p;
     a.s_origin_area = c->s_origin_area.p;
@@ -1646,6 +1615,16 @@ void transfers_columns(qrad_cuda_ctx *c) {
     }
     fprintf(stderr, "slices %d, list entries: mean %.0f, longest %d, longest in the first eighth %d\n", nslices,
             nslices ? (double) nzw / nslices : 0.0, mx, mx8);
+    for (int thr : {12000, 16000, 24000, 32000, 48000}) {
+      int cnt = 0;
+      int64_t ent = 0;
+      for (int s = 0; s < nslices; s++)
+        if (h_len[s] > thr) {
+          cnt++;
+          ent += h_len[s];
+        }
+      fprintf(stderr, "  lists longer than %d entries: %d slices, %.2f %% of all entries\n", thr, cnt, nzw ? 100.0 * ent / nzw : 0.0);
+    }
   }
   c->slice_base.upload(h_slice_base, st);
   {  // k_bounce hands this rank's slices to its warps longest list first
@@ -1683,7 +1662,7 @@ void transfers_columns(qrad_cuda_ctx *c) {
             hc[5], hc[6], hc[13], hc[14], hc[7], hc[15]);
     const double tot = (double) (hc[8] + hc[9] + hc[10] + hc[11] + hc[12]);
     if (tot > 0)
-      fprintf(stderr, "k_visibility warp cycles: box walks %.1f %%, pair tests %.1f %%, guess walks %.1f %%, full walks %.1f %%, "
+      fprintf(stderr, "k_visibility warp cycles: word proofs %.1f %%, sign tests %.1f %%, per-ray proofs %.1f %%, full walks %.1f %%, "
               "task set-up / stores %.1f %%\n", 100 * hc[8] / tot, 100 * hc[9] / tot, 100 * hc[10] / tot, 100 * hc[11] / tot, 100 * hc[12] / tot);
   }
   c->stats.rays_transfers = (int64_t) hc[0];
