@@ -413,9 +413,11 @@ struct qrad_cuda_ctx {
   qrad::DBuf<uint32_t> g_src;           // [entries] source slot
   qrad::DBuf<uint4> g_w;                // [entries/8][32] 8 u16 weights per lane
   qrad::DBuf<int32_t> slice_order;      // this rank's slices, longest list first (k_bounce work order)
-  qrad::DBuf<int32_t> bounce_next;      // [2] k_bounce work counters
+  qrad::DBuf<int32_t> coop_slices;      // the slices with the longest lists: work list of the block-cooperative role
+  int n_coop = 0, n_regular = 0;
+  qrad::DBuf<int32_t> bounce_next;      // [4] work counters of the bounce kernels
   qrad::DBuf<int32_t> negative_light;   // CheckPatches flag
-  int bounce_blocks_per_sm = 0, bounce_regs_blocks_per_sm = 0;
+  int bounce_blocks_per_sm = 0, bounce_regs_blocks_per_sm = 0, shard_blocks_per_sm = 0;
   bool transfers_done = false;
   int64_t total_transfers = 0;
   qrad::DBuf<unsigned long long> counters;

@@ -886,8 +886,7 @@ __device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t par
 // -fmad=false, which would change the rounding.)
 // Slices are handed out longest-first from a work counter (persistent warps): with one block per 8 consecutive
 // slices only 16 of 24 resident warps were alive on average (profiles/r01i_full_c5_k_bounce.txt).
-__global__ void __launch_bounds__(kThreads) k_bounce(const BounceArgs a) {
-  extern __shared__ __align__(128) unsigned char s_bounce[];
+__device__ __forceinline__ void bounce_ring_role(const BounceArgs &a, unsigned char *s_bounce, const int first_block) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   unsigned char *const wbase = s_bounce + wid * kBounceWarpBytes;
   float *const s_vec = reinterpret_cast<float *>(wbase + kBounceVecOfs);
@@ -897,7 +896,7 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const BounceArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.next[a.parity ^ 1] = 0;
+  if ((int) blockIdx.x == first_block && threadIdx.x == 0) a.next[a.parity ^ 1] = 0;
   const int nslices = a.slice_hi - a.slice_lo;
   uint32_t gb = 0;   // batches this warp has consumed so far: batch gb + i lives in buffer (gb + i) % stages
   for (;;) {
@@ -1006,6 +1005,11 @@ __global__ void __launch_bounds__(kThreads) k_bounce(const BounceArgs a) {
     if (a.rad_sum) a.rad_sum[slot] = rx + ry + rz;
     a.send_next[slot] = make_float4(rx / 65536.0f, ry / 65536.0f, rz / 65536.0f, 0.f);
   }
+}
+
+__global__ void __launch_bounds__(kThreads) k_bounce(const BounceArgs a) {
+  extern __shared__ __align__(128) unsigned char s_bounce[];
+  bounce_ring_role(a, s_bounce, 0);
 }
 
 // k_bounce with register prefetch instead of the bulk-copy ring: same arithmetic, same order; the weights of the next
@@ -1121,6 +1125,190 @@ __global__ void __launch_bounds__(kThreads) k_bounce_regs(const BounceArgs a) {
     if (a.rad_sum) a.rad_sum[slot] = rx + ry + rz;
     a.send_next[slot] = make_float4(rx / 65536.0f, ry / 65536.0f, rz / 65536.0f, 0.f);
   }
+}
+
+// ---- block-cooperative role for the few very long lists -------------------------------------------------------------
+// The sum of a receiver is a serial fold in source order, so a list cannot be split across warps -- but everything
+// EXCEPT the adds can: 7 producer warps take the batches of 32 entries in turn (batch b -> producer b mod 7), gather the
+// radiosity vectors, convert the weights and form the products send * weight exactly as k_bounce does, and park them in
+// shared memory; the consumer warp only waits for the next parked batch, pulls it into registers (24 LDS.128) and adds
+// it to the three running sums of its receiver in list order.  One warp on its own needs about 0.5 us per batch
+// (latency of the gathers and of the weight stream); the consumer's chain of dependent adds needs a fraction of that, so
+// the launch of a shard no longer lasts as long as its longest list (C5: 66 637 entries against a mean of 9 096;
+// DESIGN.md section 7).  Hand-over: one mbarrier pair (full / empty) per producer, one elected arrival each; a producer
+// parks one batch (four groups of 8 entries) and refills it as soon as the consumer has taken it, six batches of the
+// other producers later.  Two batches are in flight per producer (two register sets that swap roles), their source slots
+// are fetched three batches ahead.  Results are bit-identical to k_bounce: the same products (packed FMUL, rounded once),
+// added in the same order.
+constexpr int kCoopProducers = kWarpsPerBlock - 1;
+constexpr int kCoopGroupBytes = 6 * 32 * 16;                    // 8 entries x 3 channels x 32 lanes, as 6 float4 per lane
+constexpr int kCoopBarOfs = kCoopProducers * 4 * kCoopGroupBytes;                 // full[7], empty[7]
+constexpr int kCoopVecOfs = kCoopBarOfs + 128;                                    // parked vectors: [7][2][96] floats
+constexpr int kCoopSmemUsed = kCoopVecOfs + kCoopProducers * 2 * 96 * 4;
+constexpr int kShardSmemBytes = kCoopSmemUsed > kWarpsPerBlock * kBounceWarpBytes ? kCoopSmemUsed : kWarpsPerBlock * kBounceWarpBytes;
+
+__device__ __forceinline__ void mbar_arrive(const uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void bounce_coop_role(const BounceArgs &a, unsigned char *s_coop, const int32_t *__restrict__ coop_slices,
+                                                 const int ncoop, int32_t *__restrict__ coop_next) {
+  __shared__ int s_pick;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t sbase = smem_u32(s_coop);
+  const uint32_t bar_full = sbase + kCoopBarOfs, bar_empty = bar_full + kCoopProducers * 8;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < kCoopProducers; k++) {
+      mbar_init(bar_full + 8 * k, 1);
+      mbar_init(bar_empty + 8 * k, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) coop_next[a.parity ^ 1] = 0;
+  int uses = 0;   // consumer: lane p counts the batches taken from producer p; producer: the batches it has parked
+  constexpr int P = kCoopProducers;
+  for (;;) {
+    __syncthreads();   // everybody is done with the previous slice
+    if (threadIdx.x == 0) s_pick = atomicAdd(coop_next + a.parity, 1);
+    __syncthreads();
+    const int pick = s_pick;
+    if (pick >= ncoop) break;
+    const int slice = coop_slices[pick];
+    const int64_t base = a.slice_base[slice];
+    const int batches = (a.slice_len[slice] + 31) >> 5;
+    if (wid == 0) {
+      // ---- consumer: the serial adds, in list order ----
+      float ix = 0.f, iy = 0.f, iz = 0.f;
+      for (int b = 0; b < batches; b++) {
+        const int p = b % P;
+        const uint32_t par = (uint32_t) __shfl_sync(0xffffffffu, uses, p) & 1u;
+        if (lane == p) uses++;
+        mbar_wait(bar_full + 8 * p, par);
+        // the whole batch into registers first, so that the producer can refill at once and no add waits for shared memory
+        float4 v[4][6];
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          const float4 *grp = reinterpret_cast<const float4 *>(s_coop + (p * 4 + g) * kCoopGroupBytes) + lane;
+#pragma unroll
+          for (int k = 0; k < 6; k++) v[g][k] = grp[32 * k];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * p);
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          const float4 x0 = v[g][0], x1 = v[g][1], y0 = v[g][2], y1 = v[g][3], z0 = v[g][4], z1 = v[g][5];
+          ix = ix + x0.x; iy = iy + y0.x; iz = iz + z0.x;
+          ix = ix + x0.y; iy = iy + y0.y; iz = iz + z0.y;
+          ix = ix + x0.z; iy = iy + y0.z; iz = iz + z0.z;
+          ix = ix + x0.w; iy = iy + y0.w; iz = iz + z0.w;
+          ix = ix + x1.x; iy = iy + y1.x; iz = iz + z1.x;
+          ix = ix + x1.y; iy = iy + y1.y; iz = iz + z1.y;
+          ix = ix + x1.z; iy = iy + y1.z; iz = iz + z1.z;
+          ix = ix + x1.w; iy = iy + y1.w; iz = iz + z1.w;
+        }
+      }
+      // CollectLight, qrad3.c:383-409
+      const int slot = slice * 32 + lane;
+      const float4 ra = a.refl_area[slot];
+      float4 t = a.total[slot];
+      float rx = 0.f, ry = 0.f, rz = 0.f;
+      if (ra.w > 0) {  // not sky (and not a padding slot)
+        t.x += ix / ra.w;
+        t.y += iy / ra.w;
+        t.z += iz / ra.w;
+        rx = ix * ra.x;
+        ry = iy * ra.y;
+        rz = iz * ra.z;
+        a.total[slot] = t;
+      }
+      if (a.rad_sum) a.rad_sum[slot] = rx + ry + rz;
+      a.send_next[slot] = make_float4(rx / 65536.0f, ry / 65536.0f, rz / 65536.0f, 0.f);
+    } else {
+      // ---- producers: batch b = p, p + 7, ... ----
+      const int p = wid - 1;
+      float *const s_vec = reinterpret_cast<float *>(s_coop + kCoopVecOfs) + p * 2 * 96;
+      const uint32_t *ps = a.g_src + base + lane;
+      const uint4 *pw = a.g_w + (base >> 3) * 32 + lane;
+      uint4 wa0 = make_uint4(0, 0, 0, 0), wa1 = wa0, wa2 = wa0, wa3 = wa0, wb0 = wa0, wb1 = wa0, wb2 = wa0, wb3 = wa0;
+      float4 nxa = make_float4(0, 0, 0, 0), nxb = nxa;
+      uint32_t idx2 = 0;   // source slot of entry `lane` of the batch after the next two
+      if (p < batches) {
+        nxa = __ldg(a.send + __ldcs(ps + 32 * p));
+        const uint4 *q = pw + 128 * p;
+        wa0 = __ldcs(q); wa1 = __ldcs(q + 32); wa2 = __ldcs(q + 64); wa3 = __ldcs(q + 96);
+      }
+      if (p + P < batches) {
+        nxb = __ldg(a.send + __ldcs(ps + 32 * (p + P)));
+        const uint4 *q = pw + 128 * (p + P);
+        wb0 = __ldcs(q); wb1 = __ldcs(q + 32); wb2 = __ldcs(q + 64); wb3 = __ldcs(q + 96);
+      }
+      if (p + 2 * P < batches) idx2 = __ldcs(ps + 32 * (p + 2 * P));
+// entries 8G .. 8G+7 of the batch: weights WA (first four) and WB (last four), two 32-bit words each
+#define QRAD_COOP_GROUP(G, WA0, WA1, WB0, WB1)                                                                  \
+  do {                                                                                                           \
+    const float4 vxa = *reinterpret_cast<const float4 *>(sv + (G) * 8), vxb = *reinterpret_cast<const float4 *>(sv + (G) * 8 + 4); \
+    const float4 vya = *reinterpret_cast<const float4 *>(sv + 32 + (G) * 8), vyb = *reinterpret_cast<const float4 *>(sv + 32 + (G) * 8 + 4); \
+    const float4 vza = *reinterpret_cast<const float4 *>(sv + 64 + (G) * 8), vzb = *reinterpret_cast<const float4 *>(sv + 64 + (G) * 8 + 4); \
+    const float2 fa0 = u16x2_to_float2(WA0), fa1 = u16x2_to_float2(WA1), fb0 = u16x2_to_float2(WB0), fb1 = u16x2_to_float2(WB1); \
+    const float2 xa0 = __fmul2_rn(make_float2(vxa.x, vxa.y), fa0), xa1 = __fmul2_rn(make_float2(vxa.z, vxa.w), fa1);  \
+    const float2 xb0 = __fmul2_rn(make_float2(vxb.x, vxb.y), fb0), xb1 = __fmul2_rn(make_float2(vxb.z, vxb.w), fb1);  \
+    const float2 ya0 = __fmul2_rn(make_float2(vya.x, vya.y), fa0), ya1 = __fmul2_rn(make_float2(vya.z, vya.w), fa1);  \
+    const float2 yb0 = __fmul2_rn(make_float2(vyb.x, vyb.y), fb0), yb1 = __fmul2_rn(make_float2(vyb.z, vyb.w), fb1);  \
+    const float2 za0 = __fmul2_rn(make_float2(vza.x, vza.y), fa0), za1 = __fmul2_rn(make_float2(vza.z, vza.w), fa1);  \
+    const float2 zb0 = __fmul2_rn(make_float2(vzb.x, vzb.y), fb0), zb1 = __fmul2_rn(make_float2(vzb.z, vzb.w), fb1);  \
+    float4 *grp = reinterpret_cast<float4 *>(s_coop + (p * 4 + (G)) * kCoopGroupBytes) + lane;                   \
+    grp[0] = make_float4(xa0.x, xa0.y, xa1.x, xa1.y);                                                            \
+    grp[32] = make_float4(xb0.x, xb0.y, xb1.x, xb1.y);                                                           \
+    grp[64] = make_float4(ya0.x, ya0.y, ya1.x, ya1.y);                                                           \
+    grp[96] = make_float4(yb0.x, yb0.y, yb1.x, yb1.y);                                                           \
+    grp[128] = make_float4(za0.x, za0.y, za1.x, za1.y);                                                          \
+    grp[160] = make_float4(zb0.x, zb0.y, zb1.x, zb1.y);                                                          \
+  } while (0)
+// one batch: park the vectors V of batch B, refill V / W0..3 with batch B + 2P (its source slots are in idx2), fetch the
+// source slots of batch B + 3P, then form and park the products of the copies c0..3
+#define QRAD_COOP_BATCH(B, V, W0, W1, W2, W3)                                                                    \
+  do {                                                                                                           \
+    const int use = uses;                                                                                        \
+    float *const sv = s_vec + (use & 1) * 96;                                                                    \
+    sv[lane] = V.x;                                                                                              \
+    sv[32 + lane] = V.y;                                                                                         \
+    sv[64 + lane] = V.z;                                                                                         \
+    __syncwarp();                                                                                                \
+    const uint4 c0 = W0, c1 = W1, c2 = W2, c3 = W3;                                                              \
+    if ((B) + 2 * P < batches) {                                                                                 \
+      V = ld_vec_f4(a.send + idx2);                                                                              \
+      const uint4 *q = pw + 128 * ((B) + 2 * P);                                                                 \
+      W0 = ld_stream_u4(q); W1 = ld_stream_u4(q + 32); W2 = ld_stream_u4(q + 64); W3 = ld_stream_u4(q + 96);     \
+    }                                                                                                            \
+    if ((B) + 3 * P < batches) idx2 = ld_stream_u32(ps + 32 * ((B) + 3 * P));                                    \
+    /* the consumer must have taken this producer's previous batch */                                           \
+    if (use > 0) mbar_wait(bar_empty + 8 * p, (uint32_t) (use + 1) & 1u);                                        \
+    QRAD_COOP_GROUP(0, c0.x, c0.y, c0.z, c0.w);                                                                  \
+    QRAD_COOP_GROUP(1, c1.x, c1.y, c1.z, c1.w);                                                                  \
+    QRAD_COOP_GROUP(2, c2.x, c2.y, c2.z, c2.w);                                                                  \
+    QRAD_COOP_GROUP(3, c3.x, c3.y, c3.z, c3.w);                                                                  \
+    __syncwarp();                                                                                                \
+    if (lane == 0) mbar_arrive(bar_full + 8 * p);                                                                \
+    uses++;                                                                                                      \
+  } while (0)
+      for (int b = p; b < batches; b += 2 * P) {
+        QRAD_COOP_BATCH(b, nxa, wa0, wa1, wa2, wa3);
+        if (b + P < batches) QRAD_COOP_BATCH(b + P, nxb, wb0, wb1, wb2, wb3);
+      }
+#undef QRAD_COOP_BATCH
+#undef QRAD_COOP_GROUP
+    }
+  }
+}
+
+// One launch for a shard with very long lists: the first `coop_blocks` blocks take them block-cooperatively, the others
+// run the warp-per-slice ring on the rest.  One grid, so that the long lists start at once (a kernel on a second stream
+// only starts when the persistent blocks of the first leave room).
+__global__ void __launch_bounds__(kThreads, 2) k_bounce_shard(const BounceArgs a, const int32_t *__restrict__ coop_slices,
+                                                               const int ncoop, int32_t *__restrict__ coop_next, const int coop_blocks) {
+  extern __shared__ __align__(128) unsigned char s_shard[];
+  if ((int) blockIdx.x < coop_blocks) bounce_coop_role(a, s_shard, coop_slices, ncoop, coop_next);
+  else bounce_ring_role(a, s_shard, coop_blocks);
 }
 
 // serial float sum of rad_sum over PATCH order (CollectLight's `total`), one warp
@@ -1629,10 +1817,27 @@ void transfers_columns(qrad_cuda_ctx *c) {
   c->slice_base.upload(h_slice_base, st);
   {  // k_bounce hands this rank's slices to its warps longest list first
     std::vector<int32_t> order;
-    for (int s = lo; s < hi; s++) order.push_back(s);
+    int hi_work = hi;
+    if (const char *f = getenv("QRAD_DEBUG_BOUNCE_SHARD"))   // tools/bounce_shard_probe.py: the launches an n-GPU shard
+      hi_work = lo + std::max(1, (int) ((hi - lo) * atof(f)));   // would see, timed on one GPU (results are not lighting)
+    for (int s = lo; s < hi_work; s++) order.push_back(s);
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return h_len[x] > h_len[y]; });
-    if (order.empty()) order.push_back(0);
-    c->slice_order.upload(order, st);
+    // A launch cannot be shorter than ONE warp needs for the longest list (about 0.5 us per 32 entries).  Lists that
+    // would take a lone warp more than 0.8 of what the whole shard takes at full bandwidth go to block-cooperative
+    // blocks instead (none on one GPU with C5; the longest 2 % of the slices on an eighth of it).
+    int64_t own_entries = 0;
+    for (int s = lo; s < hi_work; s++) own_entries += (h_len[s] + 31) & ~31;
+    const double est_s = (double) own_entries * 68 / 6.0e12;
+    int64_t threshold = std::max<int64_t>(4096, (int64_t) (0.8 * est_s / 0.5e-6 * 32));
+    if (const char *e = getenv("QRAD_BOUNCE_COOP")) threshold = atoll(e);   // tests force it (0 = every slice)
+    std::vector<int32_t> coop, regular;
+    for (int32_t s : order) (h_len[s] > threshold ? coop : regular).push_back(s);
+    c->n_coop = (int) coop.size();
+    c->n_regular = (int) regular.size();
+    if (coop.empty()) coop.push_back(0);
+    if (regular.empty()) regular.push_back(0);
+    c->slice_order.upload(regular, st);
+    c->coop_slices.upload(coop, st);
   }
   // k_bounce prefetches without bounds checks: slots two batches, weights one batch past the end of a list
   c->g_src.alloc((size_t) c->sell_entries + 96);
@@ -1776,13 +1981,16 @@ void bounce_begin(qrad_cuda_ctx *c, bool want_sum) {
   c->rad_cur = c->rad_a.p;
   c->rad_nxt = c->rad_b.p;
   c->bounce_steps = 0;
-  c->bounce_next.alloc(2);
+  c->bounce_next.alloc(4);   // work counters of the warp-per-slice [0..1] and block-cooperative [2..3] roles, two parities each
   c->bounce_next.zero(st);
   c->negative_light.alloc(1);
   c->negative_light.zero(st);
   if (c->bounce_blocks_per_sm == 0) {
     int per_sm = 0;
     QCUDA(cudaFuncSetAttribute(k_bounce, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarpsPerBlock * kBounceWarpBytes));
+    QCUDA(cudaFuncSetAttribute(k_bounce_shard, cudaFuncAttributeMaxDynamicSharedMemorySize, kShardSmemBytes));
+    QCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce_shard, kThreads, kShardSmemBytes));
+    c->shard_blocks_per_sm = std::max(1, per_sm);
     QCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce, kThreads, kWarpsPerBlock * kBounceWarpBytes));
     c->bounce_blocks_per_sm = std::max(1, per_sm);
     QCUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce_regs, kThreads, 0));
@@ -1810,11 +2018,8 @@ void bounce_step(qrad_cuda_ctx *c) {
   a.next = c->bounce_next.p;
   a.parity = c->bounce_steps & 1;
   a.slice_cut = INT_MAX;
-  int nsl = a.slice_hi - a.slice_lo;
-  if (const char *f = getenv("QRAD_DEBUG_BOUNCE_SHARD")) {   // time the launch an n-GPU shard would see, on one GPU
-    nsl = std::max(1, (int) (nsl * atof(f)));
-    a.slice_cut = a.slice_lo + nsl;
-  }
+  const int nsl = c->n_regular + c->n_coop;
+  a.slice_hi = a.slice_lo + c->n_regular;   // the work list of the warp-per-slice role holds the slices without a very long list
   // persistent warps: as many blocks as fit on the chip, slices are drawn from the work counter
   const int want = std::max(1, (a.slice_hi - a.slice_lo + kWarpsPerBlock - 1) / kWarpsPerBlock);
   // CUDA events around every launch, read once at the end: no host synchronisation between bounces
@@ -1827,9 +2032,18 @@ void bounce_step(qrad_cuda_ctx *c) {
   // few slices per resident warp: the launch lasts as long as ONE warp needs for the longest list -> bulk-copy ring
   bool ring = (int64_t) nsl < (int64_t) 4 * c->sm_count * 40;
   if (const char *force = getenv("QRAD_BOUNCE_KERNEL")) ring = strcmp(force, "regs") != 0;   // tests cover both
-  if (ring) k_bounce<<<std::min(want, c->sm_count * c->bounce_blocks_per_sm), kThreads, kWarpsPerBlock * kBounceWarpBytes, st>>>(a);
-  else k_bounce_regs<<<std::min(want, c->sm_count * c->bounce_regs_blocks_per_sm), kThreads, 0, st>>>(a);
-  c->launch_check("k_bounce");
+  if (c->n_coop > 0) {
+    // a shard with very long lists: they go to block-cooperative blocks of the same launch
+    const int coop_blocks = std::min(c->n_coop, c->sm_count);
+    const int ring_blocks = c->n_regular > 0 ? std::max(0, std::min(want, c->sm_count * c->shard_blocks_per_sm - coop_blocks)) : 0;
+    k_bounce_shard<<<coop_blocks + ring_blocks, kThreads, kShardSmemBytes, st>>>(a, c->coop_slices.p, c->n_coop,
+                                                                               c->bounce_next.p + 2, coop_blocks);
+    c->launch_check("k_bounce_shard");
+  } else if (c->n_regular > 0) {
+    if (ring) k_bounce<<<std::min(want, c->sm_count * c->bounce_blocks_per_sm), kThreads, kWarpsPerBlock * kBounceWarpBytes, st>>>(a);
+    else k_bounce_regs<<<std::min(want, c->sm_count * c->bounce_regs_blocks_per_sm), kThreads, 0, st>>>(a);
+    c->launch_check("k_bounce");
+  }
   QCUDA(cudaEventRecord(c->bounce_ev[2 * c->bounce_steps + 1], st));
   c->bounce_steps++;
   std::swap(c->rad_cur, c->rad_nxt);   // rad_cur now holds the new radiosity (this rank's slots)
@@ -1849,6 +2063,9 @@ void bounce_end(qrad_cuda_ctx *c) {
   float kernel_ms = 0;
   for (int b = 0; b < c->bounce_steps; b++) kernel_ms += elapsed(c->bounce_ev[2 * b], c->bounce_ev[2 * b + 1]);
   c->stats.ms_bounce_kernel = c->bounce_steps > 0 ? kernel_ms / c->bounce_steps : 0;
+  if (getenv("QRAD_DEBUG_SLICES") && c->bounce_steps > 0)
+    fprintf(stderr, "bounce: %d slices warp-per-slice, %d slices block-cooperative, last launch %.3f ms\n", c->n_regular, c->n_coop,
+            elapsed(c->bounce_ev[2 * (c->bounce_steps - 1)], c->bounce_ev[2 * (c->bounce_steps - 1) + 1]));
   c->stats.ms_bounce = c->t_bounce.stop();
   c->stats.ms_x_radiosity = c->plan.world > 1 ? std::max(0.f, c->stats.ms_bounce - kernel_ms) : 0;
 }

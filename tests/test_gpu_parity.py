@@ -58,12 +58,18 @@ def test_lump_identical_to_reference(Q, case, tmp_path):
     assert hashlib.md5(bsp.read_bytes()).hexdigest() == meta["file_md5"]
 
 
-@pytest.mark.parametrize("kernel", ["regs", "ring"])
+@pytest.mark.parametrize("kernel", ["regs", "ring", "coop", "coop_some"])
 @pytest.mark.parametrize("case", ["samplec", "grid3_chop16", "manystyles"])
 def test_both_bounce_kernels(Q, case, kernel, tmp_path, monkeypatch):
-    """BounceLight has two kernels (register prefetch for many slices per warp, bulk-copy ring for few); the library
-    picks by problem size, QRAD_BOUNCE_KERNEL forces one.  Both must give the reference's bytes and energies."""
-    monkeypatch.setenv("QRAD_BOUNCE_KERNEL", kernel)
+    """BounceLight has three kernels (a warp per slice with register prefetch for many slices per warp or with a
+    bulk-copy ring for few, and a block-cooperative one for very long lists); the library picks by problem size,
+    QRAD_BOUNCE_KERNEL / QRAD_BOUNCE_COOP force a choice.  All must give the reference's bytes and energies."""
+    if kernel == "coop":
+        monkeypatch.setenv("QRAD_BOUNCE_COOP", "0")        # every slice with a non-empty list
+    elif kernel == "coop_some":
+        monkeypatch.setenv("QRAD_BOUNCE_COOP", "150")      # the longer lists only: both kernels side by side
+    else:
+        monkeypatch.setenv("QRAD_BOUNCE_KERNEL", kernel)
     meta, sc, dev, added, bsp = light(Q, case, tmp_path)
     assert sc.lighting() == (G.GOLDEN / (case + ".lump")).read_bytes()
     assert np.array_equal(added, np.array(meta["added"], np.float32))
