@@ -106,6 +106,7 @@ int qrad_cuda_create(int device, qrad_cuda_ctx **out) {
 
 void qrad_cuda_destroy(qrad_cuda_ctx *c) {
   if (!c) return;
+  if (c->plan_future.valid()) c->plan_future.wait();
   cudaSetDevice(c->device);
   cudaStream_t s = c->stream, x = c->xstream;
   if (s) cudaStreamSynchronize(s);
@@ -170,6 +171,8 @@ int qrad_cuda_set_count_nodes(qrad_cuda_ctx *c, int enable) {
 int qrad_cuda_upload_bsp(qrad_cuda_ctx *c, const qrad_bsp_view *b) {
   return guarded([&] {
     QCUDA(cudaSetDevice(c->device));
+    if (c->plan_future.valid()) c->plan_future.wait();   // a plan under construction reads the old PVS
+    c->plan_future = {};
     Timer t;
     t.start(c->stream);
     if (b->numnodes <= 0 || b->numleafs <= 0) dfail("Empty map");
@@ -348,6 +351,20 @@ int qrad_cuda_upload_patches(qrad_cuda_ctx *c, const qrad_patches_view *p) {
     c->d_radiosity.alloc((size_t) n * 3);
     c->d_radiosity.zero(c->stream);
     c->sync("upload_patches");
+    if (c->have_vis && c->numclusters > 0) {   // plan of the PVS-mode transfer matrix, in the background
+      if (c->plan_future.valid()) c->plan_future.wait();
+      const int world = c->world, rank = c->rank, nc = c->numclusters, pw = c->pvs_words;
+      const uint32_t *pvs = c->h_pvs.data();   // stays put until the next upload_bsp, which waits for this task
+      std::vector<int32_t> eff(c->h_cluster);
+      bool ok = true;
+      for (int cl : eff) ok = ok && cl < nc;
+      if (ok)
+        c->plan_future = std::async(std::launch::async, [eff = std::move(eff), n, nc, pvs, pw, world, rank]() {
+          auto p = std::make_shared<TransferPlan>();
+          build_plan(*p, n, eff.data(), nc, pvs, pw, world, rank, 0);
+          return p;
+        });
+    }
     c->stats.num_patches = n;
     c->transfers_done = c->facelights_done = false;
   });

@@ -8,6 +8,8 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <future>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -134,12 +136,14 @@ __device__ __forceinline__ float axis_pick(const int type, const float x, const 
 // front, the same predicate as `front > -0.1f`, and `front < ON_EPSILON` the same as
 // `front < 0.1f` (-0.1f < -0.1 and 0.1f > 0.1; checked exhaustively around the constants).
 // Returns 0 (clear) or 1 (blocked); *blocker, when given, receives the solid leaf that ended the walk.
+// `node0`: where to start.  Any node that the walk from the root provably reaches with the UNCLIPPED segment will do
+// (common_start_node() below): the nodes above it only pass the segment on.
 template <int STACK, bool COUNT>
 __device__ __forceinline__ int test_line(const Tree tree, float sx, float sy, float sz, float ex, float ey, float ez,
-                                         unsigned &visits, int *blocker = nullptr) {
+                                         unsigned &visits, int *blocker = nullptr, const int node0 = 0) {
   float4 stack[STACK];
   int sp = 0;
-  int node = 0;
+  int node = node0;
   for (;;) {
     while (node >= 0) {
       const int4 nd = __ldg(tree.nodes + node);
@@ -189,6 +193,32 @@ __device__ __forceinline__ int test_line(const Tree tree, float sx, float sy, fl
     ex = t.y;
     ey = t.z;
     ez = t.w;
+  }
+}
+
+// The deepest node that TestLine_r(0, s, e) reaches with the unclipped segment for EVERY s in box A and e in box B:
+// while both boxes lie on one side of the node's (axial) plane far enough that every segment passes the same one-sided
+// test of trace.c:124-128, the walk just descends.  `coordinate - dist` is one rounded subtraction, monotone in the
+// coordinate, so the box ends bound front / back of every segment exactly, with the very predicates test_line uses:
+//   first test  (front > -0.1f && back > -0.1f) for all  <=>  both box minima pass it            -> child 0
+//   second test (front <  0.1f && back <  0.1f) for all, and the first test fails for all: guaranteed when additionally
+//   one whole box lies at or below -0.1 (then front or back of every segment fails the first test)  -> child 1
+// Starting the walk there instead of at the root changes no result.
+__device__ __forceinline__ int common_start_node(const Tree tree, const float4 amn, const float4 amx, const float4 bmn,
+                                                 const float4 bmx) {
+  int node = 0;
+  for (;;) {
+    const int4 nd = __ldg(tree.nodes + node);
+    if (nd.y >= 3) return node;
+    const float dist = __int_as_float(nd.x);
+    const float a0 = axis_pick(nd.y, amn.x, amn.y, amn.z) - dist, a1 = axis_pick(nd.y, amx.x, amx.y, amx.z) - dist;
+    const float b0 = axis_pick(nd.y, bmn.x, bmn.y, bmn.z) - dist, b1 = axis_pick(nd.y, bmx.x, bmx.y, bmx.z) - dist;
+    int next;
+    if (a0 > -0.1f && b0 > -0.1f) next = nd.z;
+    else if (a1 < 0.1f && b1 < 0.1f && (!(a1 > -0.1f) || !(b1 > -0.1f))) next = nd.w;
+    else return node;
+    if (next < 0) return node;   // a leaf: let the walk itself read it
+    node = next;
   }
 }
 
@@ -390,6 +420,9 @@ struct qrad_cuda_ctx {
 
   // ---- transfer matrix (qrad_cuda_make_transfers): geometry in plan.hpp ----
   qrad::TransferPlan plan;
+  // the plan only needs the patch clusters and the PVS: upload_patches starts it on a host thread, so that it is ready
+  // when make_transfers asks for it (it runs beside the other uploads and BuildFacelights)
+  std::future<std::shared_ptr<qrad::TransferPlan>> plan_future;
   int M = 0;                            // number of slots (= plan.M)
   qrad::DBuf<int32_t> slot_patch, patch_slot, slot_cluster, slice_count, d_cl_slot_start, d_cl_count, d_nwords;
   qrad::DBuf<uint8_t> slot_flags;

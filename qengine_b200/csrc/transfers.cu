@@ -114,7 +114,8 @@ struct VisArgs {
   unsigned long long *counters;   // [0] rays, [1] node visits, [2] candidate pairs
   const float4 *cell_lo, *cell_hi;   // [numleafs] leaf cells (shaft_blocked)
   float margin;                   // how deep inside a solid cell a segment must pass to count as proven blocked
-  int mode;                       // bit 0: slice x word cell proofs, 1: source x word cell proofs, 2: per-ray cell proofs
+  int mode;                       // bit 0: slice x word cell proofs, 1: source x word cell proofs, 2: per-ray cell proofs,
+                                  // 5: walks start at the node all rays of (source slice, word) reach unclipped
 };
 
 // One warp lights one run = the rows of one row group (<= 128 consecutive source patches of one cluster) against one
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
   __shared__ int32_t s_wcnt[kWarpsPerBlock][kChunkWords];          // valid receivers in the word
   __shared__ int64_t s_waddr[kWarpsPerBlock][kChunkWords];         // where the word of own row 0 of the cluster is stored
   __shared__ uint16_t s_fb[kWarpsPerBlock][64];                    // rays the cell proofs left open (receiver index)
+  __shared__ uint16_t s_wstart[kWarpsPerBlock][kChunkWords];       // where the walks of (current source slice, word) may start
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1;
   const uint64_t warp0 = (uint64_t) blockIdx.x * kWarpsPerBlock + wid;
@@ -195,7 +197,17 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
     if (COUNT) { const long long t = clock64(); if (tk0) tk_misc += t - tk0; tk0 = t; }
     // ---- (1) per word: proofs that settle all 32 receivers at once; (2a) the word-level sign test ----
     // every 32 rows the sources move on to the next slice: its two-sided proofs start afresh
-    if ((r & 31) == 0) slice_proven = 0;
+    if ((r & 31) == 0) {
+      slice_proven = 0;
+      if (a.mode & 32) {   // the node every ray of (this source slice, word) reaches unclipped: their walks start there
+        s_wstart[wid][lane] = 0;
+        if (lane < nwc)
+          s_wstart[wid][lane] = (uint16_t) common_start_node(a.tree, __ldg(a.wbox_min + (sslot >> 5)), __ldg(a.wbox_max + (sslot >> 5)),
+                                                             __ldg(a.wbox_min + (s_wbase[wid][lane] >> 5)),
+                                                             __ldg(a.wbox_max + (s_wbase[wid][lane] >> 5)));
+        __syncwarp();
+      }
+    }
     bool proven = (slice_proven >> lane) & 1u;
     bool proven_now2 = false;
     int wclass = 0;   // 0: no receiver passes the sign test, 1: all do, 2: receiver by receiver
@@ -261,7 +273,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
           leaf = gw;
           if (COUNT) retested++;
         } else {
-          blocked = test_line<STACK, COUNT>(a.tree, so.x, so.y, so.z, po.x, po.y, po.z, visits, &leaf);
+          blocked = test_line<STACK, COUNT>(a.tree, so.x, so.y, so.z, po.x, po.y, po.z, visits, &leaf,
+                                            (a.mode & 32) ? (int) s_wstart[wid][cand >> 5] : 0);
           if (COUNT) walked++;
         }
         if (COUNT) visits_total += visits;
@@ -1482,16 +1495,30 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   // (PvsForOrigin fails for them, qrad3.c:208-209).  That case is one pseudo cluster holding everybody.
   const int nc = nopvs ? 1 : c->numclusters;
   {
-    std::vector<int32_t> eff((size_t) N);
-    for (int i = 0; i < N; i++) {
-      const int cl = c->h_cluster[i];
-      if (cl >= c->numclusters) dfail("patch %d has cluster %d >= numclusters %d", i, cl, c->numclusters);
-      eff[i] = nopvs ? 0 : cl;
+    bool have = false;
+    if (c->plan_future.valid()) {   // started by upload_patches
+      try {
+        std::shared_ptr<TransferPlan> p = c->plan_future.get();
+        if (!nopvs && p->N == N && p->world == c->world && p->rank == c->rank && p->nc == nc) {
+          c->plan = std::move(*p);
+          have = true;
+        }
+      } catch (const std::exception &e) {
+        dfail("%s", e.what());
+      }
     }
-    try {
-      build_plan(c->plan, N, eff.data(), nc, nopvs ? nullptr : c->h_pvs.data(), c->pvs_words, c->world, c->rank, 0);
-    } catch (const std::exception &e) {
-      dfail("%s", e.what());
+    if (!have) {
+      std::vector<int32_t> eff((size_t) N);
+      for (int i = 0; i < N; i++) {
+        const int cl = c->h_cluster[i];
+        if (cl >= c->numclusters) dfail("patch %d has cluster %d >= numclusters %d", i, cl, c->numclusters);
+        eff[i] = nopvs ? 0 : cl;
+      }
+      try {
+        build_plan(c->plan, N, eff.data(), nc, nopvs ? nullptr : c->h_pvs.data(), c->pvs_words, c->world, c->rank, 0);
+      } catch (const std::exception &e) {
+        dfail("%s", e.what());
+      }
     }
   }
   const TransferPlan &P = c->plan;
@@ -1591,7 +1618,7 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
       const float ulp = std::max(extent, 1.f) * 1.2e-7f;
       a.margin = 0.1f + std::max(0.15f, 300.f * ulp);
     }
-    a.mode = 2 | 4;
+    a.mode = 2 | 4 | 32;
     if (const char *e = getenv("QRAD_VIS_MODE")) a.mode = atoi(e);
     const uint64_t want_blocks = (runs + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const int blocks = (int) std::max<uint64_t>(1, std::min<uint64_t>(want_blocks, (uint64_t) c->sm_count * 8));
