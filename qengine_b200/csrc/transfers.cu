@@ -884,9 +884,9 @@ __device__ __forceinline__ void mbar_wait(const uint32_t bar, const uint32_t par
 // illumination[j][l] += send[l] * trans->transfer (qrad3.c:439), mul and add rounded separately.  A zero weight adds
 // +-0 and leaves the sum unchanged (the sum starts at +0 and never becomes -0).
 // Data movement: the list is consumed in batches of 32 entries = 2 KB of weights + 128 B of source slots, contiguous
-// in HBM.  Each warp owns a ring of three batch buffers in shared memory; lane 0 refills a buffer with two bulk async
-// copies (cp.async.bulk, completion counted on an mbarrier) as soon as the warp has consumed it, so two batches are
-// always in flight per warp without holding a register, and the radiosity vectors of the next batch are gathered while
+// in HBM.  Each warp owns a ring of four batch buffers (kBounceStages) in shared memory; lane 0 refills a buffer with two
+// bulk async copies (cp.async.bulk, completion counted on an mbarrier) as soon as the warp has consumed it, so three batches
+// are always in flight per warp without holding a register, and the radiosity vectors of the next batches are gathered while
 // the current one is summed.  This matters when a GPU has few slices (8-GPU shard: 3 900 slices on 148 SMs): the
 // kernel then lasts as long as its longest list, i.e. as fast as ONE warp can stream (the register-prefetch version
 // took 2.0 ms for 2.5 GB per GPU at 8 GPUs because ptxas sinks the loads next to their use).
