@@ -1855,7 +1855,9 @@ void transfers_columns(qrad_cuda_ctx *c) {
     int64_t own_entries = 0;
     for (int s = lo; s < hi_work; s++) own_entries += (h_len[s] + 31) & ~31;
     const double est_s = (double) own_entries * 68 / 6.0e12;
-    int64_t threshold = std::max<int64_t>(4096, (int64_t) (0.8 * est_s / 0.5e-6 * 32));
+    double factor = 0.8;
+    if (const char *e = getenv("QRAD_BOUNCE_COOP_FACTOR")) factor = atof(e);   // tools/bounce_shard_probe.py sweeps it
+    int64_t threshold = std::max<int64_t>(4096, (int64_t) (factor * est_s / 0.5e-6 * 32));
     if (const char *e = getenv("QRAD_BOUNCE_COOP")) threshold = atoll(e);   // tests force it (0 = every slice)
     std::vector<int32_t> coop, regular;
     for (int32_t s : order) (h_len[s] > threshold ? coop : regular).push_back(s);

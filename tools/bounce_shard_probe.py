@@ -25,12 +25,16 @@ with tempfile.TemporaryDirectory() as tmp:
     dev.build_facelights(p.extrasamples, p.numbounce)
     fracs = [float(x) for x in os.environ.get("PROBE_SHARDS", "1,0.5,0.25,0.125").split(",")]
     for frac in fracs:
-        for variant in ("warp", "warp+coop"):
+        variants = ["warp", "warp+coop"] + ["warp+coop:" + f for f in os.environ.get("PROBE_FACTORS", "").split(",") if f]
+        for variant in variants:
             os.environ["QRAD_DEBUG_BOUNCE_SHARD"] = str(frac)
+            os.environ.pop("QRAD_BOUNCE_COOP_FACTOR", None)
             if variant == "warp":
                 os.environ["QRAD_BOUNCE_COOP"] = "1000000000"
             else:
                 os.environ.pop("QRAD_BOUNCE_COOP", None)
+                if ":" in variant:
+                    os.environ["QRAD_BOUNCE_COOP_FACTOR"] = variant.split(":")[1]
             dev.make_transfers(p.nopvs)      # the work lists are chosen here
             full = dev.stats()["transfer_bytes"]
             dev.bounce(4, want_added=False)
