@@ -196,6 +196,28 @@ int64_t qrad_plan_word_address(const qrad_plan *plan, int32_t source_slot, int32
 int  qrad_plan_column_list(const qrad_plan *plan, int32_t slice, int32_t *slots, int32_t *owner, int64_t *addr_in_piece,
                            int64_t capacity, int64_t *count);
 
+/* ---- host builds of the walkers (no GPU needed): the device functions of qengine_b200/csrc/walkers.cuh -- TestLine,
+   PointInLeaf, the common start node of a bundle of rays, the cell proofs that settle rays without a walk -- compiled for
+   the host from the same source, over the same flattened tree qrad_cuda_upload_bsp builds.  For tests: they can be held
+   against the reference's golden rays and against each other without a GPU.  Not a CPU fallback: nothing in the library
+   calls them. ---- */
+typedef struct qrad_host_tree qrad_host_tree;
+const char *qrad_host_tree_last_error(void);
+int  qrad_host_tree_create(const qrad_bsp_view *bsp, qrad_host_tree **out);
+void qrad_host_tree_destroy(qrad_host_tree *tree);
+/* out[0] nodes, [1] leafs, [2] depth, [3] solid leaves that have a box cell; *extent = largest axial plane distance */
+int  qrad_host_tree_info(const qrad_host_tree *tree, int32_t *out4, float *extent);
+int  qrad_host_test_lines(const qrad_host_tree *tree, int64_t n, const float *starts, const float *stops,
+                          const int32_t *start_nodes /*or NULL*/, uint8_t *results, int32_t *blockers /*or NULL*/);
+int  qrad_host_point_in_leaf(const qrad_host_tree *tree, int64_t n, const float *points, int32_t *leafs);
+int  qrad_host_common_start_node(const qrad_host_tree *tree, const float *amn, const float *amx, const float *bmn, const float *bmx);
+/* per segment: the first leaf in [leaf_lo, leaf_hi) whose cell proves it blocked, or -1 (margin <= 0: the library's own) */
+int  qrad_host_prove_segments(const qrad_host_tree *tree, float margin, int64_t n, const float *starts, const float *stops,
+                              int32_t leaf_lo, int32_t leaf_hi, int32_t *proving_leaf);
+/* the first leaf whose cell proves ALL segments from box A to box B blocked, or -1 */
+int  qrad_host_prove_boxes(const qrad_host_tree *tree, float margin, const float *amn, const float *amx, const float *bmn,
+                           const float *bmx);
+
 /* ---- inspection (parity tests, multi-GPU exchange); not needed by a production host ---- */
 int  qrad_cuda_get_stats(qrad_cuda_ctx *ctx, qrad_cuda_stats *out);
 /* numtransfers per patch (patch->numtransfers). */

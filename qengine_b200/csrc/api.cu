@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "bsp_flat.hpp"
 #include "comm.hpp"
 #include "qrad_device.cuh"
 
@@ -175,109 +176,23 @@ int qrad_cuda_upload_bsp(qrad_cuda_ctx *c, const qrad_bsp_view *b) {
     c->plan_future = {};
     Timer t;
     t.start(c->stream);
-    if (b->numnodes <= 0 || b->numleafs <= 0) dfail("Empty map");
-    if (b->numnodes > 65536 || b->numleafs > 65536) dfail("BSP exceeds MAX_MAP_NODES / MAX_MAP_LEAFS");
-    std::vector<int4> flat((size_t) b->numnodes);
-    std::vector<float4> normals((size_t) b->numnodes);
-    std::vector<int32_t> contents(b->numleafs), cluster(b->numleafs);
-    for (int i = 0; i < b->numleafs; i++) {
-      contents[i] = b->leafs[i].contents;
-      cluster[i] = b->leafs[i].cluster;
+    FlatBsp flat;
+    try {
+      flatten_bsp(b, flat);
+    } catch (const std::exception &e) {
+      dfail("%s", e.what());
     }
-    // breadth-first numbering: queue of (disk node, depth); children get consecutive new indices
-    std::vector<int> order, depth_of, newidx((size_t) b->numnodes, -1);
-    order.push_back(0);
-    depth_of.push_back(1);
-    newidx[0] = 0;
-    int maxdepth = 0;
-    for (size_t q = 0; q < order.size(); q++) {
-      const int dn_i = order[q];
-      if (depth_of[q] > maxdepth) maxdepth = depth_of[q];
-      const qrad_dnode_t &dn = b->nodes[dn_i];
-      for (int k = 0; k < 2; k++) {
-        const int ch = dn.children[k];
-        if (ch < 0) continue;
-        if (ch >= b->numnodes) dfail("node index %d out of range", ch);
-        if (newidx[ch] >= 0) dfail("BSP node %d reached twice (not a tree)", ch);
-        newidx[ch] = (int) order.size();
-        order.push_back(ch);
-        depth_of.push_back(depth_of[q] + 1);
-      }
-    }
-    const int next_new = (int) order.size();
-    for (int me = 0; me < next_new; me++) {
-      const qrad_dnode_t &dn = b->nodes[order[me]];
-      if (dn.planenum < 0 || dn.planenum >= b->numplanes) dfail("plane index %d out of range", dn.planenum);
-      const qrad_dplane_t &pl = b->planes[dn.planenum];
-      int child[2];
-      for (int k = 0; k < 2; k++) {
-        const int ch = dn.children[k];
-        if (ch < 0) {
-          const int leaf = -ch - 1;
-          if (leaf >= b->numleafs) dfail("leaf index %d out of range", leaf);
-          child[k] = kLeafFlag | ((contents[leaf] & 1) ? kSolidBit : 0) | leaf;
-        } else
-          child[k] = newidx[ch];
-      }
-      int distbits;
-      memcpy(&distbits, &pl.dist, 4);
-      flat[me] = make_int4(distbits, pl.type, child[0], child[1]);
-      normals[me] = make_float4(pl.normal[0], pl.normal[1], pl.normal[2], pl.dist);
-    }
-    // parent links in the new numbering, for the cells of the leaves
-    {
-      std::vector<int> parent((size_t) next_new, -1), pside((size_t) next_new, 0);
-      std::vector<int> lparent((size_t) b->numleafs, -1), lside((size_t) b->numleafs, 0);
-      for (int me = 0; me < next_new; me++) {
-        const int ch[2] = {flat[me].z, flat[me].w};
-        for (int k = 0; k < 2; k++) {
-          if (ch[k] >= 0) {
-            parent[ch[k]] = me;
-            pside[ch[k]] = k;
-          } else {
-            lparent[ch[k] & kLeafMask] = me;
-            lside[ch[k] & kLeafMask] = k;
-          }
-        }
-      }
-      // cells of the leaves: a leaf whose ancestors are all axial planes is the box between the tightest of them
-      // (shaft_blocked() in qrad_device.cuh); lo.w = 1 marks a SOLID leaf with such a cell
-      std::vector<float4> cell_lo((size_t) b->numleafs), cell_hi((size_t) b->numleafs);
-      float extent = 0;
-      for (int l = 0; l < b->numleafs; l++) {
-        float lo[3] = {-1e30f, -1e30f, -1e30f}, hi[3] = {1e30f, 1e30f, 1e30f};
-        bool axial = true;
-        int node = lparent[l], sd = lside[l];
-        while (node >= 0) {
-          const int type = flat[node].y;
-          float dist;
-          memcpy(&dist, &flat[node].x, 4);
-          if (type < 3) {
-            if (sd == 0) lo[type] = std::max(lo[type], dist);   // child 0 = in front of the plane
-            else hi[type] = std::min(hi[type], dist);
-            extent = std::max(extent, fabsf(dist));
-          } else
-            axial = false;
-          sd = pside[node];
-          node = parent[node];
-        }
-        const bool solid = (contents[l] & 1) != 0;
-        cell_lo[l] = make_float4(lo[0], lo[1], lo[2], (axial && solid) ? 1.f : 0.f);
-        cell_hi[l] = make_float4(hi[0], hi[1], hi[2], 0.f);
-      }
-      c->leaf_cell_lo.upload(cell_lo, c->stream);
-      c->leaf_cell_hi.upload(cell_hi, c->stream);
-      c->bsp_extent = extent;
-    }
-    if (maxdepth > kTraceStackBig) dfail("BSP depth %d exceeds the supported trace stack (%d)", maxdepth, kTraceStackBig);
-    c->numnodes = next_new;
+    if (flat.depth > kTraceStackBig) dfail("BSP depth %d exceeds the supported trace stack (%d)", flat.depth, kTraceStackBig);
+    c->numnodes = (int) flat.nodes.size();
     c->numleafs = b->numleafs;
-    c->tree_depth = maxdepth;
-    c->nodes.upload(flat.data(), (size_t) next_new, c->stream);
-    c->node_normals.upload(normals.data(), (size_t) next_new, c->stream);
-    c->leaf_contents.upload(contents, c->stream);
-    c->leaf_cluster.upload(cluster, c->stream);
-
+    c->tree_depth = flat.depth;
+    c->bsp_extent = flat.extent;
+    c->nodes.upload(flat.nodes, c->stream);
+    c->node_normals.upload(flat.normals, c->stream);
+    c->leaf_contents.upload(flat.leaf_contents, c->stream);
+    c->leaf_cluster.upload(flat.leaf_cluster, c->stream);
+    c->leaf_cell_lo.upload(flat.cell_lo, c->stream);
+    c->leaf_cell_hi.upload(flat.cell_hi, c->stream);
     c->have_vis = b->visdatasize > 0;
     c->numclusters = 0;
     c->h_pvs.clear();
@@ -290,7 +205,7 @@ int qrad_cuda_upload_bsp(qrad_cuda_ctx *c, const qrad_bsp_view *b) {
       c->pvs.upload(c->h_pvs, c->stream);
     }
     c->sync("upload_bsp");
-    c->stats.tree_depth = maxdepth;
+    c->stats.tree_depth = c->tree_depth;
     c->stats.num_clusters = c->numclusters;
     c->stats.ms_upload = t.stop();
     c->transfers_done = c->facelights_done = false;

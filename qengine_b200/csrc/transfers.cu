@@ -35,6 +35,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "bsp_flat.hpp"
 #include "comm.hpp"
 #include "qrad_device.cuh"
 
@@ -1612,12 +1613,7 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
     a.counters = c->counters.p;
     a.cell_lo = c->leaf_cell_lo.p;
     a.cell_hi = c->leaf_cell_hi.p;
-    {
-      // ON_EPSILON + slack for the rounding of the clip points (<= ~2 ulp of the largest coordinate per split)
-      const float extent = std::max(c->bsp_extent, c->patch_extent);
-      const float ulp = std::max(extent, 1.f) * 1.2e-7f;
-      a.margin = 0.1f + std::max(0.15f, 300.f * ulp);
-    }
+    a.margin = proof_margin(std::max(c->bsp_extent, c->patch_extent));
     a.mode = 2 | 4 | 32;
     if (const char *e = getenv("QRAD_VIS_MODE")) a.mode = atoi(e);
     const uint64_t want_blocks = (runs + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -1850,12 +1846,12 @@ void transfers_columns(qrad_cuda_ctx *c) {
     for (int s = lo; s < hi_work; s++) order.push_back(s);
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return h_len[x] > h_len[y]; });
     // A launch cannot be shorter than ONE warp needs for the longest list (about 0.5 us per 32 entries).  Lists that
-    // would take a lone warp more than 0.8 of what the whole shard takes at full bandwidth go to block-cooperative
+    // would take a lone warp more than 0.7 of what the whole shard takes at full bandwidth go to block-cooperative
     // blocks instead (none on one GPU with C5; the longest 2 % of the slices on an eighth of it).
     int64_t own_entries = 0;
     for (int s = lo; s < hi_work; s++) own_entries += (h_len[s] + 31) & ~31;
     const double est_s = (double) own_entries * 68 / 6.0e12;
-    double factor = 0.8;
+    double factor = 0.7;
     if (const char *e = getenv("QRAD_BOUNCE_COOP_FACTOR")) factor = atof(e);   // tools/bounce_shard_probe.py sweeps it
     int64_t threshold = std::max<int64_t>(4096, (int64_t) (factor * est_s / 0.5e-6 * 32));
     if (const char *e = getenv("QRAD_BOUNCE_COOP")) threshold = atoll(e);   // tests force it (0 = every slice)

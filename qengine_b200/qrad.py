@@ -404,6 +404,64 @@ def rad_world(scene: Scene, dev: Device, params: HostParams, want_added: bool = 
     return added[:max(params.numbounce, 0)]
 
 
+class HostTree:
+    """Host builds of the device walkers (include/qrad_cuda.h, qrad_host_tree_*): TestLine, PointInLeaf, the common start
+    node and the cell proofs compiled for the CPU from the same source as the kernels' -- for tests, not a fallback."""
+
+    def __init__(self, scene: Scene):
+        L = lib()
+        L.qrad_host_tree_last_error.restype = C.c_char_p
+        L.qrad_host_tree_destroy.restype = None
+        bv = BspView()
+        L.qrad_host_bsp_view(scene._h, C.byref(bv))
+        self._scene = scene          # the view points into the scene's lumps
+        self._h = C.c_void_p()
+        if L.qrad_host_tree_create(C.byref(bv), C.byref(self._h)):
+            raise QradError(L.qrad_host_tree_last_error().decode(errors="replace"))
+        info = (C.c_int32 * 4)()
+        ext = C.c_float()
+        L.qrad_host_tree_info(self._h, info, C.byref(ext))
+        self.numnodes, self.numleafs, self.depth, self.celled_solid_leafs = list(info)
+        self.extent = ext.value
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().qrad_host_tree_destroy(self._h)
+            self._h = None
+
+    def test_lines(self, starts, stops, start_nodes=None):
+        starts = np.ascontiguousarray(starts, np.float32)
+        stops = np.ascontiguousarray(stops, np.float32)
+        n = len(starts)
+        res = np.zeros(n, np.uint8)
+        blk = np.zeros(n, np.int32)
+        sn = None if start_nodes is None else _ip(np.ascontiguousarray(start_nodes, np.int32))
+        lib().qrad_host_test_lines(self._h, C.c_int64(n), _fp(starts), _fp(stops), sn, res.ctypes.data_as(c_u8), _ip(blk))
+        return res, blk
+
+    def point_in_leaf(self, pts):
+        pts = np.ascontiguousarray(pts, np.float32)
+        out = np.zeros(len(pts), np.int32)
+        lib().qrad_host_point_in_leaf(self._h, C.c_int64(len(pts)), _fp(pts), _ip(out))
+        return out
+
+    def common_start_node(self, amn, amx, bmn, bmx):
+        a = [np.ascontiguousarray(x, np.float32) for x in (amn, amx, bmn, bmx)]
+        return lib().qrad_host_common_start_node(self._h, *[_fp(x) for x in a])
+
+    def prove_segments(self, starts, stops, margin=0.0, leaf_lo=0, leaf_hi=1 << 30):
+        starts = np.ascontiguousarray(starts, np.float32)
+        stops = np.ascontiguousarray(stops, np.float32)
+        out = np.zeros(len(starts), np.int32)
+        lib().qrad_host_prove_segments(self._h, C.c_float(margin), C.c_int64(len(starts)), _fp(starts), _fp(stops),
+                                       C.c_int32(leaf_lo), C.c_int32(min(leaf_hi, self.numleafs)), _ip(out))
+        return out
+
+    def prove_boxes(self, amn, amx, bmn, bmx, margin=0.0):
+        a = [np.ascontiguousarray(x, np.float32) for x in (amn, amx, bmn, bmx)]
+        return lib().qrad_host_prove_boxes(self._h, C.c_float(margin), *[_fp(x) for x in a])
+
+
 def join_communicator(dev: Device, rank: int, world: int):
     """Make `dev` rank `rank` of a `world`-GPU communicator (one process per GPU, launched by torchrun): rank 0 creates the
     NCCL id inside the library and torch.distributed only carries its 128 bytes to the other ranks.  Afterwards the same
