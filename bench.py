@@ -206,6 +206,8 @@ def main():
     torch.cuda.set_device(local_rank)
 
     p = Q.params_from_flags(flags)
+    # host threads of the set-up (the tool's own -threads flag): the ranks of one box share its cores
+    p.threads = max(1, min(64, (os.cpu_count() or 8) // max(1, world)))
     tmp = Path(tempfile.mkdtemp(prefix="qrad_bench_"))
     try:
         bsp = stage_workload(args.workload, tmp)
@@ -270,6 +272,12 @@ def main():
             st["rays_direct"] = int(t[2].item())
         rays = st["rays_transfers"] + st["rays_direct"]
         value = rays / (step_ms * 1e-3)
+        trace_by_rank = None
+        if world > 1:   # pass 1 is the bulk of the step: how evenly did it divide?
+            tr = torch.tensor([float(np.mean(trace_ms))], device="cuda", dtype=torch.float64)
+            allr = [torch.zeros_like(tr) for _ in range(world)]
+            dist.all_gather(allr, tr)
+            trace_by_rank = [round(float(x.item()), 1) for x in allr]
 
         # ---- end to end: what `qrad3 map.bsp` does, files and host buffers, every copy inside the timed region ----
         e2e_times, e2e_parts, h2d, d2h = [], [], 0, 0
@@ -336,7 +344,7 @@ def main():
             "s_per_map": step_ms * 1e-3,
             "phase_ms": dict(zip(["facelights", "transfers", "bounce", "final"], [float(x) for x in np.mean(phase, axis=0)])),
             "exchange_ms": {k: st[k] for k in ("ms_x_matrix", "ms_x_small", "ms_x_radiosity")} if world > 1 else None,
-            "trace_kernel_ms": tr_ms,
+            "trace_kernel_ms": tr_ms, "trace_kernel_ms_by_rank": trace_by_rank,
             "transfers_breakdown_ms": {k: st[k] for k in ("ms_tr_setup", "ms_transfers_trace", "ms_tr_lists", "ms_tr_rows", "ms_tr_columns")},
             "trace_rays_per_s": st["rays_transfers"] / (tr_ms * 1e-3) if tr_ms > 0 else None,
             "wall_s_per_step": wall / args.steps,

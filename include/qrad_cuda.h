@@ -220,6 +220,9 @@ int  qrad_host_prove_boxes(const qrad_host_tree *tree, float margin, const float
 
 /* ---- inspection (parity tests, multi-GPU exchange); not needed by a production host ---- */
 int  qrad_cuda_get_stats(qrad_cuda_ctx *ctx, qrad_cuda_stats *out);
+/* pass 1 of make_transfers as rank `rank` of `world` would run it, alone on this GPU and without any exchange: time and
+   rays of that rank's share (load-balance measurements without the ranks); the context is left without transfers */
+int  qrad_cuda_trace_shard(qrad_cuda_ctx *ctx, int nopvs, int rank, int world, float *trace_ms, int64_t *rays);
 /* numtransfers per patch (patch->numtransfers). */
 int  qrad_cuda_download_numtransfers(qrad_cuda_ctx *ctx, int32_t *out /*[N]*/);
 /* All transfer rows in the reference's order (by source patch, receivers ascending): row_ptr[N+1],

@@ -108,6 +108,7 @@ int qrad_cuda_create(int device, qrad_cuda_ctx **out) {
 void qrad_cuda_destroy(qrad_cuda_ctx *c) {
   if (!c) return;
   if (c->plan_future.valid()) c->plan_future.wait();
+  if (c->groups_future.valid()) c->groups_future.wait();
   cudaSetDevice(c->device);
   cudaStream_t s = c->stream, x = c->xstream;
   if (s) cudaStreamSynchronize(s);
@@ -225,8 +226,12 @@ int qrad_cuda_upload_patches(qrad_cuda_ctx *c, const qrad_patches_view *p) {
     if (n <= 0) dfail("no patches");
     c->N = n;
     c->numfaces_p = p->numfaces;
+    if (c->groups_future.valid()) c->groups_future.wait();
+    c->groups_future = {};
     c->h_cluster.assign(p->cluster, p->cluster + n);
     c->h_sky.assign(p->sky, p->sky + n);
+    c->h_next.assign(p->next, p->next + n);
+    c->h_face_head.assign(p->face_head, p->face_head + p->numfaces);
     for (int i = 0; i < n; i++) {
       if (p->face[i] < 0 || p->face[i] >= p->numfaces) dfail("patch %d has bad face %d", i, p->face[i]);
       if (p->next[i] < -1 || p->next[i] >= n) dfail("patch %d has bad next %d", i, p->next[i]);
@@ -326,6 +331,8 @@ int qrad_cuda_upload_faces(qrad_cuda_ctx *c, const qrad_faces_view *f) {
     int nf = f->numfaces;
     if (nf <= 0) dfail("no faces");
     if (c->N && nf != c->numfaces_p) dfail("faces view has %d faces, patches view %d", nf, c->numfaces_p);
+    if (c->groups_future.valid()) c->groups_future.wait();
+    c->groups_future = {};
     c->F = nf;
     c->h_lit.assign(f->lit, f->lit + nf);
     c->h_texsize.assign(f->texsize, f->texsize + (size_t) nf * 2);
@@ -361,6 +368,8 @@ int qrad_cuda_upload_faces(qrad_cuda_ctx *c, const qrad_faces_view *f) {
     c->f_luxel_first.upload(c->h_luxel_first, c->stream);
     c->luxel_face.upload(lface, c->stream);
     c->sync("upload_faces");
+    if (c->N > 0 && (int) c->h_face_head.size() == nf)   // the plane groups FinalLightFace will need, in the background
+      c->groups_future = std::async(std::launch::async, [c] { return compute_plane_groups(c); });
     c->stats.num_luxels = c->num_luxels;
     c->facelights_done = false;
   });
@@ -392,6 +401,33 @@ int qrad_cuda_make_transfers(qrad_cuda_ctx *c, int nopvs, int64_t *total_transfe
     QCUDA(cudaSetDevice(c->device));
     make_transfers_impl(c, nopvs);
     if (total_transfer) *total_transfer = c->total_transfers;
+  });
+}
+
+// Pass 1 of MakeTransfers as rank `rank` of `world` would run it, alone on this GPU (no exchange follows): how the
+// visibility work of a map divides over ranks can be measured without the ranks (tools/trace_balance.py).
+int qrad_cuda_trace_shard(qrad_cuda_ctx *c, int nopvs, int rank, int world, float *trace_ms, int64_t *rays) {
+  return guarded([&] {
+    QCUDA(cudaSetDevice(c->device));
+    if (c->comm) dfail("trace_shard: this context is part of a communicator");
+    if (world < 1 || rank < 0 || rank >= world) dfail("bad rank %d of %d", rank, world);
+    const int r0 = c->rank, w0 = c->world;
+    c->rank = rank;
+    c->world = world;
+    try {
+      transfers_trace(c, nopvs);
+    } catch (...) {
+      c->rank = r0;
+      c->world = w0;
+      throw;
+    }
+    c->rank = r0;
+    c->world = w0;
+    unsigned long long hc[16];
+    c->counters.download(hc, 16, c->stream);
+    if (trace_ms) *trace_ms = c->stats.ms_transfers_trace;
+    if (rays) *rays = (int64_t) hc[0];
+    c->transfers_done = false;
   });
 }
 

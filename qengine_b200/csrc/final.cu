@@ -416,6 +416,37 @@ __global__ void __launch_bounds__(kWarps * 32) k_final(const FinalArgs a) {
 
 }  // namespace
 
+// plane groups: the chain FinalLightFace walks from planelinks[side][planenum] (lightmap.c:1123); it stops at face index 0,
+// so face 0 never contributes (appendix C).  Pure host work on what was uploaded.
+std::shared_ptr<qrad_cuda_ctx::PlaneGroups> compute_plane_groups(const qrad_cuda_ctx *c) {
+  auto pg = std::make_shared<qrad_cuda_ctx::PlaneGroups>();
+  const int F = c->F;
+  pg->group_of_face.assign((size_t) F, -1);
+  pg->group_first.assign(1, 0);
+  std::map<int32_t, int32_t> group_of_head;
+  for (int f = 0; f < F; f++) {
+    if (!c->h_lit[f]) continue;
+    const int head = c->h_planelink_head[f];
+    auto it = group_of_head.find(head);
+    if (it == group_of_head.end()) {
+      const int g = (int) pg->group_first.size() - 1;
+      int guard = 0;
+      for (int pf = head; pf; pf = c->h_facelinks[pf]) {
+        if (pf < 0 || pf >= F || ++guard > F) {
+          pg->error = "corrupt plane face links";
+          return pg;
+        }
+        for (int pt = c->h_face_head[pf]; pt >= 0; pt = c->h_next[pt]) pg->group_patch.push_back(pt);
+      }
+      pg->group_first.push_back((int32_t) pg->group_patch.size());
+      it = group_of_head.emplace(head, g).first;
+    }
+    pg->group_of_face[f] = it->second;
+  }
+  if (pg->group_patch.empty()) pg->group_patch.push_back(0);
+  return pg;
+}
+
 void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out, int32_t cap, int32_t *size,
                       int32_t *lightofs_out, uint8_t *styles_out) {
   if (!c->facelights_done) dfail("final_light: build_facelights has not run");
@@ -451,7 +482,6 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
 
   // plane groups: the chain FinalLightFace walks from planelinks[side][planenum] (lightmap.c:1123); it stops
   // at face index 0, so face 0 never contributes (appendix C)
-  std::vector<int32_t> group_of_face(F, -1), group_first{0}, group_patch;
   // device buffers live in the context so that repeated calls reuse the allocations
   DBuf<int32_t> &d_group_of_face = c->fin_i32[0], &d_group_first = c->fin_i32[1], &d_group_patch = c->fin_i32[2],
                 &tri_count = c->fin_i32[3], &tri_points = c->fin_i32[4];
@@ -460,29 +490,14 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
   std::vector<int64_t> h_tri_first(F + 1, 0);
   int pmax = 1;
   if (p->numbounce > 0) {
-    std::vector<int32_t> h_next((size_t) c->N), h_head((size_t) F);
-    c->p_next.download(h_next.data(), h_next.size(), st);
-    c->face_head.download(h_head.data(), h_head.size(), st);
-    std::map<int32_t, int32_t> group_of_head;
-    for (int f = 0; f < F; f++) {
-      if (!c->h_lit[f]) continue;
-      const int head = c->h_planelink_head[f];
-      auto it = group_of_head.find(head);
-      if (it == group_of_head.end()) {
-        const int g = (int) group_first.size() - 1;
-        int guard = 0;
-        for (int pf = head; pf; pf = c->h_facelinks[pf]) {
-          if (pf < 0 || pf >= F || ++guard > F) dfail("corrupt plane face links");
-          for (int pt = h_head[pf]; pt >= 0; pt = h_next[pt]) group_patch.push_back(pt);
-        }
-        group_first.push_back((int32_t) group_patch.size());
-        it = group_of_head.emplace(head, g).first;
-      }
-      group_of_face[f] = it->second;
-    }
+    std::shared_ptr<qrad_cuda_ctx::PlaneGroups> pg;
+    if (c->groups_future.valid()) pg = c->groups_future.get();   // started by upload_faces
+    else pg = compute_plane_groups(c);
+    c->groups_future = {};
+    if (!pg->error.empty()) dfail("%s", pg->error.c_str());
+    std::vector<int32_t> &group_of_face = pg->group_of_face, &group_first = pg->group_first, &group_patch = pg->group_patch;
     d_group_of_face.upload(group_of_face, st);
     d_group_first.upload(group_first, st);
-    if (group_patch.empty()) group_patch.push_back(0);
     d_group_patch.upload(group_patch, st);
     tri_count.alloc((size_t) F);
     PointArgs pa{};

@@ -190,10 +190,12 @@ void build_plan(TransferPlan &p, int N, const int32_t *eff, int nc, const uint32
   const int G = (int) p.grp_cluster.size();
   p.grp_owner.assign(G, 0);
   if (world > 1) {
-    // dealt in `chunks` contiguous chunks per rank of (nearly) equal candidate words, chunk j -> rank j mod world: every
-    // rank samples the whole map (the cost of a candidate word varies over the map) and still only touches about
-    // 1 / world of the clusters, so its lists and pass 2 shrink with the rank count
-    int chunks = owner_chunks > 0 ? owner_chunks : 8;
+    // dealt in `chunks` contiguous chunks per rank of (nearly) equal candidate words, chunk j -> rank j mod world.  The
+    // cost of a candidate word varies over the map (it is the clear rays inside a room that are walked), so the chunks
+    // are small -- a couple of row groups: measured on C5 at 8 ranks (tools/trace_balance.py) the slowest rank is 12-14 %
+    // above the mean with 8-128 chunks per rank and 4.7 % with 512.  Every rank then owns rows in most clusters; its
+    // row lists cover them all, which costs a few milliseconds.
+    int chunks = owner_chunks > 0 ? owner_chunks : 512;
     if (const char *e = getenv("QRAD_OWNER_CHUNKS")) chunks = std::max(1, atoi(e));
     double total = 0;
     for (int g = 0; g < G; g++) total += (double) p.grp_rows[g] * p.nwords[p.grp_cluster[g]];

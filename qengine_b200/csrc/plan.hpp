@@ -15,7 +15,7 @@
 //            the slices [lo, hi) of another rank is ONE contiguous piece of its buffer: the exchange before pass 3 is
 //            an all-to-all of contiguous pieces, with no packing.
 // Receiver slices are owned in contiguous runs [slice_lo[r], slice_hi[r]) balanced by candidate sources; row groups
-// are dealt to the ranks in several contiguous chunks each, balanced by candidate words.
+// are dealt to the ranks in many small contiguous chunks each, balanced by candidate words.
 #pragma once
 #include <cstdint>
 #include <memory>

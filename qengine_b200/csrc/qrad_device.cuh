@@ -240,6 +240,15 @@ struct qrad_cuda_ctx {
   cudaStream_t xstream = nullptr;       // the matrix exchange runs beside the lists and pass 2
   int face_lo = 0, face_hi = 0;         // faces this rank lights (all of them on one GPU)
 
+  // ---- plane groups of FinalLightFace: for every lit face the patches of all faces on its plane chain, in chain order
+  // (lightmap.c:1123-1134).  Host work that depends on the uploads only: upload_faces starts it on a host thread. ----
+  struct PlaneGroups {
+    std::vector<int32_t> group_of_face, group_first, group_patch;
+    std::string error;
+  };
+  std::vector<int32_t> h_next, h_face_head;        // patch->next, face_patches[] as uploaded
+  std::future<std::shared_ptr<PlaneGroups>> groups_future;
+
   // ---- FinalLightFace scratch (per resident warp) ----
   qrad::DBuf<uint16_t> fin_matrix, fin_ep0, fin_ep1, fin_tedges, fin_stack;
   qrad::DBuf<int16_t> fin_etri;
@@ -269,6 +278,7 @@ struct qrad_cuda_ctx {
 namespace qrad {
 // implemented in the phase translation units
 void face_range(qrad_cuda_ctx *c);
+std::shared_ptr<qrad_cuda_ctx::PlaneGroups> compute_plane_groups(const qrad_cuda_ctx *c);
 void build_facelights_impl(qrad_cuda_ctx *c, int extrasamples, int numbounce);
 void make_transfers_impl(qrad_cuda_ctx *c, int nopvs);
 void bounce_impl(qrad_cuda_ctx *c, int numbounce, float *added_out);

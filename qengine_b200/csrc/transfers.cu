@@ -153,12 +153,17 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
   __shared__ uint16_t s_wstart[kWarpsPerBlock][kChunkWords];       // where the walks of (current source slice, word) may start
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1;
-  const uint64_t warp0 = (uint64_t) blockIdx.x * kWarpsPerBlock + wid;
-  const uint64_t nwarps = (uint64_t) gridDim.x * kWarpsPerBlock;
   unsigned long long rays = 0, pairs = 0, visits_total = 0, boxed = 0, shafted = 0;
   unsigned long long grazed = 0, uncelled = 0, wrong_guess = 0, grazed_other = 0, retested = 0, walked = 0;
   long long tk0 = 0, tk_box = 0, tk_pairs = 0, tk_guess = 0, tk_full = 0, tk_misc = 0;   // COUNT: warp cycles per phase
-  for (uint64_t run = warp0; run < a.num_runs; run += nwarps) {
+  for (;;) {
+    // runs are drawn from a counter: their cost varies by an order of magnitude (a run whose words are all proven costs
+    // a few microseconds, one inside a room with thousands of clear rays a millisecond), and a shard has only ~20 runs
+    // per resident warp -- with a fixed stride the last warps set the kernel time (8 ranks: 31 % more warp time than 1)
+    unsigned long long run = 0;
+    if (lane == 0) run = atomicAdd(a.counters + 16, 1ull);
+    run = __shfl_sync(0xffffffffu, run, 0);
+    if (run >= a.num_runs) break;
     // ---- decode the run: row group, chunk ----
     int lo = 0, hi = a.n_own_groups;
     while (hi - lo > 1) {
@@ -1586,7 +1591,7 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   }
   const int64_t W = P.rowbuf_words();
   c->bits.alloc((size_t) W + 1);
-  c->counters.alloc(16);
+  c->counters.alloc(24);   // [0..15] statistics of k_visibility, [16] its run counter
   c->counters.zero(st);
   c->sync("make_transfers set-up");
   c->stats.ms_tr_setup = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
@@ -1632,7 +1637,7 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   // several GPUs: while this rank goes on with its lists and pass 2, every peer receives the contiguous piece of the
   // row buffer that describes its receiver slices (second stream; pass 3 waits for it)
   c->stats.ms_x_matrix = 0;
-  if (P.world > 1) {
+  if (P.world > 1 && c->comm) {   // (no communicator: qrad_cuda_trace_shard times a hypothetical rank's pass 1 on its own)
     const NcclApi &n = nccl();
     int64_t recv_total = 0;
     c->piece_first.assign(P.world, 0);
