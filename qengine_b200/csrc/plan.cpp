@@ -68,7 +68,7 @@ int64_t TransferPlan::column_offset(int q, int d, int slot) const {
 
 void build_plan(TransferPlan &p, int N, const int32_t *eff, int nc, const uint32_t *pvs, int pvs_words, int world, int rank,
                 int owner_chunks) {
-  if (world < 1 || rank < 0 || rank >= world) pfail("bad rank / world");
+  if (world < 1 || world > 64 || rank < 0 || rank >= world) pfail("bad rank / world");
   if (nc <= 0) pfail("make_transfers: no clusters");
   const bool timing = getenv("QRAD_DEBUG_TIMING") != nullptr;
   auto tp = std::chrono::steady_clock::now();
@@ -190,7 +190,7 @@ void build_plan(TransferPlan &p, int N, const int32_t *eff, int nc, const uint32
   const int G = (int) p.grp_cluster.size();
   p.grp_owner.assign(G, 0);
   if (world > 1) {
-    // dealt in `chunks` contiguous chunks per rank of (nearly) equal candidate words, chunk j -> rank j mod world.  The
+    // dealt in `chunks` contiguous chunks per rank of (nearly) equal candidate words, shuffled among the ranks.  The
     // cost of a candidate word varies over the map (it is the clear rays inside a room that are walked), so the chunks
     // are small -- a couple of row groups: measured on C5 at 8 ranks (tools/trace_balance.py) the slowest rank is 12-14 %
     // above the mean with 8-128 chunks per rank and 4.7 % with 512.  Every rank then owns rows in most clusters; its
@@ -206,7 +206,18 @@ void build_plan(TransferPlan &p, int N, const int32_t *eff, int nc, const uint32
       const double w = (double) p.grp_rows[g] * p.nwords[p.grp_cluster[g]];
       int ch = (int) ((cum + 0.5 * w) / per);
       ch = std::max(0, std::min(nchunks - 1, ch));
-      p.grp_owner[g] = ch % world;
+      // every `world` consecutive chunks go to the `world` ranks in a pseudo-random order of their own (a rotation would
+      // alias with the 3-4 row groups a cluster has: the first group of a cluster is not like its last)
+      const int block = ch / world, pos = ch % world;
+      uint32_t h = (uint32_t) block * 2654435761u + 0x9e3779b9u;
+      int perm[64];
+      for (int k = 0; k < world; k++) perm[k] = k;
+      for (int k = world - 1; k > 0; k--) {   // Fisher-Yates with an LCG
+        h = h * 1664525u + 1013904223u;
+        const int j = (int) ((h >> 8) % (uint32_t) (k + 1));
+        std::swap(perm[k], perm[j]);
+      }
+      p.grp_owner[g] = perm[pos];
       cum += w;
     }
   }

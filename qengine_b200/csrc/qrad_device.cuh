@@ -201,15 +201,17 @@ struct qrad_cuda_ctx {
   int M = 0;                            // number of slots (= plan.M)
   qrad::DBuf<int32_t> slot_patch, patch_slot, slot_cluster, slice_count, d_cl_slot_start, d_cl_count, d_nwords;
   qrad::DBuf<uint8_t> slot_flags;
-  qrad::DBuf<int64_t> d_wb_first, d_sbase, d_own_runbase, wbase;
+  qrad::DBuf<int64_t> d_wb_first, d_sbase, wbase;
   qrad::DBuf<int32_t> wslice, d_vis_ptr, d_vis_cluster, d_vis_woff, d_vis_seer, d_vis_src, d_coff;
-  qrad::DBuf<int32_t> d_grp_first, d_grp_cluster, d_grp_slot0, d_grp_rows, d_grp_owner, d_grp_ownbase, d_own_groups;
+  qrad::DBuf<int32_t> d_grp_first, d_grp_cluster, d_grp_slot0, d_grp_rows, d_grp_owner, d_grp_ownbase;
   qrad::DBuf<int32_t> d_rowslice_slot0, d_rowslice_row0;
   qrad::DBuf<float4> s_origin_area, s_normal, wbox_min, wbox_max;
   qrad::DBuf<uint32_t> bits;            // this rank's rows of the visibility*formfactor>0 bit matrix, slice-major
   qrad::DBuf<uint32_t> colbuf;          // several GPUs: the other ranks' words about this rank's slices
   std::vector<int64_t> piece_first;     // [world] where rank q's piece starts in colbuf
   qrad::DBuf<int2> d_runs;              // the patch order as runs of consecutive slots
+  qrad::DBuf<int4> d_run_list;          // pass 1: this rank's (row group, chunk, first row, rows) runs in the order the warps draw them
+  int64_t num_runs = 0;
   qrad::DBuf<int64_t> d_vl_ptr, d_vr_ptr;
   qrad::DBuf<int4> vl, vr;              // row / column run lists (transfers.cu)
   qrad::DBuf<float> row_total;          // [M]

@@ -106,9 +106,7 @@ struct VisArgs {
   const float4 *wbox_min, *wbox_max;  // [M/32] bounding box of the patch origins of each slice
   const float4 *s_origin_area, *s_normal;
   Geo g;
-  const int32_t *own_groups;      // this rank's row groups ...
-  const int64_t *own_runbase;     // ... and the prefix of their chunk counts: run r = (group, chunk)
-  int n_own_groups;
+  const int4 *run_list;           // this rank's runs = (row group, chunk, first row, rows), the expensive ones first
   const int32_t *grp_cluster, *grp_slot0, *grp_rows, *grp_ownbase;
   uint64_t num_runs;
   uint32_t *bits;
@@ -164,19 +162,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
     if (lane == 0) run = atomicAdd(a.counters + 16, 1ull);
     run = __shfl_sync(0xffffffffu, run, 0);
     if (run >= a.num_runs) break;
-    // ---- decode the run: row group, chunk ----
-    int lo = 0, hi = a.n_own_groups;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if ((uint64_t) a.own_runbase[mid] <= run) lo = mid; else hi = mid;
-    }
-    const int grp = a.own_groups[lo];
-    const int chunk = (int) (run - (uint64_t) a.own_runbase[lo]);
+    const int4 rc = __ldg(a.run_list + run);
+    const int grp = rc.x, chunk = rc.y;
     const int c = a.grp_cluster[grp];
     const int nw = a.g.nwords[c];
     const int w0 = chunk * kChunkWords;
     const int nwc = min(kChunkWords, nw - w0);
-    const int slot0 = a.grp_slot0[grp], nrows = a.grp_rows[grp], ownbase = a.grp_ownbase[grp];
+    const int slot0 = a.grp_slot0[grp], row_lo = rc.z, row_hi = rc.z + rc.w, ownbase = a.grp_ownbase[grp];
     __syncwarp();
     if (lane < nwc) {
       const int64_t e = a.g.wb_first[c] + w0 + lane;
@@ -189,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
     s_wguess[wid][lane] = 0xffffu;
     unsigned slice_proven = 0;      // words proven blocked for ALL sources of the current source slice
     __syncwarp();
-  for (int r = 0; r < nrows; r++) {
+  for (int r = row_lo; r < row_hi; r++) {
     const int sslot = slot0 + r;
     const unsigned flags = a.g.slot_flags[sslot];
     if (!(flags & 2u)) {   // padding slot at the end of a cluster, or (only under -nopvs) a source in solid, which never
@@ -203,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_visibility(const VisArgs a) {
     if (COUNT) { const long long t = clock64(); if (tk0) tk_misc += t - tk0; tk0 = t; }
     // ---- (1) per word: proofs that settle all 32 receivers at once; (2a) the word-level sign test ----
     // every 32 rows the sources move on to the next slice: its two-sided proofs start afresh
-    if ((r & 31) == 0) {
+    if ((r & 31) == 0 || r == row_lo) {
       slice_proven = 0;
       if (a.mode & 32) {   // the node every ray of (this source slice, word) reaches unclipped: their walks start there
         s_wstart[wid][lane] = 0;
@@ -1560,10 +1552,39 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   c->d_grp_owner.upload(P.grp_owner, st);
   c->d_grp_ownbase.upload(P.grp_ownbase, st);
   {
-    std::vector<int32_t> og(P.own_groups);
-    if (og.empty()) og.push_back(0);
-    c->d_own_groups.upload(og, st);
-    c->d_own_runbase.upload(P.own_runbase, st);
+    // The runs of this rank, the expensive ones first: a run costs what its clear rays cost (they are walked), and those
+    // are the pairs inside one room -- the chunks that hold the source cluster's own words.  Warps draw runs from a
+    // counter, so starting with the long ones keeps the tail of the kernel short (a run is 128 rows x 1 024 receivers:
+    // milliseconds; a shard has only ~20 of them per resident warp).
+    std::vector<int4> heavy, light;
+    // A run covers all rows of its group when there are plenty of runs per resident warp; a shard has few, and then the
+    // runs that end last set the kernel time, so they are cut in halves / quarters (each part starts with cold guesses:
+    // 32-row runs cost 5.6 % more work on one GPU, and save 20 % of the kernel time on an eighth of C5).
+    int run_rows = kGroupRows;
+    {
+      const int64_t warps = (int64_t) c->sm_count * 4 * kWarpsPerBlock;
+      while (run_rows > 32 && P.own_runbase.back() * (kGroupRows / run_rows) < 100 * warps) run_rows /= 2;
+    }
+    if (const char *e = getenv("QRAD_RUN_ROWS")) run_rows = std::max(32, atoi(e) & ~31);
+    light.reserve((size_t) P.own_runbase.back() * (kGroupRows / run_rows));
+    for (int g : P.own_groups) {
+      const int cl = P.grp_cluster[g];
+      const int nchunks = (P.nwords[cl] + kChunkWords - 1) / kChunkWords;
+      int self_lo = -1, self_hi = -1;   // chunks that hold words of the group's own cluster
+      for (int v = P.vis_ptr[cl]; v < P.vis_ptr[cl + 1]; v++)
+        if (P.vis_cluster[v] == cl) {
+          const int w0 = P.vis_woff[v], w1 = w0 + ((P.cl_slot_start[cl + 1] - P.cl_slot_start[cl]) >> 5);
+          self_lo = w0 / kChunkWords;
+          self_hi = (w1 - 1) / kChunkWords;
+        }
+      for (int ch = 0; ch < nchunks; ch++)
+        for (int r0 = 0; r0 < P.grp_rows[g]; r0 += run_rows)
+          (ch >= self_lo && ch <= self_hi ? heavy : light).push_back(make_int4(g, ch, r0, std::min(run_rows, P.grp_rows[g] - r0)));
+    }
+    heavy.insert(heavy.end(), light.begin(), light.end());
+    if (heavy.empty()) heavy.push_back(make_int4(0, 0, 0, 0));
+    c->num_runs = (int64_t) (P.own_groups.empty() ? 0 : heavy.size());
+    c->d_run_list.upload(heavy, st);
   }
   const int nvis = (int) P.vis_cluster.size();
   {
@@ -1597,7 +1618,7 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   c->stats.ms_tr_setup = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   // ---- pass 1 ----
   QCUDA(cudaEventRecord(c->ev[0], st));
-  const uint64_t runs = (uint64_t) P.own_runbase.back();
+  const uint64_t runs = (uint64_t) c->num_runs;
   if (runs) {
     VisArgs a{};
     a.tree = c->tree();
@@ -1606,9 +1627,7 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
     a.s_origin_area = c->s_origin_area.p;
     a.s_normal = c->s_normal.p;
     a.g = geo_of(c);
-    a.own_groups = c->d_own_groups.p;
-    a.own_runbase = c->d_own_runbase.p;
-    a.n_own_groups = (int) P.own_groups.size();
+    a.run_list = c->d_run_list.p;
     a.grp_cluster = c->d_grp_cluster.p;
     a.grp_slot0 = c->d_grp_slot0.p;
     a.grp_rows = c->d_grp_rows.p;
