@@ -328,8 +328,18 @@ def main():
                             "+ 32 x u16 weights per list entry, 3.6 B per transfer on C5) / CUDA-event time of k_bounce / "
                             "measured copy bandwidth. algorithmic_* uses SURVEY 8d's record (nnz*b + 64*N, b = 6 B): that "
                             "count is not a lower bound for this layout, so its fraction can exceed 1. traffic: ncu "
-                            "dram__bytes of one launch is on file for N = 1 only (profiles/), null here.",
+                            "dram__bytes of one launch, from the capture named in traffic_source (one GPU only; null on shards).",
                     "ms_per_launch": kb_ms, "launches_per_step": p.numbounce, "per_gpu": world > 1}
+        # DRAM traffic of one launch from an ncu --set full capture: on file only for the one-GPU run of this workload
+        tfile = ROOT / "profiles" / "bounce_traffic.json"
+        if world == 1 and tfile.exists():
+            try:
+                t = json.loads(tfile.read_text()).get(args.workload)
+                if t and t.get("n_gpus") == 1:
+                    roofline["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
+                    roofline["traffic_source"] = t["source"]
+            except Exception:
+                pass
         tr_ms = float(np.mean(trace_ms))
 
         line = {
