@@ -40,6 +40,12 @@ struct CudaError : std::runtime_error {
 
 // Host <-> device traffic of this thread's contexts, counted where the copies are issued (qrad_cuda_stats.h2d_bytes /
 // d2h_bytes report the totals since the context was created).
+// where the runs of one own row group go in k_visibility's run list (transfers.cu: k_run_list)
+struct RunGroup {
+  int grp, nchunks, rows, self_lo, self_hi;
+  int64_t heavy_at, light_at;
+};
+
 struct Traffic {
   int64_t h2d = 0, d2h = 0;
 };
@@ -210,6 +216,7 @@ struct qrad_cuda_ctx {
   qrad::DBuf<uint32_t> colbuf;          // several GPUs: the other ranks' words about this rank's slices
   std::vector<int64_t> piece_first;     // [world] where rank q's piece starts in colbuf
   qrad::DBuf<int2> d_runs;              // the patch order as runs of consecutive slots
+  qrad::DBuf<qrad::RunGroup> d_run_groups;
   qrad::DBuf<int4> d_run_list;          // pass 1: this rank's (row group, chunk, first row, rows) runs in the order the warps draw them
   int64_t num_runs = 0;
   qrad::DBuf<int64_t> d_vl_ptr, d_vr_ptr;

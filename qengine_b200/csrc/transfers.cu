@@ -1392,6 +1392,19 @@ __global__ void k_finish_bounce(int N, const int32_t *__restrict__ patch_slot, c
 
 
 // slot-order copies of the patch geometry, and the bounding box of every slice's patch origins (shaft_blocked)
+// The run list of k_visibility: per own row group (one block) its (chunk, part) runs, the ones that hold words of the group's
+// own cluster in the front section of the list ("heavy": their rays are mostly clear and get walked), the rest behind.
+__global__ void __launch_bounds__(128) k_run_list(const RunGroup *groups, int run_rows, int4 *list) {
+  const RunGroup r = groups[blockIdx.x];
+  const int parts = (r.rows + run_rows - 1) / run_rows, nself = r.self_hi - r.self_lo + 1;
+  for (int k = threadIdx.x; k < r.nchunks * parts; k += blockDim.x) {
+    const int ch = k / parts, part = k - ch * parts, r0 = part * run_rows;
+    const int4 e = make_int4(r.grp, ch, r0, min(run_rows, r.rows - r0));
+    if (ch >= r.self_lo && ch <= r.self_hi) list[r.heavy_at + (int64_t) (ch - r.self_lo) * parts + part] = e;
+    else list[r.light_at + (int64_t) (ch < r.self_lo ? ch : ch - nself) * parts + part] = e;
+  }
+}
+
 __global__ void k_slot_geometry(int M, const int32_t *__restrict__ slot_patch, const float4 *__restrict__ p_origin_area,
                                 const float4 *__restrict__ p_normal, float4 *__restrict__ s_origin_area,
                                 float4 *__restrict__ s_normal, float4 *__restrict__ box_min, float4 *__restrict__ box_max) {
@@ -1556,7 +1569,6 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
     // are the pairs inside one room -- the chunks that hold the source cluster's own words.  Warps draw runs from a
     // counter, so starting with the long ones keeps the tail of the kernel short (a run is 128 rows x 1 024 receivers:
     // milliseconds; a shard has only ~20 of them per resident warp).
-    std::vector<int4> heavy, light;
     // A run covers all rows of its group when there are plenty of runs per resident warp; a shard has few, and then the
     // runs that end last set the kernel time, so they are cut in halves / quarters (each part starts with cold guesses:
     // 32-row runs cost 5.6 % more work on one GPU, and save 20 % of the kernel time on an eighth of C5).
@@ -1566,25 +1578,38 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
       while (run_rows > 32 && P.own_runbase.back() * (kGroupRows / run_rows) < 100 * warps) run_rows /= 2;
     }
     if (const char *e = getenv("QRAD_RUN_ROWS")) run_rows = std::max(32, atoi(e) & ~31);
-    light.reserve((size_t) P.own_runbase.back() * (kGroupRows / run_rows));
+    // The list has a million entries on one GPU: the host only says where each group's entries go, a kernel writes them
+    std::vector<RunGroup> rg;
+    rg.reserve(P.own_groups.size());
+    int64_t nheavy = 0, nlight = 0;
     for (int g : P.own_groups) {
       const int cl = P.grp_cluster[g];
-      const int nchunks = (P.nwords[cl] + kChunkWords - 1) / kChunkWords;
-      int self_lo = -1, self_hi = -1;   // chunks that hold words of the group's own cluster
+      RunGroup r{};
+      r.grp = g;
+      r.nchunks = (P.nwords[cl] + kChunkWords - 1) / kChunkWords;
+      r.rows = P.grp_rows[g];
+      r.self_lo = 0, r.self_hi = -1;   // chunks that hold words of the group's own cluster
       for (int v = P.vis_ptr[cl]; v < P.vis_ptr[cl + 1]; v++)
         if (P.vis_cluster[v] == cl) {
           const int w0 = P.vis_woff[v], w1 = w0 + ((P.cl_slot_start[cl + 1] - P.cl_slot_start[cl]) >> 5);
-          self_lo = w0 / kChunkWords;
-          self_hi = (w1 - 1) / kChunkWords;
+          r.self_lo = w0 / kChunkWords;
+          r.self_hi = (w1 - 1) / kChunkWords;
         }
-      for (int ch = 0; ch < nchunks; ch++)
-        for (int r0 = 0; r0 < P.grp_rows[g]; r0 += run_rows)
-          (ch >= self_lo && ch <= self_hi ? heavy : light).push_back(make_int4(g, ch, r0, std::min(run_rows, P.grp_rows[g] - r0)));
+      const int parts = (r.rows + run_rows - 1) / run_rows, nself = r.self_hi - r.self_lo + 1;
+      r.heavy_at = nheavy;
+      r.light_at = nlight;
+      nheavy += (int64_t) nself * parts;
+      nlight += (int64_t) (r.nchunks - nself) * parts;
+      rg.push_back(r);
     }
-    heavy.insert(heavy.end(), light.begin(), light.end());
-    if (heavy.empty()) heavy.push_back(make_int4(0, 0, 0, 0));
-    c->num_runs = (int64_t) (P.own_groups.empty() ? 0 : heavy.size());
-    c->d_run_list.upload(heavy, st);
+    for (RunGroup &r : rg) r.light_at += nheavy;
+    c->num_runs = nheavy + nlight;
+    c->d_run_list.alloc((size_t) c->num_runs + 1);
+    if (!rg.empty()) {
+      c->d_run_groups.upload(rg, st);
+      k_run_list<<<(int) rg.size(), 128, 0, st>>>(c->d_run_groups.p, run_rows, c->d_run_list.p);
+      c->launch_check("k_run_list");
+    }
   }
   const int nvis = (int) P.vis_cluster.size();
   {
