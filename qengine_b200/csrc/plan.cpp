@@ -83,14 +83,51 @@ void build_plan(TransferPlan &p, int N, const int32_t *eff, int nc, const uint32
   p.nc = nc;
   p.world = world;
   p.rank = rank;
+  // Both counting sorts below (patches by cluster, visible pairs by receiver) run on T threads: thread t takes a
+  // contiguous range of the input, counts into a histogram of its own, and after a prefix over (bucket, thread) writes its
+  // items behind those of the threads before it -- the order inside a bucket stays the input order.
+  int T = (int) std::thread::hardware_concurrency() / std::max(world, 1);
+  T = std::max(1, std::min(T, 8));
+  if (const char *e = getenv("QRAD_PLAN_THREADS")) T = std::max(1, std::min(64, atoi(e)));
+  auto run_threads = [&](auto &&fn) {
+    if (T == 1) {
+      fn(0);
+      return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) th.emplace_back([&fn, t] { fn(t); });
+    for (auto &x : th) x.join();
+  };
   // ---- slots ----
+  std::vector<int32_t> hist((size_t) T * nc, 0);
+  std::vector<int> bad_patch((size_t) T, -1);
+  run_threads([&](int t) {
+    int32_t *h = &hist[(size_t) t * nc];
+    const int i0 = (int) ((int64_t) N * t / T), i1 = (int) ((int64_t) N * (t + 1) / T);
+    for (int i = i0; i < i1; i++) {
+      if (eff[i] >= nc) {
+        if (bad_patch[t] < 0) bad_patch[t] = i;
+      } else if (eff[i] >= 0)
+        h[eff[i]]++;
+    }
+  });
+  for (int t = 0; t < T; t++)
+    if (bad_patch[t] >= 0)
+      pfail("patch " + std::to_string(bad_patch[t]) + " has cluster " + std::to_string(eff[bad_patch[t]]) + " >= numclusters");
   p.cl_count.assign(nc, 0);
-  for (int i = 0; i < N; i++) {
-    if (eff[i] >= nc) pfail("patch " + std::to_string(i) + " has cluster " + std::to_string(eff[i]) + " >= numclusters");
-    if (eff[i] >= 0) p.cl_count[eff[i]]++;
-  }
   p.cl_slot_start.assign(nc + 1, 0);
-  for (int k = 0; k < nc; k++) p.cl_slot_start[k + 1] = p.cl_slot_start[k] + ((p.cl_count[k] + 31) & ~31);
+  for (int k = 0; k < nc; k++) {
+    int32_t n = 0;
+    for (int t = 0; t < T; t++) n += hist[(size_t) t * nc + k];
+    p.cl_count[k] = n;
+    p.cl_slot_start[k + 1] = p.cl_slot_start[k] + ((n + 31) & ~31);
+    int32_t at = p.cl_slot_start[k];   // hist becomes: first slot of thread t in cluster k
+    for (int t = 0; t < T; t++) {
+      const int32_t c = hist[(size_t) t * nc + k];
+      hist[(size_t) t * nc + k] = at;
+      at += c;
+    }
+  }
   const int M = p.cl_slot_start[nc];
   p.M = M;
   p.nslices = M / 32;
@@ -98,22 +135,23 @@ void build_plan(TransferPlan &p, int N, const int32_t *eff, int nc, const uint32
   p.slot_patch.assign(M, -1);
   p.patch_slot.assign(N, -1);
   p.slot_cluster.assign(M, 0);
-  {
-    std::vector<int32_t> fill(p.cl_slot_start.begin(), p.cl_slot_start.end() - 1);
-    for (int i = 0; i < N; i++)
+  p.slice_count.assign(p.nslices, 0);
+  run_threads([&](int t) {
+    int32_t *fill = &hist[(size_t) t * nc];
+    const int i0 = (int) ((int64_t) N * t / T), i1 = (int) ((int64_t) N * (t + 1) / T);
+    for (int i = i0; i < i1; i++)
       if (eff[i] >= 0) {
         const int s = fill[eff[i]]++;
         p.slot_patch[s] = i;
         p.patch_slot[i] = s;
       }
-    for (int k = 0; k < nc; k++)
+    const int k0 = (int) ((int64_t) nc * t / T), k1 = (int) ((int64_t) nc * (t + 1) / T);
+    for (int k = k0; k < k1; k++) {
       for (int s = p.cl_slot_start[k]; s < p.cl_slot_start[k + 1]; s++) p.slot_cluster[s] = k;
-  }
-  p.slice_count.assign(p.nslices, 0);
-  for (int s = 0; s < p.nslices; s++) {
-    const int c = p.slot_cluster[(size_t) s * 32];
-    p.slice_count[s] = std::min(32, p.cl_count[c] - (s * 32 - p.cl_slot_start[c]));
-  }
+      for (int s = p.cl_slot_start[k] >> 5; s < p.cl_slot_start[k + 1] >> 5; s++)
+        p.slice_count[s] = std::min(32, p.cl_count[k] - (s * 32 - p.cl_slot_start[k]));
+    }
+  });
   lap("slots");
   // ---- who sees whom ----
   p.vis_ptr.assign(nc + 1, 0);
@@ -121,59 +159,80 @@ void build_plan(TransferPlan &p, int N, const int32_t *eff, int nc, const uint32
   p.wb_first.assign(nc + 1, 0);
   p.Lptr.assign(nc + 1, 0);
   p.Rptr.assign(nc + 1, 0);
-  std::vector<int32_t> seer_n(nc + 1, 0);
-  {
-    // clusters that hold patches, as a bit row: a visible list is (PVS row & this) scanned word by word
-    std::vector<uint32_t> populated((size_t) ((nc + 31) >> 5), 0);
-    size_t visible = 0;
-    for (int d = 0; d < nc; d++)
-      if (p.cl_count[d] > 0) populated[d >> 5] |= 1u << (d & 31);
-    const int nw32 = (nc + 31) >> 5;
-    if (pvs)
-      for (int a = 0; a < nc; a++)
-        if (p.cl_count[a] > 0)
-          for (int k = 0; k < nw32; k++) visible += (size_t) __builtin_popcount(pvs[(size_t) a * pvs_words + k] & populated[k]);
-    p.vis_cluster.reserve(visible + 16);
-    p.vis_woff.reserve(visible + 16);
-    for (int a = 0; a < nc; a++) {
-      int w = 0;
-      int64_t cand = 0;
-      if (p.cl_count[a] > 0)
-        for (int k = 0; k < nw32; k++) {
-          uint32_t bits = (pvs ? pvs[(size_t) a * pvs_words + k] : 0xffffffffu) & populated[k];
-          while (bits) {
-            const int d = k * 32 + __builtin_ctz(bits);
-            bits &= bits - 1;
-            p.vis_cluster.push_back(d);
-            p.vis_woff.push_back(w);
-            w += (p.cl_slot_start[d + 1] - p.cl_slot_start[d]) >> 5;
-            cand += p.cl_count[d];
-            p.Rptr[d + 1] += p.cl_count[a];
-            seer_n[d + 1]++;
-          }
-        }
-      p.vis_ptr[a + 1] = (int32_t) p.vis_cluster.size();
-      p.nwords[a] = w;
-      p.wb_first[a + 1] = p.wb_first[a] + w;
-      p.Lptr[a + 1] = p.Lptr[a] + cand;
-    }
+  // clusters that hold patches, as a bit row: a visible list is (PVS row & this) scanned word by word
+  const int nw32 = (nc + 31) >> 5;
+  std::vector<uint32_t> populated((size_t) nw32, 0);
+  for (int d = 0; d < nc; d++)
+    if (p.cl_count[d] > 0) populated[d >> 5] |= 1u << (d & 31);
+  auto row_bits = [&](int a, int k) -> uint32_t { return (pvs ? pvs[(size_t) a * pvs_words + k] : 0xffffffffu) & populated[k]; };
+  for (int a = 0; a < nc; a++) {
+    int n = 0;
+    if (p.cl_count[a] > 0)
+      for (int k = 0; k < nw32; k++) n += __builtin_popcount(row_bits(a, k));
+    p.vis_ptr[a + 1] = p.vis_ptr[a] + n;
   }
-  for (int d = 0; d < nc; d++) p.Rptr[d + 1] += p.Rptr[d];
-  if (p.Lptr[nc] >= ((int64_t) 1 << 40)) pfail("make_transfers: candidate lists too large");
+  const size_t E = (size_t) p.vis_ptr[nc];
+  p.vis_cluster.resize(E);
+  p.vis_woff.resize(E);
+  p.seer_cluster.assign(E, 0);
+  p.vis_seer.assign(E, 0);
+  std::vector<int32_t> seen((size_t) T * nc, 0);      // [t][d] sources of thread t's range that see d
+  std::vector<int64_t> rsum((size_t) T * nc, 0);      // [t][d] their patches
+  std::vector<int64_t> cand((size_t) nc, 0);
+  run_threads([&](int t) {
+    const int a0 = (int) ((int64_t) nc * t / T), a1 = (int) ((int64_t) nc * (t + 1) / T);
+    int32_t *sn = &seen[(size_t) t * nc];
+    int64_t *rs = &rsum[(size_t) t * nc];
+    for (int a = a0; a < a1; a++) {
+      if (p.cl_count[a] == 0) continue;
+      int w = 0, v = p.vis_ptr[a];
+      int64_t cnd = 0;
+      for (int k = 0; k < nw32; k++) {
+        uint32_t bits = row_bits(a, k);
+        while (bits) {
+          const int d = k * 32 + __builtin_ctz(bits);
+          bits &= bits - 1;
+          p.vis_cluster[v] = d;
+          p.vis_woff[v] = w;
+          v++;
+          w += (p.cl_slot_start[d + 1] - p.cl_slot_start[d]) >> 5;
+          cnd += p.cl_count[d];
+          rs[d] += p.cl_count[a];
+          sn[d]++;
+        }
+      }
+      p.nwords[a] = w;
+      cand[a] = cnd;
+    }
+  });
   p.seer_ptr.assign(nc + 1, 0);
-  for (int d = 0; d < nc; d++) p.seer_ptr[d + 1] = p.seer_ptr[d] + seer_n[d + 1];
-  p.seer_cluster.assign(p.vis_cluster.size(), 0);
-  p.vis_seer.assign(p.vis_cluster.size(), 0);
-  {
-    std::vector<int32_t> fill(p.seer_ptr.begin(), p.seer_ptr.end() - 1);
-    for (int a = 0; a < nc; a++)   // a ascending: every seer list comes out sorted
+  for (int a = 0; a < nc; a++) {
+    p.wb_first[a + 1] = p.wb_first[a] + p.nwords[a];
+    p.Lptr[a + 1] = p.Lptr[a] + cand[a];
+  }
+  for (int d = 0; d < nc; d++) {
+    int32_t at = p.seer_ptr[d];
+    int64_t r = 0;
+    for (int t = 0; t < T; t++) {   // seen becomes: where thread t's first seer of d goes
+      const int32_t c = seen[(size_t) t * nc + d];
+      seen[(size_t) t * nc + d] = at;
+      at += c;
+      r += rsum[(size_t) t * nc + d];
+    }
+    p.seer_ptr[d + 1] = at;
+    p.Rptr[d + 1] = p.Rptr[d] + r;
+  }
+  if (p.Lptr[nc] >= ((int64_t) 1 << 40)) pfail("make_transfers: candidate lists too large");
+  run_threads([&](int t) {   // a ascending inside a thread, threads in order: every seer list comes out sorted
+    const int a0 = (int) ((int64_t) nc * t / T), a1 = (int) ((int64_t) nc * (t + 1) / T);
+    int32_t *fill = &seen[(size_t) t * nc];
+    for (int a = a0; a < a1; a++)
       for (int v = p.vis_ptr[a]; v < p.vis_ptr[a + 1]; v++) {
         const int e = fill[p.vis_cluster[v]]++;
         p.seer_cluster[e] = a;
         p.vis_seer[v] = e;
       }
-  }
-  const size_t E = p.seer_cluster.size();
+  });
   lap("visibility lists");
   // ---- row groups and their owners ----
   p.grp_first.assign(nc + 1, 0);
