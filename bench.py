@@ -278,6 +278,15 @@ def main():
             allr = [torch.zeros_like(tr) for _ in range(world)]
             dist.all_gather(allr, tr)
             trace_by_rank = [round(float(x.item()), 1) for x in allr]
+        # the library's own phase clocks of the last step, rank by rank (waits for other ranks show up in the phase that waits)
+        PHASE_KEYS = ("ms_facelights", "ms_tr_setup", "ms_transfers_trace", "ms_tr_lists", "ms_tr_rows", "ms_tr_columns",
+                      "ms_bounce", "ms_bounce_kernel", "ms_final", "ms_x_matrix", "ms_x_radiosity")
+        phases_by_rank = None
+        if world > 1:
+            pv = torch.tensor([float(st.get(k) or 0.0) for k in PHASE_KEYS], device="cuda", dtype=torch.float64)
+            allp = [torch.zeros_like(pv) for _ in range(world)]
+            dist.all_gather(allp, pv)
+            phases_by_rank = {k: [round(float(x[i].item()), 1) for x in allp] for i, k in enumerate(PHASE_KEYS)}
 
         # ---- end to end: what `qrad3 map.bsp` does, files and host buffers, every copy inside the timed region ----
         e2e_times, e2e_parts, h2d, d2h = [], [], 0, 0
@@ -354,7 +363,7 @@ def main():
             "s_per_map": step_ms * 1e-3,
             "phase_ms": dict(zip(["facelights", "transfers", "bounce", "final"], [float(x) for x in np.mean(phase, axis=0)])),
             "exchange_ms": {k: st[k] for k in ("ms_x_matrix", "ms_x_small", "ms_x_radiosity")} if world > 1 else None,
-            "trace_kernel_ms": tr_ms, "trace_kernel_ms_by_rank": trace_by_rank,
+            "trace_kernel_ms": tr_ms, "trace_kernel_ms_by_rank": trace_by_rank, "phases_ms_by_rank": phases_by_rank,
             "transfers_breakdown_ms": {k: st[k] for k in ("ms_tr_setup", "ms_transfers_trace", "ms_tr_lists", "ms_tr_rows", "ms_tr_columns")},
             "trace_rays_per_s": st["rays_transfers"] / (tr_ms * 1e-3) if tr_ms > 0 else None,
             "wall_s_per_step": wall / args.steps,

@@ -228,6 +228,7 @@ int qrad_cuda_upload_patches(qrad_cuda_ctx *c, const qrad_patches_view *p) {
     c->numfaces_p = p->numfaces;
     if (c->groups_future.valid()) c->groups_future.wait();
     c->groups_future = {};
+    c->plane_groups.reset();
     c->h_cluster.assign(p->cluster, p->cluster + n);
     c->h_sky.assign(p->sky, p->sky + n);
     c->h_next.assign(p->next, p->next + n);
@@ -333,6 +334,7 @@ int qrad_cuda_upload_faces(qrad_cuda_ctx *c, const qrad_faces_view *f) {
     if (c->N && nf != c->numfaces_p) dfail("faces view has %d faces, patches view %d", nf, c->numfaces_p);
     if (c->groups_future.valid()) c->groups_future.wait();
     c->groups_future = {};
+    c->plane_groups.reset();
     c->F = nf;
     c->h_lit.assign(f->lit, f->lit + nf);
     c->h_texsize.assign(f->texsize, f->texsize + (size_t) nf * 2);

@@ -32,37 +32,56 @@ struct PointArgs {
   const float4 *p_origin_area;
   const float *f_bounds;          // [F][6]
   float subdiv2;                  // subdiv * 2
-  int32_t *tri_count;             // [F]
-  const int64_t *tri_first;       // [F+1] (fill mode)
-  int32_t *tri_points;            // fill mode output
+  int32_t *tri_count;             // [F] points of the face (may exceed kMaxTriPoints: the host reports the reference's error)
+  int32_t *tri_points;            // [F][kMaxTriPoints] patch indices in chain order
+  int32_t *pmax;                  // largest count
 };
 
-template <bool FILL>
+// One block per face of this rank.  The chain of a large plane (the floor of a whole map) holds hundreds of thousands of
+// patches and the points must come out in chain order: the block takes 256 candidates at a time and compacts them with
+// a ballot per warp and a prefix over the warps.  (One warp per face, and a counting pass before the filling pass, took
+// 14 ms on C5 however many GPUs shared the faces: the time of the longest chain.)
 __global__ void __launch_bounds__(256) k_tri_points(const PointArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int f = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (f >= a.F) return;
+  __shared__ int s_cnt[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int f = a.face_lo + blockIdx.x;
+  if (f >= a.face_hi) return;
+  const int g = a.f_lit[f] ? a.group_of_face[f] : -1;
   int total = 0;
-  const int g = (a.f_lit[f] && f >= a.face_lo && f < a.face_hi) ? a.group_of_face[f] : -1;
   if (g >= 0) {
     const float *mn = a.f_bounds + (size_t) f * 6, *mx = mn + 3;
+    const float mn0 = mn[0], mn1 = mn[1], mn2 = mn[2], mx0 = mx[0], mx1 = mx[1], mx2 = mx[2];
     const int k0 = a.group_first[g], k1 = a.group_first[g + 1];
-    const int64_t base = FILL ? a.tri_first[f] : 0;
-    for (int k = k0; k < k1; k += 32) {
+    int32_t *out = a.tri_points + (size_t) f * kMaxTriPoints;
+    for (int k = k0; k < k1; k += 256) {
       bool keep = false;
       int p = -1;
-      if (k + lane < k1) {
-        p = a.group_patch[k + lane];
+      if (k + (int) threadIdx.x < k1) {
+        p = a.group_patch[k + threadIdx.x];
         const float4 o = a.p_origin_area[p];
-        keep = !(mn[0] - o.x > a.subdiv2 || o.x - mx[0] > a.subdiv2 || mn[1] - o.y > a.subdiv2 || o.y - mx[1] > a.subdiv2 ||
-                 mn[2] - o.z > a.subdiv2 || o.z - mx[2] > a.subdiv2);
+        keep = !(mn0 - o.x > a.subdiv2 || o.x - mx0 > a.subdiv2 || mn1 - o.y > a.subdiv2 || o.y - mx1 > a.subdiv2 ||
+                 mn2 - o.z > a.subdiv2 || o.z - mx2 > a.subdiv2);
       }
       const unsigned m = __ballot_sync(0xffffffffu, keep);
-      if (FILL && keep) a.tri_points[base + total + __popc(m & ((1u << lane) - 1))] = p;
-      total += __popc(m);
+      if (lane == 0) s_cnt[wid] = __popc(m);
+      __syncthreads();
+      int before = 0, all = 0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) {
+        const int cw = s_cnt[w];
+        before += w < wid ? cw : 0;
+        all += cw;
+      }
+      const int at = total + before + __popc(m & ((1u << lane) - 1));
+      if (keep && at < kMaxTriPoints) out[at] = p;
+      total += all;
+      __syncthreads();
     }
   }
-  if (!FILL && lane == 0) a.tri_count[f] = total;
+  if (threadIdx.x == 0) {
+    a.tri_count[f] = total;
+    atomicMax(a.pmax, total);
+  }
 }
 
 // ---- per-warp scratch --------------------------------------------------------------------------
@@ -82,8 +101,7 @@ struct FinalArgs {
   const uint8_t *f_lit;
   const int32_t *luxel_first;
   const int32_t *tri_count;
-  const int64_t *tri_first;
-  const int32_t *tri_points;
+  const int32_t *tri_points;      // [F][kMaxTriPoints]
   const float4 *p_origin_area;
   const float *p_totallight;
   const float *f_plane_normal;
@@ -165,7 +183,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_final(const FinalArgs a) {
     if (f >= a.face_hi) break;   // the counter starts at this rank's first face
     if (!a.f_lit[f]) continue;
     const int P = a.numbounce > 0 ? a.tri_count[f] : 0;
-    const int32_t *pidx = a.tri_points + (a.numbounce > 0 ? a.tri_first[f] : 0);
+    const int32_t *pidx = a.tri_points + (size_t) f * kMaxTriPoints;
     int numedges = 0, numtris = 0;
     const float pnx = a.f_plane_normal[f * 3], pny = a.f_plane_normal[f * 3 + 1], pnz = a.f_plane_normal[f * 3 + 2];
 
@@ -454,6 +472,7 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
   Timer t;
   t.start(c->stream);
   cudaStream_t st = c->stream;
+  DebugLaps laps("final_light", st);
   const int F = c->F, L = c->num_luxels;
   // lightofs in face order with the UNCLAMPED style count (lightmap.c:1086-1099), styles[] (1101-1102, 1158)
   std::vector<int32_t> lightofs(F, 0);
@@ -479,27 +498,37 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
     if (c->h_minlight[f] > 0) any_minlight = true;
   }
   *size = (int32_t) total;
+  laps.lap("lightofs / styles");
 
   // plane groups: the chain FinalLightFace walks from planelinks[side][planenum] (lightmap.c:1123); it stops
   // at face index 0, so face 0 never contributes (appendix C)
   // device buffers live in the context so that repeated calls reuse the allocations
   DBuf<int32_t> &d_group_of_face = c->fin_i32[0], &d_group_first = c->fin_i32[1], &d_group_patch = c->fin_i32[2],
                 &tri_count = c->fin_i32[3], &tri_points = c->fin_i32[4];
-  DBuf<int64_t> &d_tri_first = c->fin_i64;
-  std::vector<int32_t> h_tri_count(F, 0);
-  std::vector<int64_t> h_tri_first(F + 1, 0);
+  DBuf<int32_t> &d_pmax = c->fin_i32[10];
   int pmax = 1;
+  tri_count.alloc((size_t) F);
+  tri_count.zero(st);
   if (p->numbounce > 0) {
-    std::shared_ptr<qrad_cuda_ctx::PlaneGroups> pg;
-    if (c->groups_future.valid()) pg = c->groups_future.get();   // started by upload_faces
-    else pg = compute_plane_groups(c);
-    c->groups_future = {};
+    std::shared_ptr<qrad_cuda_ctx::PlaneGroups> pg = c->plane_groups;   // kept from the last call while the faces stay
+    if (!pg) {
+      if (c->groups_future.valid()) pg = c->groups_future.get();   // started by upload_faces
+      else pg = compute_plane_groups(c);
+      c->groups_future = {};
+      c->plane_groups = pg;
+      c->plane_groups_uploaded = false;
+    }
     if (!pg->error.empty()) dfail("%s", pg->error.c_str());
-    std::vector<int32_t> &group_of_face = pg->group_of_face, &group_first = pg->group_first, &group_patch = pg->group_patch;
-    d_group_of_face.upload(group_of_face, st);
-    d_group_first.upload(group_first, st);
-    d_group_patch.upload(group_patch, st);
-    tri_count.alloc((size_t) F);
+    laps.lap("plane groups (wait)");
+    if (!c->plane_groups_uploaded) {
+      d_group_of_face.upload(pg->group_of_face, st);
+      d_group_first.upload(pg->group_first, st);
+      d_group_patch.upload(pg->group_patch, st);
+      c->plane_groups_uploaded = true;
+    }
+    tri_points.alloc((size_t) F * kMaxTriPoints + 1);
+    d_pmax.alloc(1);
+    d_pmax.zero(st);
     PointArgs pa{};
     pa.F = F;
     pa.face_lo = c->face_lo;
@@ -512,24 +541,17 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
     pa.f_bounds = c->f_bounds.p;
     pa.subdiv2 = p->subdiv * 2;
     pa.tri_count = tri_count.p;
-    k_tri_points<false><<<(F + 7) / 8, 256, 0, st>>>(pa);
-    c->launch_check("k_tri_points<count>");
-    tri_count.download(h_tri_count.data(), (size_t) F, st);
-    for (int f = 0; f < F; f++) {
-      if (h_tri_count[f] > kMaxTriPoints) dfail("trian->numpoints == MAX_TRI_POINTS");
-      pmax = std::max(pmax, h_tri_count[f]);
-      h_tri_first[f + 1] = h_tri_first[f] + h_tri_count[f];
-    }
-    d_tri_first.upload(h_tri_first, st);
-    tri_points.alloc((size_t) h_tri_first[F] + 1);
-    pa.tri_first = d_tri_first.p;
     pa.tri_points = tri_points.p;
-    k_tri_points<true><<<(F + 7) / 8, 256, 0, st>>>(pa);
-    c->launch_check("k_tri_points<fill>");
+    pa.pmax = d_pmax.p;
+    if (c->face_hi > c->face_lo) {
+      k_tri_points<<<c->face_hi - c->face_lo, 256, 0, st>>>(pa);
+      c->launch_check("k_tri_points");
+    }
+    d_pmax.download(&pmax, 1, st);
+    if (pmax > kMaxTriPoints) dfail("trian->numpoints == MAX_TRI_POINTS");
+    pmax = std::max(pmax, 1);
+    laps.lap("tri points");
   } else {
-    tri_count.alloc((size_t) F);
-    tri_count.zero(st);
-    d_tri_first.upload(h_tri_first, st);
     tri_points.alloc(1);
   }
 
@@ -565,6 +587,7 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
   etri.alloc(nw * (kMaxTriEdges + 2));
   tedges.alloc(nw * kMaxTriTris * 3);
   stack.alloc(nw * kStackCap);
+  laps.lap("uploads, pools");
 
   FinalArgs fa{};
   fa.F = F;
@@ -573,7 +596,6 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
   fa.f_lit = c->f_lit.p;
   fa.luxel_first = c->f_luxel_first.p;
   fa.tri_count = tri_count.p;
-  fa.tri_first = d_tri_first.p;
   fa.tri_points = tri_points.p;
   fa.p_origin_area = c->p_origin_area.p;
   fa.p_totallight = c->p_totallight.p;
@@ -603,6 +625,7 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
   fa.face_counter = d_counter.p;
   k_final<<<blocks, kWarps * 32, 0, st>>>(fa);
   c->launch_check("k_final");
+  laps.lap("k_final");
   if (c->world > 1) {   // all ranks must agree on failure before anybody enters the sums below
     ncclResult_t r = nccl().AllReduce(d_err.p, d_err.p, 1, ncclInt32, ncclMax, c->comm, st);
     if (r != ncclSuccess) dfail("ncclAllReduce(error flag) failed: %s", nccl().GetErrorString(r));
@@ -620,6 +643,7 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
     if (r != ncclSuccess) dfail("ncclAllReduce(lightmap) failed: %s", n.GetErrorString(r));
   }
   if (total) d_out.download(out, (size_t) total, st);
+  laps.lap("all-reduce, read-back");
 
   if (any_minlight) {
     // _minlight faces: the mottling uses the C library rand() in face / style / luxel order on one thread

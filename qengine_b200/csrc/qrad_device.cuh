@@ -5,6 +5,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -114,6 +118,27 @@ __device__ __forceinline__ float vnormalize(float &x, float &y, float &z) {
   return len;
 }
 #endif  // __CUDACC__
+
+// QRAD_DEBUG_TIMING=1: wall-clock laps of a host function, the stream drained at every lap (tools only: it serialises)
+struct DebugLaps {
+  bool on = getenv("QRAD_DEBUG_TIMING") != nullptr;
+  const char *who;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point tp;
+  DebugLaps(const char *who_, cudaStream_t st_) : who(who_), st(st_) {
+    if (on) {
+      cudaStreamSynchronize(st);
+      tp = std::chrono::steady_clock::now();
+    }
+  }
+  void lap(const char *what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "%s: %-28s %7.2f ms\n", who, what, std::chrono::duration<double, std::milli>(now - tp).count());
+    tp = now;
+  }
+};
 
 struct Timer {
   cudaEvent_t a = nullptr, b = nullptr;
@@ -230,6 +255,7 @@ struct qrad_cuda_ctx {
   qrad::DBuf<uint32_t> g_src;           // [entries] source slot
   qrad::DBuf<uint4> g_w;                // [entries/8][32] 8 u16 weights per lane
   qrad::DBuf<int32_t> slice_order;      // this rank's slices, longest list first (k_bounce work order)
+  qrad::DBuf<int32_t> col_order;        // all of this rank's slices, longest list first (k_columns: one block each)
   qrad::DBuf<int32_t> coop_slices;      // the slices with the longest lists: work list of the block-cooperative role
   int n_coop = 0, n_regular = 0;
   qrad::DBuf<int32_t> bounce_next;      // [4] work counters of the bounce kernels
@@ -257,12 +283,14 @@ struct qrad_cuda_ctx {
   };
   std::vector<int32_t> h_next, h_face_head;        // patch->next, face_patches[] as uploaded
   std::future<std::shared_ptr<PlaneGroups>> groups_future;
+  std::shared_ptr<PlaneGroups> plane_groups;   // of the faces and patches uploaded last (final_light keeps them between calls)
+  bool plane_groups_uploaded = false;
 
   // ---- FinalLightFace scratch (per resident warp) ----
   qrad::DBuf<uint16_t> fin_matrix, fin_ep0, fin_ep1, fin_tedges, fin_stack;
   qrad::DBuf<int16_t> fin_etri;
   qrad::DBuf<float4> fin_pts, fin_eplane;
-  qrad::DBuf<int32_t> fin_i32[10];
+  qrad::DBuf<int32_t> fin_i32[11];
   qrad::DBuf<int64_t> fin_i64;
   qrad::DBuf<uint8_t> fin_out;
   qrad::DBuf<float> fin_lb;

@@ -686,6 +686,7 @@ struct ColArgs {
   int nslices;
   const float *row_total;
   int slice_lo, slice_hi;          // this rank's slices
+  const int32_t *col_order;        // fill mode: this rank's slices, longest list first (one block each)
   int32_t *slice_len;              // count mode output: list entries of the slice
   const int64_t *slice_base;       // fill mode: first entry of the slice (multiple of 32)
   uint32_t *g_src;                 // [entries]      source slot
@@ -716,17 +717,27 @@ __global__ void __launch_bounds__(kThreads) k_column_counts(const ColArgs a, con
   if (lane == 0) a.slice_len[slice] = cnt;
 }
 
-// pass 3b: the lists.  One warp per slice, lane = receiver.  The sources come in runs of <= 32 consecutive slots whose
-// words are consecutive in the slice's column: lane k fetches the word of source k of the run (the next run's words are
-// requested one run ahead); when some word is non-zero the sources that own one are staged in shared memory (origin,
-// normal, row total: one gather per run instead of a dependent L2 round trip per list entry), and the warp then emits
-// the entries in source order.
-__global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
+// pass 3b: the lists, lane = receiver.  The slice's sources come in runs of <= 32 consecutive slots whose words are
+// consecutive in the slice's column: lane k fetches the word of source k of a run (the words of four runs are in flight
+// while the previous four are emitted); when some word is non-zero the sources that own one are staged in shared memory
+// (origin, normal, row total: one gather per run instead of a dependent L2 round trip per list entry), and the warp
+// writes the entries in source order.
+// SPLIT = false: one warp per slice, slices longest list first -- for many waves of slices (one GPU: 95 ms on C5).
+// SPLIT = true:  one BLOCK per slice.  A shard of an eighth of C5 is less than one wave of warps, and took as long as its
+//                longest list (20 of 33 ms).  The eight warps first count the non-zero words -- the list entries -- of the
+//                run list in cells of 32 runs, a prefix over the cells cuts the list into eight parts of (nearly) equal
+//                entries at cell boundaries, and every warp emits one part from the entry the prefix names.
+constexpr int kColCells = 1024;
+template <bool SPLIT>
+__global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a, const int nslices_own) {
   __shared__ float4 s_so[kWarpsPerBlock][32], s_sn[kWarpsPerBlock][32];
   __shared__ float s_rt[kWarpsPerBlock][32];
+  __shared__ int s_cell[SPLIT ? kColCells + 1 : 1];
+  __shared__ int s_wsum[kWarpsPerBlock];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int slice = a.slice_lo + blockIdx.x * kWarpsPerBlock + wid;
-  if (slice >= a.slice_hi) return;
+  const int oi = SPLIT ? (int) blockIdx.x : (int) blockIdx.x * kWarpsPerBlock + wid;
+  if (oi >= nslices_own) return;   // (SPLIT: the whole block)
+  const int slice = a.col_order[oi];
   const int rslot = slice * 32 + lane;
   const int d = a.g.slot_cluster[slice * 32];
   const bool valid = (a.g.slot_flags[rslot] & 1u) != 0;
@@ -735,15 +746,92 @@ __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
     po = a.s_origin_area[rslot];
     pn = a.s_normal[rslot];
   }
-  const int64_t e0 = a.vr_ptr[d], e1 = a.vr_ptr[d + 1];
-  int n = 0;                                           // list entries so far (uniform)
+  const int64_t l0 = a.vr_ptr[d], nruns = a.vr_ptr[d + 1] - l0;
+  auto run_ptr = [&](const int4 run) -> const uint32_t * {
+    return a.col[run.w & (kMaxWorld - 1)] + a.sbase[(int64_t) run.w * (a.nslices + 1) + slice] + run.y;
+  };
+  int64_t e0 = l0, e1 = l0 + nruns;   // this warp's part of the run list
+  int n = 0;                          // list entries before this warp's next one (uniform)
+  if (SPLIT) {
+    const int64_t nbatches = (nruns + 31) >> 5;
+    const int per_cell = (int) ((nbatches + kColCells - 1) / kColCells);   // batches of 32 runs per cell (1 unless the list is huge)
+    const int ncells = per_cell ? (int) ((nbatches + per_cell - 1) / per_cell) : 0;
+    for (int cidx = wid; cidx < ncells; cidx += kWarpsPerBlock) {
+      int cnt = 0;
+      const int64_t b0 = l0 + (int64_t) cidx * per_cell * 32, b1 = min(l0 + nruns, b0 + (int64_t) per_cell * 32);
+      for (int64_t eb = b0; eb < b1; eb += 32) {
+        const int nb = (int) min((int64_t) 32, b1 - eb);
+        const int4 mine = lane < nb ? __ldg(a.vr + eb + lane) : make_int4(0, 0, 0, 0);
+        const uint32_t *myptr = run_ptr(mine);
+        for (int j = 0; j < nb; j += 4) {
+          uint32_t w[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const unsigned long long pj = __shfl_sync(0xffffffffu, (unsigned long long) myptr, (j + k) & 31);
+            const int len = __shfl_sync(0xffffffffu, mine.z, (j + k) & 31);
+            w[k] = (j + k < nb && lane < len) ? __ldg(reinterpret_cast<const uint32_t *>(pj) + lane) : 0u;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; k++) cnt += w[k] != 0;
+        }
+      }
+      for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (lane == 0) s_cell[cidx] = cnt;
+    }
+    __syncthreads();
+    // exclusive prefix over the cells (kColCells = 4 per thread)
+    int v[4], tsum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int cidx = threadIdx.x * 4 + k;
+      v[k] = cidx < ncells ? s_cell[cidx] : 0;
+      tsum += v[k];
+    }
+    int incl = tsum;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_wsum[wid] = incl;
+    __syncthreads();
+    int before = incl - tsum;
+    for (int w = 0; w < wid; w++) before += s_wsum[w];
+    int total = 0;
+    for (int w = 0; w < kWarpsPerBlock; w++) total += s_wsum[w];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int cidx = threadIdx.x * 4 + k;
+      if (cidx <= ncells && cidx <= kColCells) s_cell[cidx] = before;
+      before += v[k];
+    }
+    __syncthreads();
+    // warp w takes the cells from the first whose prefix reaches total * w / 8
+    auto first_cell = [&](const int w) -> int {
+      if (w >= kWarpsPerBlock) return ncells;
+      const int target = (int) ((int64_t) total * w / kWarpsPerBlock);
+      int lo = 0, hi = ncells;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_cell[mid] < target) lo = mid + 1;
+        else hi = mid;
+      }
+      return lo;
+    };
+    const int c0 = first_cell(wid), c1 = first_cell(wid + 1);
+    e0 = min(l0 + nruns, l0 + (int64_t) c0 * per_cell * 32);
+    e1 = min(l0 + nruns, l0 + (int64_t) c1 * per_cell * 32);
+    n = c0 < ncells ? s_cell[c0] : total;
+  }
+  const int head_end = (n + 7) & ~7;                   // entries before this one share their group of 8 with the previous warp
   const int64_t base = a.slice_base[slice];
+  uint16_t *const w16 = reinterpret_cast<uint16_t *>(a.g_w);
   uint32_t wq[4] = {0, 0, 0, 0};                       // this lane's weights of the current group of 8 entries
   // 32 runs at a time (lane j holds run j), the words of four runs in flight while the previous four are emitted
   for (int64_t eb = e0; eb < e1; eb += 32) {
     const int nb = (int) min((int64_t) 32, e1 - eb);
     const int4 mine = lane < nb ? __ldg(a.vr + eb + lane) : make_int4(0, 0, 0, 0);
-    const uint32_t *myptr = a.col[mine.w & (kMaxWorld - 1)] + a.sbase[(int64_t) mine.w * (a.nslices + 1) + slice] + mine.y;
+    const uint32_t *myptr = run_ptr(mine);
     auto fetch = [&](const int j) -> uint32_t {   // the word of source `lane` of run j (0 past the run / the batch)
       const unsigned long long pj = __shfl_sync(0xffffffffu, (unsigned long long) myptr, j & 31);
       const int len = __shfl_sync(0xffffffffu, mine.z, j & 31);
@@ -783,10 +871,11 @@ __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
             itrans = (uint32_t) (int) (trans * 65536.0f / s_rt[wid][src]) & 0xffffu;   // u16 store wraps (qrad3.c:283-285)
           }
           const int q = n & 7;
-          wq[q >> 1] |= itrans << ((q & 1) * 16);
+          if (SPLIT && n < head_end) w16[(((base + n) >> 3) * 32 + lane) * 8 + q] = (uint16_t) itrans;   // group shared with the warp before
+          else wq[q >> 1] |= itrans << ((q & 1) * 16);
           if (lane == 0) a.g_src[base + n] = slot0 + src;
           n++;
-          if ((n & 7) == 0) {
+          if ((n & 7) == 0 && n > head_end) {
             a.g_w[((base + n) / 8 - 1) * 32 + lane] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
             wq[0] = wq[1] = wq[2] = wq[3] = 0;
           }
@@ -796,9 +885,13 @@ __global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a) {
       for (int k = 0; k < 4; k++) cur[k] = nxt[k];
     }
   }
-  if (n & 7) {
-    // last, partial group; the rest of the 32-entry batch stays zero (source slot 0, zero weights: buffers are cleared)
-    a.g_w[((base + n) / 8) * 32 + lane] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+  if ((n & 7) && n > head_end) {
+    // last, partial group: followed by the next warp's entries, or by zeros up to the end of the 32-entry batch (source
+    // slot 0, zero weights: the buffers are cleared)
+    if (SPLIT) {
+      for (int q = 0; q < (n & 7); q++) w16[(((base + n) >> 3) * 32 + lane) * 8 + q] = (uint16_t) (wq[q >> 1] >> ((q & 1) * 16));
+    } else
+      a.g_w[((base + n) / 8) * 32 + lane] = make_uint4(wq[0], wq[1], wq[2], wq[3]);
   }
 }
 
@@ -1906,6 +1999,13 @@ void transfers_columns(qrad_cuda_ctx *c) {
     if (const char *e = getenv("QRAD_BOUNCE_COOP")) threshold = atoll(e);   // tests force it (0 = every slice)
     std::vector<int32_t> coop, regular;
     for (int32_t s : order) (h_len[s] > threshold ? coop : regular).push_back(s);
+    {
+      std::vector<int32_t> all;
+      for (int s = lo; s < hi; s++) all.push_back(s);
+      std::stable_sort(all.begin(), all.end(), [&](int32_t x, int32_t y) { return h_len[x] > h_len[y]; });
+      if (all.empty()) all.push_back(0);
+      c->col_order.upload(all, st);
+    }
     c->n_coop = (int) coop.size();
     c->n_regular = (int) regular.size();
     if (coop.empty()) coop.push_back(0);
@@ -1921,8 +2021,13 @@ void transfers_columns(qrad_cuda_ctx *c) {
   ca.slice_base = c->slice_base.p;
   ca.g_src = c->g_src.p;
   ca.g_w = c->g_w.p;
-  if (cblocks > 0) {
-    k_columns<<<cblocks, kThreads, 0, st>>>(ca);
+  ca.col_order = c->col_order.p;
+  if (hi > lo) {
+    // fewer than three waves of warps: the longest lists would set the time of a warp-per-slice launch
+    bool split = (int64_t) (hi - lo) < (int64_t) 3 * c->sm_count * 32;
+    if (const char *e = getenv("QRAD_COLUMNS_SPLIT")) split = atoi(e) != 0;   // tests run both
+    if (split) k_columns<true><<<hi - lo, kThreads, 0, st>>>(ca, hi - lo);
+    else k_columns<false><<<(hi - lo + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(ca, hi - lo);
     c->launch_check("k_columns");
   }
   std::vector<int32_t> h_rc((size_t) M);

@@ -75,6 +75,18 @@ def test_both_bounce_kernels(Q, case, kernel, tmp_path, monkeypatch):
     assert np.array_equal(added, np.array(meta["added"], np.float32))
 
 
+@pytest.mark.parametrize("split", ["0", "1"])
+@pytest.mark.parametrize("case", ["samplec", "grid3_chop16", "manystyles", "angled"])
+def test_both_column_kernels(Q, case, split, tmp_path, monkeypatch):
+    """Pass 3 of make_transfers builds the gather lists with a warp per receiver slice (many slices per warp slot) or with
+    a block per slice whose warps share the slice's list by entry count (shards); QRAD_COLUMNS_SPLIT forces one.  Both
+    must write the same lists: the reference's transfers, lump and energies."""
+    monkeypatch.setenv("QRAD_COLUMNS_SPLIT", split)
+    meta, sc, dev, added, bsp = light(Q, case, tmp_path)
+    assert sc.lighting() == (G.GOLDEN / (case + ".lump")).read_bytes()
+    assert np.array_equal(added, np.array(meta["added"], np.float32))
+
+
 @pytest.mark.parametrize("case", ["samplec", "grid2", "grid3_chop16", "hall"])
 def test_testline_decisions(Q, case, tmp_path):
     meta, flags = G.load_case(case)
