@@ -100,6 +100,8 @@ int qrad_cuda_create(int device, qrad_cuda_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     QCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     QCUDA(cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking));
+    QCUDA(cudaStreamCreateWithFlags(&c->lstream, cudaStreamNonBlocking));
+    QCUDA(cudaEventCreate(&c->ev_lists));
     for (auto &e : c->ev) QCUDA(cudaEventCreate(&e));
     *out = c;
   });
@@ -113,6 +115,8 @@ void qrad_cuda_destroy(qrad_cuda_ctx *c) {
   cudaStream_t s = c->stream, x = c->xstream;
   if (s) cudaStreamSynchronize(s);
   if (x) cudaStreamSynchronize(x);
+  if (c->lstream) cudaStreamSynchronize(c->lstream);
+  if (c->ev_lists) cudaEventDestroy(c->ev_lists);
   if (c->comm) {
     try {
       nccl().CommDestroy(c->comm);

@@ -32,6 +32,7 @@ const NcclApi &nccl() {
     api.CommDestroy = (decltype(api.CommDestroy)) need("ncclCommDestroy");
     api.AllReduce = (decltype(api.AllReduce)) need("ncclAllReduce");
     api.Broadcast = (decltype(api.Broadcast)) need("ncclBroadcast");
+    api.AllGather = (decltype(api.AllGather)) need("ncclAllGather");
     api.Send = (decltype(api.Send)) need("ncclSend");
     api.Recv = (decltype(api.Recv)) need("ncclRecv");
     api.GroupStart = (decltype(api.GroupStart)) need("ncclGroupStart");

@@ -273,6 +273,10 @@ struct qrad_cuda_ctx {
   // ---- several GPUs ----
   ncclComm_t comm = nullptr;
   cudaStream_t xstream = nullptr;       // the matrix exchange runs beside the lists and pass 2
+  cudaStream_t lstream = nullptr;       // the lists of passes 2 and 3 are prepared beside pass 1
+  cudaEvent_t ev_lists = nullptr;
+  qrad::DBuf<int32_t> lists_i32[4];
+  qrad::DBuf<float4> share_staging;     // share_slices: `world` equal parts for the all-gather of a per-slot array
   int face_lo = 0, face_hi = 0;         // faces this rank lights (all of them on one GPU)
 
   // ---- plane groups of FinalLightFace: for every lit face the patches of all faces on its plane chain, in chain order

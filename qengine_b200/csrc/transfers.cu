@@ -1563,10 +1563,48 @@ RowArgs row_args(qrad_cuda_ctx *c) {
   return ra;
 }
 
-// Every owner sends its part of a per-slot array to everybody (in place): one broadcast per rank, grouped.
+// Every owner sends its part of a per-slot array to everybody (in place).  The parts differ in length (receiver slices are
+// dealt by work, not by count), so there is no all-gather that fits the array as it lies; a grouped broadcast per rank
+// does, at 0.45 ms per call on eight GPUs -- and BounceLight calls this once per bounce.  16-byte records therefore go
+// through a staging buffer of `world` equal parts: pack the own part, ONE in-place all-gather, unpack the others.
+struct ShareArgs {
+  int world, rank, maxlen;
+  int first[kMaxWorld], len[kMaxWorld];   // slots
+};
+__global__ void __launch_bounds__(256) k_share_pack(const ShareArgs a, const float4 *__restrict__ buf, float4 *__restrict__ staging) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.len[a.rank]) staging[(size_t) a.rank * a.maxlen + i] = buf[a.first[a.rank] + i];
+}
+__global__ void __launch_bounds__(256) k_share_unpack(const ShareArgs a, const float4 *__restrict__ staging, float4 *__restrict__ buf) {
+  const int q = blockIdx.y;
+  if (q == a.rank) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.len[q]) buf[a.first[q] + i] = staging[(size_t) q * a.maxlen + i];
+}
+
 void share_slices(qrad_cuda_ctx *c, void *buf, size_t bytes_per_slot, cudaStream_t st) {
   const TransferPlan &P = c->plan;
   const NcclApi &n = nccl();
+  if (bytes_per_slot == sizeof(float4) && P.world <= kMaxWorld && !getenv("QRAD_SHARE_BROADCAST")) {
+    ShareArgs a{};
+    a.world = P.world;
+    a.rank = P.rank;
+    for (int q = 0; q < P.world; q++) {
+      a.first[q] = P.slice_lo[q] * 32;
+      a.len[q] = (P.slice_hi[q] - P.slice_lo[q]) * 32;
+      a.maxlen = std::max(a.maxlen, a.len[q]);
+    }
+    if (a.maxlen == 0) return;
+    c->share_staging.alloc((size_t) a.maxlen * P.world);
+    const int blocks = (a.maxlen + 255) / 256;
+    k_share_pack<<<blocks, 256, 0, st>>>(a, (const float4 *) buf, c->share_staging.p);
+    c->launch_check("k_share_pack");
+    nccl_ok(n.AllGather(c->share_staging.p + (size_t) a.rank * a.maxlen, c->share_staging.p, (size_t) a.maxlen * 4, ncclFloat, c->comm, st),
+            "ncclAllGather");
+    k_share_unpack<<<dim3(blocks, P.world), 256, 0, st>>>(a, c->share_staging.p, (float4 *) buf);
+    c->launch_check("k_share_unpack");
+    return;
+  }
   nccl_ok(n.GroupStart(), "ncclGroupStart");
   for (int q = 0; q < P.world; q++) {
     const size_t first = (size_t) P.slice_lo[q] * 32 * bytes_per_slot, count = (size_t) (P.slice_hi[q] - P.slice_lo[q]) * 32 * bytes_per_slot;
@@ -1586,6 +1624,8 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+static void transfers_lists(qrad_cuda_ctx *c);
+
 // phase 0: the plan, slot order, word tables, pass 1 (this rank's row groups)
 void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
   if (!c->numnodes || !c->N) dfail("make_transfers: BSP and patches must be uploaded first");
@@ -1796,14 +1836,16 @@ void transfers_trace(qrad_cuda_ctx *c, int nopvs) {
     nccl_ok(n.GroupEnd(), "ncclGroupEnd");
     QCUDA(cudaEventRecord(c->ev[3], c->xstream));
   }
+  if (!(P.world > 1 && !c->comm)) transfers_lists(c);   // (not for qrad_cuda_trace_shard)
   c->sync("make_transfers pass 1");
   c->stats.ms_transfers_trace = elapsed(c->ev[0], c->ev[1]);
 }
 
-// phase 1: ordered run lists + pass 2 (row totals of this rank's rows)
-void transfers_rows(qrad_cuda_ctx *c) {
-  cudaStream_t st = c->stream;
-  auto wall0 = std::chrono::steady_clock::now();
+// phase 1: ordered run lists, pass 2 (row totals of this rank's rows)
+// The row and column lists of passes 2 and 3 follow from the plan alone, not from pass 1: they are prepared on a stream
+// of their own while k_visibility runs (the host part overlaps it entirely, the kernels fill the SMs its last runs leave).
+static void transfers_lists(qrad_cuda_ctx *c) {
+  cudaStream_t st = c->lstream;
   const TransferPlan &P = c->plan;
   const int N = c->N, M = P.M, nc = P.nc;
   // ---- the patch order as runs of consecutive slots inside one slice ----
@@ -1845,7 +1887,7 @@ void transfers_rows(qrad_cuda_ctx *c) {
   la.grp_slot0 = c->d_grp_slot0.p;
   la.coff = c->d_coff.p;
   la.E = (int64_t) P.seer_cluster.size();
-  DBuf<int32_t> d_rowcl, d_colcl, d_cnt_row, d_cnt_col;
+  DBuf<int32_t> &d_rowcl = c->lists_i32[0], &d_colcl = c->lists_i32[1], &d_cnt_row = c->lists_i32[2], &d_cnt_col = c->lists_i32[3];
   d_rowcl.upload(row_clusters, st);
   d_colcl.upload(col_clusters, st);
   d_cnt_row.alloc((size_t) nc);
@@ -1890,7 +1932,16 @@ void transfers_rows(qrad_cuda_ctx *c) {
     k_run_lists<true, true><<<(int) col_clusters.size(), 1024, 0, st>>>(la);
     c->launch_check("k_run_lists(columns)");
   }
-  c->sync("make_transfers lists");
+  QCUDA(cudaEventRecord(c->ev_lists, st));
+}
+
+void transfers_rows(qrad_cuda_ctx *c) {
+  cudaStream_t st = c->stream;
+  auto wall0 = std::chrono::steady_clock::now();
+  const TransferPlan &P = c->plan;
+  const int M = P.M;
+  QCUDA(cudaStreamWaitEvent(st, c->ev_lists, 0));
+  c->sync("make_transfers lists");   // what is left of them once pass 1 has ended
   c->stats.ms_tr_lists = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   wall0 = std::chrono::steady_clock::now();
   // ---- pass 2 ----
