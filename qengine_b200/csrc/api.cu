@@ -107,15 +107,39 @@ int qrad_cuda_create(int device, qrad_cuda_ctx **out) {
   });
 }
 
+// Host-side derived data of a lighting pass, computed in the background while the GPU works on the phases before the one
+// that needs it: the plan of the transfer matrix (make_transfers) and the plane groups (final_light).  Started by the
+// uploads and again by build_facelights -- the first call of every pass -- so that a pass over data uploaded earlier
+// does the same work as the first one.
+static void start_plan(qrad_cuda_ctx *c) {
+  if (c->plan_future.valid() || !c->have_vis || c->numclusters <= 0 || c->N <= 0) return;
+  const int n = c->N, world = c->world, rank = c->rank, nc = c->numclusters, pw = c->pvs_words;
+  const uint32_t *pvs = c->h_pvs.data();   // stays put until the next upload_bsp, which waits for this task
+  std::vector<int32_t> eff(c->h_cluster);
+  bool ok = true;
+  for (int cl : eff) ok = ok && cl < nc;
+  if (ok)
+    c->plan_future = std::async(std::launch::async, [eff = std::move(eff), n, nc, pvs, pw, world, rank]() {
+      auto p = std::make_shared<TransferPlan>();
+      build_plan(*p, n, eff.data(), nc, pvs, pw, world, rank, 0);
+      return p;
+    });
+}
+
+static void start_plane_groups(qrad_cuda_ctx *c) {
+  if (c->groups_future.valid() || c->N <= 0 || c->F <= 0 || (int) c->h_face_head.size() != c->F) return;
+  c->groups_future = std::async(std::launch::async, [c] { return compute_plane_groups(c); });
+}
+
 void qrad_cuda_destroy(qrad_cuda_ctx *c) {
   if (!c) return;
   if (c->plan_future.valid()) c->plan_future.wait();
   if (c->groups_future.valid()) c->groups_future.wait();
   cudaSetDevice(c->device);
-  cudaStream_t s = c->stream, x = c->xstream;
+  cudaStream_t s = c->stream, x = c->xstream, l = c->lstream;
   if (s) cudaStreamSynchronize(s);
   if (x) cudaStreamSynchronize(x);
-  if (c->lstream) cudaStreamSynchronize(c->lstream);
+  if (l) cudaStreamSynchronize(l);
   if (c->ev_lists) cudaEventDestroy(c->ev_lists);
   if (c->comm) {
     try {
@@ -129,6 +153,7 @@ void qrad_cuda_destroy(qrad_cuda_ctx *c) {
   delete c;
   if (s) cudaStreamDestroy(s);
   if (x) cudaStreamDestroy(x);
+  if (l) cudaStreamDestroy(l);
 }
 
 // ---- several GPUs: the context joins an NCCL communicator; from then on the same entry points do their share of the work
@@ -232,7 +257,6 @@ int qrad_cuda_upload_patches(qrad_cuda_ctx *c, const qrad_patches_view *p) {
     c->numfaces_p = p->numfaces;
     if (c->groups_future.valid()) c->groups_future.wait();
     c->groups_future = {};
-    c->plane_groups.reset();
     c->h_cluster.assign(p->cluster, p->cluster + n);
     c->h_sky.assign(p->sky, p->sky + n);
     c->h_next.assign(p->next, p->next + n);
@@ -276,20 +300,9 @@ int qrad_cuda_upload_patches(qrad_cuda_ctx *c, const qrad_patches_view *p) {
     c->d_radiosity.alloc((size_t) n * 3);
     c->d_radiosity.zero(c->stream);
     c->sync("upload_patches");
-    if (c->have_vis && c->numclusters > 0) {   // plan of the PVS-mode transfer matrix, in the background
-      if (c->plan_future.valid()) c->plan_future.wait();
-      const int world = c->world, rank = c->rank, nc = c->numclusters, pw = c->pvs_words;
-      const uint32_t *pvs = c->h_pvs.data();   // stays put until the next upload_bsp, which waits for this task
-      std::vector<int32_t> eff(c->h_cluster);
-      bool ok = true;
-      for (int cl : eff) ok = ok && cl < nc;
-      if (ok)
-        c->plan_future = std::async(std::launch::async, [eff = std::move(eff), n, nc, pvs, pw, world, rank]() {
-          auto p = std::make_shared<TransferPlan>();
-          build_plan(*p, n, eff.data(), nc, pvs, pw, world, rank, 0);
-          return p;
-        });
-    }
+    if (c->plan_future.valid()) c->plan_future.wait();
+    c->plan_future = {};
+    start_plan(c);   // plan of the PVS-mode transfer matrix, in the background
     c->stats.num_patches = n;
     c->transfers_done = c->facelights_done = false;
   });
@@ -338,7 +351,6 @@ int qrad_cuda_upload_faces(qrad_cuda_ctx *c, const qrad_faces_view *f) {
     if (c->N && nf != c->numfaces_p) dfail("faces view has %d faces, patches view %d", nf, c->numfaces_p);
     if (c->groups_future.valid()) c->groups_future.wait();
     c->groups_future = {};
-    c->plane_groups.reset();
     c->F = nf;
     c->h_lit.assign(f->lit, f->lit + nf);
     c->h_texsize.assign(f->texsize, f->texsize + (size_t) nf * 2);
@@ -374,8 +386,7 @@ int qrad_cuda_upload_faces(qrad_cuda_ctx *c, const qrad_faces_view *f) {
     c->f_luxel_first.upload(c->h_luxel_first, c->stream);
     c->luxel_face.upload(lface, c->stream);
     c->sync("upload_faces");
-    if (c->N > 0 && (int) c->h_face_head.size() == nf)   // the plane groups FinalLightFace will need, in the background
-      c->groups_future = std::async(std::launch::async, [c] { return compute_plane_groups(c); });
+    start_plane_groups(c);   // the plane groups FinalLightFace will need, in the background
     c->stats.num_luxels = c->num_luxels;
     c->facelights_done = false;
   });
@@ -398,6 +409,10 @@ int qrad_cuda_point_in_leaf(qrad_cuda_ctx *c, int64_t n, const float *points, in
 int qrad_cuda_build_facelights(qrad_cuda_ctx *c, int extrasamples, int numbounce) {
   return guarded([&] {
     QCUDA(cudaSetDevice(c->device));
+    if (numbounce > 0) {
+      start_plan(c);
+      start_plane_groups(c);
+    }
     build_facelights_impl(c, extrasamples, numbounce);
   });
 }

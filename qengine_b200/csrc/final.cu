@@ -510,22 +510,15 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
   tri_count.alloc((size_t) F);
   tri_count.zero(st);
   if (p->numbounce > 0) {
-    std::shared_ptr<qrad_cuda_ctx::PlaneGroups> pg = c->plane_groups;   // kept from the last call while the faces stay
-    if (!pg) {
-      if (c->groups_future.valid()) pg = c->groups_future.get();   // started by upload_faces
-      else pg = compute_plane_groups(c);
-      c->groups_future = {};
-      c->plane_groups = pg;
-      c->plane_groups_uploaded = false;
-    }
+    std::shared_ptr<qrad_cuda_ctx::PlaneGroups> pg;
+    if (c->groups_future.valid()) pg = c->groups_future.get();   // started by upload_faces / build_facelights
+    else pg = compute_plane_groups(c);
+    c->groups_future = {};
     if (!pg->error.empty()) dfail("%s", pg->error.c_str());
     laps.lap("plane groups (wait)");
-    if (!c->plane_groups_uploaded) {
-      d_group_of_face.upload(pg->group_of_face, st);
-      d_group_first.upload(pg->group_first, st);
-      d_group_patch.upload(pg->group_patch, st);
-      c->plane_groups_uploaded = true;
-    }
+    d_group_of_face.upload(pg->group_of_face, st);
+    d_group_first.upload(pg->group_first, st);
+    d_group_patch.upload(pg->group_patch, st);
     tri_points.alloc((size_t) F * kMaxTriPoints + 1);
     d_pmax.alloc(1);
     d_pmax.zero(st);

@@ -287,8 +287,6 @@ struct qrad_cuda_ctx {
   };
   std::vector<int32_t> h_next, h_face_head;        // patch->next, face_patches[] as uploaded
   std::future<std::shared_ptr<PlaneGroups>> groups_future;
-  std::shared_ptr<PlaneGroups> plane_groups;   // of the faces and patches uploaded last (final_light keeps them between calls)
-  bool plane_groups_uploaded = false;
 
   // ---- FinalLightFace scratch (per resident warp) ----
   qrad::DBuf<uint16_t> fin_matrix, fin_ep0, fin_ep1, fin_tedges, fin_stack;
