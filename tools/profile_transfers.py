@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""One make_transfers + one bounce on a workload: the target of the ncu captures kept under profiles/.
+"""One make_transfers + one bounce + final_light on a workload: the target of the ncu captures kept under profiles/.
 usage: python tools/profile_transfers.py [workload]   (default c5_chop16, the C5 map at -chop 16: its kernels fit a replay)"""
 import sys
 import tempfile
@@ -19,5 +19,6 @@ with tempfile.TemporaryDirectory() as tmp:
     dev.build_facelights(p.extrasamples, p.numbounce)
     dev.make_transfers(p.nopvs)
     dev.bounce(1, want_added=False)
+    dev.final_light(p.ambient, p.maxlight, p.lightscale, p.subdiv, p.numbounce)
     st = dev.stats()
     print({k: st[k] for k in ("num_patches", "total_transfers", "rays_transfers", "ms_transfers_trace", "ms_tr_rows", "ms_tr_columns")})
