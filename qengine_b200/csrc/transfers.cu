@@ -608,6 +608,85 @@ __global__ void __launch_bounds__(kThreads) k_row_totals32(const RowArgs a) {
   }
 }
 
+// The same sums with four times the warps: a warp takes 8 of the 32 rows of a slice, lane = (row, one of four receivers).
+// The four lanes of a row compute the form factors of four accepted-or-not receivers at once, then every one of them adds
+// the four values in receiver order (a rejected receiver contributes +0.0f, which leaves a float sum as it is): the sum
+// is the same serial sum, the square roots and divisions run four abreast.  One warp per 32 rows needs 20 ms for the
+// longest row list of C5 all by itself -- the whole pass on an eighth of the map should take 8.
+__global__ void __launch_bounds__(kThreads) k_row_totals8(const RowArgs a) {
+  __shared__ float4 s_po[kWarpsPerBlock][32], s_pn[kWarpsPerBlock][32];
+  __shared__ uint8_t s_hot[kWarpsPerBlock][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1;
+  const int q = blockIdx.x * kWarpsPerBlock + wid;
+  const int rs = q >> 2, part = q & 3;
+  if (rs >= a.n_rowslices) return;
+  const int r = lane >> 2, sub = lane & 3;
+  const int sslot = a.rowslice_slot0[rs] + part * 8 + r;
+  const int64_t row = (int64_t) a.rowslice_row0[rs] + part * 8 + r;
+  const int c = a.g.slot_cluster[a.rowslice_slot0[rs]];
+  const bool live_row = (a.g.slot_flags[sslot] & 2u) != 0;
+  const float4 so = a.s_origin_area[sslot];
+  const float4 sn = a.s_normal[sslot];
+  const int64_t e0 = a.vl_ptr[c], e1 = a.vl_ptr[c + 1];
+  float total = 0.f;
+  int count = 0;
+  for (int64_t eb = e0; eb < e1; eb += 32) {
+    const int nb = (int) min((int64_t) 32, e1 - eb);
+    const int4 mine = lane < nb ? __ldg(a.vl + eb + lane) : make_int4(0, 0, 0, 0);
+    const int64_t myaddr = vl_addr(mine);
+    auto fetch = [&](const int j) -> uint32_t {   // this lane's row's word of run j (0 past the end of the batch)
+      const int64_t ad = __shfl_sync(0xffffffffu, myaddr, j & 31);
+      return j < nb ? __ldcs(a.bits + ad + row) : 0u;
+    };
+    uint32_t cur[4], nxt[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) cur[k] = fetch(k);
+    for (int j0 = 0; j0 < nb; j0 += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) nxt[k] = fetch(j0 + 4 + k);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int j = j0 + k;
+        if (j >= nb) break;
+        const uint32_t mask = (uint32_t) __shfl_sync(0xffffffffu, mine.z, j);
+        const int slice = __shfl_sync(0xffffffffu, mine.w, j);
+        const uint32_t acc = live_row ? (cur[k] & mask) : 0u;
+        const unsigned hot = __reduce_or_sync(0xffffffffu, acc);
+        if (!hot) continue;
+        __syncwarp();
+        if ((hot >> lane) & 1u) {
+          s_po[wid][lane] = a.s_origin_area[slice * 32 + lane];
+          s_pn[wid][lane] = a.s_normal[slice * 32 + lane];
+          s_hot[wid][__popc(hot & lt)] = (uint8_t) lane;
+        }
+        __syncwarp();
+        count += __popc(acc);
+        const int nh = __popc(hot);
+        for (int g = 0; g < nh; g += 4) {
+          float t = 0.f;
+          if (g + sub < nh) {
+            const int kk = s_hot[wid][g + sub];
+            if ((acc >> kk) & 1u) {
+              float dist;
+              bool wr;
+              t = form_factor_pre(so, sn, s_po[wid][kk], s_pn[wid][kk], dist, wr);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) total += __shfl_sync(0xffffffffu, t, (lane & ~3) + i);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) cur[k] = nxt[k];
+    }
+  }
+  if (sub == 0 && (a.g.slot_flags[sslot] & 1u)) {
+    a.row_total[sslot] = total;
+    a.row_count[sslot] = count;
+  }
+}
+
 // Reference row format of selected rows (parity tests): one warp per row; the receivers of a run are tested by 32 lanes
 // and written in ascending patch index: {patch, (int)(trans * 0x10000 / total)} (qrad3.c:283-289).
 __global__ void __launch_bounds__(kThreads) k_rows_emit(const RowArgs a) {
@@ -1957,8 +2036,13 @@ void transfers_rows(qrad_cuda_ctx *c) {
     ra.rowslice_slot0 = c->d_rowslice_slot0.p;
     ra.rowslice_row0 = c->d_rowslice_row0.p;
     ra.n_rowslices = nrs;
-    k_row_totals32<<<(nrs + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(ra);
-    c->launch_check("k_row_totals32");
+    // about one wave of 32-row warps or less (a shard): the longest row list would set the time of the launch; the
+    // quarter-slice kernel does 1.7 times the work (every warp scans the whole row list) in a quarter of the time per slice
+    bool quarters = (int64_t) nrs * 4 < (int64_t) 5 * c->sm_count * 32;
+    if (const char *e = getenv("QRAD_ROWS_KERNEL")) quarters = atoi(e) == 8;   // tests run both
+    if (quarters) k_row_totals8<<<(4 * nrs + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(ra);
+    else k_row_totals32<<<(nrs + kWarpsPerBlock - 1) / kWarpsPerBlock, kThreads, 0, st>>>(ra);
+    c->launch_check("k_row_totals");
   }
   if (P.world > 1) {   // every row was summed by exactly one rank
     // one communicator: its collectives are kept in one order by making this stream wait for the matrix exchange

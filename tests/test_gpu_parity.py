@@ -75,6 +75,20 @@ def test_both_bounce_kernels(Q, case, kernel, tmp_path, monkeypatch):
     assert np.array_equal(added, np.array(meta["added"], np.float32))
 
 
+@pytest.mark.parametrize("rows", ["32", "8"])
+@pytest.mark.parametrize("case", ["samplec", "grid3_chop16", "manystyles", "angled"])
+def test_both_row_kernels(Q, case, rows, tmp_path, monkeypatch):
+    """Pass 2 of make_transfers (the serial float sum `total += trans`, qrad3.c:254) with a warp per 32 source rows or with
+    a warp per 8 rows whose four lanes per row evaluate four form factors at once and add them in receiver order;
+    QRAD_ROWS_KERNEL forces one.  The totals scale every transfer, so the lump and the energies notice any difference;
+    numtransfers is the other output of the pass."""
+    monkeypatch.setenv("QRAD_ROWS_KERNEL", rows)
+    meta, sc, dev, added, bsp = light(Q, case, tmp_path)
+    assert sc.lighting() == (G.GOLDEN / (case + ".lump")).read_bytes()
+    assert np.array_equal(added, np.array(meta["added"], np.float32))
+    assert np.array_equal(dev.numtransfers(), G.golden_numtransfers(case))
+
+
 @pytest.mark.parametrize("split", ["0", "1"])
 @pytest.mark.parametrize("case", ["samplec", "grid3_chop16", "manystyles", "angled"])
 def test_both_column_kernels(Q, case, split, tmp_path, monkeypatch):
