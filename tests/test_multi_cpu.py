@@ -98,6 +98,29 @@ def word_value(slot, sl):
     return np.uint32((slot * 2654435761 + sl * 40503 + 12345) & 0xffffffff)
 
 
+@pytest.mark.parametrize("case", ["samplec", "grid3_chop16", "manystyles"])
+def test_plan_does_not_depend_on_its_threads(case, tmp_path, monkeypatch):
+    """build_plan runs its two counting sorts (patches by cluster, visible pairs by receiver) on several threads; slot
+    order, ownership, pieces and word addresses must come out as with one."""
+    cluster, vis = scene_inputs(case, tmp_path)
+    ref = None
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("QRAD_PLAN_THREADS", threads)
+        p = Plan(cluster, vis, 3, 1)
+        owner, pslot = p.slot_tables()
+        lo, hi = p.slices()
+        rng = np.random.default_rng(11)
+        slots = rng.integers(0, p.slots, 400)
+        sls = rng.integers(0, p.nslices, 400)
+        addr = np.array([p.word_address(int(a), int(b)) for a, b in zip(slots, sls)])
+        cols = [np.concatenate(p.column_list(int(sl))) for sl in range(0, p.nslices, max(1, p.nslices // 8))]
+        got = (p.slots, p.nslices, p.rowbuf_words, p.ngroups, p.total_words, owner.tobytes(), pslot.tobytes(), lo.tobytes(),
+               hi.tobytes(), [p.piece(q, r) for q in range(3) for r in range(3)], addr.tobytes(), [c.tobytes() for c in cols])
+        if ref is None:
+            ref = got
+        assert got == ref, threads
+
+
 @pytest.mark.parametrize("case", ["samplec", "grid3_chop16", "angled"])
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 def test_every_word_has_one_home(case, world, tmp_path):
