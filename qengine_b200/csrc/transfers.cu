@@ -2030,8 +2030,19 @@ void transfers_rows(qrad_cuda_ctx *c) {
   c->row_count.zero(st);
   const int nrs = (int) P.own_rowslice_slot0.size();
   if (nrs > 0) {
-    c->d_rowslice_slot0.upload(P.own_rowslice_slot0, st);
-    c->d_rowslice_row0.upload(P.own_rowslice_row0, st);
+    // the slices with the longest row lists first: a warp is serial in its list, the last wave should hold the short ones
+    std::vector<int32_t> ord((size_t) nrs), slot0((size_t) nrs), row0((size_t) nrs);
+    for (int i = 0; i < nrs; i++) ord[i] = i;
+    std::stable_sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) {
+      const int cx = P.slot_cluster[P.own_rowslice_slot0[x]], cy = P.slot_cluster[P.own_rowslice_slot0[y]];
+      return P.Lptr[cx + 1] - P.Lptr[cx] > P.Lptr[cy + 1] - P.Lptr[cy];
+    });
+    for (int i = 0; i < nrs; i++) {
+      slot0[i] = P.own_rowslice_slot0[ord[i]];
+      row0[i] = P.own_rowslice_row0[ord[i]];
+    }
+    c->d_rowslice_slot0.upload(slot0, st);
+    c->d_rowslice_row0.upload(row0, st);
     RowArgs ra = row_args(c);
     ra.rowslice_slot0 = c->d_rowslice_slot0.p;
     ra.rowslice_row0 = c->d_rowslice_row0.p;
