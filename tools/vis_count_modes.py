@@ -1,6 +1,6 @@
 import json, os, sys, tempfile
 from pathlib import Path
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from qengine_b200 import qrad as Q
 from qengine_b200 import workloads as W
 name = "c5_grid16_chop8"
