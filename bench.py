@@ -228,6 +228,30 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize()
 
+        pinned = {}
+
+        def gather_blobs(blob, world, xbytes):
+            """all-gather of the ranks' byte blobs (different lengths) through the GPUs; xbytes += [h2d, d2h]"""
+            n = torch.tensor([blob.size], device="cuda", dtype=torch.int64)
+            sizes = [torch.zeros_like(n) for _ in range(world)]
+            dist.all_gather(sizes, n)
+            sizes = [int(x.item()) for x in sizes]
+            mx = (max(sizes) + 255) & ~255
+            mine = torch.zeros(mx, dtype=torch.uint8, device="cuda")
+            mine[:blob.size].copy_(torch.from_numpy(blob), non_blocking=True)
+            out = torch.empty(world * mx, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(out, mine)
+            if pinned.get("n", 0) < world * mx:
+                pinned["buf"] = torch.empty(world * mx, dtype=torch.uint8, pin_memory=True)
+                pinned["n"] = world * mx
+            host = pinned["buf"][:world * mx]
+            host.copy_(out)
+            torch.cuda.synchronize()
+            xbytes[0] += int(blob.size)
+            xbytes[1] += world * mx
+            a = host.numpy()
+            return [a[q * mx:q * mx + sizes[q]] for q in range(world)]
+
         def device_step():
             dev.build_facelights(p.extrasamples, p.numbounce)
             if p.numbounce > 0:
@@ -297,7 +321,14 @@ def main():
             t0 = time.perf_counter()
             sc2 = Q.Scene(bsp)
             t1 = time.perf_counter()
-            sc2.prepare(p)
+            xb = [0, 0]
+            if world > 1:
+                # the processes share the dicing (90 % of prepare): every rank dices its range of the faces, the blobs
+                # travel through the GPUs (NCCL all-gather), every rank stitches all of them -- the same scene everywhere
+                blob = sc2.prepare_part(p, rank, world, copy=False)
+                sc2.prepare_merge(gather_blobs(blob, world, xb))
+            else:
+                sc2.prepare(p)
             t2 = time.perf_counter()
             Q.rad_world(sc2, dev, p, want_added=False)
             t3 = time.perf_counter()
@@ -310,7 +341,7 @@ def main():
             if i:
                 e2e_times.append(t4 - t0)
                 e2e_parts.append([t1 - t0, t2 - t1, t3 - t2, t4 - t3])
-                h2d, d2h = s1["h2d_bytes"] - s0["h2d_bytes"], s1["d2h_bytes"] - s0["d2h_bytes"]
+                h2d, d2h = s1["h2d_bytes"] - s0["h2d_bytes"] + xb[0], s1["d2h_bytes"] - s0["d2h_bytes"] + xb[1]
             sc2.close()
         e2e_s = float(np.mean(e2e_times))
         t = torch.tensor([e2e_s], device="cuda")
@@ -371,7 +402,9 @@ def main():
                     "d2h_bytes_per_step": int(d2h),
                     "parts_s": dict(zip(["host_load", "host_prepare", "rad_world", "host_write"], [float(x) for x in parts])),
                     "includes": "LoadBSPFile+ParseEntities+CalcTextureReflectivity, MakePatches+SubdividePatches+"
-                                "CreateDirectLights, uploads + all device phases + lump read-back, WriteBSPFile"},
+                                "CreateDirectLights, uploads + all device phases + lump read-back, WriteBSPFile"
+                                + ("; the ranks share the dicing (qrad_host_prepare_part / _merge, blobs all-gathered "
+                                   "through the GPUs, counted in the byte figures)" if world > 1 else "")},
             "host_prepare_s": float(parts[1]), "host_load_s": float(parts[0]),
             "gpu_launches": int(launches),
             "roofline": roofline,

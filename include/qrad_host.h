@@ -67,6 +67,15 @@ int  qrad_host_load_as(const char *file_path, const char *qdir_path, qrad_host_s
 void qrad_host_free(qrad_host_scene *s);
 /* After load: numbounce/ambient are forced like qrad3.c:627-631 when the map has no vis data. */
 int  qrad_host_prepare(qrad_host_scene *s, qrad_host_params *params);
+/* The same, shared by `parts` processes that light the same map (one per GPU): each loads the map, calls prepare_part
+   with its own index -- MakePatches, then SubdividePatches for a contiguous range of the faces (ranges of equal face
+   area, the same in every process) -- and gets a blob (owned by the scene, valid until the next call on it).  The host
+   program gathers all blobs in every process by whatever means it has (MPI_Allgatherv, torch.distributed, a file) and
+   calls prepare_merge with all of them in part order: the patches come out exactly as qrad_host_prepare leaves them,
+   then CreateDirectLights and the face frames follow.  Dicing is 90 % of prepare and linear in the threads. */
+int  qrad_host_prepare_part(qrad_host_scene *s, qrad_host_params *params, int part, int parts, const uint8_t **blob,
+                            int64_t *bytes);
+int  qrad_host_prepare_merge(qrad_host_scene *s, int parts, const uint8_t *const *blobs, const int64_t *bytes);
 
 int  qrad_host_bsp_view(qrad_host_scene *s, qrad_bsp_view *out);
 int  qrad_host_patches_view(qrad_host_scene *s, qrad_patches_view *out);

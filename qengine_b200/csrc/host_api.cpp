@@ -57,19 +57,25 @@ int qrad_host_load(const char *bsp_path, qrad_host_scene **out) { return qrad_ho
 
 void qrad_host_free(qrad_host_scene *s) { delete s; }
 
+// what every flavour of prepare starts with: qrad3.c:627-631, and a clean slate
+static void prepare_begin(Scene &s, qrad_host_params *params) {
+  if (!s.bsp.visdatasize()) {  // qrad3.c:627-631
+    printf("No vis information, direct lighting only.\n");
+    params->numbounce = 0;
+    params->ambient = 0.1f;
+  }
+  s.params = *params;
+  if (s.bsp.numnodes() == 0 || s.bsp.numfaces() == 0) fail("Empty map");
+  s.winding.clear(); s.origin.clear(); s.normal.clear(); s.reflectivity.clear(); s.baselight.clear();
+  s.totallight.clear(); s.planedist.clear(); s.area.clear(); s.cluster.clear(); s.face.clear();
+  s.next.clear(); s.sky.clear(); s.wpts.clear(); s.wfirst.clear(); s.wcount.clear(); s.bounds.clear();
+  s.prepared = false;
+}
+
 int qrad_host_prepare(qrad_host_scene *hs, qrad_host_params *params) {
   return guarded([&] {
     Scene &s = hs->scene;
-    if (!s.bsp.visdatasize()) {  // qrad3.c:627-631
-      printf("No vis information, direct lighting only.\n");
-      params->numbounce = 0;
-      params->ambient = 0.1f;
-    }
-    s.params = *params;
-    if (s.bsp.numnodes() == 0 || s.bsp.numfaces() == 0) fail("Empty map");
-    s.winding.clear(); s.origin.clear(); s.normal.clear(); s.reflectivity.clear(); s.baselight.clear();
-    s.totallight.clear(); s.planedist.clear(); s.area.clear(); s.cluster.clear(); s.face.clear();
-    s.next.clear(); s.sky.clear(); s.wpts.clear(); s.wfirst.clear(); s.wcount.clear(); s.bounds.clear();
+    prepare_begin(s, params);
     const bool timing = getenv("QRAD_DEBUG_TIMING") != nullptr;
     auto tp = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
@@ -86,6 +92,34 @@ int qrad_host_prepare(qrad_host_scene *hs, qrad_host_params *params) {
     lap("CreateDirectLights");
     build_face_frames(s);
     lap("face frames");
+    s.prepared = true;
+  });
+}
+
+int qrad_host_prepare_part(qrad_host_scene *hs, qrad_host_params *params, int part, int parts, const uint8_t **blob,
+                           int64_t *bytes) {
+  *blob = nullptr;
+  *bytes = 0;
+  return guarded([&] {
+    Scene &s = hs->scene;
+    prepare_begin(s, params);
+    make_patches(s);
+    subdivide_part(s, part, parts, hs->part_blob);
+    *blob = hs->part_blob.data();
+    *bytes = (int64_t) hs->part_blob.size();
+  });
+}
+
+int qrad_host_prepare_merge(qrad_host_scene *hs, int parts, const uint8_t *const *blobs, const int64_t *bytes) {
+  return guarded([&] {
+    Scene &s = hs->scene;
+    if (s.prepared || s.winding.empty()) fail("prepare_merge: prepare_part has not run on this scene");
+    if (parts < 1) fail("prepare_merge: no parts");
+    subdivide_merge(s, parts, blobs, bytes);
+    hs->part_blob.clear();
+    hs->part_blob.shrink_to_fit();
+    create_direct_lights(s);
+    build_face_frames(s);
     s.prepared = true;
   });
 }

@@ -125,6 +125,8 @@ struct Scene {
 void calc_texture_reflectivity(Scene &s);  // patches.c:40-112
 void make_patches(Scene &s);               // patches.c:275-309 (+ MakeBackplanes, qrad3.c:88-96)
 void subdivide_patches(Scene &s);          // patches.c:425-492
+void subdivide_part(Scene &s, int part, int parts, std::vector<uint8_t> &blob);   // the same, shared by several processes
+void subdivide_merge(Scene &s, int parts, const uint8_t *const *blobs, const int64_t *bytes);
 void create_direct_lights(Scene &s);       // lightmap.c:721-838
 void build_face_frames(Scene &s);          // lightmap.c:480-603, 42-52, 1109-1117
 
@@ -132,6 +134,7 @@ void build_face_frames(Scene &s);          // lightmap.c:480-603, 42-52, 1109-11
 
 struct qrad_host_scene {
   qrad::Scene scene;
+  std::vector<uint8_t> part_blob;   // qrad_host_prepare_part: this process's share of the dicing
 };
 
 namespace qrad {

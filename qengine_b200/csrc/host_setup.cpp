@@ -514,29 +514,30 @@ void make_patches(Scene &s) {
   if (s.params.verbose) printf("%i sqaure feet\n", (int) (totalarea / 64));
 }
 
-void subdivide_patches(Scene &s) {  // patches.c:477-492
-  const int num = s.num_patches();   // the originals: one per face
+namespace {
+struct Where { int32_t pool, first, count; };   // original i: its patches are `count` consecutive entries of pools[pool]
+struct PoolView {              // what stitch_patches reads of a pool: a thread's LocalPatches, or another process's blob
+  const Vec3 *pts, *origin;
+  const int64_t *wfirst;
+  const int32_t *wcount, *next, *cluster;
+  const float *area;
+};
+PoolView view_of(const LocalPatches &L) {
+  return PoolView{L.pts.data(), L.origin.data(), L.wfirst.data(), L.wcount.data(), L.next.data(), L.cluster.data(), L.area.data()};
+}
+
+// DicePatch for the originals [lo, hi) on `nth` threads, each into a pool of its own
+void dice_range(Scene &s, int lo, int hi, int nth, std::vector<LocalPatches> &locals, std::vector<Where> &where) {
   const qrad_dleaf_t *leafs = s.bsp.as<qrad_dleaf_t>(kLumpLeafs);
   const bool dice = !(s.params.subdiv < 1);
-  const int nth = host_threads(s, num / 16);
-  const bool timing = getenv("QRAD_DEBUG_TIMING") != nullptr;
-  auto tp = std::chrono::steady_clock::now();
-  auto lap = [&](const char *what) {
-    if (!timing) return;
-    auto now = std::chrono::steady_clock::now();
-    fprintf(stderr, "  subdivide: %-18s %7.1f ms (%d threads)\n", what, std::chrono::duration<double, std::milli>(now - tp).count(), nth);
-    tp = now;
-  };
-  std::vector<LocalPatches> locals((size_t) nth);
-  struct Where { int32_t thread, first, count; };
-  std::vector<Where> where((size_t) num);
-  std::atomic<int> cursor{0};
+  locals.assign((size_t) nth, LocalPatches());
+  std::atomic<int> cursor{lo};
   parallel_for(nth, [&](int t) {
     LocalPatches &L = locals[t];
     for (;;) {
       const int i0 = cursor.fetch_add(16);
-      if (i0 >= num) break;
-      for (int i = i0; i < std::min(num, i0 + 16); i++) {
+      if (i0 >= hi) break;
+      for (int i = i0; i < std::min(hi, i0 + 16); i++) {
         Dicer d{s, L, s.normal[i].v, 0, leafs};
         d.base = L.add();
         d.set_winding(d.base, s.winding[i].p.data(), (int) s.winding[i].p.size());
@@ -548,14 +549,17 @@ void subdivide_patches(Scene &s) {  // patches.c:477-492
       }
     }
   });
-  lap("dice");
-  // global indices: original i stays i, its created patches follow the originals in creation order
+}
+
+// The results in the reference's order: original i stays i, its created patches follow the originals in creation order
+void stitch_patches(Scene &s, const std::vector<PoolView> &locals, const std::vector<Where> &where, int nth) {
+  const int num = s.num_patches();
   std::vector<int64_t> created_before((size_t) num + 1, 0), pts_before((size_t) num + 1, 0);
   for (int i = 0; i < num; i++) {
     const Where &w = where[i];
     created_before[i + 1] = created_before[i] + (w.count - 1);
     int64_t np = 0;
-    const LocalPatches &L = locals[w.thread];
+    const PoolView &L = locals[w.pool];
     for (int k = 0; k < w.count; k++) np += L.wcount[w.first + k];
     pts_before[i + 1] = pts_before[i] + np;
   }
@@ -567,7 +571,6 @@ void subdivide_patches(Scene &s) {  // patches.c:477-492
   s.planedist.resize(N); s.area.resize(N); s.cluster.resize(N); s.face.resize(N); s.next.resize(N); s.sky.resize(N);
   s.wfirst.resize(N); s.wcount.resize(N); s.bounds.resize(N * 6);
   s.wpts.resize((size_t) pts_before[num]);
-  lap("prefix + resize");
   std::atomic<int> cursor2{0};
   parallel_for(nth, [&](int) {
     for (;;) {
@@ -575,7 +578,7 @@ void subdivide_patches(Scene &s) {  // patches.c:477-492
       if (i0 >= num) break;
       for (int i = i0; i < std::min(num, i0 + 64); i++) {
         const Where &w = where[i];
-        const LocalPatches &L = locals[w.thread];
+        const PoolView &L = locals[w.pool];
         const int64_t gbase = num + created_before[i];
         auto gidx = [&](int k) -> int64_t { return k == 0 ? i : gbase + k - 1; };
         const int32_t orig_next = s.next[i];
@@ -609,14 +612,165 @@ void subdivide_patches(Scene &s) {  // patches.c:477-492
       }
     }
   });
-  lap("merge");
   if (s.params.verbose) {
+    const bool dice = !(s.params.subdiv < 1);
     for (size_t g = 0; g < N; g++)
       if (s.cluster[g] == -1 && (int) g >= num) printf("patch->cluster == -1\n");
     if (dice) printf("%i patches after subdivision\n", s.num_patches());
   }
   s.winding.clear();
   s.winding.shrink_to_fit();
+}
+
+// Several processes that light the same map (one per GPU) share the dicing: part k of n dices a contiguous range of the
+// originals -- ranges of equal winding area, the same on every process -- and hands its results on as one flat blob;
+// every process then stitches all the blobs together exactly as it stitches its own threads' pools.
+void part_range(const Scene &s, int part, int parts, int &lo, int &hi) {
+  const int num = s.num_patches();
+  std::vector<double> cum((size_t) num + 1, 0.0);
+  for (int i = 0; i < num; i++) cum[i + 1] = cum[i] + (double) std::max(s.area[i], 1.0f);
+  auto cut = [&](int k) -> int {
+    if (k <= 0) return 0;
+    if (k >= parts) return num;
+    const double target = cum[num] * k / parts;
+    return (int) (std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+  };
+  lo = std::min(cut(part), num);
+  hi = std::max(lo, std::min(cut(part + 1), num));
+}
+
+struct BlobHeader {
+  uint32_t magic;
+  int32_t lo, hi, num;       // originals [lo, hi) of num
+  int64_t patches, points;   // entries that follow
+};
+constexpr uint32_t kBlobMagic = 0x51504431;   // "QPD1"
+}  // namespace
+
+void subdivide_patches(Scene &s) {  // patches.c:477-492
+  const int num = s.num_patches();   // the originals: one per face
+  const int nth = host_threads(s, num / 16);
+  const bool timing = getenv("QRAD_DEBUG_TIMING") != nullptr;
+  auto tp = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "  subdivide: %-18s %7.1f ms (%d threads)\n", what, std::chrono::duration<double, std::milli>(now - tp).count(), nth);
+    tp = now;
+  };
+  std::vector<LocalPatches> locals;
+  std::vector<Where> where((size_t) num);
+  dice_range(s, 0, num, nth, locals, where);
+  lap("dice");
+  std::vector<PoolView> views;
+  for (const LocalPatches &L : locals) views.push_back(view_of(L));
+  stitch_patches(s, views, where, nth);
+  lap("merge");
+}
+
+// part `part` of `parts`: dices its range of the originals; `blob` = {header, patches per original, then per patch origin,
+// area, cluster, next, winding point count, and all winding points} in the order of the originals
+void subdivide_part(Scene &s, int part, int parts, std::vector<uint8_t> &blob) {
+  if (parts < 1 || part < 0 || part >= parts) fail("prepare_part: bad part");
+  const int num = s.num_patches();
+  int lo, hi;
+  part_range(s, part, parts, lo, hi);
+  const int nth = host_threads(s, (hi - lo) / 16);
+  std::vector<LocalPatches> locals;
+  std::vector<Where> where((size_t) num);
+  dice_range(s, lo, hi, nth, locals, where);
+  BlobHeader h{kBlobMagic, lo, hi, num, 0, 0};
+  for (int i = lo; i < hi; i++) {
+    h.patches += where[i].count;
+    const LocalPatches &L = locals[where[i].pool];
+    for (int k = 0; k < where[i].count; k++) h.points += L.wcount[where[i].first + k];
+  }
+  const size_t n = (size_t) h.patches;
+  blob.resize(sizeof h + (size_t) (hi - lo) * 4 + n * (12 + 4 + 4 + 4 + 4) + (size_t) h.points * 12);
+  uint8_t *o = blob.data();
+  memcpy(o, &h, sizeof h);
+  int32_t *counts = reinterpret_cast<int32_t *>(o + sizeof h);
+  Vec3 *origin = reinterpret_cast<Vec3 *>(counts + (hi - lo));
+  float *area = reinterpret_cast<float *>(origin + n);
+  int32_t *cluster = reinterpret_cast<int32_t *>(area + n), *next = cluster + n, *wcount = next + n;
+  Vec3 *pts = reinterpret_cast<Vec3 *>(wcount + n);
+  std::vector<int64_t> at_of((size_t) (hi - lo) + 1, 0), pat_of((size_t) (hi - lo) + 1, 0);
+  for (int i = lo; i < hi; i++) {
+    const Where &w = where[i];
+    const LocalPatches &L = locals[w.pool];
+    int64_t np = 0;
+    for (int k = 0; k < w.count; k++) np += L.wcount[w.first + k];
+    at_of[i - lo + 1] = at_of[i - lo] + w.count;
+    pat_of[i - lo + 1] = pat_of[i - lo] + np;
+  }
+  std::atomic<int> cursor{lo};
+  parallel_for(nth, [&](int) {
+    for (;;) {
+      const int i0 = cursor.fetch_add(64);
+      if (i0 >= hi) break;
+      for (int i = i0; i < std::min(hi, i0 + 64); i++) {
+        const Where &w = where[i];
+        const LocalPatches &L = locals[w.pool];
+        counts[i - lo] = w.count;
+        size_t at = (size_t) at_of[i - lo], pat = (size_t) pat_of[i - lo];
+        for (int k = 0; k < w.count; k++, at++) {
+          const int l = w.first + k;
+          origin[at] = L.origin[l];
+          area[at] = L.area[l];
+          cluster[at] = L.cluster[l];
+          next[at] = L.next[l];
+          wcount[at] = L.wcount[l];
+          memcpy(pts + pat, &L.pts[(size_t) L.wfirst[l]], (size_t) L.wcount[l] * 12);
+          pat += (size_t) L.wcount[l];
+        }
+      }
+    }
+  });
+}
+
+// all parts' blobs (own one included) -> the patches, as subdivide_patches leaves them
+void subdivide_merge(Scene &s, int parts, const uint8_t *const *blobs, const int64_t *bytes) {
+  const int num = s.num_patches();
+  std::vector<PoolView> views((size_t) parts);        // straight into the blobs (4-byte aligned: the header is 32 bytes)
+  std::vector<std::vector<int64_t>> wfirsts((size_t) parts);
+  std::vector<Where> where((size_t) num, Where{-1, 0, 0});
+  for (int q = 0; q < parts; q++) {
+    BlobHeader h;
+    if (bytes[q] < (int64_t) sizeof h) fail("prepare_merge: blob too small");
+    if ((uintptr_t) blobs[q] & 3) fail("prepare_merge: blobs must be 4-byte aligned");
+    memcpy(&h, blobs[q], sizeof h);
+    if (h.magic != kBlobMagic || h.num != num || h.lo < 0 || h.hi < h.lo || h.hi > num || h.patches < h.hi - h.lo || h.points < 0)
+      fail("prepare_merge: blob of part %d does not belong to this map", q);
+    const size_t n = (size_t) h.patches;
+    if ((uint64_t) bytes[q] != sizeof h + (size_t) (h.hi - h.lo) * 4 + n * 28 + (size_t) h.points * 12) fail("prepare_merge: blob size");
+    const uint8_t *o = blobs[q] + sizeof h;
+    const int32_t *counts = reinterpret_cast<const int32_t *>(o);
+    const Vec3 *origin = reinterpret_cast<const Vec3 *>(counts + (h.hi - h.lo));
+    const float *area = reinterpret_cast<const float *>(origin + n);
+    const int32_t *cluster = reinterpret_cast<const int32_t *>(area + n), *next = cluster + n, *wcount = next + n;
+    const Vec3 *pts = reinterpret_cast<const Vec3 *>(wcount + n);
+    std::vector<int64_t> &wf = wfirsts[q];
+    wf.resize(n);
+    int64_t pat = 0;
+    for (size_t k = 0; k < n; k++) {
+      if (wcount[k] < 0 || wcount[k] > kMaxWindingPoints + 4) fail("prepare_merge: bad winding");
+      wf[k] = pat;
+      pat += wcount[k];
+    }
+    if (pat != h.points) fail("prepare_merge: point count");
+    views[q] = PoolView{pts, origin, wf.data(), wcount, next, cluster, area};
+    int64_t at = 0;
+    for (int i = h.lo; i < h.hi; i++) {
+      const int cnt = counts[i - h.lo];
+      if (cnt < 1 || at + cnt > h.patches || where[i].pool >= 0) fail("prepare_merge: parts overlap or are malformed");
+      where[i] = Where{q, (int32_t) at, cnt};
+      at += cnt;
+    }
+    if (at != h.patches) fail("prepare_merge: patch count");
+  }
+  for (int i = 0; i < num; i++)
+    if (where[i].pool < 0) fail("prepare_merge: original %d is in no part", i);
+  stitch_patches(s, views, where, host_threads(s, num / 16));
 }
 
 // ---------------------------------------------------------------------------

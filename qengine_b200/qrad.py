@@ -177,6 +177,23 @@ class Scene:
         self.params = params
         return self
 
+    def prepare_part(self, params: HostParams, part: int, parts: int, copy: bool = True) -> np.ndarray:
+        """This process's share of the dicing (qrad_host_prepare_part): a byte blob for prepare_merge of every process.
+        copy=False returns the scene's own buffer, valid until the next prepare call on this scene."""
+        self.params = params
+        blob, n = C.POINTER(C.c_uint8)(), C.c_int64()
+        _hck(lib().qrad_host_prepare_part(self._h, C.byref(params), C.c_int(part), C.c_int(parts), C.byref(blob), C.byref(n)))
+        a = np.ctypeslib.as_array(blob, shape=(n.value,))
+        return a.copy() if copy else a
+
+    def prepare_merge(self, blobs):
+        """All processes' blobs, in part order (the own one included): finishes what prepare() does."""
+        arrs = [np.ascontiguousarray(b, np.uint8) for b in blobs]
+        ptrs = (C.POINTER(C.c_uint8) * len(arrs))(*[a.ctypes.data_as(C.POINTER(C.c_uint8)) for a in arrs])
+        sizes = (C.c_int64 * len(arrs))(*[a.size for a in arrs])
+        _hck(lib().qrad_host_prepare_merge(self._h, C.c_int(len(arrs)), ptrs, sizes))
+        return self
+
     def counts(self):
         a = (C.c_int32 * 8)()
         lib().qrad_host_counts(self._h, a)

@@ -147,3 +147,42 @@ def test_host_setup_matches_reference_dumps(Q, case, flags, tmp_path):
     assert np.array_equal(np.repeat(np.arange(len(ml["light_first"]) - 1), np.diff(ml["light_first"])), rl["cluster"])
     for k in ("type", "intensity", "style", "origin", "color", "normal", "stopdot"):
         assert np.array_equal(ml[k], rl[k]), k
+
+
+@pytest.mark.parametrize("parts", [1, 2, 3, 5])
+@pytest.mark.parametrize("case", ["samplec", "grid3_chop16", "manystyles", "angled"])
+def test_shared_prepare_gives_the_same_scene(Q, case, parts, tmp_path):
+    """Several processes that light one map share the dicing (qrad_host_prepare_part / _merge): whatever the number of
+    parts, every process must end with the patches, windings and lights of a plain prepare -- itself pinned to the
+    reference's dumps above."""
+    meta, flags = G.load_case(case)
+    bsp = G.stage_case(case, tmp_path)
+    want = Q.Scene(bsp).prepare(G.params_from_flags(flags))
+    scenes = [Q.Scene(bsp) for _ in range(parts)]
+    blobs = [sc.prepare_part(G.params_from_flags(flags), k, parts) for k, sc in enumerate(scenes)]
+    assert sum(len(b) for b in blobs) > 0
+    for sc in scenes[:2]:   # every process merges all blobs; two of them are enough here
+        sc.prepare_merge(blobs)
+        assert sc.counts() == want.counts()
+        a, b = sc.patches(), want.patches()
+        for k in b:
+            assert np.array_equal(a[k], b[k]), k
+        la, lb = sc.lights(), want.lights()
+        for k in lb:
+            assert np.array_equal(la[k], lb[k]), k
+        (ca, pa), (cb, pb) = sc.windings(), want.windings()
+        assert np.array_equal(ca, cb) and np.array_equal(pa, pb)
+
+
+def test_shared_prepare_rejects_bad_parts(Q, tmp_path):
+    meta, flags = G.load_case("samplec")
+    bsp = G.stage_case("samplec", tmp_path)
+    scenes = [Q.Scene(bsp) for _ in range(2)]
+    blobs = [sc.prepare_part(G.params_from_flags(flags), k, 2) for k, sc in enumerate(scenes)]
+    with pytest.raises(Q.QradError):
+        scenes[0].prepare_merge([blobs[0], blobs[0]])          # a range twice, another missing
+    scenes[0].prepare_part(G.params_from_flags(flags), 0, 2)
+    with pytest.raises(Q.QradError):
+        scenes[0].prepare_merge([blobs[0], blobs[1][:-4]])      # truncated
+    with pytest.raises(Q.QradError):
+        Q.Scene(bsp).prepare_merge(blobs)                       # prepare_part has not run
