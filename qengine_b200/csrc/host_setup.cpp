@@ -872,7 +872,10 @@ void create_direct_lights(Scene &s) {
     }
     s.light_first[l.cluster + 1]++;
   }
-  if (dropped) printf("WARNING: %d direct lights sit in solid (cluster -1) and are ignored\n", dropped);
+  if (dropped && nc == 0)   // no vis lump: leaves carry no cluster, and the reference's GatherSampleLight finds no light either
+    printf("WARNING: the map has no vis information, its %d direct lights cannot be gathered\n", dropped);
+  else if (dropped)
+    printf("WARNING: %d direct lights sit in solid (cluster -1) and are ignored\n", dropped);
   for (int c = 0; c < nc; c++) s.light_first[c + 1] += s.light_first[c];
   int total = s.light_first[nc];
   s.light_type.assign(total, 0);

@@ -233,3 +233,47 @@ def test_matrix_exchange_protocol_gloo(case, tmp_path):
     port = s.getsockname()[1]
     s.close()
     mp.spawn(_worker, args=(2, port, case, tmp_path), nprocs=2, join=True)
+
+
+def _prepare_worker(rank, world, port, case, tmpdir):
+    """what a process-per-GPU host does before the device phases: its share of the dicing, an all-gather of the ranks'
+    blobs (different lengths: sizes first, then padded payloads), the merge -- and then it must hold the scene a plain
+    prepare builds"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        meta, flags = G.load_case(case)
+        bsp = G.stage_case(case, tmpdir / f"rank{rank}")
+        sc = Q.Scene(bsp)
+        blob = sc.prepare_part(G.params_from_flags(flags), rank, world, copy=False)
+        n = torch.tensor([blob.size], dtype=torch.int64)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n)
+        sizes = [int(x.item()) for x in sizes]
+        mx = (max(sizes) + 255) & ~255
+        mine = torch.zeros(mx, dtype=torch.uint8)
+        mine[:blob.size] = torch.from_numpy(blob)
+        parts = [torch.zeros(mx, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        sc.prepare_merge([parts[q].numpy()[:sizes[q]] for q in range(world)])
+        want = Q.Scene(bsp).prepare(G.params_from_flags(flags))
+        a, b = sc.patches(), want.patches()
+        for k in b:
+            assert np.array_equal(a[k], b[k]), (rank, k)
+        (ca, pa), (cb, pb) = sc.windings(), want.windings()
+        assert np.array_equal(ca, cb) and np.array_equal(pa, pb)
+        la, lb = sc.lights(), want.lights()
+        for k in lb:
+            assert np.array_equal(la[k], lb[k]), (rank, k)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["grid3_chop16", "manystyles"])
+def test_shared_prepare_over_gloo(case, tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_prepare_worker, args=(2, port, case, tmp_path), nprocs=2, join=True)
