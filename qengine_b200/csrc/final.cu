@@ -566,7 +566,12 @@ void final_light_impl(qrad_cuda_ctx *c, const qrad_final_params *p, uint8_t *out
   d_err.zero(st);
   d_counter.upload(&c->face_lo, 1, st);   // k_final draws faces from here
 
-  const int blocks = std::max(1, std::min((c->face_hi - c->face_lo + kWarps - 1) / kWarps, c->sm_count * 2));
+  // the triangulation is a serial walk per face (lane 0 keeps the edge / triangle books): latency, not throughput, so as
+  // many faces in flight as the scratch pools allow
+  int per_sm = 6;
+  if (const char *e = getenv("QRAD_FINAL_BLOCKS")) per_sm = std::max(1, atoi(e));
+  while (per_sm > 2 && (size_t) c->sm_count * per_sm * kWarps * pmax * pmax * 2 > ((size_t) 2 << 30)) per_sm--;   // edge matrices <= 2 GB
+  const int blocks = std::max(1, std::min((c->face_hi - c->face_lo + kWarps - 1) / kWarps, c->sm_count * per_sm));
   const size_t nw = (size_t) blocks * kWarps;
   // scratch pools live in the context so that repeated calls reuse the allocations
   DBuf<uint16_t> &matrix_pool = c->fin_matrix, &ep0 = c->fin_ep0, &ep1 = c->fin_ep1, &tedges = c->fin_tedges, &stack = c->fin_stack;
