@@ -4,7 +4,13 @@ restates BasePortalVis + SimpleFlood (flow.c:576-652) in numpy, sorts the portal
 (qvis3.c:118-129) and levels the dependency graph "portal k consults the finished portals j < k of its flood set"
 (flow.c:391-396).  Evidence for DESIGN.md section 9; not part of the product.
   usage: python tools/qvis_order_probe.py map.prt"""
+import sys
+import time
 from pathlib import Path
+
+import numpy as np
+
+
 def load_prt(path):
     lines = Path(path).read_text().split("\n")
     assert lines[0].strip() == "PRT1"
