@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(kThreads) k_column_counts(const ColArgs a, con
 //                entries at cell boundaries, and every warp emits one part from the entry the prefix names.
 constexpr int kColCells = 1024;
 template <bool SPLIT>
-__global__ void __launch_bounds__(kThreads) k_columns(const ColArgs a, const int nslices_own) {
+__global__ void __launch_bounds__(kThreads, 4) k_columns(const ColArgs a, const int nslices_own) {
   __shared__ float4 s_so[kWarpsPerBlock][32], s_sn[kWarpsPerBlock][32];
   __shared__ float s_rt[kWarpsPerBlock][32];
   __shared__ int s_cell[SPLIT ? kColCells + 1 : 1];
