@@ -539,7 +539,7 @@ struct RowArgs {
 // one slice) every lane reads its own word of that slice -- 32 consecutive words -- and a run no row accepts is skipped.
 // Otherwise the receivers some row accepts are staged in shared memory and every accepting lane adds its own form factor
 // to its own SERIAL sum (qrad3.c:254): `total` stays bit-identical while 32 sums advance together.
-__global__ void __launch_bounds__(kThreads) k_row_totals32(const RowArgs a) {
+__global__ void __launch_bounds__(kThreads, 5) k_row_totals32(const RowArgs a) {
   __shared__ float4 s_po[kWarpsPerBlock][32], s_pn[kWarpsPerBlock][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int rs = blockIdx.x * kWarpsPerBlock + wid;
