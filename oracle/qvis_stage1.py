@@ -154,3 +154,61 @@ def read_dump(path):
             bits = np.unpackbits(np.frombuffer(d, np.uint8, pb, o + 28 + j * pb), bitorder="little")[:P]
             out[name][k] = bits.astype(bool)
     return out
+
+
+# ---- stage 2: PortalFlow through the C restatement (oracle/qvis_oracle.c) ------------------------------------------------
+def _lib():
+    import ctypes as C
+    so = Path(__file__).resolve().parent / "libqvis_oracle.so"
+    lib = C.CDLL(str(so))
+    lib.qvo_portal_flow.restype = C.c_long
+    return lib
+
+
+def pack_bits(m):
+    """bool [P, P] -> the reference's bit vectors [P, portalbytes] (portalbytes = ((P + 63) & ~63) >> 3, qvis3.c:336)"""
+    P = m.shape[0]
+    pb = ((P + 63) & ~63) >> 3
+    out = np.zeros((P, pb), np.uint8)
+    packed = np.packbits(m, axis=1, bitorder="little")
+    out[:, :packed.shape[1]] = packed
+    return out
+
+
+class FlowOracle:
+    """portal_flow(k, done_vis): the portalvis vector of portal k when every portal ranked before k is finished with the
+    vectors in done_vis (bool [P, P]) and every other portal is not."""
+
+    def __init__(self, pt: Portals, flood, rank):
+        import ctypes as C
+        self.C, self.pt, self.lib = C, pt, _lib()
+        self.planes = np.ascontiguousarray(np.concatenate([pt.normal, pt.dist[:, None]], 1), np.float32)
+        self.leaf = np.ascontiguousarray(pt.leaf, np.int32)
+        cnt = np.array([len(w) for w in pt.windings], np.int32)
+        self.wfirst = np.zeros(pt.P + 1, np.int32)
+        self.wfirst[1:] = np.cumsum(cnt)
+        self.points = np.ascontiguousarray(np.concatenate(pt.windings, 0), np.float32)
+        self.leaf_first = np.zeros(pt.nc + 1, np.int32)
+        self.leaf_first[1:] = np.cumsum([len(l) for l in pt.leaf_portals])
+        self.leaf_portals = np.array([q for l in pt.leaf_portals for q in l], np.int32)
+        self.flood = pack_bits(flood)
+        self.rank = np.ascontiguousarray(rank, np.int32)
+        self.pb = self.flood.shape[1]
+
+    def portal_flow(self, k, done_bits):
+        C = self.C
+        out = np.zeros(self.pb, np.uint8)
+        p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        chains = self.lib.qvo_portal_flow(
+            C.c_int(self.pt.P), C.c_int(self.pt.nc), C.c_int(self.pb), p(self.planes, C.c_float), p(self.leaf, C.c_int32),
+            p(self.wfirst, C.c_int32), p(self.points, C.c_float), p(self.leaf_first, C.c_int32), p(self.leaf_portals, C.c_int32),
+            p(self.flood, C.c_uint8), p(done_bits, C.c_uint8), p(self.rank, C.c_int32), C.c_int(int(k)), p(out, C.c_uint8))
+        assert chains >= 0
+        return out, chains
+
+    def full(self, order):
+        """the reference's run: portals one after the other in sorted order, each seeing the earlier ones finished"""
+        done = np.zeros_like(self.flood)
+        for k in order:
+            done[k], _ = self.portal_flow(k, done)
+        return done

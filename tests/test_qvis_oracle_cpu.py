@@ -6,7 +6,10 @@ skipped where they are absent.  They pin
   * the harness: it writes the visibility lump the unmodified reference qvis3 writes (full vis, and -fast);
   * the numpy restatement of the order-independent first stage (oracle/qvis_stage1.py): planes, portalfront, portalflood,
     nummightsee and the sorted order equal the reference's, bit for bit;
-  * the fact the design of a GPU PortalFlow must start from: the reference's result depends on the portal order.
+  * the fact the design of a GPU PortalFlow must start from: the reference's result depends on the portal order;
+  * the C restatement of PortalFlow (oracle/qvis_oracle.c) and the schedule rule it is built on -- "portal j counts as
+    finished for portal k iff j comes before k in the sorted order": every portal, computed on its own from the
+    reference's finished vectors, and the whole run in sorted order, reproduce the reference's portalvis bit for bit.
 """
 from __future__ import annotations
 
@@ -44,8 +47,11 @@ def compile_bsp(tmp: Path, name: str, text: str):
 
 def maps():
     from qengine_b200 import mapgen
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    import make_golden as MG
     return {"grid3": mapgen.room_grid_map(3, 3, seed=1, clutter=0.5, lamps=0.3),
-            "grid5": mapgen.room_grid_map(5, 5, seed=2, clutter=1.0, lamps=0.3)}
+            "grid5": mapgen.room_grid_map(5, 5, seed=2, clutter=1.0, lamps=0.3),
+            "angled": MG.angled_map_text()}          # brushes with non-axial faces: general separating planes
 
 
 @pytest.mark.parametrize("name", ["grid3", "grid5"])
@@ -102,3 +108,27 @@ def test_portal_order_changes_the_result(tmp_path):
         assert r.returncode == 0
         lumps.append(vis_lump(bsp))
     assert lumps[0] != lumps[1]
+
+
+@pytest.mark.parametrize("name", ["grid3", "grid5", "angled"])
+def test_portal_flow_restatement_and_schedule_rule(name, tmp_path):
+    import qvis_stage1 as V
+    if not (ROOT / "oracle" / "libqvis_oracle.so").exists():
+        subprocess.run(["make", "-C", str(ROOT / "oracle"), "libqvis_oracle.so"], check=True, capture_output=True)
+    bsp, prt = compile_bsp(tmp_path, name, maps()[name])
+    r = subprocess.run([str(REF / "qvis_harness"), str(bsp), str(prt), str(tmp_path / "dump.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-500:]
+    ref = V.read_dump(tmp_path / "dump.bin")
+    pt = V.Portals(prt)
+    flood = V.simple_flood(pt, V.base_portal_vis(pt))
+    order, rank = V.sorted_rank(flood.sum(1))
+    assert np.array_equal(rank, ref["rank"])
+    fo = V.FlowOracle(pt, flood, rank)
+    want = V.pack_bits(ref["vis"])
+    # every portal on its own, with the reference's vectors for the portals ranked before it
+    for k in range(pt.P):
+        got, chains = fo.portal_flow(k, want)
+        assert np.array_equal(got, want[k]), (name, k)
+        assert chains >= 1
+    # and the whole run in sorted order, from nothing
+    assert np.array_equal(fo.full(order), want)
