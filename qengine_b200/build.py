@@ -22,8 +22,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-Xptxas", "-v"]
 CXX_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-Wall", "-I/usr/local/cuda/include"]
-CU = ["api.cu", "transfers.cu", "direct.cu", "final.cu", "comm.cu"]
-CPP = ["host_bsp.cpp", "host_setup.cpp", "host_api.cpp", "host_multi.cpp", "plan.cpp", "host_walkers.cpp"]
+CU = ["api.cu", "transfers.cu", "direct.cu", "final.cu", "comm.cu", "qvis.cu"]
+CPP = ["host_bsp.cpp", "host_setup.cpp", "host_api.cpp", "host_multi.cpp", "plan.cpp", "host_walkers.cpp", "qvis_host.cpp"]
 
 
 def _newer(src: Path, dst: Path, deps=()) -> bool:

@@ -32,7 +32,7 @@ def declared_symbols():
     names = set()
     for h in (ROOT / "include").glob("*.h"):
         txt = re.sub(r"/\*.*?\*/", "", h.read_text(), flags=re.S)
-        for m in re.finditer(r"^\s*(?:const\s+)?(?:int|void|char|int64_t)\s*\*?\s*(qrad\w+)\s*\(", txt, flags=re.M):
+        for m in re.finditer(r"^\s*(?:const\s+)?(?:int|void|char|int64_t)\s*\*?\s*(q(?:rad|vis)\w+)\s*\(", txt, flags=re.M):
             names.add(m.group(1))
     return sorted(names)
 

@@ -1,0 +1,63 @@
+"""Host half of the qvis3 first stage (include/qvis_cuda.h) against fixtures made by the reference
+(tests/golden/make_golden_vis.py): LoadPortals / PlaneFromWinding, and the boundary's error behaviour without a GPU."""
+from __future__ import annotations
+
+import gzip
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+CASES = ["grid3", "grid5", "angled"]
+
+
+def stage(case, tmp: Path) -> Path:
+    prt = tmp / (case + ".prt")
+    prt.write_bytes(gzip.decompress((GOLDEN / f"vis_{case}.prt.gz").read_bytes()))
+    return prt
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_load_portals_matches_the_reference(case, tmp_path):
+    from qengine_b200 import qvis
+    want = np.load(GOLDEN / f"vis_{case}.npz")
+    pt = qvis.Portals(stage(case, tmp_path))
+    a = pt.arrays()
+    assert pt.numportals == len(want["leaf"]) and pt.portalbytes == want["front"].shape[1]
+    assert np.array_equal(a["planes"], want["planes"])          # bit-identical floats
+    assert np.array_equal(a["leaf"], want["leaf"])
+    # two memory portals per file portal: the second is the first one reversed, with the opposite plane
+    wf, pts = a["winding_first"], a["points"]
+    for k in range(0, pt.numportals, 2):
+        f, b = pts[wf[k]:wf[k + 1]], pts[wf[k + 1]:wf[k + 2]]
+        assert np.array_equal(f, b[::-1])
+        assert np.array_equal(a["planes"][k], -a["planes"][k + 1])
+    # every portal leaves exactly one cluster: the one its twin leads into
+    owner = np.full(pt.numportals, -1)
+    for l in range(pt.numclusters):
+        owner[a["leaf_portals"][a["leaf_first"][l]:a["leaf_first"][l + 1]]] = l
+    assert np.array_equal(owner[0::2], a["leaf"][1::2]) and np.array_equal(owner[1::2], a["leaf"][0::2])
+
+
+def test_load_portals_errors(tmp_path):
+    from qengine_b200 import qvis
+    with pytest.raises(qvis.QvisError, match="couldn't read"):
+        qvis.Portals(tmp_path / "missing.prt")
+    bad = tmp_path / "bad.prt"
+    bad.write_text("PRT2\n1\n0\n")
+    with pytest.raises(qvis.QvisError, match="not a portal file"):
+        qvis.Portals(bad)
+    bad.write_text("PRT1\n2\n1\n4 0 5 (0 0 0 ) (0 1 0 ) (1 1 0 ) (1 0 0 ) \n")
+    with pytest.raises(qvis.QvisError, match="reading portal 0"):
+        qvis.Portals(bad)
+
+
+def test_no_cpu_fallback(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from qengine_b200 import qvis
+    pt = qvis.Portals(stage("grid3", tmp_path))
+    with pytest.raises(qvis.QvisError, match="no CPU fallback"):
+        pt.base_portal_vis(0)
