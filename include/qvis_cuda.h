@@ -44,6 +44,14 @@ int  qvis_portal_bytes(int32_t numportals);
 int  qvis_cuda_base_portal_vis(int device, const qvis_portals_view *portals, uint8_t *portalfront, uint8_t *portalflood,
                                int32_t *nummightsee, float *ms_front, float *ms_flood);
 
+/* ClusterMerge for every cluster + CalcPHS + CompressVis (qvis3.c:168-224, 427-486, bspfile.c:95): the visibility lump
+   from the portals' FINAL vectors [numportals][qvis_portal_bytes] (with -fast: the flood vectors).  Host work.  Errors
+   carry the reference's text ("Vismap expansion overflow" when the lump passes `cap`). */
+int  qvis_host_merge_lump(const qvis_host_portals *p, const uint8_t *portalvis, uint8_t *lump, int32_t cap, int32_t *size,
+                          int32_t *avg_visible, int32_t *avg_hearable, int32_t *saw_into_leaf);
+/* `qvis3 -fast map.bsp` (fastvis, qvis3.c:235-241): BasePortalVis on the GPU, the rest on the host; writes bsp_out. */
+int  qvis_host_fast_vis(const char *bsp_in, const char *prt_path, const char *bsp_out, int device);
+
 #ifdef __cplusplus
 }
 #endif

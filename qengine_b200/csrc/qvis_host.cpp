@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/qvis_cuda.h"
+#include "host_scene.hpp"
 
 namespace {
 thread_local std::string g_qvis_error;
@@ -126,6 +127,151 @@ int qvis_host_portals_view(const qvis_host_portals *p, qvis_portals_view *o) {
   o->leaf_first = p->leaf_first.data();
   o->leaf_portals = p->leaf_portals.data();
   return 0;
+}
+
+
+// ClusterMerge for every cluster + CalcPHS, qvis3.c:168-224, 427-486: the visibility lump {numclusters, bitofs[][2], the
+// compressed PVS rows in cluster order, then the PHS rows} from the portals' final vectors.  Host work: a few OR-ed bit
+// rows per cluster, serial in the lump offsets.  Returns 0, or 1 with the reference's error text.
+int qvis_host_merge_lump(const qvis_host_portals *p, const uint8_t *portalvis, uint8_t *lump, int32_t cap, int32_t *size,
+                         int32_t *avg_visible, int32_t *avg_hearable, int32_t *saw_into_leaf) {
+  const int P = p->numportals, nc = p->numclusters;
+  const int pb = qvis_portal_bytes(P), leafbytes = ((nc + 63) & ~63) >> 3, visrow = (nc + 7) >> 3;
+  if (nc <= 0) {
+    g_qvis_error = "ClusterMerge: no clusters";
+    return 1;
+  }
+  int64_t at = 4 + (int64_t) 8 * nc;   // vismap_p starts behind bitofs[portalclusters], qvis3.c:352
+  if (at > cap) {
+    g_qvis_error = "Vismap expansion overflow";
+    return 1;
+  }
+  memset(lump, 0, (size_t) at);
+  int32_t n32 = nc;
+  memcpy(lump, &n32, 4);
+  std::vector<uint8_t> uncompressedvis((size_t) nc * leafbytes, 0), portalvector((size_t) pb), row((size_t) leafbytes), packed((size_t) 2 * visrow + 4);
+  auto compress = [&](const uint8_t *vis) -> int {   // CompressVis, bspfile.c:95-124
+    int o = 0;
+    for (int j = 0; j < visrow; j++) {
+      packed[o++] = vis[j];
+      if (vis[j]) continue;
+      int rep = 1;
+      for (j++; j < visrow; j++)
+        if (vis[j] || rep == 255) break;
+        else rep++;
+      packed[o++] = (uint8_t) rep;
+      j--;
+    }
+    return o;
+  };
+  auto append = [&](int cluster, int which, int n) -> bool {
+    if (at + n > cap) return false;
+    const int32_t ofs = (int32_t) at;
+    memcpy(lump + 4 + (size_t) 8 * cluster + 4 * which, &ofs, 4);
+    memcpy(lump + at, packed.data(), (size_t) n);
+    at += n;
+    return true;
+  };
+  int64_t totalvis = 0;
+  int warned = 0;
+  for (int leafnum = 0; leafnum < nc; leafnum++) {
+    std::fill(portalvector.begin(), portalvector.end(), 0);
+    for (int e = p->leaf_first[leafnum]; e < p->leaf_first[leafnum + 1]; e++) {
+      const int pnum = p->leaf_portals[e];
+      const uint8_t *v = portalvis + (size_t) pnum * pb;
+      for (int j = 0; j < pb; j++) portalvector[j] |= v[j];
+      portalvector[pnum >> 3] |= (uint8_t) (1 << (pnum & 7));
+    }
+    // LeafVectorFromPortalVector, qvis3.c:138-156
+    std::fill(row.begin(), row.end(), 0);
+    for (int i = 0; i < P; i++)
+      if (portalvector[i >> 3] & (1 << (i & 7))) row[p->leaf[i] >> 3] |= (uint8_t) (1 << (p->leaf[i] & 7));
+    int numvis = 0;
+    for (int i = 0; i < nc; i++) numvis += (row[i >> 3] >> (i & 7)) & 1;
+    if (row[leafnum >> 3] & (1 << (leafnum & 7))) {
+      printf("WARNING: Leaf portals saw into leaf\n");
+      warned++;
+    }
+    row[leafnum >> 3] |= (uint8_t) (1 << (leafnum & 7));
+    numvis++;   // (the reference counts the leaf itself again even when its portals saw into it)
+    memcpy(&uncompressedvis[(size_t) leafnum * leafbytes], row.data(), (size_t) leafbytes);
+    totalvis += numvis;
+    if (!append(leafnum, 0, compress(row.data()))) {
+      g_qvis_error = "Vismap expansion overflow";
+      return 1;
+    }
+  }
+  // CalcPHS: OR the PVS rows of everything a cluster sees
+  int64_t count = 0;
+  for (int i = 0; i < nc; i++) {
+    const uint8_t *scan = &uncompressedvis[(size_t) i * leafbytes];
+    memcpy(row.data(), scan, (size_t) leafbytes);
+    for (int j = 0; j < leafbytes; j++) {
+      const int bitbyte = scan[j];
+      if (!bitbyte) continue;
+      for (int k = 0; k < 8; k++) {
+        if (!(bitbyte & (1 << k))) continue;
+        const int index = (j << 3) + k;
+        if (index >= nc) {
+          g_qvis_error = "Bad bit in PVS";
+          return 1;
+        }
+        const uint8_t *src = &uncompressedvis[(size_t) index * leafbytes];
+        for (int l = 0; l < leafbytes; l++) row[l] |= src[l];
+      }
+    }
+    for (int j = 0; j < nc; j++) count += (row[j >> 3] >> (j & 7)) & 1;
+    if (!append(i, 1, compress(row.data()))) {
+      g_qvis_error = "Vismap expansion overflow";
+      return 1;
+    }
+  }
+  *size = (int32_t) at;
+  if (avg_visible) *avg_visible = (int32_t) (totalvis / nc);
+  if (avg_hearable) *avg_hearable = (int32_t) (count / nc);
+  if (saw_into_leaf) *saw_into_leaf = warned;
+  return 0;
+}
+
+// qvis3 -fast (qvis3.c:493-560 with fastvis: CalcPortalVis takes portalflood for portalvis, :235-241): reads map.bsp and
+// map.prt, BasePortalVis on the GPU, ClusterMerge + CalcPHS on the host, writes the BSP with the new visibility lump.
+int qvis_host_fast_vis(const char *bsp_in, const char *prt_path, const char *bsp_out, int device) {
+  try {
+    qrad::Bsp bsp;
+    qrad::load_bsp(bsp_in, bsp);
+    if (bsp.numnodes() == 0 || bsp.numfaces() == 0) throw std::runtime_error("Empty map");
+    qvis_host_portals *p = nullptr;
+    printf("reading %s\n", prt_path);
+    if (qvis_host_portals_load(prt_path, &p)) return 1;
+    struct Guard {
+      qvis_host_portals *p;
+      ~Guard() { qvis_host_portals_free(p); }
+    } guard{p};
+    printf("%4i portalclusters\n", p->numclusters);
+    printf("%4i numportals\n", p->numportals / 2);
+    qvis_portals_view v;
+    qvis_host_portals_view(p, &v);
+    const int pb = qvis_portal_bytes(p->numportals);
+    std::vector<uint8_t> front((size_t) p->numportals * pb), flood((size_t) p->numportals * pb);
+    std::vector<int32_t> might((size_t) p->numportals);
+    if (qvis_cuda_base_portal_vis(device, &v, front.data(), flood.data(), might.data(), nullptr, nullptr)) return 1;
+    constexpr int kMaxMapVisibility = 0x100000;   // MAX_MAP_VISIBILITY, qfiles.h
+    std::vector<uint8_t> lump((size_t) kMaxMapVisibility);
+    int32_t size = 0, vis = 0, hear = 0, warned = 0;
+    if (qvis_host_merge_lump(p, flood.data(), lump.data(), kMaxMapVisibility, &size, &vis, &hear, &warned)) return 1;
+    printf("Average clusters visible: %i\n", vis);
+    printf("Building PHS...\n");
+    printf("Average clusters hearable: %i\n", hear);
+    const int leafbytes = ((p->numclusters + 63) & ~63) >> 3;
+    printf("visdatasize:%i  compressed from %i\n", size, p->numclusters * leafbytes * 2);
+    bsp.lump[qrad::kLumpVisibility].assign(lump.begin(), lump.begin() + size);
+    printf("writing %s\n", bsp_out);
+    qrad::write_bsp(bsp, bsp_out);
+    return 0;
+  } catch (const std::exception &e) {
+    g_qvis_error = e.what();
+    return 1;
+  }
 }
 
 }  // extern "C"

@@ -69,3 +69,18 @@ class Portals:
         _ck(_lib().qvis_cuda_base_portal_vis(C.c_int(device), C.byref(self.view), front.ctypes.data_as(c_u8), flood.ctypes.data_as(c_u8),
                                              might.ctypes.data_as(c_i), C.byref(t0), C.byref(t1)))
         return front, flood, might, (t0.value, t1.value)
+
+    def merge_lump(self, portalvis, cap: int = 0x100000):
+        """ClusterMerge + CalcPHS + CompressVis on the host: (lump bytes, average clusters visible, hearable, warnings)."""
+        pv = np.ascontiguousarray(portalvis, np.uint8)
+        assert pv.shape == (self.numportals, self.portalbytes)
+        lump = np.zeros(cap, np.uint8)
+        size, vis, hear, warned = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        _ck(_lib().qvis_host_merge_lump(self._h, pv.ctypes.data_as(c_u8), lump.ctypes.data_as(c_u8), C.c_int32(cap), C.byref(size),
+                                        C.byref(vis), C.byref(hear), C.byref(warned)))
+        return lump[:size.value].tobytes(), vis.value, hear.value, warned.value
+
+
+def fast_vis(bsp_in, prt_path, bsp_out, device: int = 0):
+    """`qvis3 -fast`: BasePortalVis on the GPU, ClusterMerge / CalcPHS on the host, writes bsp_out."""
+    _ck(_lib().qvis_host_fast_vis(str(bsp_in).encode(), str(prt_path).encode(), str(bsp_out).encode(), C.c_int(device)))

@@ -45,3 +45,17 @@ def test_base_portal_vis_on_the_c5_map(tmp_path):
     assert hashlib.md5(flood.tobytes()).hexdigest() == str(want["flood_md5"])
     assert np.array_equal(might, want["might"])
     print(f"BasePortalVis on the C5 map: k_portal_front {ms[0]:.2f} ms, k_simple_flood {ms[1]:.2f} ms")
+
+
+@pytest.mark.parametrize("case", ["grid3", "grid5", "angled"])
+def test_fast_vis_writes_the_reference_file(case, tmp_path):
+    """`qvis3 -fast` end to end: qbsp3's BSP + portal file in, the file the unmodified reference tool writes out."""
+    import hashlib
+    from qengine_b200 import qvis
+    want = np.load(GOLDEN / f"vis_{case}.npz")
+    bsp = tmp_path / (case + ".bsp")
+    bsp.write_bytes(gzip.decompress((GOLDEN / f"vis_{case}.bsp.gz").read_bytes()))
+    prt = tmp_path / (case + ".prt")
+    prt.write_bytes(gzip.decompress((GOLDEN / f"vis_{case}.prt.gz").read_bytes()))
+    qvis.fast_vis(bsp, prt, bsp, 0)
+    assert hashlib.md5(bsp.read_bytes()).hexdigest() == str(want["fast_file_md5"])

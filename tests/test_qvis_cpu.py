@@ -61,3 +61,21 @@ def test_no_cpu_fallback(tmp_path):
     pt = qvis.Portals(stage("grid3", tmp_path))
     with pytest.raises(qvis.QvisError, match="no CPU fallback"):
         pt.base_portal_vis(0)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_merge_lump_matches_the_reference(case, tmp_path):
+    """ClusterMerge + CalcPHS + CompressVis on the host: from the reference's FINAL vectors the lump the reference wrote
+    (full vis), from its flood vectors the lump of `qvis3 -fast` (fastvis takes portalflood for portalvis, qvis3.c:235)."""
+    import hashlib
+    from qengine_b200 import qvis
+    want = np.load(GOLDEN / f"vis_{case}.npz")
+    pt = qvis.Portals(stage(case, tmp_path))
+    lump, vis, hear, warned = pt.merge_lump(want["vis"])
+    assert hashlib.md5(lump).hexdigest() == str(want["lump_md5"])
+    assert 0 < vis <= hear <= pt.numclusters
+    lump, vis2, hear2, _ = pt.merge_lump(want["flood"])
+    assert hashlib.md5(lump).hexdigest() == str(want["fast_lump_md5"])
+    assert vis2 >= vis
+    with pytest.raises(qvis.QvisError, match="Vismap expansion overflow"):
+        pt.merge_lump(want["vis"], cap=4 + 8 * pt.numclusters + 16)
