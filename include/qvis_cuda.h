@@ -51,6 +51,8 @@ int  qvis_host_merge_lump(const qvis_host_portals *p, const uint8_t *portalvis, 
                           int32_t *avg_visible, int32_t *avg_hearable, int32_t *saw_into_leaf);
 /* `qvis3 -fast map.bsp` (fastvis, qvis3.c:235-241): BasePortalVis on the GPU, the rest on the host; writes bsp_out. */
 int  qvis_host_fast_vis(const char *bsp_in, const char *prt_path, const char *bsp_out, int device);
+/* main() of the tool for what is built: the reference's flags, path rules, chatter and error banner; stops without -fast. */
+int  qvis3_main(int argc, char **argv);
 
 #ifdef __cplusplus
 }

@@ -67,6 +67,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if force or _newer(CSRC / "qrad3_main.cpp", EXE, [LIB]):
         _run(["g++", "-O2", "-o", str(EXE), str(CSRC / "qrad3_main.cpp"), "-L" + str(HERE), "-lqrad_cuda",
               "-Wl,-rpath,$ORIGIN"])
+    if force or _newer(CSRC / "qvis3_main.cpp", HERE / "qvis3", [LIB]):
+        _run(["g++", "-O2", "-o", str(HERE / "qvis3"), str(CSRC / "qvis3_main.cpp"), "-L" + str(HERE), "-lqrad_cuda",
+              "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 

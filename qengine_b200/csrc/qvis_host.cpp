@@ -1,7 +1,9 @@
 // Host half of the qvis3 first stage (include/qvis_cuda.h): LoadPortals and PlaneFromWinding.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <unistd.h>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -272,6 +274,53 @@ int qvis_host_fast_vis(const char *bsp_in, const char *prt_path, const char *bsp
     g_qvis_error = e.what();
     return 1;
   }
+}
+
+
+// main() of the reference's qvis3 (qvis3.c:493-566) for what is built: the same flags are accepted, the same path rules
+// apply (the map argument expanded against the working directory, extension replaced by .bsp / .prt, -tmpin / -tmpout
+// prefix "/tmp"), the same chatter and error banner are printed.  Without -fast the tool stops: PortalFlow is not built.
+int qvis3_main(int argc, char **argv) {
+  printf("---- vis ----\n");
+  bool fast = false, tmpin = false, tmpout = false;
+  int device = 0, i;
+  auto die = [](const std::string &msg) {   // Error(), cmdlib.c:142-155
+    printf("\n************ ERROR ************\n%s\n", msg.c_str());
+    return 1;
+  };
+  for (i = 1; i < argc; i++) {
+    const char *a = argv[i];
+    if (!strcmp(a, "-threads")) i++;   // (the reference's Linux build runs one thread whatever is asked, threads.c:379-420)
+    else if (!strcmp(a, "-fast")) {
+      printf("fastvis = true\n");
+      fast = true;
+    } else if (!strcmp(a, "-level")) {
+      printf("testlevel = %i\n", i + 1 < argc ? atoi(argv[i + 1]) : 0);
+      i++;
+    } else if (!strcmp(a, "-v")) printf("verbose = true\n");
+    else if (!strcmp(a, "-nosort")) printf("nosort = true\n");
+    else if (!strcmp(a, "-tmpin")) tmpin = true;
+    else if (!strcmp(a, "-tmpout")) tmpout = true;
+    else if (!strcmp(a, "-gpu")) device = i + 1 < argc ? atoi(argv[++i]) : 0;   // extension: CUDA device ordinal
+    else if (a[0] == '-') return die(std::string("Unknown option \"") + a + "\"");
+    else break;
+  }
+  if (i != argc - 1) return die("usage: vis [-threads #] [-level 0-4] [-fast] [-v] bspfile");
+  if (!fast)
+    return die("PortalFlow is not built in this library (DESIGN.md section 9): run with -fast, or use the reference's qvis3");
+  std::string source = argv[i];
+  if (source[0] != '/') {   // ExpandArg, cmdlib.c:219-229
+    char cwd[1024];
+    if (!getcwd(cwd, sizeof cwd - 1)) return die("Couldn't determine current directory");
+    source = std::string(cwd) + "/" + source;
+  }
+  const size_t slash = source.find_last_of('/'), dot = source.find_last_of('.');
+  if (dot != std::string::npos && (slash == std::string::npos || dot > slash)) source.resize(dot);
+  const std::string inname = (tmpin ? "/tmp" : "") + source + ".bsp", prt = (tmpin ? "/tmp" : "") + source + ".prt",
+                    outname = (tmpout ? "/tmp" : "") + source + ".bsp";
+  printf("reading %s\n", inname.c_str());
+  if (qvis_host_fast_vis(inname.c_str(), prt.c_str(), outname.c_str(), device)) return die(g_qvis_error);
+  return 0;
 }
 
 }  // extern "C"

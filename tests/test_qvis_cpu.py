@@ -79,3 +79,29 @@ def test_merge_lump_matches_the_reference(case, tmp_path):
     assert vis2 >= vis
     with pytest.raises(qvis.QvisError, match="Vismap expansion overflow"):
         pt.merge_lump(want["vis"], cap=4 + 8 * pt.numclusters + 16)
+
+
+def test_qvis3_cli_errors(tmp_path):
+    """The drop-in executable speaks the reference's command line (qvis3.c:493-566): banner, usage, unknown options; it
+    stops without -fast (PortalFlow is not built) and, with -fast but no GPU, says there is no CPU fallback."""
+    import subprocess
+    import torch
+    exe = Path(__file__).resolve().parent.parent / "qengine_b200" / "qvis3"
+    if not exe.exists():
+        pytest.skip("qvis3 executable not built")
+    def run(*a):
+        return subprocess.run([str(exe), *a], capture_output=True, text=True, cwd=tmp_path)
+    r = run("-fast")
+    assert r.returncode == 1 and "---- vis ----" in r.stdout and "usage: vis" in r.stdout
+    r = run("-bogus", "x.bsp")
+    assert r.returncode == 1 and 'Unknown option "-bogus"' in r.stdout
+    r = run("x.bsp")
+    assert r.returncode == 1 and "PortalFlow is not built" in r.stdout
+    r = run("-fast", "missing.bsp")
+    assert r.returncode == 1 and "************ ERROR ************" in r.stdout
+    if not torch.cuda.is_available():
+        import gzip as gz
+        (tmp_path / "grid3.bsp").write_bytes(gz.decompress((GOLDEN / "vis_grid3.bsp.gz").read_bytes()))
+        (tmp_path / "grid3.prt").write_bytes(gz.decompress((GOLDEN / "vis_grid3.prt.gz").read_bytes()))
+        r = run("-fast", "grid3.bsp")
+        assert r.returncode == 1 and "no CPU fallback" in r.stdout and "121 numportals" in r.stdout
